@@ -1,0 +1,168 @@
+/*
+ * mosaic_b200.h — C ABI of the B200-native mosaic matching engine (libmosaic_b200.so).
+ *
+ * Drop-in boundary for the data-parallel matching path of naporin0624/mosaic-art-rust.
+ * The reference has no FFI of its own (pure Rust); these entry points are cut at
+ * the reference call sites a Rust `extern "C"` block would replace (file:line under
+ * /root/reference/src/ cited per function; the Rust-side binding is in INTEGRATION.md).
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every function returns 0 (MOSAIC_OK) or a negative status and
+ *    never unwinds across the ABI; mosaic_last_error() gives the message of the last failure.
+ *  - the caller owns every host pointer for the duration of the call only.
+ *  - one mosaic_ctx is used from one thread at a time (the reference runs the whole path on one
+ *    thread, main.rs:529; GUI: one spawn_blocking, gui/app_full.rs:1282).
+ *  - material index = position in the array given to mosaic_set_materials_rgb8 = `tiles[idx]`
+ *    after truncate (main.rs:255-257) = similarity-DB index of a freshly built DB (main.rs:123-125).
+ *  - there is NO CPU fallback: every compute entry point runs hand-written sm_100a CUDA kernels
+ *    and fails with MOSAIC_ERR_CUDA when no usable device is present.
+ *  - results: placements / annealed grids bit-exact, similarity entries bit-equal, Lab means
+ *    <= 1e-4 relative, output pixels <= 1 LSB vs the CPU oracle.
+ */
+#ifndef MOSAIC_B200_H
+#define MOSAIC_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MOSAIC_OK 0
+#define MOSAIC_ERR_INVALID (-1) /* bad argument */
+#define MOSAIC_ERR_CUDA (-2)    /* CUDA runtime / launch failure, or no device */
+#define MOSAIC_ERR_STATE (-3)   /* call order: a required input has not been set */
+#define MOSAIC_ERR_NCCL (-4)    /* collective failure (sharded contexts only) */
+#define MOSAIC_ERR_NOMEM (-5)
+
+#define MOSAIC_MAX_K 100 /* main.rs:348 `self.tiles.len().min(100)` */
+
+typedef struct mosaic_ctx mosaic_ctx;
+
+/* mirrors OptimizationResult, optimizer.rs:203-210 */
+typedef struct {
+  float initial_cost, final_cost, best_cost;
+  uint64_t improved_count, accepted_count, iterations;
+} mosaic_opt_result;
+
+/* stages for mosaic_stage_ms(): device time (CUDA events) of the most recent run of each kernel group */
+enum {
+  MOSAIC_STAGE_MATERIAL_LAB = 0, /* K1 lab_mean over materials */
+  MOSAIC_STAGE_CELL_LAB = 1,     /* K1 lab_mean over target cells */
+  MOSAIC_STAGE_TOPK = 2,         /* K2 nn_topk */
+  MOSAIC_STAGE_PLACE = 3,        /* K2b greedy replay */
+  MOSAIC_STAGE_SIMILARITY = 4,   /* K3 similarity_tri */
+  MOSAIC_STAGE_ANNEAL = 5,       /* K5 anneal */
+  MOSAIC_STAGE_RENDER = 6,       /* K4 resize+adjust+composite */
+  MOSAIC_STAGE_COUNT = 7
+};
+
+/* ---- context ------------------------------------------------------------------------------- */
+/* One context = one GPU (`device` = CUDA ordinal).  Owns device buffers, a stream and events. */
+int mosaic_ctx_create(mosaic_ctx** out, int device);
+/* Sharded context: rank `rank` of `world` single-GPU processes of ONE host (1/2/4/8).  Grid rows,
+ * material indices and similarity entries are partitioned over ranks; Lab means, candidate lists,
+ * material pixels and placements are exchanged with NCCL over NVLink.
+ * `nccl_unique_id` is the 128-byte ncclUniqueId created on rank 0 (mosaic_nccl_unique_id) and
+ * distributed by the host (e.g. torch.distributed broadcast / MPI / a file). */
+int mosaic_ctx_create_sharded(mosaic_ctx** out, int device, int rank, int world,
+                              const void* nccl_unique_id, size_t id_bytes);
+int mosaic_nccl_unique_id(void* id_out, size_t id_bytes);
+void mosaic_ctx_destroy(mosaic_ctx* ctx);
+const char* mosaic_last_error(const mosaic_ctx* ctx); /* ctx may be NULL: creation errors */
+/* Launch on a caller-owned CUDA stream (cudaStream_t as void*); NULL restores the context's own. */
+int mosaic_ctx_set_stream(mosaic_ctx* ctx, void* cuda_stream);
+int mosaic_ctx_sync(mosaic_ctx* ctx);
+int mosaic_stage_ms(mosaic_ctx* ctx, int stage, float* ms_out);
+/* number of kernels this library has launched on ctx since creation */
+uint64_t mosaic_kernel_launches(const mosaic_ctx* ctx);
+
+/* ---- inputs -------------------------------------------------------------------------------- */
+/* n uniform-size RGB8 materials, n*h*w*3 bytes, host memory (replaces the decoded `image::open`
+ * results of process_tile, main.rs:263-301).  Copies H2D. */
+int mosaic_set_materials_rgb8(mosaic_ctx* ctx, const uint8_t* rgb, int n, int w, int h);
+/* Same, but `dev_rgb` is device memory on ctx's GPU that stays valid until replaced (no copy). */
+int mosaic_set_materials_device(mosaic_ctx* ctx, const void* dev_rgb, int n, int w, int h);
+/* Target image w*h*3 RGB8 and the grid (main.rs:492-496: tile = img / grid, u32 floor). */
+int mosaic_set_target_rgb8(mosaic_ctx* ctx, const uint8_t* rgb, int w, int h, int grid_w, int grid_h);
+int mosaic_set_target_device(mosaic_ctx* ctx, const void* dev_rgb, int w, int h, int grid_w, int grid_h);
+/* Inject Lab means instead of computing them (similarity-database-only use, and stage-wise parity
+ * tests): n*3 / (grid_w*grid_h)*3 floats, host memory. */
+int mosaic_set_material_lab(mosaic_ctx* ctx, const float* lab, int n);
+int mosaic_set_cell_lab(mosaic_ctx* ctx, const float* lab, int grid_w, int grid_h);
+
+/* ---- B1/B2: Lab means  (MosaicGeneratorImpl::calculate_average_lab, lib.rs:94-119) ---------- */
+/* B1: all materials (call sites main.rs:280, 294).  lab_out: n*3 floats or NULL (keep on device). */
+int mosaic_material_lab(mosaic_ctx* ctx, float* lab_out);
+/* B2: all cells of the target grid, raster order (call site main.rs:540-541). */
+int mosaic_cell_lab(mosaic_ctx* ctx, float* lab_out);
+
+/* ---- B3: similarity matrix (SimilarityDatabase::build_similarities, similarity.rs:69-82) ---- */
+/* packed upper triangle, n(n-1)/2 floats, entry (i<j) at i*n - i(i+1)/2 + j - i - 1
+ * (similarity.rs:100).  sim_out may be NULL (matrix stays on the device). */
+int mosaic_similarity_tri(mosaic_ctx* ctx, float* sim_out);
+
+/* ---- B4: matching + greedy placement -------------------------------------------------------- */
+/* K nearest materials per cell (kdtree.nearest_n::<SquaredEuclidean>, main.rs:348-352), ascending
+ * by (squared distance, material index); k = min(n, k) <= MOSAIC_MAX_K entries per cell.
+ * idx_out / d2_out: C*k each, or NULL. */
+int mosaic_candidates(mosaic_ctx* ctx, int k, uint32_t* idx_out, float* d2_out);
+/* Raster-order greedy placement with usage cap, same-image-adjacent rule, adjacency penalty and the
+ * usage-reset fallback (find_and_use_best_tile_with_position + fallback_tile_selection,
+ * main.rs:335-475; UsageTracker lib.rs:57-89; calculate_penalty adjacency.rs:63-88).
+ * placed_out: C material indices, raster order (NULL = keep on device).  n_fallbacks: number of
+ * cells at which the fallback fired.  Runs mosaic_candidates first if it has not been run. */
+int mosaic_place(mosaic_ctx* ctx, int max_usage, float adjacency_weight,
+                 int32_t* placed_out, uint32_t* n_fallbacks);
+/* Raster indices of the first `cap` cells at which the fallback fired during the last mosaic_place. */
+int mosaic_fallback_cells(mosaic_ctx* ctx, uint32_t* cells_out, uint32_t cap, uint32_t* n_out);
+/* Replace the context's placement (C ids, -1 = empty), e.g. to anneal or render a given grid. */
+int mosaic_set_placement(mosaic_ctx* ctx, const int32_t* placed);
+
+/* ---- B5: annealing (MosaicOptimizer::optimize, optimizer.rs:41-129) ------------------------- */
+/* Works on the context's placement; placed_out (may be NULL) receives the annealed grid.
+ * The RNG stream is rand 0.8.5 StdRng::seed_from_u64(seed) (ChaCha12) — the reference uses the
+ * unseeded thread_rng (optimizer.rs:48), so the seed is an extension. */
+int mosaic_anneal(mosaic_ctx* ctx, uint64_t iterations, float t0, float decay, uint64_t seed,
+                  int32_t* placed_out, mosaic_opt_result* res);
+
+/* ---- B6: render (resize + colour adjustment + composite; main.rs:547-592, 625-664, 687-738;
+ *          color_adjustment.rs:40-154) ---------------------------------------------------------- */
+/* out_rgb: (grid_h*tile_h) x (grid_w*tile_w) x 3 bytes, or NULL (image stays on the device). */
+int mosaic_render(mosaic_ctx* ctx, float color_strength, uint8_t* out_rgb);
+
+/* ---- whole path in one call (generate_mosaic, main.rs:477-685, minus disk I/O and codecs) ---- */
+typedef struct {
+  int max_usage;             /* --max-usage-per-image (default 3) */
+  float adjacency_weight;    /* --adjacency-penalty-weight (0.3) */
+  float color_strength;      /* --color-adjustment-strength (0.3) */
+  int enable_optimization;   /* --enable-optimization (true) */
+  uint64_t optimization_iterations; /* --optimization-iterations (1000) */
+  uint64_t seed;             /* extension: annealer seed */
+  int build_similarity;      /* materialise the packed matrix (main.rs:126,143); it is never read by
+                                the kernels (they recompute entries bit-identically from Lab) */
+} mosaic_params;
+typedef struct {
+  uint32_t n_fallbacks;
+  mosaic_opt_result opt; /* zero if annealing did not run */
+  int annealed;          /* 1 if the optimisation phase ran (main.rs:608) */
+} mosaic_report;
+/* Requires materials + target to be set.  placed_out (C) and out_rgb may be NULL. */
+int mosaic_generate(mosaic_ctx* ctx, const mosaic_params* params, int32_t* placed_out,
+                    uint8_t* out_rgb, mosaic_report* report);
+
+/* ---- introspection -------------------------------------------------------------------------- */
+int mosaic_dims(const mosaic_ctx* ctx, int* n_materials, int* grid_w, int* grid_h, int* tile_w, int* tile_h);
+/* device pointers of resident results (NULL if absent): for zero-copy consumers */
+const void* mosaic_device_output(const mosaic_ctx* ctx);
+const void* mosaic_device_placement(const mosaic_ctx* ctx);
+const void* mosaic_device_similarity(const mosaic_ctx* ctx);
+/* sharding of this context: rows [row_begin,row_end) of the grid, materials [mat_begin,mat_end),
+ * packed similarity entries [tri_begin,tri_end) */
+int mosaic_shard(const mosaic_ctx* ctx, int* row_begin, int* row_end, int* mat_begin, int* mat_end,
+                 uint64_t* tri_begin, uint64_t* tri_end);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

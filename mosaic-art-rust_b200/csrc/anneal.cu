@@ -1,0 +1,285 @@
+// anneal.cu — K5: simulated annealing of the placement as ONE persistent kernel.
+//
+// Replaces MosaicOptimizer::optimize (reference src/optimizer.rs:41-129) with
+// AdjacencyPenaltyCalculator::calculate_total_cost / calculate_swap_delta (adjacency.rs:91-214).
+// The Markov chain is serial, so it runs as a single warp that never leaves the SM:
+//   * RNG: the reference draws from rand::thread_rng() (optimizer.rs:48), which is OS-seeded; the
+//     stream is therefore DEFINED as rand 0.8.5 StdRng::seed_from_u64(seed) = ChaCha12 (rand_chacha
+//     0.3.1: 64-bit block counter, stream 0, key = PCG32 expansion of the seed).  The 32 lanes each
+//     compute one ChaCha12 block (32 blocks = 512 words per refill) into a shared-memory ring; the
+//     chain consumes words exactly like BlockRng: next_u64 = two consecutive words (low first),
+//     gen_range(0..n) = widening-multiply rejection sampling, gen::<f32>() = (next_u32 >> 8) * 2^-24.
+//   * swap delta: the <= 8 neighbour terms 1/(sim+1) for the old and the new assignment are
+//     evaluated in parallel across lanes, then summed in the reference's order (pos1: Up, Down,
+//     Left, Right skipping pos2; pos2 likewise skipping pos1; then the mutual term) so the f32 sums
+//     are bit-identical.  sim is recomputed from the Lab means exactly like the packed matrix entry.
+//   * acceptance: exp(-delta / T) uses a deterministic double-precision exp (argument reduction +
+//     degree-13 Horner, unfused) rounded once to f32 — the same operation sequence as the oracle.
+//   * initial cost: calculate_total_cost's raster-order f32 sum is evaluated in 32-pair batches
+//     (terms in parallel, accumulation in order).
+#include "common.cuh"
+
+namespace mosaic {
+
+namespace {
+
+constexpr int RNG_RING_WORDS = 512;  // 32 ChaCha blocks
+
+__device__ __forceinline__ unsigned rotl32(unsigned v, int c) { return __funnelshift_l(v, v, c); }
+
+#define MOSAIC_QR(a, b, c, d) \
+  a += b; d ^= a; d = rotl32(d, 16); \
+  c += d; b ^= c; b = rotl32(b, 12); \
+  a += b; d ^= a; d = rotl32(d, 8);  \
+  c += d; b ^= c; b = rotl32(b, 7);
+
+__device__ void chacha12_block(const unsigned* key, unsigned long long counter, unsigned* out /* 16 words, stride 1 */) {
+  unsigned s0 = 0x61707865u, s1 = 0x3320646eu, s2 = 0x79622d32u, s3 = 0x6b206574u;
+  unsigned s4 = key[0], s5 = key[1], s6 = key[2], s7 = key[3], s8 = key[4], s9 = key[5], s10 = key[6], s11 = key[7];
+  unsigned s12 = (unsigned)counter, s13 = (unsigned)(counter >> 32), s14 = 0u, s15 = 0u;
+  unsigned x0 = s0, x1 = s1, x2 = s2, x3 = s3, x4 = s4, x5 = s5, x6 = s6, x7 = s7, x8 = s8, x9 = s9, x10 = s10,
+           x11 = s11, x12 = s12, x13 = s13, x14 = s14, x15 = s15;
+#pragma unroll
+  for (int r = 0; r < 6; ++r) {
+    MOSAIC_QR(x0, x4, x8, x12) MOSAIC_QR(x1, x5, x9, x13) MOSAIC_QR(x2, x6, x10, x14) MOSAIC_QR(x3, x7, x11, x15)
+    MOSAIC_QR(x0, x5, x10, x15) MOSAIC_QR(x1, x6, x11, x12) MOSAIC_QR(x2, x7, x8, x13) MOSAIC_QR(x3, x4, x9, x14)
+  }
+  out[0] = x0 + s0;   out[1] = x1 + s1;   out[2] = x2 + s2;    out[3] = x3 + s3;
+  out[4] = x4 + s4;   out[5] = x5 + s5;   out[6] = x6 + s6;    out[7] = x7 + s7;
+  out[8] = x8 + s8;   out[9] = x9 + s9;   out[10] = x10 + s10; out[11] = x11 + s11;
+  out[12] = x12 + s12; out[13] = x13 + s13; out[14] = x14 + s14; out[15] = x15 + s15;
+}
+
+struct Rng {
+  unsigned key[8];
+  unsigned long long next_block;  // counter of the first block of the next refill
+  unsigned* ring;                 // shared memory, RNG_RING_WORDS
+  int pos;                        // next unread word; RNG_RING_WORDS = empty
+
+  __device__ void refill(int lane) {
+    __syncwarp();
+    chacha12_block(key, next_block + (unsigned long long)lane, ring + 16 * lane);
+    next_block += 32ull;
+    pos = 0;
+    __syncwarp();
+  }
+  __device__ unsigned next_u32(int lane) {
+    if (pos >= RNG_RING_WORDS) refill(lane);
+    return ring[pos++];
+  }
+  __device__ unsigned long long next_u64(int lane) {  // BlockRng::next_u64: two consecutive words, low first
+    const unsigned lo = next_u32(lane);
+    const unsigned hi = next_u32(lane);
+    return ((unsigned long long)hi << 32) | lo;
+  }
+  __device__ unsigned long long gen_range(unsigned long long n, int lane) {  // UniformInt<usize>::sample_single
+    const unsigned long long zone = (n << __clzll((long long)n)) - 1ull;
+    for (;;) {
+      const unsigned long long v = next_u64(lane);
+      const unsigned long long hi = __umul64hi(v, n), lo = v * n;
+      if (lo <= zone) return hi;
+    }
+  }
+  __device__ float gen_f32(int lane) { return __fmul_rn((float)(next_u32(lane) >> 8), 1.0f / 16777216.0f); }
+};
+
+// deterministic f32 exp: identical operation sequence to the oracle (all IEEE double, unfused)
+__device__ float exp_det(float xf) {
+  if (xf != xf) return xf;
+  if (xf > 88.8f) return __int_as_float(0x7f800000);
+  if (xf < -104.0f) return 0.0f;
+  const double x = (double)xf;
+  const double kd = floor(__dadd_rn(__dmul_rn(x, 1.4426950408889634), 0.5));
+  double r = __dsub_rn(x, __dmul_rn(kd, 0.693147180369123816490e+00));
+  r = __dsub_rn(r, __dmul_rn(kd, 1.90821492927058770002e-10));
+  const double c[14] = {1.0, 1.0, 1.0 / 2, 1.0 / 6, 1.0 / 24, 1.0 / 120, 1.0 / 720, 1.0 / 5040,
+                        1.0 / 40320, 1.0 / 362880, 1.0 / 3628800, 1.0 / 39916800,
+                        1.0 / 479001600, 1.0 / 6227020800.0};
+  double p = c[13];
+#pragma unroll
+  for (int i = 12; i >= 0; --i) p = __dadd_rn(__dmul_rn(p, r), c[i]);
+  const int k = (int)kd;
+  const double scale = __longlong_as_double((long long)(k + 1023) << 52);
+  return __double2float_rn(__dmul_rn(p, scale));
+}
+
+__device__ __forceinline__ float pair_term(const float4* __restrict__ lab4, int a, int b) {
+  // get_similarity (similarity.rs:85-103): same index -> 0.0, else entry of (min, max)
+  if (a == b) return adjacency_term(0.0f);
+  const int lo = min(a, b), hi = max(a, b);
+  const float4 p = __ldg(&lab4[lo]), q = __ldg(&lab4[hi]);
+  return adjacency_term(lab_distance_rn(p.x, p.y, p.z, q.x, q.y, q.z));
+}
+
+template <bool GRID_SMEM>
+__global__ void __launch_bounds__(32, 1) anneal_kernel(const float4* __restrict__ lab4, int32_t* grid_gmem, int gw,
+                                                       int gh, unsigned long long iterations, float t0, float decay,
+                                                       unsigned long long seed, mosaic_opt_result* res) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  unsigned* ring = reinterpret_cast<unsigned*>(smem_raw);
+  volatile int32_t* grid = GRID_SMEM ? reinterpret_cast<int32_t*>(smem_raw + RNG_RING_WORDS * 4) : grid_gmem;
+  const int lane = threadIdx.x;
+  const int cells = gw * gh;
+  if (GRID_SMEM) {
+    for (int i = lane; i < cells; i += 32) grid[i] = grid_gmem[i];
+    __syncwarp();
+  }
+
+  // ---- calculate_total_cost (adjacency.rs:91-130): raster order, right then down ----
+  float current = 0.0f;
+  {
+    const long long pairs = 2ll * cells;  // slot 2*c = right pair of cell c, 2*c+1 = down pair
+    for (long long base = 0; base < pairs; base += 32) {
+      const long long s = base + lane;
+      float term = 0.0f;
+      bool present = false;
+      if (s < pairs) {
+        const int c = (int)(s >> 1), x = c % gw, y = c / gw;
+        const int cur = grid[c];
+        if (cur >= 0) {
+          if ((s & 1) == 0) {
+            if (x < gw - 1) {
+              const int r = grid[c + 1];
+              if (r >= 0) { term = pair_term(lab4, cur, r); present = true; }
+            }
+          } else if (y < gh - 1) {
+            const int d = grid[c + gw];
+            if (d >= 0) { term = pair_term(lab4, cur, d); present = true; }
+          }
+        }
+      }
+      const unsigned mask = __ballot_sync(0xffffffffu, present);
+#pragma unroll 4
+      for (int l = 0; l < 32; ++l) {
+        const float t = __shfl_sync(0xffffffffu, term, l);
+        if ((mask >> l) & 1u) current = __fadd_rn(current, t);
+      }
+    }
+  }
+  const float initial = current;
+  float best = current;
+  unsigned long long improved = 0, accepted = 0;
+  float temperature = t0;
+
+  Rng rng;
+  {
+    unsigned long long state = seed;  // rand_core seed_from_u64: PCG32 stream fills the 32-byte key
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      state = state * 6364136223846793005ull + 11634580027462260723ull;
+      const unsigned xorshifted = (unsigned)(((state >> 18) ^ state) >> 27);
+      const unsigned rot = (unsigned)(state >> 59);
+      rng.key[i] = __funnelshift_r(xorshifted, xorshifted, rot);
+    }
+    rng.next_block = 0ull;
+    rng.ring = ring;
+    rng.pos = RNG_RING_WORDS;
+  }
+
+  for (unsigned long long it = 0; it < iterations; ++it) {
+    const int x1 = (int)rng.gen_range((unsigned long long)gw, lane);  // optimizer.rs:60-63: x before y
+    const int y1 = (int)rng.gen_range((unsigned long long)gh, lane);
+    const int x2 = (int)rng.gen_range((unsigned long long)gw, lane);
+    const int y2 = (int)rng.gen_range((unsigned long long)gh, lane);
+    if (x1 == x2 && y1 == y2) continue;              // optimizer.rs:66-68 (no temperature decay)
+    const int i1 = y1 * gw + x1, i2 = y2 * gw + x2;
+    const int p1 = grid[i1], p2 = grid[i2];
+    if (p1 < 0 || p2 < 0) continue;                  // optimizer.rs:71-73
+
+    float delta = 0.0f;
+    if (p1 != p2) {                                  // adjacency.rs:156-158
+      // lanes 0-3: neighbours of pos1 (Up, Down, Left, Right); lanes 4-7: neighbours of pos2
+      const int side = (lane >> 2) & 1, dir = lane & 3;
+      const int cx = side ? x2 : x1, cy = side ? y2 : y1;
+      const int ox = side ? x1 : x2, oy = side ? y1 : y2;  // the other swap position (skipped)
+      const int nx = cx + (dir == 3) - (dir == 2), ny = cy + (dir == 1) - (dir == 0);
+      bool present = lane < 8 && nx >= 0 && nx < gw && ny >= 0 && ny < gh && !(nx == ox && ny == oy);
+      int nb = -1;
+      if (present) {
+        nb = grid[ny * gw + nx];
+        present = nb >= 0;
+      }
+      float t_old = 0.0f, t_new = 0.0f;
+      if (present) {
+        const int mine = side ? p2 : p1, other = side ? p1 : p2;
+        t_old = pair_term(lab4, mine, nb);   // cost with the current material at this position
+        t_new = pair_term(lab4, other, nb);  // cost after the swap
+      }
+      const unsigned mask = __ballot_sync(0xffffffffu, present);
+      float old_cost = 0.0f, new_cost = 0.0f;
+#pragma unroll
+      for (int l = 0; l < 8; ++l) {
+        const float to = __shfl_sync(0xffffffffu, t_old, l), tn = __shfl_sync(0xffffffffu, t_new, l);
+        if ((mask >> l) & 1u) {
+          old_cost = __fadd_rn(old_cost, to);
+          new_cost = __fadd_rn(new_cost, tn);
+        }
+      }
+      const bool adjacent12 = (x1 == x2 && (y1 - y2 == 1 || y2 - y1 == 1)) || (y1 == y2 && (x1 - x2 == 1 || x2 - x1 == 1));
+      if (adjacent12) {                              // adjacency.rs:203-211
+        const float cost = pair_term(lab4, p1, p2);
+        old_cost = __fadd_rn(old_cost, cost);
+        new_cost = __fadd_rn(new_cost, cost);
+      }
+      delta = __fsub_rn(new_cost, old_cost);
+    }
+
+    bool accept;
+    if (delta < 0.0f) {
+      accept = true;
+    } else {
+      const float probability = exp_det(__fdiv_rn(-delta, temperature));  // optimizer.rs:82
+      accept = rng.gen_f32(lane) < probability;                           // optimizer.rs:83
+    }
+    if (accept) {
+      if (lane == 0) {
+        grid[i1] = p2;
+        grid[i2] = p1;
+      }
+      __syncwarp();
+      current = __fadd_rn(current, delta);
+      accepted += 1;
+      if (current < best) {
+        best = current;
+        improved += 1;
+      }
+    }
+    temperature = __fmul_rn(temperature, decay);     // optimizer.rs:102
+  }
+
+  if (GRID_SMEM) {
+    __syncwarp();
+    for (int i = lane; i < cells; i += 32) grid_gmem[i] = grid[i];
+  }
+  if (lane == 0) {
+    res->initial_cost = initial;
+    res->final_cost = current;
+    res->best_cost = best;
+    res->improved_count = improved;
+    res->accepted_count = accepted;
+    res->iterations = iterations;  // optimizer.rs:127
+  }
+}
+
+}  // namespace
+
+int launch_anneal(mosaic_ctx* ctx, uint64_t iterations, float t0, float decay, uint64_t seed) {
+  const size_t cells = (size_t)ctx->gw * ctx->gh;
+  const size_t ring_bytes = RNG_RING_WORDS * 4;
+  const size_t smem_grid = ring_bytes + cells * 4;
+  StageTimer t(ctx, MOSAIC_STAGE_ANNEAL);
+  if (smem_grid <= 200 * 1024) {
+    MOSAIC_CUDA(ctx, cudaFuncSetAttribute(anneal_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_grid));
+    anneal_kernel<true><<<1, 32, smem_grid, ctx->stream>>>(ctx->d_mat_lab4, ctx->d_placed, ctx->gw, ctx->gh, iterations,
+                                                           t0, decay, seed, (mosaic_opt_result*)ctx->d_opt_res);
+  } else {
+    anneal_kernel<false><<<1, 32, ring_bytes, ctx->stream>>>(ctx->d_mat_lab4, ctx->d_placed, ctx->gw, ctx->gh,
+                                                             iterations, t0, decay, seed,
+                                                             (mosaic_opt_result*)ctx->d_opt_res);
+  }
+  ctx->launches++;
+  MOSAIC_CUDA(ctx, cudaGetLastError());
+  return MOSAIC_OK;
+}
+
+}  // namespace mosaic

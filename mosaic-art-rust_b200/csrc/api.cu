@@ -1,0 +1,683 @@
+// api.cu — the extern "C" ABI of include/mosaic_b200.h: context, inputs, stage entry points and
+// the fused whole-path call.  Host code only; every compute step is one of the sm_100a kernels in
+// lab_mean.cu / nn_topk.cu / greedy.cu / similarity.cu / anneal.cu / render.cu.  There is no CPU
+// fallback: without a usable CUDA device every entry point fails with MOSAIC_ERR_CUDA.
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "common.cuh"
+
+namespace mosaic {
+
+static std::mutex g_err_mu;
+static std::string g_err;  // errors that happen before a context exists
+
+void set_global_error(const std::string& msg) {
+  std::lock_guard<std::mutex> lk(g_err_mu);
+  g_err = msg;
+}
+
+int fail(mosaic_ctx* ctx, int code, const std::string& msg) {
+  if (ctx)
+    ctx->err = msg;
+  else
+    set_global_error(msg);
+  return code;
+}
+
+int cuda_fail(mosaic_ctx* ctx, cudaError_t e, const char* what) {
+  std::string m = std::string(what) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")";
+  (void)cudaGetLastError();  // clear the sticky-less error state
+  return fail(ctx, MOSAIC_ERR_CUDA, m);
+}
+
+namespace {
+
+inline size_t cells_of(const mosaic_ctx* c) { return (size_t)c->gw * (size_t)c->gh; }
+
+// contiguous split of [0, total) over `world` ranks, boundaries rounded down to `align`
+inline void split_range(uint64_t total, int world, int rank, uint64_t align, uint64_t* b, uint64_t* e) {
+  auto bound = [&](int r) -> uint64_t {
+    if (r <= 0) return 0;
+    if (r >= world) return total;
+    uint64_t v = (total / (uint64_t)world) * (uint64_t)r + std::min<uint64_t>((uint64_t)r, total % (uint64_t)world);
+    return align > 1 ? (v / align) * align : v;
+  };
+  *b = bound(rank);
+  *e = bound(rank + 1);
+}
+
+void shard_rows(const mosaic_ctx* c, int rank, int* b, int* e) {
+  uint64_t rb, re;
+  split_range((uint64_t)c->gh, c->world, rank, 1, &rb, &re);
+  *b = (int)rb;
+  *e = (int)re;
+}
+void shard_mats(const mosaic_ctx* c, int rank, int* b, int* e) {
+  uint64_t rb, re;
+  split_range((uint64_t)c->n, c->world, rank, 1, &rb, &re);
+  *b = (int)rb;
+  *e = (int)re;
+}
+void shard_tri(const mosaic_ctx* c, int rank, uint64_t* b, uint64_t* e) {
+  const uint64_t n = (uint64_t)c->n;
+  const uint64_t total = n > 1 ? n * (n - 1) / 2 : 0;
+  split_range(total, c->world, rank, 512, b, e);  // 512-entry (2 KB) aligned: whole warp steps, 16-byte stores
+}
+
+// gather per-rank contiguous slices [off_r, off_r+size_r) of one device buffer on every rank
+template <class F>
+int allgather_slices(mosaic_ctx* c, void* buf, size_t elem_bytes, F slice_of_rank) {
+  if (c->world == 1) return MOSAIC_OK;
+  std::vector<size_t> offs(c->world), sizes(c->world);
+  for (int r = 0; r < c->world; ++r) {
+    uint64_t b, e;
+    slice_of_rank(r, &b, &e);
+    offs[r] = (size_t)b * elem_bytes;
+    sizes[r] = (size_t)(e - b) * elem_bytes;
+  }
+  return dist_allgatherv_inplace(c, buf, offs.data(), sizes.data());
+}
+
+int require(mosaic_ctx* c, bool cond, const char* what) {
+  if (!cond) return fail(c, MOSAIC_ERR_STATE, std::string("missing input: ") + what);
+  return MOSAIC_OK;
+}
+
+int ensure_mat_lab_buffers(mosaic_ctx* c, int n) {
+  const int n_pad = (n + 3) & ~3;
+  if (c->mat_lab_cap < (size_t)n_pad || !c->d_mat_lab) {
+    if (c->d_mat_lab) cudaFree(c->d_mat_lab);
+    if (c->d_mat_lab4) cudaFree(c->d_mat_lab4);
+    if (c->d_mat_soa) cudaFree(c->d_mat_soa);
+    c->d_mat_lab = nullptr;
+    c->d_mat_lab4 = nullptr;
+    c->d_mat_soa = nullptr;
+    c->mat_lab_cap = 0;
+    MOSAIC_CUDA(c, cudaMalloc((void**)&c->d_mat_lab, sizeof(float) * 3 * (size_t)n_pad));
+    MOSAIC_CUDA(c, cudaMalloc((void**)&c->d_mat_lab4, sizeof(float4) * (size_t)n_pad));
+    MOSAIC_CUDA(c, cudaMalloc((void**)&c->d_mat_soa, sizeof(float) * 3 * (size_t)n_pad));
+    c->mat_lab_cap = (size_t)n_pad;
+  }
+  c->n_pad = n_pad;
+  return MOSAIC_OK;
+}
+
+int ensure_cell_buffers(mosaic_ctx* c) {
+  const size_t cells = cells_of(c);
+  if (c->cell_cap < cells || !c->d_cell_lab) {
+    if (c->d_cell_lab) cudaFree(c->d_cell_lab);
+    if (c->d_cell_rgbsum) cudaFree(c->d_cell_rgbsum);
+    c->d_cell_lab = nullptr;
+    c->d_cell_rgbsum = nullptr;
+    c->cell_cap = 0;
+    MOSAIC_CUDA(c, cudaMalloc((void**)&c->d_cell_lab, sizeof(float) * 3 * cells));
+    MOSAIC_CUDA(c, cudaMalloc((void**)&c->d_cell_rgbsum, sizeof(unsigned long long) * 3 * cells));
+    c->cell_cap = cells;
+  }
+  return MOSAIC_OK;
+}
+
+int set_grid(mosaic_ctx* c, int w, int h, int gw, int gh) {
+  if (w <= 0 || h <= 0 || gw <= 0 || gh <= 0) return fail(c, MOSAIC_ERR_INVALID, "target/grid dimensions must be positive");
+  if (w / gw == 0 || h / gh == 0) return fail(c, MOSAIC_ERR_INVALID, "grid finer than the target image (tile size 0)");
+  if ((uint64_t)gw * (uint64_t)gh > 0x7fffffffull) return fail(c, MOSAIC_ERR_INVALID, "too many cells");
+  c->tw_img = w;
+  c->th_img = h;
+  c->gw = gw;
+  c->gh = gh;
+  c->tile_w = w / gw;  // main.rs:495-496
+  c->tile_h = h / gh;
+  c->have_cell_lab = c->have_cell_rgbsum = c->have_cand = c->have_placed = c->have_out = false;
+  return MOSAIC_OK;
+}
+
+int d2h(mosaic_ctx* c, void* dst, const void* src, size_t bytes) {
+  if (!dst || bytes == 0) return MOSAIC_OK;
+  MOSAIC_CUDA(c, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
+  return MOSAIC_OK;
+}
+
+int sync(mosaic_ctx* c) {
+  MOSAIC_CUDA(c, cudaStreamSynchronize(c->stream));
+  return MOSAIC_OK;
+}
+
+// ---- stage drivers (no host synchronisation inside) ------------------------------------------
+int run_material_lab(mosaic_ctx* c) {
+  MOSAIC_TRY(require(c, c->have_materials, "materials (mosaic_set_materials_rgb8)"));
+  MOSAIC_TRY(ensure_mat_lab_buffers(c, c->n));
+  if (c->world == 1) {
+    MOSAIC_TRY(launch_material_lab(c));
+  } else {
+    // index-sharded: this rank's slice, then allgather of 12 B x N
+    int b, e;
+    shard_mats(c, c->rank, &b, &e);
+    const uint8_t* all = c->d_materials;
+    float* lab_all = c->d_mat_lab;
+    const int n_all = c->n;
+    c->d_materials = all + (size_t)b * c->mw * c->mh * 3;
+    c->d_mat_lab = lab_all + 3 * (size_t)b;
+    c->n = e - b;
+    int rc = c->n > 0 ? launch_material_lab(c) : MOSAIC_OK;
+    c->d_materials = all;
+    c->d_mat_lab = lab_all;
+    c->n = n_all;
+    MOSAIC_TRY(rc);
+    MOSAIC_TRY(allgather_slices(c, c->d_mat_lab, 3 * sizeof(float), [&](int r, uint64_t* sb, uint64_t* se) {
+      int ib, ie;
+      shard_mats(c, r, &ib, &ie);
+      *sb = (uint64_t)ib;
+      *se = (uint64_t)ie;
+    }));
+  }
+  MOSAIC_TRY(launch_pack_lab(c));
+  c->have_mat_lab = true;
+  c->have_cand = false;
+  c->have_sim = false;
+  return MOSAIC_OK;
+}
+
+int run_cell_lab(mosaic_ctx* c) {
+  MOSAIC_TRY(require(c, c->have_target, "target (mosaic_set_target_rgb8)"));
+  MOSAIC_TRY(ensure_cell_buffers(c));
+  int rb, re;
+  shard_rows(c, c->rank, &rb, &re);
+  MOSAIC_TRY(launch_cell_lab_range(c, rb * c->gw, re * c->gw));
+  MOSAIC_TRY(allgather_slices(c, c->d_cell_lab, 3 * sizeof(float) * (size_t)c->gw,
+                              [&](int r, uint64_t* sb, uint64_t* se) {
+                                int ib, ie;
+                                shard_rows(c, r, &ib, &ie);
+                                *sb = (uint64_t)ib;
+                                *se = (uint64_t)ie;
+                              }));
+  c->have_cell_lab = true;
+  c->have_cell_rgbsum = true;  // valid for this rank's rows (all the render kernel needs)
+  c->have_cand = false;
+  return MOSAIC_OK;
+}
+
+int run_candidates(mosaic_ctx* c, int k) {
+  if (!c->have_mat_lab) MOSAIC_TRY(run_material_lab(c));
+  if (!c->have_cell_lab) MOSAIC_TRY(run_cell_lab(c));
+  if (k <= 0 || k > kMaxK) k = kMaxK;
+  if (k > c->n) k = c->n;  // main.rs:348 min(len, 100)
+  if (k <= 0) return fail(c, MOSAIC_ERR_STATE, "no materials");
+  const size_t cells = cells_of(c);
+  if (c->cand_cap < cells * (size_t)kMaxK || !c->d_cand_idx) {
+    if (c->d_cand_idx) cudaFree(c->d_cand_idx);
+    if (c->d_cand_d2) cudaFree(c->d_cand_d2);
+    c->d_cand_idx = nullptr;
+    c->d_cand_d2 = nullptr;
+    c->cand_cap = 0;
+    MOSAIC_CUDA(c, cudaMalloc((void**)&c->d_cand_idx, sizeof(uint32_t) * cells * kMaxK));
+    MOSAIC_CUDA(c, cudaMalloc((void**)&c->d_cand_d2, sizeof(float) * cells * kMaxK));
+    c->cand_cap = cells * (size_t)kMaxK;
+  }
+  c->k = k;
+  int rb, re;
+  shard_rows(c, c->rank, &rb, &re);
+  MOSAIC_TRY(launch_topk_range(c, k, rb * c->gw, re * c->gw));
+  auto rows = [&](int r, uint64_t* sb, uint64_t* se) {
+    int ib, ie;
+    shard_rows(c, r, &ib, &ie);
+    *sb = (uint64_t)ib;
+    *se = (uint64_t)ie;
+  };
+  MOSAIC_TRY(allgather_slices(c, c->d_cand_idx, sizeof(uint32_t) * (size_t)c->gw * k, rows));
+  MOSAIC_TRY(allgather_slices(c, c->d_cand_d2, sizeof(float) * (size_t)c->gw * k, rows));
+  c->have_cand = true;
+  return MOSAIC_OK;
+}
+
+int ensure_placed(mosaic_ctx* c) { return ensure(c, &c->d_placed, &c->placed_cap, cells_of(c)); }
+
+int run_place(mosaic_ctx* c, int max_usage, float weight) {
+  if (!c->have_cand) MOSAIC_TRY(run_candidates(c, kMaxK));
+  MOSAIC_TRY(ensure_placed(c));
+  if (c->rank == 0) MOSAIC_TRY(launch_place(c, max_usage, weight));  // serial chain: one GPU
+  if (c->world > 1) {
+    MOSAIC_TRY(dist_broadcast(c, c->d_placed, cells_of(c) * sizeof(int32_t), 0));
+    MOSAIC_TRY(dist_broadcast(c, c->d_place_info, (1 + mosaic_ctx::kFallbackCap) * sizeof(uint32_t), 0));
+  }
+  c->have_placed = true;
+  return MOSAIC_OK;
+}
+
+int run_anneal(mosaic_ctx* c, uint64_t iterations, float t0, float decay, uint64_t seed) {
+  MOSAIC_TRY(require(c, c->have_placed, "placement (mosaic_place / mosaic_set_placement)"));
+  MOSAIC_TRY(require(c, c->have_mat_lab, "material Lab means"));
+  if (c->rank == 0) MOSAIC_TRY(launch_anneal(c, iterations, t0, decay, seed));  // one Markov chain: one GPU
+  if (c->world > 1) {
+    MOSAIC_TRY(dist_broadcast(c, c->d_placed, cells_of(c) * sizeof(int32_t), 0));
+    MOSAIC_TRY(dist_broadcast(c, c->d_opt_res, sizeof(mosaic_opt_result), 0));
+  }
+  return MOSAIC_OK;
+}
+
+int run_similarity(mosaic_ctx* c) {
+  if (!c->have_mat_lab) MOSAIC_TRY(run_material_lab(c));
+  const uint64_t n = (uint64_t)c->n;
+  const uint64_t total = n > 1 ? n * (n - 1) / 2 : 0;  // similarity.rs:71 (n == 0 underflows in the reference)
+  MOSAIC_TRY(ensure(c, &c->d_sim, &c->sim_cap, (size_t)total));
+  uint64_t b, e;
+  shard_tri(c, c->rank, &b, &e);
+  if (c->world == 1) {
+    MOSAIC_TRY(launch_similarity(c, 0, total));
+  } else {
+    float* full = c->d_sim;
+    c->d_sim = full + b;  // the kernel writes entry `begin` at out[0]
+    int rc = launch_similarity(c, b, e);
+    c->d_sim = full;
+    MOSAIC_TRY(rc);
+    MOSAIC_TRY(allgather_slices(c, c->d_sim, sizeof(float), [&](int r, uint64_t* sb, uint64_t* se) { shard_tri(c, r, sb, se); }));
+  }
+  c->have_sim = true;
+  return MOSAIC_OK;
+}
+
+int run_render(mosaic_ctx* c, float strength) {
+  MOSAIC_TRY(require(c, c->have_materials, "materials"));
+  MOSAIC_TRY(require(c, c->have_target, "target"));
+  MOSAIC_TRY(require(c, c->have_placed, "placement"));
+  if (strength > 0.0f && !c->have_cell_rgbsum) MOSAIC_TRY(run_cell_lab(c));
+  if (!c->d_cell_rgbsum) MOSAIC_TRY(ensure_cell_buffers(c));
+  const size_t out_bytes = (size_t)c->gw * c->tile_w * (size_t)c->gh * c->tile_h * 3;
+  MOSAIC_TRY(ensure(c, &c->d_out, &c->out_cap, out_bytes));
+  int rb, re;
+  shard_rows(c, c->rank, &rb, &re);
+  MOSAIC_TRY(launch_render(c, strength, rb, re));
+  c->have_out = true;
+  return MOSAIC_OK;
+}
+
+int copy_out_image(mosaic_ctx* c, uint8_t* out_rgb) {
+  if (!out_rgb) return MOSAIC_OK;
+  int rb, re;
+  shard_rows(c, c->rank, &rb, &re);  // sharded contexts deliver their own row band (other rows untouched)
+  const size_t row_bytes = (size_t)c->gw * c->tile_w * 3 * (size_t)c->tile_h;
+  return d2h(c, out_rgb + (size_t)rb * row_bytes, c->d_out + (size_t)rb * row_bytes, (size_t)(re - rb) * row_bytes);
+}
+
+}  // namespace
+}  // namespace mosaic
+
+using namespace mosaic;
+
+extern "C" {
+
+const char* mosaic_last_error(const mosaic_ctx* ctx) {
+  if (ctx) return ctx->err.c_str();
+  std::lock_guard<std::mutex> lk(g_err_mu);
+  static thread_local std::string copy;
+  copy = g_err;
+  return copy.c_str();
+}
+
+static int ctx_create_common(mosaic_ctx** out, int device) {
+  if (!out) return fail(nullptr, MOSAIC_ERR_INVALID, "out is NULL");
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    (void)cudaGetLastError();
+    return fail(nullptr, MOSAIC_ERR_CUDA,
+                std::string("no usable CUDA device (this library has no CPU fallback): ") +
+                    (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
+  }
+  if (device < 0 || device >= count) return fail(nullptr, MOSAIC_ERR_INVALID, "device ordinal out of range");
+  e = cudaSetDevice(device);
+  if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaSetDevice");
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaGetDeviceProperties");
+  if (prop.major != 10)
+    return fail(nullptr, MOSAIC_ERR_CUDA,
+                std::string("device ") + prop.name + " is sm_" + std::to_string(prop.major) + std::to_string(prop.minor) +
+                    "; this library ships sm_100a code only");
+  mosaic_ctx* c = new mosaic_ctx();
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) {
+    delete c;
+    return cuda_fail(nullptr, e, "cudaStreamCreate");
+  }
+  c->stream = c->own_stream;
+  for (int i = 0; i < MOSAIC_STAGE_COUNT; ++i) {
+    cudaEventCreate(&c->ev_begin[i]);
+    cudaEventCreate(&c->ev_end[i]);
+  }
+  bool ok = cudaMalloc((void**)&c->d_place_info, (1 + mosaic_ctx::kFallbackCap) * sizeof(uint32_t)) == cudaSuccess &&
+            cudaMalloc(&c->d_opt_res, sizeof(mosaic_opt_result)) == cudaSuccess &&
+            cudaMemset(c->d_place_info, 0, (1 + mosaic_ctx::kFallbackCap) * sizeof(uint32_t)) == cudaSuccess &&
+            cudaMemset(c->d_opt_res, 0, sizeof(mosaic_opt_result)) == cudaSuccess;
+  if (!ok) {
+    mosaic_ctx_destroy(c);
+    return fail(nullptr, MOSAIC_ERR_CUDA, "context allocation failed");
+  }
+  *out = c;
+  return MOSAIC_OK;
+}
+
+int mosaic_ctx_create(mosaic_ctx** out, int device) { return ctx_create_common(out, device); }
+
+int mosaic_ctx_create_sharded(mosaic_ctx** out, int device, int rank, int world, const void* nccl_unique_id,
+                              size_t id_bytes) {
+  if (world < 1 || rank < 0 || rank >= world) return fail(nullptr, MOSAIC_ERR_INVALID, "bad rank/world");
+  MOSAIC_TRY(ctx_create_common(out, device));
+  mosaic_ctx* c = *out;
+  c->rank = rank;
+  c->world = world;
+  if (world > 1) {
+    int rc = dist_init(c, nccl_unique_id, id_bytes);
+    if (rc != MOSAIC_OK) {
+      set_global_error(c->err);
+      mosaic_ctx_destroy(c);
+      *out = nullptr;
+      return rc;
+    }
+  }
+  return MOSAIC_OK;
+}
+
+int mosaic_nccl_unique_id(void* id_out, size_t id_bytes) { return dist_unique_id(id_out, id_bytes); }
+
+void mosaic_ctx_destroy(mosaic_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  dist_destroy(c);
+  void* bufs[] = {c->d_materials_owned, c->d_mat_lab, c->d_mat_lab4, c->d_mat_soa, c->d_target_owned, c->d_cell_lab,
+                  c->d_cell_rgbsum,     c->d_cand_idx, c->d_cand_d2, c->d_placed,  c->d_usage,        c->d_place_info,
+                  c->d_sim,             c->d_opt_res,  c->d_rng_ring, c->d_out,    c->axis_h.start,   c->axis_h.size,
+                  c->axis_h.w,          c->axis_v.start, c->axis_v.size, c->axis_v.w};
+  for (void* p : bufs)
+    if (p) cudaFree(p);
+  if (c->h_pinned) cudaFreeHost(c->h_pinned);
+  for (int i = 0; i < MOSAIC_STAGE_COUNT; ++i) {
+    if (c->ev_begin[i]) cudaEventDestroy(c->ev_begin[i]);
+    if (c->ev_end[i]) cudaEventDestroy(c->ev_end[i]);
+  }
+  if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  delete c;
+}
+
+int mosaic_ctx_set_stream(mosaic_ctx* c, void* cuda_stream) {
+  if (!c) return MOSAIC_ERR_INVALID;
+  MOSAIC_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->stream = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream;
+  return MOSAIC_OK;
+}
+
+int mosaic_ctx_sync(mosaic_ctx* c) {
+  if (!c) return MOSAIC_ERR_INVALID;
+  return sync(c);
+}
+
+int mosaic_stage_ms(mosaic_ctx* c, int stage, float* ms_out) {
+  if (!c || !ms_out || stage < 0 || stage >= MOSAIC_STAGE_COUNT) return MOSAIC_ERR_INVALID;
+  if (!c->ev_valid[stage]) return fail(c, MOSAIC_ERR_STATE, "stage has not run");
+  MOSAIC_CUDA(c, cudaEventSynchronize(c->ev_end[stage]));
+  MOSAIC_CUDA(c, cudaEventElapsedTime(ms_out, c->ev_begin[stage], c->ev_end[stage]));
+  return MOSAIC_OK;
+}
+
+uint64_t mosaic_kernel_launches(const mosaic_ctx* c) { return c ? c->launches : 0; }
+
+// ---- inputs ----------------------------------------------------------------------------------
+static int set_materials_common(mosaic_ctx* c, int n, int w, int h) {
+  if (n <= 0 || w <= 0 || h <= 0) return fail(c, MOSAIC_ERR_INVALID, "materials: n, w, h must be positive");
+  c->n = n;
+  c->mw = w;
+  c->mh = h;
+  c->have_materials = true;
+  c->have_mat_lab = c->have_cand = c->have_placed = c->have_sim = c->have_out = false;
+  return MOSAIC_OK;
+}
+
+int mosaic_set_materials_rgb8(mosaic_ctx* c, const uint8_t* rgb, int n, int w, int h) {
+  if (!c) return MOSAIC_ERR_INVALID;
+  if (!rgb) return fail(c, MOSAIC_ERR_INVALID, "materials pointer is NULL");
+  MOSAIC_CUDA(c, cudaSetDevice(c->device));
+  MOSAIC_TRY(set_materials_common(c, n, w, h));
+  c->have_materials = false;
+  const size_t per = (size_t)w * h * 3;
+  MOSAIC_TRY(ensure(c, &c->d_materials_owned, &c->materials_cap, per * (size_t)n));
+  c->d_materials = c->d_materials_owned;
+  int b = 0, e = n;
+  if (c->world > 1) shard_mats(c, c->rank, &b, &e);
+  // each rank uploads its slice over its own PCIe link; slices are exchanged over NVLink
+  MOSAIC_CUDA(c, cudaMemcpyAsync(c->d_materials_owned + (size_t)b * per, rgb + (size_t)b * per, (size_t)(e - b) * per,
+                                 cudaMemcpyHostToDevice, c->stream));
+  MOSAIC_TRY(allgather_slices(c, c->d_materials_owned, per, [&](int r, uint64_t* sb, uint64_t* se) {
+    int ib, ie;
+    shard_mats(c, r, &ib, &ie);
+    *sb = (uint64_t)ib;
+    *se = (uint64_t)ie;
+  }));
+  c->have_materials = true;
+  return MOSAIC_OK;
+}
+
+int mosaic_set_materials_device(mosaic_ctx* c, const void* dev_rgb, int n, int w, int h) {
+  if (!c) return MOSAIC_ERR_INVALID;
+  if (!dev_rgb) return fail(c, MOSAIC_ERR_INVALID, "materials pointer is NULL");
+  MOSAIC_CUDA(c, cudaSetDevice(c->device));
+  MOSAIC_TRY(set_materials_common(c, n, w, h));
+  c->d_materials = (const uint8_t*)dev_rgb;
+  return MOSAIC_OK;
+}
+
+int mosaic_set_target_rgb8(mosaic_ctx* c, const uint8_t* rgb, int w, int h, int grid_w, int grid_h) {
+  if (!c) return MOSAIC_ERR_INVALID;
+  if (!rgb) return fail(c, MOSAIC_ERR_INVALID, "target pointer is NULL");
+  MOSAIC_CUDA(c, cudaSetDevice(c->device));
+  MOSAIC_TRY(set_grid(c, w, h, grid_w, grid_h));
+  c->have_target = false;
+  MOSAIC_TRY(ensure(c, &c->d_target_owned, &c->target_cap, (size_t)w * h * 3));
+  c->d_target = c->d_target_owned;
+  int rb = 0, re = grid_h;
+  if (c->world > 1) shard_rows(c, c->rank, &rb, &re);  // only this rank's band of pixel rows is uploaded
+  const size_t row_bytes = (size_t)w * 3;
+  const size_t y0 = (size_t)rb * c->tile_h, y1 = (c->world > 1) ? (size_t)re * c->tile_h : (size_t)h;
+  if (y1 > y0)
+    MOSAIC_CUDA(c, cudaMemcpyAsync(c->d_target_owned + y0 * row_bytes, rgb + y0 * row_bytes, (y1 - y0) * row_bytes,
+                                   cudaMemcpyHostToDevice, c->stream));
+  c->have_target = true;
+  return MOSAIC_OK;
+}
+
+int mosaic_set_target_device(mosaic_ctx* c, const void* dev_rgb, int w, int h, int grid_w, int grid_h) {
+  if (!c) return MOSAIC_ERR_INVALID;
+  if (!dev_rgb) return fail(c, MOSAIC_ERR_INVALID, "target pointer is NULL");
+  MOSAIC_CUDA(c, cudaSetDevice(c->device));
+  MOSAIC_TRY(set_grid(c, w, h, grid_w, grid_h));
+  c->d_target = (const uint8_t*)dev_rgb;
+  c->have_target = true;
+  return MOSAIC_OK;
+}
+
+int mosaic_set_material_lab(mosaic_ctx* c, const float* lab, int n) {
+  if (!c) return MOSAIC_ERR_INVALID;
+  if (!lab || n <= 0) return fail(c, MOSAIC_ERR_INVALID, "material Lab: bad arguments");
+  MOSAIC_CUDA(c, cudaSetDevice(c->device));
+  if (c->have_materials && n != c->n) return fail(c, MOSAIC_ERR_INVALID, "material Lab count differs from the material count");
+  c->n = n;
+  MOSAIC_TRY(ensure_mat_lab_buffers(c, n));
+  MOSAIC_CUDA(c, cudaMemcpyAsync(c->d_mat_lab, lab, sizeof(float) * 3 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+  MOSAIC_TRY(launch_pack_lab(c));
+  MOSAIC_TRY(sync(c));
+  c->have_mat_lab = true;
+  c->have_cand = c->have_sim = false;
+  return MOSAIC_OK;
+}
+
+int mosaic_set_cell_lab(mosaic_ctx* c, const float* lab, int grid_w, int grid_h) {
+  if (!c) return MOSAIC_ERR_INVALID;
+  if (!lab || grid_w <= 0 || grid_h <= 0) return fail(c, MOSAIC_ERR_INVALID, "cell Lab: bad arguments");
+  MOSAIC_CUDA(c, cudaSetDevice(c->device));
+  if (c->have_target) {
+    if (grid_w != c->gw || grid_h != c->gh) return fail(c, MOSAIC_ERR_INVALID, "cell Lab grid differs from the target grid");
+  } else {
+    c->gw = grid_w;
+    c->gh = grid_h;
+  }
+  MOSAIC_TRY(ensure_cell_buffers(c));
+  MOSAIC_CUDA(c, cudaMemcpyAsync(c->d_cell_lab, lab, sizeof(float) * 3 * cells_of(c), cudaMemcpyHostToDevice, c->stream));
+  MOSAIC_TRY(sync(c));
+  c->have_cell_lab = true;
+  c->have_cand = false;
+  return MOSAIC_OK;
+}
+
+// ---- stages ----------------------------------------------------------------------------------
+int mosaic_material_lab(mosaic_ctx* c, float* lab_out) {
+  if (!c) return MOSAIC_ERR_INVALID;
+  MOSAIC_CUDA(c, cudaSetDevice(c->device));
+  MOSAIC_TRY(run_material_lab(c));
+  MOSAIC_TRY(d2h(c, lab_out, c->d_mat_lab, sizeof(float) * 3 * (size_t)c->n));
+  return sync(c);
+}
+
+int mosaic_cell_lab(mosaic_ctx* c, float* lab_out) {
+  if (!c) return MOSAIC_ERR_INVALID;
+  MOSAIC_CUDA(c, cudaSetDevice(c->device));
+  MOSAIC_TRY(run_cell_lab(c));
+  MOSAIC_TRY(d2h(c, lab_out, c->d_cell_lab, sizeof(float) * 3 * cells_of(c)));
+  return sync(c);
+}
+
+int mosaic_similarity_tri(mosaic_ctx* c, float* sim_out) {
+  if (!c) return MOSAIC_ERR_INVALID;
+  MOSAIC_CUDA(c, cudaSetDevice(c->device));
+  MOSAIC_TRY(run_similarity(c));
+  const uint64_t n = (uint64_t)c->n;
+  MOSAIC_TRY(d2h(c, sim_out, c->d_sim, sizeof(float) * (size_t)(n > 1 ? n * (n - 1) / 2 : 0)));
+  return sync(c);
+}
+
+int mosaic_candidates(mosaic_ctx* c, int k, uint32_t* idx_out, float* d2_out) {
+  if (!c) return MOSAIC_ERR_INVALID;
+  MOSAIC_CUDA(c, cudaSetDevice(c->device));
+  MOSAIC_TRY(run_candidates(c, k));
+  MOSAIC_TRY(d2h(c, idx_out, c->d_cand_idx, sizeof(uint32_t) * cells_of(c) * c->k));
+  MOSAIC_TRY(d2h(c, d2_out, c->d_cand_d2, sizeof(float) * cells_of(c) * c->k));
+  return sync(c);
+}
+
+int mosaic_place(mosaic_ctx* c, int max_usage, float adjacency_weight, int32_t* placed_out, uint32_t* n_fallbacks) {
+  if (!c) return MOSAIC_ERR_INVALID;
+  MOSAIC_CUDA(c, cudaSetDevice(c->device));
+  MOSAIC_TRY(run_place(c, max_usage, adjacency_weight));
+  MOSAIC_TRY(d2h(c, placed_out, c->d_placed, sizeof(int32_t) * cells_of(c)));
+  MOSAIC_TRY(d2h(c, n_fallbacks, c->d_place_info, sizeof(uint32_t)));
+  return sync(c);
+}
+
+int mosaic_fallback_cells(mosaic_ctx* c, uint32_t* cells_out, uint32_t cap, uint32_t* n_out) {
+  if (!c || !n_out) return MOSAIC_ERR_INVALID;
+  MOSAIC_CUDA(c, cudaSetDevice(c->device));
+  MOSAIC_TRY(require(c, c->have_placed, "placement"));
+  uint32_t nfb = 0;
+  MOSAIC_CUDA(c, cudaMemcpyAsync(&nfb, c->d_place_info, sizeof nfb, cudaMemcpyDeviceToHost, c->stream));
+  MOSAIC_TRY(sync(c));
+  uint32_t m = std::min(std::min(nfb, cap), mosaic_ctx::kFallbackCap);
+  if (m && cells_out) {
+    MOSAIC_CUDA(c, cudaMemcpyAsync(cells_out, c->d_place_info + 1, sizeof(uint32_t) * m, cudaMemcpyDeviceToHost, c->stream));
+    MOSAIC_TRY(sync(c));
+  }
+  *n_out = nfb;
+  return MOSAIC_OK;
+}
+
+int mosaic_set_placement(mosaic_ctx* c, const int32_t* placed) {
+  if (!c) return MOSAIC_ERR_INVALID;
+  if (!placed) return fail(c, MOSAIC_ERR_INVALID, "placement pointer is NULL");
+  MOSAIC_CUDA(c, cudaSetDevice(c->device));
+  if (c->gw <= 0 || c->gh <= 0) return fail(c, MOSAIC_ERR_STATE, "grid is not set");
+  MOSAIC_TRY(ensure_placed(c));
+  MOSAIC_CUDA(c, cudaMemcpyAsync(c->d_placed, placed, sizeof(int32_t) * cells_of(c), cudaMemcpyHostToDevice, c->stream));
+  MOSAIC_TRY(sync(c));
+  c->have_placed = true;
+  return MOSAIC_OK;
+}
+
+int mosaic_anneal(mosaic_ctx* c, uint64_t iterations, float t0, float decay, uint64_t seed, int32_t* placed_out,
+                  mosaic_opt_result* res) {
+  if (!c) return MOSAIC_ERR_INVALID;
+  MOSAIC_CUDA(c, cudaSetDevice(c->device));
+  MOSAIC_TRY(run_anneal(c, iterations, t0, decay, seed));
+  MOSAIC_TRY(d2h(c, placed_out, c->d_placed, sizeof(int32_t) * cells_of(c)));
+  MOSAIC_TRY(d2h(c, res, c->d_opt_res, sizeof(mosaic_opt_result)));
+  return sync(c);
+}
+
+int mosaic_render(mosaic_ctx* c, float color_strength, uint8_t* out_rgb) {
+  if (!c) return MOSAIC_ERR_INVALID;
+  MOSAIC_CUDA(c, cudaSetDevice(c->device));
+  MOSAIC_TRY(run_render(c, color_strength));
+  MOSAIC_TRY(copy_out_image(c, out_rgb));
+  return sync(c);
+}
+
+int mosaic_generate(mosaic_ctx* c, const mosaic_params* p, int32_t* placed_out, uint8_t* out_rgb, mosaic_report* report) {
+  if (!c) return MOSAIC_ERR_INVALID;
+  if (!p) return fail(c, MOSAIC_ERR_INVALID, "params is NULL");
+  MOSAIC_CUDA(c, cudaSetDevice(c->device));
+  MOSAIC_TRY(require(c, c->have_materials, "materials"));
+  MOSAIC_TRY(require(c, c->have_target, "target"));
+  // main.rs:105-164 (MosaicGenerator::new) ...
+  MOSAIC_TRY(run_material_lab(c));
+  if (p->build_similarity) MOSAIC_TRY(run_similarity(c));
+  // ... main.rs:477-685 (generate_mosaic)
+  MOSAIC_TRY(run_cell_lab(c));
+  MOSAIC_TRY(run_candidates(c, kMaxK));
+  MOSAIC_TRY(run_place(c, p->max_usage, p->adjacency_weight));
+  const bool anneal = p->enable_optimization && p->adjacency_weight > 0.0f;  // main.rs:608
+  if (anneal) MOSAIC_TRY(run_anneal(c, p->optimization_iterations, 100.0f, 0.99995f, p->seed));  // optimizer.rs:18-27
+  MOSAIC_TRY(run_render(c, p->color_strength));
+  MOSAIC_TRY(d2h(c, placed_out, c->d_placed, sizeof(int32_t) * cells_of(c)));
+  MOSAIC_TRY(copy_out_image(c, out_rgb));
+  if (report) {
+    std::memset(report, 0, sizeof *report);
+    MOSAIC_TRY(d2h(c, &report->n_fallbacks, c->d_place_info, sizeof(uint32_t)));
+    if (anneal) MOSAIC_TRY(d2h(c, &report->opt, c->d_opt_res, sizeof(mosaic_opt_result)));
+    report->annealed = anneal ? 1 : 0;
+  }
+  return sync(c);
+}
+
+int mosaic_dims(const mosaic_ctx* c, int* n_materials, int* grid_w, int* grid_h, int* tile_w, int* tile_h) {
+  if (!c) return MOSAIC_ERR_INVALID;
+  if (n_materials) *n_materials = c->n;
+  if (grid_w) *grid_w = c->gw;
+  if (grid_h) *grid_h = c->gh;
+  if (tile_w) *tile_w = c->tile_w;
+  if (tile_h) *tile_h = c->tile_h;
+  return MOSAIC_OK;
+}
+
+const void* mosaic_device_output(const mosaic_ctx* c) { return c && c->have_out ? c->d_out : nullptr; }
+const void* mosaic_device_placement(const mosaic_ctx* c) { return c && c->have_placed ? c->d_placed : nullptr; }
+const void* mosaic_device_similarity(const mosaic_ctx* c) { return c && c->have_sim ? c->d_sim : nullptr; }
+
+int mosaic_shard(const mosaic_ctx* c, int* row_begin, int* row_end, int* mat_begin, int* mat_end, uint64_t* tri_begin,
+                 uint64_t* tri_end) {
+  if (!c) return MOSAIC_ERR_INVALID;
+  int rb, re, mb, me;
+  uint64_t tb, te;
+  shard_rows(c, c->rank, &rb, &re);
+  shard_mats(c, c->rank, &mb, &me);
+  shard_tri(c, c->rank, &tb, &te);
+  if (row_begin) *row_begin = rb;
+  if (row_end) *row_end = re;
+  if (mat_begin) *mat_begin = mb;
+  if (mat_end) *mat_end = me;
+  if (tri_begin) *tri_begin = tb;
+  if (tri_end) *tri_end = te;
+  return MOSAIC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,242 @@
+// lab_mean.cu — K1: mean CIE L*a*b* (D65) of RGB8 images / target-grid cells.
+//
+// Replaces MosaicGeneratorImpl::calculate_average_lab (reference src/lib.rs:94-119) at its call
+// sites main.rs:280/294 (materials) and main.rs:540-541 (crop of every grid cell).
+//
+// Per pixel: 3 sRGB->linear lookups (256-entry table, replicated x8 in shared memory so that the
+// 32 lanes of a warp rarely collide on a bank), a 3x3 linear-RGB -> XYZ/white matrix (9 FMA), three
+// f(t) = cbrt(t) | kappa*t+delta evaluations (cbrt = MUFU lg2/ex2 seed + one Newton step, ~1 ulp),
+// and three running sums  sum(fy), sum(fx-fy), sum(fy-fz)  — L, a, b are affine in those, so the
+// affine map is applied once per image.  One warp owns one image / one cell: per-lane partial sums
+// in a fixed pixel order + a fixed shuffle tree => results are run-to-run deterministic.
+// The reference folds the pixels sequentially in f32; a tree differs from that in the last bits,
+// which is what the <= 1e-4 relative tolerance of the north star covers.
+#include "common.cuh"
+
+#include <cmath>
+
+namespace mosaic {
+
+__constant__ float c_srgb_lin[256];
+
+constexpr int kLutRep = 8;
+
+__device__ __forceinline__ float lab_f(float t) {
+  // palette lab.rs: epsilon = (6/29)^3, kappa = 841/108, delta = 4/29
+  const float eps = 0.008856452f, kappa = 7.787037f, delta = 0.13793103f;
+  float lg, y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(t));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(lg * 0.33333334f));  // MUFU seed, ~2^-21 relative
+  // one Newton step on y^3 = t:  y += (t - y^3) / (3 y^2)
+  float y2 = y * y;
+  float e = fmaf(-y2, y, t);
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(y2 * 3.0f));
+  y = fmaf(e, r, y);
+  float lin = fmaf(kappa, t, delta);
+  return t > eps ? y : lin;
+}
+
+struct LabAcc {
+  float fy = 0.f, dxy = 0.f, dyz = 0.f;
+  unsigned r = 0, g = 0, b = 0;  // integer channel sums (calculate_average_rgb, main.rs:687-708)
+};
+
+__device__ __forceinline__ void accumulate_pixel(const float* __restrict__ lut, unsigned r8, unsigned g8,
+                                                 unsigned b8, LabAcc& acc) {
+  float r = lut[r8 * kLutRep], g = lut[g8 * kLutRep], b = lut[b8 * kLutRep];
+  // sRGB/D65 matrix (Lindbloom constants used by palette) with the division by the white point
+  // (0.95047, 1, 1.08883) folded into the rows.
+  float x = fmaf(0.18984029f, b, fmaf(0.37620977f, g, 0.433949941f * r));
+  float y = fmaf(0.0721750f, b, fmaf(0.7151522f, g, 0.2126729f * r));
+  float z = fmaf(0.872775456f, b, fmaf(0.109467961f, g, 0.0177565828f * r));
+  float fx = lab_f(x), fy = lab_f(y), fz = lab_f(z);
+  acc.fy += fy;
+  acc.dxy += fx - fy;
+  acc.dyz += fy - fz;
+}
+
+__device__ __forceinline__ void load_lut(float* lut) {
+  for (int i = threadIdx.x; i < 256 * kLutRep; i += blockDim.x) lut[i] = c_srgb_lin[i / kLutRep];
+  __syncthreads();
+}
+
+__device__ __forceinline__ void finish(LabAcc acc, float inv_count_num, float* out) {
+  float sfy = warp_sum(acc.fy), sxy = warp_sum(acc.dxy), syz = warp_sum(acc.dyz);
+  if ((threadIdx.x & 31) == 0) {
+    float mfy = sfy / inv_count_num, mxy = sxy / inv_count_num, myz = syz / inv_count_num;
+    out[0] = fmaf(116.0f, mfy, -16.0f);
+    out[1] = 500.0f * mxy;
+    out[2] = 200.0f * myz;
+  }
+}
+
+// One warp per image; images are contiguous RGB8 of `pixels` pixels, 16-byte aligned when
+// (pixels*3) % 16 == 0 (the vector path: each lane streams 48-byte groups = 16 pixels as 3 x LDG.128).
+__global__ void __launch_bounds__(256) lab_mean_images_kernel(const uint8_t* __restrict__ imgs, int n, int pixels,
+                                                              int vec_ok, float* __restrict__ lab_out) {
+  __shared__ float lut_s[256 * kLutRep];
+  load_lut(lut_s);
+  const int lane = threadIdx.x & 31;
+  const float* lut = lut_s + (lane & (kLutRep - 1));
+  const int warps_per_grid = (gridDim.x * blockDim.x) >> 5;
+  for (int img = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; img < n; img += warps_per_grid) {
+    const uint8_t* base = imgs + (size_t)img * pixels * 3;
+    LabAcc acc;
+    int done = 0;
+    if (vec_ok) {
+      const uint4* p = reinterpret_cast<const uint4*>(base);
+      const int groups = pixels / 16;
+      for (int gidx = lane; gidx < groups; gidx += 32) {
+        uint4 v0 = __ldg(p + 3 * gidx), v1 = __ldg(p + 3 * gidx + 1), v2 = __ldg(p + 3 * gidx + 2);
+        unsigned w[12] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {  // 12 bytes = 4 pixels per 3 words
+          unsigned a = w[3 * q], b = w[3 * q + 1], c = w[3 * q + 2];
+          accumulate_pixel(lut, a & 255u, (a >> 8) & 255u, (a >> 16) & 255u, acc);
+          accumulate_pixel(lut, a >> 24, b & 255u, (b >> 8) & 255u, acc);
+          accumulate_pixel(lut, (b >> 16) & 255u, b >> 24, c & 255u, acc);
+          accumulate_pixel(lut, (c >> 8) & 255u, (c >> 16) & 255u, c >> 24, acc);
+        }
+      }
+      done = groups * 16;
+    }
+    for (int px = done + lane; px < pixels; px += 32) {
+      const uint8_t* q = base + 3 * (size_t)px;
+      accumulate_pixel(lut, q[0], q[1], q[2], acc);
+    }
+    finish(acc, (float)pixels, lab_out + 3 * (size_t)img);
+  }
+}
+
+// One warp per grid cell: the tile_w x tile_h crop at (x*tile_w, y*tile_h) of the target
+// (main.rs:536-541).  Pixels are visited in the crop's row-major order, lane-strided.  Also emits
+// the integer channel sums of the crop (target_avg_rgb of main.rs:554, used by the render kernel).
+__global__ void __launch_bounds__(256) lab_mean_cells_kernel(const uint8_t* __restrict__ img, int img_w, int gw,
+                                                             int cell_begin, int cell_end, int tile_w, int tile_h,
+                                                             float* __restrict__ lab_out,
+                                                             unsigned long long* __restrict__ rgbsum_out) {
+  __shared__ float lut_s[256 * kLutRep];
+  load_lut(lut_s);
+  const int lane = threadIdx.x & 31;
+  const float* lut = lut_s + (lane & (kLutRep - 1));
+  const int warps_per_grid = (gridDim.x * blockDim.x) >> 5;
+  const int pixels = tile_w * tile_h;
+  for (int cell = cell_begin + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5); cell < cell_end;
+       cell += warps_per_grid) {
+    const int cx = cell % gw, cy = cell / gw;
+    const uint8_t* base = img + ((size_t)cy * tile_h * img_w + (size_t)cx * tile_w) * 3;
+    LabAcc acc;
+    int py = lane / tile_w, px = lane - py * tile_w;  // lane < 32 <= any sensible tile_w is NOT assumed
+    const int step_y = 32 / tile_w, step_x = 32 - step_y * tile_w;
+    for (int p = lane; p < pixels; p += 32) {
+      const uint8_t* q = base + ((size_t)py * img_w + px) * 3;
+      unsigned r8 = q[0], g8 = q[1], b8 = q[2];
+      accumulate_pixel(lut, r8, g8, b8, acc);
+      acc.r += r8;
+      acc.g += g8;
+      acc.b += b8;
+      px += step_x;
+      py += step_y;
+      if (px >= tile_w) {
+        px -= tile_w;
+        py += 1;
+      }
+    }
+    finish(acc, (float)pixels, lab_out + 3 * (size_t)cell);
+    unsigned long long sr = acc.r, sg = acc.g, sb = acc.b;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      sr += __shfl_xor_sync(0xffffffffu, sr, o);
+      sg += __shfl_xor_sync(0xffffffffu, sg, o);
+      sb += __shfl_xor_sync(0xffffffffu, sb, o);
+    }
+    if (lane == 0) {
+      rgbsum_out[3 * (size_t)cell] = sr;
+      rgbsum_out[3 * (size_t)cell + 1] = sg;
+      rgbsum_out[3 * (size_t)cell + 2] = sb;
+    }
+  }
+}
+
+// n*3 packed Lab -> float4 gather table + SoA (l[], a[], b[]; padded with +inf so that padding can
+// never rank among the nearest).
+__global__ void pack_lab_kernel(const float* __restrict__ lab, int n, int n_pad, float4* __restrict__ lab4,
+                                float* __restrict__ soa) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_pad) return;
+  float l = __int_as_float(0x7f800000), a = l, b = l;
+  if (i < n) {
+    l = lab[3 * i];
+    a = lab[3 * i + 1];
+    b = lab[3 * i + 2];
+    lab4[i] = make_float4(l, a, b, 0.f);
+  }
+  soa[i] = l;
+  soa[n_pad + i] = a;
+  soa[2 * n_pad + i] = b;
+}
+
+static int upload_lut(mosaic_ctx* ctx) {
+  static bool done[64] = {};
+  if (ctx->device < 64 && done[ctx->device]) return MOSAIC_OK;
+  float lut[256];
+  for (int i = 0; i < 256; ++i) {
+    // palette 0.7.6 Srgb::into_linear on `u8 as f32 / 255.0` (lib.rs:103): evaluated once per code
+    // value on the host with the same f32 formula the reference applies per pixel.
+    float x = (float)i / 255.0f;
+    lut[i] = x <= 0.04045f ? (float)(1.0 / 12.92) * x
+                           : powf(fmaf(x, (float)(1.0 / 1.055), (float)(0.055 / 1.055)), 2.4f);
+  }
+  MOSAIC_CUDA(ctx, cudaMemcpyToSymbolAsync(c_srgb_lin, lut, sizeof lut, 0, cudaMemcpyHostToDevice, ctx->stream));
+  MOSAIC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (ctx->device < 64) done[ctx->device] = true;
+  return MOSAIC_OK;
+}
+
+int launch_material_lab(mosaic_ctx* ctx) {
+  MOSAIC_TRY(upload_lut(ctx));
+  const int pixels = ctx->mw * ctx->mh;
+  const int vec_ok = ((size_t)pixels * 3) % 16 == 0 && ((uintptr_t)ctx->d_materials % 16) == 0;
+  // one warp per image, 8 warps per CTA; at most 8 resident CTAs per SM worth of grid
+  int blocks = (ctx->n + 7) / 8;
+  int max_blocks = ctx->sm_count * 8;
+  if (blocks > max_blocks) blocks = max_blocks;
+  if (blocks < 1) blocks = 1;
+  {
+    StageTimer t(ctx, MOSAIC_STAGE_MATERIAL_LAB);
+    lab_mean_images_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->d_materials, ctx->n, pixels, vec_ok, ctx->d_mat_lab);
+    ctx->launches++;
+  }
+  MOSAIC_CUDA(ctx, cudaGetLastError());
+  return MOSAIC_OK;
+}
+
+int launch_pack_lab(mosaic_ctx* ctx) {
+  int threads = 256, blocks = (ctx->n_pad + threads - 1) / threads;
+  pack_lab_kernel<<<blocks, threads, 0, ctx->stream>>>(ctx->d_mat_lab, ctx->n, ctx->n_pad, ctx->d_mat_lab4,
+                                                       ctx->d_mat_soa);
+  ctx->launches++;
+  MOSAIC_CUDA(ctx, cudaGetLastError());
+  return MOSAIC_OK;
+}
+
+int launch_cell_lab_range(mosaic_ctx* ctx, int cell_begin, int cell_end) {
+  MOSAIC_TRY(upload_lut(ctx));
+  int cells = cell_end - cell_begin;
+  if (cells <= 0) return MOSAIC_OK;
+  int blocks = (cells + 7) / 8;
+  int max_blocks = ctx->sm_count * 8;
+  if (blocks > max_blocks) blocks = max_blocks;
+  {
+    StageTimer t(ctx, MOSAIC_STAGE_CELL_LAB);
+    lab_mean_cells_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->d_target, ctx->tw_img, ctx->gw, cell_begin, cell_end,
+                                                           ctx->tile_w, ctx->tile_h, ctx->d_cell_lab,
+                                                           ctx->d_cell_rgbsum);
+    ctx->launches++;
+  }
+  MOSAIC_CUDA(ctx, cudaGetLastError());
+  return MOSAIC_OK;
+}
+
+}  // namespace mosaic

@@ -1,0 +1,305 @@
+"""mosaic_b200 — thin ctypes binding of libmosaic_b200.so (include/mosaic_b200.h).
+
+This is the Python face of the C ABI used by tests/, bench.py and __graft_entry__.py.  It contains no
+compute: every method forwards to a C entry point that launches hand-written sm_100a kernels, and it
+raises MosaicError when the shared library or a CUDA device is missing (there is no CPU fallback).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_PKG_DIR), "libmosaic_b200.so")
+
+MAX_K = 100
+STAGES = ("material_lab", "cell_lab", "topk", "place", "similarity", "anneal", "render")
+
+
+class MosaicError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"mosaic_b200 error {code}: {msg}")
+        self.code = code
+
+
+class OptResult(C.Structure):
+    """OptimizationResult (reference src/optimizer.rs:203-210)."""
+    _fields_ = [("initial_cost", C.c_float), ("final_cost", C.c_float), ("best_cost", C.c_float),
+                ("improved_count", C.c_uint64), ("accepted_count", C.c_uint64), ("iterations", C.c_uint64)]
+
+    def improvement_percentage(self):  # optimizer.rs:212-220
+        if self.initial_cost > 0.0:
+            return float(np.float32((np.float32(self.initial_cost) - np.float32(self.final_cost))
+                                    / np.float32(self.initial_cost)) * np.float32(100.0))
+        return 0.0
+
+
+class Params(C.Structure):
+    _fields_ = [("max_usage", C.c_int), ("adjacency_weight", C.c_float), ("color_strength", C.c_float),
+                ("enable_optimization", C.c_int), ("optimization_iterations", C.c_uint64), ("seed", C.c_uint64),
+                ("build_similarity", C.c_int)]
+
+
+class Report(C.Structure):
+    _fields_ = [("n_fallbacks", C.c_uint32), ("opt", OptResult), ("annealed", C.c_int)]
+
+
+_lib = None
+
+
+def load_library():
+    """Load libmosaic_b200.so; fails loudly when it has not been built (no fallback path exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise MosaicError(-100, f"{LIB_PATH} is missing: build it with `make -C {os.path.dirname(LIB_PATH)}` "
+                                "(python -c 'import __graft_entry__ as g; g.build()')")
+    L = C.CDLL(LIB_PATH)
+    vp, u8p, f32p, i32p, u32p, u64p = (C.c_void_p, C.POINTER(C.c_uint8), C.POINTER(C.c_float),
+                                       C.POINTER(C.c_int32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64))
+    sig = {
+        "mosaic_ctx_create": ([C.POINTER(vp), C.c_int], C.c_int),
+        "mosaic_ctx_create_sharded": ([C.POINTER(vp), C.c_int, C.c_int, C.c_int, vp, C.c_size_t], C.c_int),
+        "mosaic_nccl_unique_id": ([vp, C.c_size_t], C.c_int),
+        "mosaic_ctx_destroy": ([vp], None),
+        "mosaic_last_error": ([vp], C.c_char_p),
+        "mosaic_ctx_set_stream": ([vp, vp], C.c_int),
+        "mosaic_ctx_sync": ([vp], C.c_int),
+        "mosaic_stage_ms": ([vp, C.c_int, f32p], C.c_int),
+        "mosaic_kernel_launches": ([vp], C.c_uint64),
+        "mosaic_set_materials_rgb8": ([vp, vp, C.c_int, C.c_int, C.c_int], C.c_int),
+        "mosaic_set_materials_device": ([vp, vp, C.c_int, C.c_int, C.c_int], C.c_int),
+        "mosaic_set_target_rgb8": ([vp, vp, C.c_int, C.c_int, C.c_int, C.c_int], C.c_int),
+        "mosaic_set_target_device": ([vp, vp, C.c_int, C.c_int, C.c_int, C.c_int], C.c_int),
+        "mosaic_set_material_lab": ([vp, f32p, C.c_int], C.c_int),
+        "mosaic_set_cell_lab": ([vp, f32p, C.c_int, C.c_int], C.c_int),
+        "mosaic_material_lab": ([vp, vp], C.c_int),
+        "mosaic_cell_lab": ([vp, vp], C.c_int),
+        "mosaic_similarity_tri": ([vp, vp], C.c_int),
+        "mosaic_candidates": ([vp, C.c_int, vp, vp], C.c_int),
+        "mosaic_place": ([vp, C.c_int, C.c_float, vp, u32p], C.c_int),
+        "mosaic_fallback_cells": ([vp, u32p, C.c_uint32, u32p], C.c_int),
+        "mosaic_set_placement": ([vp, i32p], C.c_int),
+        "mosaic_anneal": ([vp, C.c_uint64, C.c_float, C.c_float, C.c_uint64, vp, C.POINTER(OptResult)], C.c_int),
+        "mosaic_render": ([vp, C.c_float, vp], C.c_int),
+        "mosaic_generate": ([vp, C.POINTER(Params), vp, vp, C.POINTER(Report)], C.c_int),
+        "mosaic_dims": ([vp] + [C.POINTER(C.c_int)] * 5, C.c_int),
+        "mosaic_device_output": ([vp], vp),
+        "mosaic_device_placement": ([vp], vp),
+        "mosaic_device_similarity": ([vp], vp),
+        "mosaic_shard": ([vp] + [C.POINTER(C.c_int)] * 4 + [u64p, u64p], C.c_int),
+    }
+    for name, (args, res) in sig.items():
+        fn = getattr(L, name)  # AttributeError here = the library does not export what the header declares
+        fn.argtypes = args
+        fn.restype = res
+    _lib = L
+    return L
+
+
+EXPORTED_SYMBOLS = (
+    "mosaic_ctx_create", "mosaic_ctx_create_sharded", "mosaic_nccl_unique_id", "mosaic_ctx_destroy",
+    "mosaic_last_error", "mosaic_ctx_set_stream", "mosaic_ctx_sync", "mosaic_stage_ms", "mosaic_kernel_launches",
+    "mosaic_set_materials_rgb8", "mosaic_set_materials_device", "mosaic_set_target_rgb8",
+    "mosaic_set_target_device", "mosaic_set_material_lab", "mosaic_set_cell_lab", "mosaic_material_lab",
+    "mosaic_cell_lab", "mosaic_similarity_tri", "mosaic_candidates", "mosaic_place", "mosaic_fallback_cells",
+    "mosaic_set_placement", "mosaic_anneal", "mosaic_render", "mosaic_generate", "mosaic_dims",
+    "mosaic_device_output", "mosaic_device_placement", "mosaic_device_similarity", "mosaic_shard",
+)
+
+
+def _ptr(a):
+    """numpy array / torch tensor / int address / None -> c_void_p."""
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    if isinstance(a, np.ndarray):
+        assert a.flags["C_CONTIGUOUS"]
+        return C.c_void_p(a.ctypes.data)
+    if hasattr(a, "data_ptr"):  # torch tensor (pinned host or device memory)
+        return C.c_void_p(a.data_ptr())
+    raise TypeError(type(a))
+
+
+class Context:
+    """One GPU's mosaic context (mosaic_ctx).  Mirrors the call sequence of the reference's
+    MosaicGenerator::new + generate_mosaic (src/main.rs:105-164, 477-685)."""
+
+    def __init__(self, device=0, rank=0, world=1, nccl_id: bytes | None = None):
+        self._L = load_library()
+        h = C.c_void_p()
+        if world > 1:
+            buf = C.create_string_buffer(nccl_id, 128)
+            rc = self._L.mosaic_ctx_create_sharded(C.byref(h), device, rank, world, buf, 128)
+        else:
+            rc = self._L.mosaic_ctx_create(C.byref(h), device)
+        if rc != 0:
+            raise MosaicError(rc, (self._L.mosaic_last_error(None) or b"").decode())
+        self._h = h
+        self.rank, self.world = rank, world
+        self._keep = []
+
+    @staticmethod
+    def nccl_unique_id() -> bytes:
+        L = load_library()
+        buf = C.create_string_buffer(128)
+        rc = L.mosaic_nccl_unique_id(buf, 128)
+        if rc != 0:
+            raise MosaicError(rc, (L.mosaic_last_error(None) or b"").decode())
+        return buf.raw
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.mosaic_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, rc):
+        if rc != 0:
+            raise MosaicError(rc, (self._L.mosaic_last_error(self._h) or b"").decode())
+
+    # ---- plumbing
+    def set_stream(self, cuda_stream: int | None):
+        self._check(self._L.mosaic_ctx_set_stream(self._h, C.c_void_p(cuda_stream) if cuda_stream else None))
+
+    def sync(self):
+        self._check(self._L.mosaic_ctx_sync(self._h))
+
+    def stage_ms(self, stage) -> float:
+        idx = STAGES.index(stage) if isinstance(stage, str) else int(stage)
+        ms = C.c_float()
+        self._check(self._L.mosaic_stage_ms(self._h, idx, C.byref(ms)))
+        return ms.value
+
+    def kernel_launches(self) -> int:
+        return int(self._L.mosaic_kernel_launches(self._h))
+
+    def dims(self):
+        v = [C.c_int() for _ in range(5)]
+        self._check(self._L.mosaic_dims(self._h, *[C.byref(x) for x in v]))
+        return dict(zip(("n", "grid_w", "grid_h", "tile_w", "tile_h"), (x.value for x in v)))
+
+    def shard(self):
+        v = [C.c_int() for _ in range(4)]
+        t = [C.c_uint64(), C.c_uint64()]
+        self._check(self._L.mosaic_shard(self._h, *[C.byref(x) for x in v], C.byref(t[0]), C.byref(t[1])))
+        return dict(rows=(v[0].value, v[1].value), materials=(v[2].value, v[3].value), tri=(t[0].value, t[1].value))
+
+    # ---- inputs
+    def set_materials(self, mats):
+        """mats: (n, h, w, 3) uint8 numpy array or pinned torch tensor (host)."""
+        n, h, w, c = mats.shape
+        assert c == 3
+        self._check(self._L.mosaic_set_materials_rgb8(self._h, _ptr(mats), n, w, h))
+
+    def set_materials_device(self, dev_tensor):
+        n, h, w, c = dev_tensor.shape
+        self._keep.append(dev_tensor)
+        self._check(self._L.mosaic_set_materials_device(self._h, _ptr(dev_tensor), n, w, h))
+
+    def set_target(self, img, grid_w, grid_h):
+        h, w, c = img.shape
+        assert c == 3
+        self._check(self._L.mosaic_set_target_rgb8(self._h, _ptr(img), w, h, grid_w, grid_h))
+
+    def set_target_device(self, dev_tensor, grid_w, grid_h):
+        h, w, c = dev_tensor.shape
+        self._keep.append(dev_tensor)
+        self._check(self._L.mosaic_set_target_device(self._h, _ptr(dev_tensor), w, h, grid_w, grid_h))
+
+    def set_material_lab(self, lab):
+        lab = np.ascontiguousarray(lab, np.float32)
+        self._check(self._L.mosaic_set_material_lab(self._h, lab.ctypes.data_as(C.POINTER(C.c_float)), lab.shape[0]))
+
+    def set_cell_lab(self, lab, grid_w, grid_h):
+        lab = np.ascontiguousarray(lab, np.float32)
+        assert lab.shape[0] == grid_w * grid_h
+        self._check(self._L.mosaic_set_cell_lab(self._h, lab.ctypes.data_as(C.POINTER(C.c_float)), grid_w, grid_h))
+
+    def set_placement(self, placed):
+        placed = np.ascontiguousarray(placed, np.int32).ravel()
+        self._check(self._L.mosaic_set_placement(self._h, placed.ctypes.data_as(C.POINTER(C.c_int32))))
+
+    # ---- stages
+    def material_lab(self, fetch=True):
+        out = np.empty((self.dims()["n"], 3), np.float32) if fetch else None
+        self._check(self._L.mosaic_material_lab(self._h, _ptr(out)))
+        return out
+
+    def cell_lab(self, fetch=True):
+        d = self.dims()
+        out = np.empty((d["grid_w"] * d["grid_h"], 3), np.float32) if fetch else None
+        self._check(self._L.mosaic_cell_lab(self._h, _ptr(out)))
+        return out
+
+    def similarity_tri(self, fetch=True):
+        n = self.dims()["n"]
+        out = np.empty(n * (n - 1) // 2 if n > 1 else 0, np.float32) if fetch else None
+        self._check(self._L.mosaic_similarity_tri(self._h, _ptr(out)))
+        return out
+
+    def candidates(self, k=MAX_K, fetch=True):
+        d = self.dims()
+        kk = min(k if 0 < k <= MAX_K else MAX_K, d["n"])
+        cells = d["grid_w"] * d["grid_h"]
+        idx = np.empty((cells, kk), np.uint32) if fetch else None
+        d2 = np.empty((cells, kk), np.float32) if fetch else None
+        self._check(self._L.mosaic_candidates(self._h, k, _ptr(idx), _ptr(d2)))
+        return idx, d2
+
+    def place(self, max_usage=3, adjacency_weight=0.3, fetch=True):
+        d = self.dims()
+        placed = np.empty(d["grid_w"] * d["grid_h"], np.int32) if fetch else None
+        nfb = C.c_uint32()
+        self._check(self._L.mosaic_place(self._h, max_usage, adjacency_weight, _ptr(placed), C.byref(nfb)))
+        return placed, nfb.value
+
+    def fallback_cells(self, cap=4096):
+        buf = np.zeros(cap, np.uint32)
+        n = C.c_uint32()
+        self._check(self._L.mosaic_fallback_cells(self._h, buf.ctypes.data_as(C.POINTER(C.c_uint32)), cap, C.byref(n)))
+        return buf[:min(n.value, cap)].copy()
+
+    def anneal(self, iterations=1000, seed=0, t0=100.0, decay=0.99995, fetch=True):
+        d = self.dims()
+        placed = np.empty(d["grid_w"] * d["grid_h"], np.int32) if fetch else None
+        res = OptResult()
+        self._check(self._L.mosaic_anneal(self._h, iterations, t0, decay, seed, _ptr(placed), C.byref(res)))
+        return placed, res
+
+    def render(self, color_strength=0.3, out=None, fetch=True):
+        d = self.dims()
+        shape = (d["grid_h"] * d["tile_h"], d["grid_w"] * d["tile_w"], 3)
+        if out is None and fetch:
+            out = np.zeros(shape, np.uint8)
+        self._check(self._L.mosaic_render(self._h, color_strength, _ptr(out)))
+        return out
+
+    def generate(self, max_usage=3, adjacency_weight=0.3, color_strength=0.3, enable_optimization=True,
+                 optimization_iterations=1000, seed=0, build_similarity=False, placed_out=None, image_out=None):
+        """Whole path in one call (generate_mosaic, main.rs:477-685).  placed_out / image_out: host buffers
+        (numpy or pinned torch) or None to keep results on the device."""
+        p = Params(max_usage, adjacency_weight, color_strength, 1 if enable_optimization else 0,
+                   optimization_iterations, seed, 1 if build_similarity else 0)
+        rep = Report()
+        self._check(self._L.mosaic_generate(self._h, C.byref(p), _ptr(placed_out), _ptr(image_out), C.byref(rep)))
+        return rep
+
+    def output_shape(self):
+        d = self.dims()
+        return (d["grid_h"] * d["tile_h"], d["grid_w"] * d["tile_w"], 3)

@@ -1,0 +1,255 @@
+"""GPU parity tests: every stage of the CUDA path, called through the C ABI, against the CPU oracle.
+
+Stage-wise protocol: Lab means within 1e-4 relative; candidate lists, placements,
+annealed grids and similarity entries bit-exact GIVEN IDENTICAL INPUTS (the oracle is fed the GPU's
+Lab means); output pixels <= 1 LSB given identical placements.
+"""
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from mosaic_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+LAB_RTOL = 1e-4   # north star: Lab means <= 1e-4 relative ...
+LAB_ATOL = 1e-4   # ... with an absolute floor of 1e-4 for a/b near zero
+
+
+def assert_lab_close(gpu, ref):
+    tol = np.maximum(LAB_RTOL * np.abs(ref), LAB_ATOL)
+    err = np.abs(gpu - ref)
+    assert (err <= tol).all(), f"max err {err.max()} at {np.unravel_index(err.argmax(), err.shape)}"
+
+
+# ---------------------------------------------------------------- K1 lab_mean
+def test_material_lab_matches_oracle(ctx):
+    mats = synth.materials(257)
+    ctx.set_materials(mats)
+    assert_lab_close(ctx.material_lab(), orc.material_lab(mats, threads=8))
+
+
+def test_material_lab_reference_goldens(ctx):
+    # lib.rs:133-158: solid red -> (53.24, 80.09, 67.20) +-1.0, gray128 -> L 53.59 +-1.0, |a|,|b| < 1
+    cols = [(255, 0, 0), (128, 128, 128), (0, 255, 0), (0, 0, 255), (255, 255, 255), (0, 0, 0)]
+    mats = np.zeros((len(cols), 10, 10, 3), np.uint8)
+    for i, c in enumerate(cols):
+        mats[i] = c
+    ctx.set_materials(mats)
+    lab = ctx.material_lab()
+    assert abs(lab[0, 0] - 53.24) < 1.0 and abs(lab[0, 1] - 80.09) < 1.0 and abs(lab[0, 2] - 67.20) < 1.0
+    assert abs(lab[1, 0] - 53.59) < 1.0 and abs(lab[1, 1]) < 1.0 and abs(lab[1, 2]) < 1.0
+    exp = np.array([[53.2408, 80.09243, 67.20321], [53.585022, 0, 0], [87.73472, -86.182686, 83.17931],
+                    [32.29701, 79.187546, -107.86017], [100, 0, 0], [0, 0, 0]], np.float32)
+    assert_lab_close(lab, exp)
+
+
+@pytest.mark.parametrize("w,h", [(64, 64), (7, 5), (33, 17), (128, 96), (1, 1)])
+def test_material_lab_odd_sizes(ctx, w, h):
+    mats = synth.materials(19, w=w, h=h)
+    ctx.set_materials(mats)
+    assert_lab_close(ctx.material_lab(), orc.material_lab(mats))
+
+
+@pytest.mark.parametrize("w,h,gw,gh", [(480, 288, 24, 16), (250, 130, 7, 3), (97, 61, 5, 4), (64, 64, 64, 64),
+                                        (300, 200, 3, 2)])
+def test_cell_lab_matches_oracle(ctx, w, h, gw, gh):
+    tgt = synth.target(w, h)
+    ctx.set_target(tgt, gw, gh)
+    assert_lab_close(ctx.cell_lab(), orc.cell_lab(tgt, gw, gh, threads=8))
+
+
+# ---------------------------------------------------------------- K2 nn_topk
+@pytest.mark.parametrize("n,c", [(300, 384), (5000, 200), (100, 50), (37, 33), (1, 4), (2049, 70), (4100, 129)])
+def test_candidates_bit_exact(ctx, n, c):
+    mat_lab = synth.lab_points(n)
+    cell_lab = (synth.lab_points(c, seed=99) * np.float32(0.9)).astype(np.float32)
+    if n >= 300:  # exact duplicates and exact ties in distance
+        mat_lab[10] = mat_lab[3]
+        mat_lab[200] = mat_lab[3]
+        cell_lab[5] = mat_lab[3]
+    ctx.set_material_lab(mat_lab)
+    ctx.set_cell_lab(cell_lab, c, 1)
+    idx, d2 = ctx.candidates()
+    ridx, rd2 = orc.topk(mat_lab, cell_lab, 100, threads=8)
+    assert idx.shape == ridx.shape
+    assert (idx == ridx).all()
+    assert (d2.view(np.uint32) == rd2.view(np.uint32)).all()
+
+
+def test_candidates_ties_quantised(ctx):
+    # heavy ties: Lab values on a coarse lattice -> many equal distances; order must be (d2, index)
+    rng = np.random.default_rng(5)
+    mat_lab = rng.integers(0, 6, (3000, 3)).astype(np.float32) * 10
+    cell_lab = rng.integers(0, 6, (256, 3)).astype(np.float32) * 10
+    ctx.set_material_lab(mat_lab)
+    ctx.set_cell_lab(cell_lab, 16, 16)
+    idx, d2 = ctx.candidates()
+    ridx, rd2 = orc.topk(mat_lab, cell_lab, 100, threads=8)
+    assert (idx == ridx).all() and (d2.view(np.uint32) == rd2.view(np.uint32)).all()
+
+
+# ---------------------------------------------------------------- K2b greedy placement
+@pytest.mark.parametrize("n,gw,gh,max_usage,weight", [
+    (300, 24, 16, 3, 0.3),     # capacity 900 > 384
+    (100, 24, 16, 3, 0.3),     # capacity 300 < 384 -> fallback/reset fires
+    (100, 24, 16, 3, 0.0),     # no adjacency calculator (main.rs:355-362)
+    (40, 20, 20, 1, 1.0),      # k = n < 100, many resets
+    (500, 50, 28, 3, 0.3),     # C1 shape
+    (5, 9, 7, 0, 0.3),         # max_usage 0 -> every cell takes the fallback
+    (1, 4, 4, 3, 0.3),         # single material: final nearest_one fallback
+    (300, 1, 40, 2, 0.5),      # one-column grid (no Left)
+    (300, 40, 1, 2, 0.5),      # one-row grid (no Up)
+])
+def test_place_bit_exact(ctx, n, gw, gh, max_usage, weight):
+    mat_lab = synth.lab_points(n, seed=n)
+    # smooth cell field: neighbours want the same materials
+    yy, xx = np.mgrid[0:gh, 0:gw]
+    cell_lab = np.stack([50 + 30 * np.sin(xx / 5.0), 40 * np.cos(yy / 4.0), 30 * np.sin((xx + yy) / 6.0)], -1)
+    cell_lab = cell_lab.reshape(-1, 3).astype(np.float32)
+    ctx.set_material_lab(mat_lab)
+    ctx.set_cell_lab(cell_lab, gw, gh)
+    idx, d2 = ctx.candidates()
+    placed, nfb = ctx.place(max_usage, weight)
+    rplaced, rnfb, rfb, _ = orc.place(idx, d2, mat_lab, gw, gh, max_usage, weight)
+    assert nfb == rnfb
+    assert (ctx.fallback_cells() == rfb).all()
+    assert (placed == rplaced).all()
+
+
+def test_place_full_pipeline_c1(ctx):
+    cfg = synth.CONFIGS["C1"]
+    mats = synth.materials(cfg["n_materials"])
+    tgt = synth.target(cfg["target_w"], cfg["target_h"])
+    ctx.set_materials(mats)
+    ctx.set_target(tgt, cfg["grid_w"], cfg["grid_h"])
+    mlab, clab = ctx.material_lab(), ctx.cell_lab()
+    idx, d2 = ctx.candidates()
+    ridx, rd2 = orc.topk(mlab, clab, 100, threads=8)  # oracle fed with the GPU's Lab means
+    assert (idx == ridx).all() and (d2.view(np.uint32) == rd2.view(np.uint32)).all()
+    placed, nfb = ctx.place(cfg["max_usage"], cfg["adjacency_weight"])
+    rplaced, rnfb, rfb, _ = orc.place(ridx, rd2, mlab, cfg["grid_w"], cfg["grid_h"], cfg["max_usage"],
+                                      cfg["adjacency_weight"])
+    assert nfb == rnfb and (placed == rplaced).all()
+
+
+# ---------------------------------------------------------------- K3 similarity
+@pytest.mark.parametrize("n", [2, 3, 4, 17, 500, 1500, 2311])
+def test_similarity_bit_equal(ctx, n):
+    lab = synth.lab_points(n, seed=n + 1)
+    ctx.set_material_lab(lab)
+    sim = ctx.similarity_tri()
+    ref = orc.similarity_tri(lab, threads=8)
+    assert sim.shape == ref.shape
+    assert (sim.view(np.uint32) == ref.view(np.uint32)).all()
+
+
+def test_similarity_reference_fixtures(ctx):
+    # similarity.rs:190-192 fixtures; App. B: sqrt(300), sqrt(1200); packed index n=3
+    lab = np.array([[50, 0, 0], [60, 10, 10], [40, -10, -10]], np.float32)
+    ctx.set_material_lab(lab)
+    sim = ctx.similarity_tri()
+    assert sim[0] == np.float32(17.320509) and sim[1] == np.float32(17.320509) and sim[2] == np.float32(34.641018)
+
+
+# ---------------------------------------------------------------- K5 anneal
+@pytest.mark.parametrize("n,gw,gh,iters,seed", [(300, 24, 16, 2000, 42), (50, 8, 8, 5000, 0), (300, 2, 2, 500, 7),
+                                                 (300, 1, 1, 100, 1), (300, 1, 30, 1000, 3), (20, 30, 20, 3000, 9)])
+def test_anneal_bit_exact(ctx, n, gw, gh, iters, seed):
+    mat_lab = synth.lab_points(n, seed=n + 3)
+    rng = np.random.default_rng(seed)
+    grid = rng.integers(0, n, (gh, gw)).astype(np.int32)
+    ctx.set_material_lab(mat_lab)
+    ctx.set_cell_lab(np.zeros((gw * gh, 3), np.float32), gw, gh)
+    ctx.set_placement(grid)
+    placed, res = ctx.anneal(iters, seed)
+    rgrid, rres = orc.anneal(mat_lab, grid, iters, seed)
+    assert (placed.reshape(gh, gw) == rgrid).all()
+    for f in ("initial_cost", "final_cost", "best_cost"):
+        assert np.float32(getattr(res, f)).view(np.uint32) == np.float32(getattr(rres, f)).view(np.uint32), f
+    assert res.accepted_count == rres.accepted_count and res.improved_count == rres.improved_count
+    assert res.iterations == iters
+
+
+def test_anneal_cold_rejects(ctx):
+    # low temperature: the acceptance test (exp + uniform draw) actually rejects -> exercises the RNG stream
+    n, gw, gh = 200, 16, 12
+    mat_lab = synth.lab_points(n, seed=11)
+    grid = np.random.default_rng(1).integers(0, n, (gh, gw)).astype(np.int32)
+    ctx.set_material_lab(mat_lab)
+    ctx.set_cell_lab(np.zeros((gw * gh, 3), np.float32), gw, gh)
+    ctx.set_placement(grid)
+    placed, res = ctx.anneal(4000, 5, t0=0.01, decay=0.999)
+    rgrid, rres = orc.anneal(mat_lab, grid, 4000, 5, t0=0.01, decay=0.999)
+    assert 0 < rres.accepted_count < 4000
+    assert (placed.reshape(gh, gw) == rgrid).all()
+    assert res.accepted_count == rres.accepted_count and res.improved_count == rres.improved_count
+    assert np.float32(res.final_cost).view(np.uint32) == np.float32(rres.final_cost).view(np.uint32)
+
+
+# ---------------------------------------------------------------- K4 render
+@pytest.mark.parametrize("w,h,gw,gh,strength", [(480, 288, 24, 16, 0.3), (480, 288, 24, 16, 0.0), (250, 130, 7, 3, 1.0),
+                                                 (512, 512, 8, 8, 0.4), (1920, 1080, 50, 28, 0.3)])
+def test_render_within_one_lsb(ctx, w, h, gw, gh, strength):
+    n = 64
+    mats = synth.materials(n)
+    tgt = synth.target(w, h)
+    placed = np.random.default_rng(3).integers(0, n, gw * gh).astype(np.int32)
+    placed[5] = -1  # an empty cell stays black
+    ctx.set_materials(mats)
+    ctx.set_target(tgt, gw, gh)
+    ctx.cell_lab(fetch=False)
+    ctx.set_placement(placed)
+    out = ctx.render(strength)
+    ref = orc.render(tgt, gw, gh, mats, placed, strength, threads=8)
+    assert out.shape == ref.shape
+    diff = np.abs(out.astype(np.int16) - ref.astype(np.int16))
+    assert diff.max() <= 1, f"max diff {diff.max()}"
+    # tighter: the arithmetic is restated operation by operation, so in practice it is bit-exact
+    assert (diff > 0).mean() < 1e-3
+
+
+def test_render_identity_resize(ctx):
+    # material already tile-sized: both resampling passes are skipped (fast_image_resize skips equal axes)
+    mats = synth.materials(8, w=20, h=18)
+    tgt = synth.target(200, 180)
+    placed = (np.arange(100) % 8).astype(np.int32)
+    ctx.set_materials(mats)
+    ctx.set_target(tgt, 10, 10)
+    ctx.cell_lab(fetch=False)
+    ctx.set_placement(placed)
+    out = ctx.render(0.0)
+    ref = orc.render(tgt, 10, 10, mats, placed, 0.0)
+    assert (out == ref).all()
+
+
+# ---------------------------------------------------------------- whole path
+def test_generate_matches_stagewise(ctx):
+    cfg = synth.CONFIGS["C2"]
+    mats = synth.materials(cfg["n_materials"])
+    tgt = synth.target(cfg["target_w"], cfg["target_h"])
+    gw, gh = cfg["grid_w"], cfg["grid_h"]
+    ctx.set_materials(mats)
+    ctx.set_target(tgt, gw, gh)
+    placed = np.zeros(gw * gh, np.int32)
+    img = np.zeros(ctx.output_shape(), np.uint8)
+    rep = ctx.generate(cfg["max_usage"], cfg["adjacency_weight"], cfg["color_strength"], True, cfg["sa_iterations"],
+                       cfg["seed"], build_similarity=True, placed_out=placed, image_out=img)
+    # oracle, stage by stage, fed with the GPU Lab means
+    mlab, clab = ctx.material_lab(), ctx.cell_lab()
+    ridx, rd2 = orc.topk(mlab, clab, 100, threads=8)
+    rplaced, rnfb, _, _ = orc.place(ridx, rd2, mlab, gw, gh, cfg["max_usage"], cfg["adjacency_weight"])
+    assert rep.n_fallbacks == rnfb and rnfb > 0  # C2: capacity 4500 < 4800 cells
+    rgrid, rres = orc.anneal(mlab, rplaced.reshape(gh, gw), cfg["sa_iterations"], cfg["seed"])
+    assert rep.annealed == 1 and rep.opt.accepted_count == rres.accepted_count
+    assert (placed == rgrid.ravel()).all()
+    ref = orc.render(tgt, gw, gh, mats, placed, cfg["color_strength"], threads=8)
+    assert np.abs(img.astype(np.int16) - ref.astype(np.int16)).max() <= 1
+
+
+def test_errors_are_loud(ctx):
+    import mosaic_b200
+    with pytest.raises(mosaic_b200.MosaicError):
+        ctx.material_lab()          # nothing set
+    with pytest.raises(mosaic_b200.MosaicError):
+        ctx.set_target(np.zeros((4, 4, 3), np.uint8), 8, 8)   # grid finer than the image
