@@ -1,0 +1,410 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200-native mosaic matching path.
+
+Metric (BASELINE.json): cells placed / second (+ end-to-end ms per mosaic = ms_per_step).
+Workload at every N: the 24,000-tile mosaic (BASELINE.json configs[2], the one the north-star target
+"<50 ms on 1 B200" is quoted on): synthetic 7680x4320 target, 10,000 synthetic 64x64 materials,
+grid 200x120, max-usage 3, adjacency 0.3, colour 0.3, 1000 annealing iterations, similarity matrix
+built every run (main.rs:143).  A step = one whole mosaic: material Lab means, similarity matrix,
+cell Lab means, top-100 candidates, greedy placement, annealing, resize+adjust+composite.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config C3]
+
+`value`  : inputs already resident in HBM, results left in HBM (CUDA events, max over ranks).
+`e2e`    : same metric through the C ABI with pinned HOST buffers: H2D of materials + target and D2H of
+           the placement + output image are inside the timed region, every step.
+`--impl reference`: the CPU path (oracle/ = C++ restatement of the reference; the Rust reference cannot
+           be built in this image) on the box's host cores, same metric/config.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "mosaic-art-rust_b200")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+
+METRIC = "cells_placed_per_sec"
+UNIT = "cells/s"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def workload_config(name):
+    from mosaic_b200 import synth
+    cfg = dict(synth.CONFIGS[name])
+    cfg["name"] = name
+    return cfg
+
+
+def describe(cfg):
+    return (f"{cfg['name']}: {cfg['grid_w']}x{cfg['grid_h']} grid ({cfg['grid_w'] * cfg['grid_h']} cells) from a synthetic "
+            f"{cfg['target_w']}x{cfg['target_h']} target vs {cfg['n_materials']} synthetic 64x64 materials")
+
+
+# --------------------------------------------------------------------------- CPU arm (oracle)
+def cpu_pipeline(orc, mats, tgt, cfg, threads):
+    """One whole mosaic on the CPU with the reference's structure: parallel over materials where the reference
+    uses Rayon (main.rs:193-208) and — as a courtesy the reference does not have — over cells / rows for the
+    other data-parallel stages; greedy placement and annealing are serial (as in the reference)."""
+    t = {}
+    gw, gh = cfg["grid_w"], cfg["grid_h"]
+    t0 = time.perf_counter()
+    mlab = orc.material_lab(mats, threads=threads)
+    t["material_lab"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    orc.similarity_tri(mlab, threads=threads)
+    t["similarity"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    clab = orc.cell_lab(tgt, gw, gh, threads=threads)
+    t["cell_lab"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    idx, d2 = orc.topk(mlab, clab, 100, threads=threads)
+    t["topk"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    placed, nfb, _, _ = orc.place(idx, d2, mlab, gw, gh, cfg["max_usage"], cfg["adjacency_weight"])
+    t["place"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    if cfg["sa_iterations"] > 0 and cfg["adjacency_weight"] > 0:
+        grid, _ = orc.anneal(mlab, placed.reshape(gh, gw), cfg["sa_iterations"], cfg["seed"])
+        placed = grid.ravel()
+    t["anneal"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    orc.render(tgt, gw, gh, mats, placed, cfg["color_strength"], threads=threads)
+    t["render"] = time.perf_counter() - t0
+    return t
+
+
+def scaled_config(cfg, scale):
+    """A bounded sample of the workload: `scale` of the grid rows and of the materials."""
+    if scale >= 1.0:
+        return dict(cfg), "whole workload"
+    c = dict(cfg)
+    c["grid_h"] = max(2, int(round(cfg["grid_h"] * scale)))
+    c["target_h"] = (cfg["target_h"] // cfg["grid_h"]) * c["grid_h"]
+    c["n_materials"] = max(200, int(round(cfg["n_materials"] * scale)))
+    return c, (f"{c['grid_w']}x{c['grid_h']} grid rows and {c['n_materials']} materials of {cfg['name']} "
+               f"(scale {scale:.3f})")
+
+
+def run_cpu(cfg, steps, warmup, budget_s):
+    from mosaic_b200 import synth
+    from oracle import oracle as orc
+    orc.lib()
+    threads = os.cpu_count() or 1
+    sample_cfg, sample = dict(cfg), "whole workload"
+    mats = synth.materials(sample_cfg["n_materials"])
+    tgt = synth.target(sample_cfg["target_w"], sample_cfg["target_h"])
+    t0 = time.perf_counter()
+    cpu_pipeline(orc, mats, tgt, sample_cfg, threads)  # probe (doubles as the first warm-up)
+    probe = time.perf_counter() - t0
+    total_runs = steps + max(warmup - 1, 0)
+    if probe * total_runs > budget_s:  # shrink the sample so that the run ends within the budget
+        scale = max(0.02, budget_s / (probe * total_runs))
+        sample_cfg, sample = scaled_config(cfg, scale)
+        mats = mats[:sample_cfg["n_materials"]]
+        tgt = np.ascontiguousarray(tgt[:sample_cfg["target_h"]])
+    for _ in range(max(warmup - 1, 0)):
+        cpu_pipeline(orc, mats, tgt, sample_cfg, threads)
+    stage_acc, times = {}, []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        st = cpu_pipeline(orc, mats, tgt, sample_cfg, threads)
+        times.append(time.perf_counter() - t0)
+        for k, v in st.items():
+            stage_acc[k] = stage_acc.get(k, 0.0) + v
+    cells = sample_cfg["grid_w"] * sample_cfg["grid_h"]
+    sec = sum(times) / len(times)
+    return dict(value=cells / sec, ms_per_step=sec * 1e3, cores=threads, sample=sample, cells=cells,
+                stage_ms={k: v / steps * 1e3 for k, v in stage_acc.items()})
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.path = f"/tmp/mosaic_clocks_{os.getpid()}.csv"
+
+    def start(self):
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.gpu_index), "-lms", "100"], stdout=self.f,
+                                         stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        with open(self.path) as f:
+            for line in f:
+                parts = [p.strip() for p in line.split(",")]
+                if len(parts) < 9:
+                    continue
+                try:
+                    sm.append(float(parts[1]))
+                    smax.append(float(parts[2]))
+                except ValueError:
+                    continue
+                for nm, val in zip(names, parts[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(nm)
+        try:
+            os.remove(self.path)
+        except OSError:
+            pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(smax), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------- GPU arm
+def hbm_kernels(cfg, world):
+    """Algorithmic HBM bytes per launch of the throughput kernels (SURVEY.md §8(d) per-unit figures x units of
+    one launch on ONE rank)."""
+    n, cells = cfg["n_materials"], cfg["grid_w"] * cfg["grid_h"]
+    tw, th = cfg["target_w"] // cfg["grid_w"], cfg["target_h"] // cfg["grid_h"]
+    mat_px = 64 * 64
+    return {
+        "material_lab": (n / world) * mat_px * 3 + (n / world) * 12,           # 3 B per pixel read + 12 B per image
+        "cell_lab": (cells / world) * tw * th * 3 + (cells / world) * (12 + 24),  # 3 B per pixel + Lab + rgb sums
+        "similarity": (n * (n - 1) / 2 / world) * 4,                             # 4 B written per pair
+        "render": (cells / world) * (mat_px * 3 + tw * th * 3),                  # material read + tile written
+    }
+
+
+def run_gpu(args, cfg):
+    import torch
+    import torch.distributed as dist
+
+    import mosaic_b200
+    from mosaic_b200 import synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback (use --impl reference "
+                         "for the CPU baseline)")
+    torch.cuda.set_device(local_rank)
+    nccl_id = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        ids = [mosaic_b200.Context.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        nccl_id = ids[0]
+
+    gw, gh, n = cfg["grid_w"], cfg["grid_h"], cfg["n_materials"]
+    cells = gw * gh
+    # synthetic inputs in pinned host memory
+    mats_h = torch.empty((n, 64, 64, 3), dtype=torch.uint8, pin_memory=True)
+    mats_h.numpy()[...] = synth.materials(n)
+    tgt_h = torch.empty((cfg["target_h"], cfg["target_w"], 3), dtype=torch.uint8, pin_memory=True)
+    tgt_h.numpy()[...] = synth.target(cfg["target_w"], cfg["target_h"])
+
+    ctx = mosaic_b200.Context(local_rank, rank, world, nccl_id)
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+    gen_kw = dict(max_usage=cfg["max_usage"], adjacency_weight=cfg["adjacency_weight"],
+                  color_strength=cfg["color_strength"], enable_optimization=cfg["sa_iterations"] > 0,
+                  optimization_iterations=cfg["sa_iterations"], seed=cfg["seed"], build_similarity=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---------------- value: inputs resident in HBM, outputs left in HBM
+    ctx.set_materials(mats_h)            # (sharded: own slice over PCIe + NVLink allgather)
+    ctx.set_target(tgt_h, gw, gh)
+    for _ in range(args.warmup):
+        rep = ctx.generate(**gen_kw)
+    stage_acc = {s: 0.0 for s in mosaic_b200.STAGES}
+    clocks = ClockSampler(local_rank)
+    barrier()
+    launches0 = ctx.kernel_launches()
+    if rank == 0:
+        clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        rep = ctx.generate(**gen_kw)
+        for s in mosaic_b200.STAGES:
+            try:
+                stage_acc[s] += ctx.stage_ms(s)
+            except mosaic_b200.MosaicError:
+                pass
+    e1.record(stream)
+    barrier()
+    clk = clocks.stop() if rank == 0 else None
+    launches = ctx.kernel_launches() - launches0
+    ms_value = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+    stage_ms = {s: max_over_ranks(v / args.steps) for s, v in stage_acc.items()}
+
+    # ---------------- e2e: host buffers in, host buffers out, every step
+    placed_h = torch.empty(cells, dtype=torch.int32, pin_memory=True)
+    out_shape = ctx.output_shape()
+    img_h = torch.empty(out_shape, dtype=torch.uint8, pin_memory=True)
+    shard = ctx.shard()
+    rows = shard["rows"][1] - shard["rows"][0]
+    nmat = shard["materials"][1] - shard["materials"][0]
+    th = cfg["target_h"] // gh
+    h2d = nmat * 64 * 64 * 3 + (rows * th if world > 1 else cfg["target_h"]) * cfg["target_w"] * 3
+    d2h = cells * 4 + rows * th * out_shape[1] * 3 + 4
+
+    def e2e_step():
+        ctx.set_materials(mats_h)
+        ctx.set_target(tgt_h, gw, gh)
+        return ctx.generate(placed_out=placed_h, image_out=img_h, **gen_kw)
+
+    for _ in range(max(1, min(args.warmup, 3))):
+        e2e_step()
+    barrier()
+    w0 = time.perf_counter()
+    e0.record(stream)
+    for _ in range(args.steps):
+        rep = e2e_step()
+    e1.record(stream)
+    barrier()
+    wall_ms = (time.perf_counter() - w0) * 1e3 / args.steps
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+    h2d_total = max_over_ranks(float(h2d))
+    d2h_total = max_over_ranks(float(d2h))
+
+    result = None
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        algo = hbm_kernels(cfg, world)
+        dominant = max(algo, key=lambda s: stage_ms.get(s, 0.0))
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            with open(tpath) as f:
+                traffic = json.load(f).get(f"{cfg['name']}:{dominant}:{world}")
+        achieved = algo[dominant] / (stage_ms[dominant] * 1e-3) / 1e9
+        kernels = []
+        for s in mosaic_b200.STAGES:
+            ent = {"kernel": s, "ms": round(stage_ms[s], 4), "share_of_step": round(stage_ms[s] / ms_value, 4)}
+            if s in algo:
+                ent.update(bound="hbm", algorithmic_bytes=int(algo[s]),
+                           achieved_gbs=round(algo[s] / (stage_ms[s] * 1e-3) / 1e9, 1) if stage_ms[s] > 0 else None)
+            elif s == "topk":
+                pairs = cells / world * n
+                ent.update(bound="fp32", pairs=int(pairs),
+                           achieved_tflops=round(8 * pairs / (stage_ms[s] * 1e-3) / 1e12, 3) if stage_ms[s] > 0 else None)
+            elif s == "place":
+                ent.update(bound="latency", ns_per_cell=round(stage_ms[s] * 1e6 / cells, 1))
+            elif s == "anneal":
+                ent.update(bound="latency", ns_per_iteration=round(stage_ms[s] * 1e6 / max(cfg["sa_iterations"], 1), 1))
+            kernels.append(ent)
+        result = {
+            "metric": METRIC, "value": cells / (ms_value * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_value, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": describe(cfg), "grid": [gw, gh], "materials": n,
+                       "max_usage": cfg["max_usage"], "adjacency_weight": cfg["adjacency_weight"],
+                       "color_strength": cfg["color_strength"], "sa_iterations": cfg["sa_iterations"],
+                       "seed": cfg["seed"], "similarity_matrix_built": True,
+                       "l2": "inputs (222 MB of RGB8) are larger than the 126 MB L2; no explicit flush",
+                       "parallelism": ("1 GPU" if world == 1 else
+                                       f"grid rows / material indices / similarity ranges sharded over {world} GPUs, "
+                                       "NCCL allgather of Lab means + candidate lists, greedy + annealing on rank 0")},
+            "e2e": {"value": cells / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e, "wall_ms_per_step": wall_ms,
+                    "h2d_bytes_per_step": int(h2d_total), "d2h_bytes_per_step": int(d2h_total)},
+            "gpu_launches": int(launches),
+            "clocks": clk,
+            "roofline": {"kernel": dominant, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "note": "dominant HBM-roofline kernel of the step; the greedy placement and annealing "
+                                 "kernels are serial latency-bound chains (see kernels[])"},
+            "kernels": kernels,
+            "report": {"n_fallbacks": int(rep.n_fallbacks), "annealed": int(rep.annealed),
+                       "accepted": int(rep.opt.accepted_count)},
+        }
+    ctx.close()
+    return result, rank, world
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="C3")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-budget-s", type=float, default=150.0)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    cfg = workload_config(args.config)
+    rank = int(os.environ.get("RANK", "0"))
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0  # the CPU arm runs once, on rank 0
+        r = run_cpu(cfg, args.steps, args.warmup, args.cpu_budget_s)
+        line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": {"workload": describe(cfg)},
+                "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+                                 "sample": r["sample"], "stage_ms": r["stage_ms"],
+                                 "note": "C++ restatement of the reference CPU path (Rust toolchain unavailable); "
+                                         "brute-force k-NN instead of kiddo's k-d tree; threads over materials as "
+                                         "Rayon does, plus over cells/rows as a courtesy; greedy + annealing serial"},
+                "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line), flush=True)
+        return 0
+
+    result, rank, world = run_gpu(args, cfg)
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            r = run_cpu(cfg, 1, 1, 30.0)
+            result["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+                                      "sample": r["sample"], "ms_per_step": r["ms_per_step"],
+                                      "stage_ms": r["stage_ms"]}
+        print(json.dumps(result), flush=True)
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
