@@ -151,6 +151,11 @@ typedef struct {
 int mosaic_generate(mosaic_ctx* ctx, const mosaic_params* params, int32_t* placed_out,
                     uint8_t* out_rgb, mosaic_report* report);
 
+/* ---- self test ------------------------------------------------------------------------------ */
+/* Checks the branch-free IEEE sqrt / reciprocal sequences used on the serial chains against the
+ * correctly rounded builtins over all 2^32 float bit patterns.  mismatches[0] = sqrt, [1] = rcp. */
+int mosaic_selftest(mosaic_ctx* ctx, uint64_t mismatches[2]);
+
 /* ---- introspection -------------------------------------------------------------------------- */
 int mosaic_dims(const mosaic_ctx* ctx, int* n_materials, int* grid_w, int* grid_h, int* tile_w, int* tile_h);
 /* device pointers of resident results (NULL if absent): for zero-copy consumers */

@@ -649,6 +649,16 @@ int mosaic_generate(mosaic_ctx* c, const mosaic_params* p, int32_t* placed_out, 
   return sync(c);
 }
 
+int mosaic_selftest(mosaic_ctx* c, uint64_t mismatches[2]) {
+  if (!c || !mismatches) return MOSAIC_ERR_INVALID;
+  MOSAIC_CUDA(c, cudaSetDevice(c->device));
+  unsigned long long m[2] = {0, 0};
+  MOSAIC_TRY(launch_selftest(c, m));
+  mismatches[0] = m[0];
+  mismatches[1] = m[1];
+  return MOSAIC_OK;
+}
+
 int mosaic_dims(const mosaic_ctx* c, int* n_materials, int* grid_w, int* grid_h, int* tile_w, int* tile_h) {
   if (!c) return MOSAIC_ERR_INVALID;
   if (n_materials) *n_materials = c->n;

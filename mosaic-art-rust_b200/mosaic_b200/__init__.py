@@ -86,6 +86,7 @@ def load_library():
         "mosaic_anneal": ([vp, C.c_uint64, C.c_float, C.c_float, C.c_uint64, vp, C.POINTER(OptResult)], C.c_int),
         "mosaic_render": ([vp, C.c_float, vp], C.c_int),
         "mosaic_generate": ([vp, C.POINTER(Params), vp, vp, C.POINTER(Report)], C.c_int),
+        "mosaic_selftest": ([vp, u64p], C.c_int),
         "mosaic_dims": ([vp] + [C.POINTER(C.c_int)] * 5, C.c_int),
         "mosaic_device_output": ([vp], vp),
         "mosaic_device_placement": ([vp], vp),
@@ -106,7 +107,7 @@ EXPORTED_SYMBOLS = (
     "mosaic_set_materials_rgb8", "mosaic_set_materials_device", "mosaic_set_target_rgb8",
     "mosaic_set_target_device", "mosaic_set_material_lab", "mosaic_set_cell_lab", "mosaic_material_lab",
     "mosaic_cell_lab", "mosaic_similarity_tri", "mosaic_candidates", "mosaic_place", "mosaic_fallback_cells",
-    "mosaic_set_placement", "mosaic_anneal", "mosaic_render", "mosaic_generate", "mosaic_dims",
+    "mosaic_set_placement", "mosaic_anneal", "mosaic_render", "mosaic_generate", "mosaic_selftest", "mosaic_dims",
     "mosaic_device_output", "mosaic_device_placement", "mosaic_device_similarity", "mosaic_shard",
 )
 
@@ -299,6 +300,11 @@ class Context:
         rep = Report()
         self._check(self._L.mosaic_generate(self._h, C.byref(p), _ptr(placed_out), _ptr(image_out), C.byref(rep)))
         return rep
+
+    def selftest(self):
+        m = (C.c_uint64 * 2)()
+        self._check(self._L.mosaic_selftest(self._h, m))
+        return int(m[0]), int(m[1])
 
     def output_shape(self):
         d = self.dims()

@@ -247,6 +247,11 @@ def test_generate_matches_stagewise(ctx):
     assert np.abs(img.astype(np.int16) - ref.astype(np.int16)).max() <= 1
 
 
+def test_fast_ieee_helpers_exhaustive(ctx):
+    # sqrt/rcp sequences of the serial chains == correctly rounded builtins on all 2^32 bit patterns
+    assert ctx.selftest() == (0, 0)
+
+
 def test_errors_are_loud(ctx):
     import mosaic_b200
     with pytest.raises(mosaic_b200.MosaicError):
