@@ -171,63 +171,85 @@ __global__ void __launch_bounds__(32, 1) greedy_generic_kernel(const uint32_t* _
 
 
 // ------------------------------------------------------------------------------------------------
-// Fast path: producer warps + one consumer warp.
+// Fast path: one CTA, three warp roles around shared-memory rings.
 //
-// Everything the serial chain needs that does NOT depend on earlier placements (candidate ids, d2,
-// candidate Lab of the first 32 candidates of each cell, d2 of candidate 32) is staged by 7 producer
-// warps into a shared-memory ring, 64 cells deep, so the consumer never waits on HBM/L2 latency.
-// Usage counters (u8/u16), the previous row's material ids and their Lab values live in shared
-// memory too.  The consumer's per-cell critical path is: Lab of the Left winner (3 shuffles) ->
-// sim -> 1/(sim+1) -> (t_up + t_left) * w -> d2 + pen -> warp min -> ballot.  The term with the Up
-// neighbour and the usage lookups of the NEXT cell are issued in the shadow of that chain.
-// Cells whose first 32 candidates do not decide the winner (exhausted or early-exit bound not met)
-// take the generic multi-chunk path against the global candidate lists.
-constexpr int RING_DEPTH = 64;
-constexpr int RING_BATCH = 4;        // cells a producer warp keeps in flight
-constexpr int RING_PRODUCERS = 7;    // producer warps (CTA = 8 warps)
+//   producers (6 warps)  stream the state-independent data of each cell — ids, d2 and Lab of its first 32
+//                        candidates, d2 of candidate 32 — from HBM/L2 into a 64-slot ring, far ahead, and
+//                        derive per candidate j the CONTENDER MASK
+//                            cont[j] = { j' > j : d2[j'] < hi[j] },  hi[j] = fl(d2[j] + fl(2 * w))
+//                        (all ones if d2 of candidate 32 < hi[j]).  hi[j] bounds the candidate's total from
+//                        above: total = fl(d2 + fl(fl(t_up + t_left) * w)) with t_up, t_left in [0, 1] and
+//                        IEEE rounding monotone; and every total is bounded from below by its d2.
+//   consumer   (1 warp)   walks the cells in raster order.  Its loop-carried chain is integer-only in the
+//                        common case: valid = (id != Up) & (id != Left) & (usage < cap); j0 = first valid
+//                        lane; if no other valid lane is a contender of j0 then no candidate can be
+//                        STRICTLY better than j0 (total_j' >= d2_j' >= hi_j0 >= total_j0), so j0 is exactly
+//                        the reference's winner — without evaluating a single penalty (91 % of the cells
+//                        of the 24,000-tile config).  Otherwise the exact totals of the chunk are evaluated
+//                        (sqrt / reciprocal sequences bit-identical to IEEE), and cells the first chunk
+//                        cannot decide (all 32 rejected, or the early-exit bound fails) take the generic
+//                        multi-chunk + reset-fallback path.  Every shortcut is an exact bound: placements
+//                        are bit-identical to the serial loop of main.rs:335-475.
+//   committer  (1 warp)   drains the consumer's decisions, up to 32 cells at a time (one per lane): row
+//                        buffers (material id + Lab of the row above), the placement array in HBM, and
+//                        the `decided` counter that frees ring slots.
+constexpr int CH_DEPTH = 64;
+constexpr int CH_GUARD = 3;   // slots of the last decided cells stay intact (the exact path re-reads them)
+constexpr int CH_BATCH = 4;
+constexpr int CH_PWARPS = 6;
+constexpr int CH_MIN_GW = 33;  // the committer handles up to 32 consecutive cells at once: one per column
 
-struct RingSlot {
-  uint32_t id[32];
-  float d2[32];
-  float l[32], a[32], b[32];
+struct CSlot {
+  uint32_t id[32];  // material id, or the dummy id `n` (usage pinned at the cap) for lanes >= k
+  float d2[32], l[32], a[32], b[32];
+  uint32_t cont[32];
 };
 
 template <typename UsageT>
-__global__ void __launch_bounds__((RING_PRODUCERS + 1) * 32, 1)
-    greedy_ring_kernel(const uint32_t* __restrict__ cand_idx, const float* __restrict__ cand_d2, int k,
-                       const float4* __restrict__ lab4, int n, int gw, int gh, unsigned max_usage, float weight,
-                       int32_t* __restrict__ placed, uint32_t* __restrict__ info, uint32_t fallback_cap) {
+__global__ void __launch_bounds__((2 + CH_PWARPS) * 32, 1)
+    greedy_chain_kernel(const uint32_t* __restrict__ cand_idx, const float* __restrict__ cand_d2, int k,
+                        const float4* __restrict__ lab4, int n, int gw, int gh, unsigned max_usage, float weight,
+                        int32_t* __restrict__ placed, uint32_t* __restrict__ info, uint32_t fallback_cap) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  RingSlot* ring = reinterpret_cast<RingSlot*>(smem_raw);
-  float* ring_d2_32 = reinterpret_cast<float*>(smem_raw + sizeof(RingSlot) * RING_DEPTH);
-  volatile uint32_t* ready = reinterpret_cast<volatile uint32_t*>(ring_d2_32 + RING_DEPTH);
-  volatile uint32_t* consumed = ready + RING_DEPTH;  // [0]: number of cells whose slot has been read
-  float4* rowlab = reinterpret_cast<float4*>(const_cast<uint32_t*>(consumed) + 4);
+  CSlot* ring = reinterpret_cast<CSlot*>(smem_raw);
+  float* s_d2_32 = reinterpret_cast<float*>(smem_raw + sizeof(CSlot) * CH_DEPTH);
+  volatile unsigned long long* queue = reinterpret_cast<volatile unsigned long long*>(s_d2_32 + CH_DEPTH);
+  volatile uint32_t* readyP = reinterpret_cast<volatile uint32_t*>(const_cast<unsigned long long*>(queue) + CH_DEPTH);
+  volatile uint32_t* decided = readyP + CH_DEPTH;  // [0] = number of cells committed
+  float4* rowlab = reinterpret_cast<float4*>(const_cast<uint32_t*>(decided) + 4);
   int32_t* rowbuf = reinterpret_cast<int32_t*>(rowlab + gw);
   UsageT* usage = reinterpret_cast<UsageT*>(rowbuf + ((gw + 3) & ~3));
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int cells = gw * gh;
+  const bool use_penalty = weight > 0.0f;  // main.rs:355-362
   for (int i = tid; i < n; i += blockDim.x) usage[i] = 0;
   for (int i = tid; i < gw; i += blockDim.x) rowbuf[i] = -1;
-  for (int i = tid; i < RING_DEPTH; i += blockDim.x) ready[i] = 0u;
-  if (tid == 0) consumed[0] = 0u;
+  for (int i = tid; i < CH_DEPTH; i += blockDim.x) {
+    readyP[i] = 0u;
+    queue[i] = 0ull;
+  }
+  if (tid == 0) {
+    decided[0] = 0u;
+    usage[n] = (UsageT)~(UsageT)0;  // dummy material: never usable
+  }
   __syncthreads();
 
-  if (warp > 0) {
+  if (warp >= 2) {
     // ---------------- producers ----------------
-    const int pw = warp - 1;
-    for (int c0 = pw * RING_BATCH; c0 < cells; c0 += RING_PRODUCERS * RING_BATCH) {
-      const int last = min(c0 + RING_BATCH, cells) - 1;
-      while ((int)consumed[0] + RING_DEPTH <= last) __nanosleep(40);  // wait for free slots
-      uint32_t id[RING_BATCH];
-      float d2[RING_BATCH], d32[RING_BATCH];
-      float4 lab[RING_BATCH];
+    const int pw = warp - 2;
+    const float two_w = __fmul_rn(2.0f, weight);
+    for (int c0 = pw * CH_BATCH; c0 < cells; c0 += CH_PWARPS * CH_BATCH) {
+      const int last = min(c0 + CH_BATCH, cells) - 1;
+      while ((int)decided[0] + (CH_DEPTH - CH_GUARD) <= last) __nanosleep(64);  // slot still in use
+      uint32_t id[CH_BATCH];
+      float d2[CH_BATCH], d32[CH_BATCH];
+      float4 lab[CH_BATCH];
 #pragma unroll
-      for (int b = 0; b < RING_BATCH; ++b) {
+      for (int b = 0; b < CH_BATCH; ++b) {
         const int c = min(c0 + b, cells - 1);
-        id[b] = 0u;
-        d2[b] = 0.f;
+        id[b] = (uint32_t)n;
+        d2[b] = __int_as_float(0x7f800000);
         if (lane < k) {
           id[b] = __ldg(cand_idx + (size_t)c * k + lane);
           d2[b] = __ldg(cand_d2 + (size_t)c * k + lane);
@@ -235,90 +257,135 @@ __global__ void __launch_bounds__((RING_PRODUCERS + 1) * 32, 1)
         d32[b] = k > 32 ? __ldg(cand_d2 + (size_t)c * k + 32) : __int_as_float(0x7f800000);
       }
 #pragma unroll
-      for (int b = 0; b < RING_BATCH; ++b) lab[b] = __ldg(&lab4[id[b]]);
+      for (int b = 0; b < CH_BATCH; ++b)
+        lab[b] = lane < k ? __ldg(&lab4[id[b]]) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-      for (int b = 0; b < RING_BATCH; ++b) {
+      for (int b = 0; b < CH_BATCH; ++b) {
         const int c = c0 + b;
-        if (c < cells) {
-          RingSlot& s = ring[c % RING_DEPTH];
+        if (c < cells) {  // warp-uniform
+          CSlot& s = ring[c % CH_DEPTH];
           s.id[lane] = id[b];
           s.d2[lane] = d2[b];
           s.l[lane] = lab[b].x;
           s.a[lane] = lab[b].y;
           s.b[lane] = lab[b].z;
-          if (lane == 0) ring_d2_32[c % RING_DEPTH] = d32[b];
+          __syncwarp();
+          const float hi = use_penalty ? __fadd_rn(d2[b], two_w) : d2[b];
+          int r = lane + 1;
+          while (r < 32 && s.d2[r] < hi) ++r;  // d2 ascending: contenders are the lanes (lane, r)
+          uint32_t cont = (r >= 32 ? 0xFFFFFFFFu : ((1u << r) - 1u)) & ~((2u << lane) - 1u);
+          if (r >= 32 && d32[b] < hi) cont = 0xFFFFFFFFu;  // the next chunk may hold a contender
+          s.cont[lane] = cont;
+          if (lane == 0) s_d2_32[c % CH_DEPTH] = d32[b];
         }
       }
       __threadfence_block();
       __syncwarp();
       if (lane == 0) {
 #pragma unroll
-        for (int b = 0; b < RING_BATCH; ++b)
-          if (c0 + b < cells) ready[(c0 + b) % RING_DEPTH] = (uint32_t)(c0 + b) + 1u;
+        for (int b = 0; b < CH_BATCH; ++b)
+          if (c0 + b < cells) readyP[(c0 + b) % CH_DEPTH] = (uint32_t)(c0 + b) + 1u;
       }
     }
     return;
   }
 
-  // ---------------- consumer (warp 0) ----------------
-  // Per-lane registers of one cell: candidate `lane` of its first chunk + what is known ahead of time.
-  struct CellRegs {
-    uint32_t id;
-    float d2, l, a, b, d2_32;
-    float t_up;    // 1/(sim(candidate, Up)+1), 0 when there is no Up neighbour
-    int32_t up;    // material above, -1 if none
-    bool flag;     // t_up left the fast-math domain -> resolve this cell on the exact generic path
-  };
-  const bool use_penalty = weight > 0.0f;  // main.rs:355-362
-  uint32_t n_fallbacks = 0;
-  int32_t left = -1;
-  float left_l = 0.f, left_a = 0.f, left_b = 0.f;
-  const volatile RingSlot* vring = ring;  // volatile: ptxas must not hoist slot reads above the flag poll
-  const volatile float* vd2_32 = ring_d2_32;
+  if (warp == 1) {
+    // ---------------- committer ----------------
+    const volatile CSlot* vring = ring;
+    int base = 0;
+    while (base < cells) {
+      const int cell = base + lane;
+      const int s = cell % CH_DEPTH;
+      const unsigned long long e = queue[s];
+      const bool have = cell < cells && (uint32_t)(e >> 32) == (uint32_t)cell + 1u;
+      const unsigned ready_mask = __ballot_sync(0xffffffffu, have);
+      const int cnt = __ffs(~ready_mask) - 1 < 0 ? 32 : __ffs(~ready_mask) - 1;  // consecutive from lane 0
+      if (cnt == 0) {
+        __nanosleep(20);
+        continue;
+      }
+      if (lane < cnt) {
+        const int32_t chosen = (int32_t)((uint32_t)e & 0x03FFFFFFu);
+        const unsigned who = ((uint32_t)e >> 26) & 63u;
+        float4 lab;
+        if (who < 32u)
+          lab = make_float4(vring[s].l[who], vring[s].a[who], vring[s].b[who], 0.f);
+        else
+          lab = __ldg(&lab4[chosen]);
+        const int x = cell % gw;
+        rowbuf[x] = chosen;
+        rowlab[x] = lab;
+        placed[cell] = chosen;  // main.rs:412
+      }
+      __threadfence_block();
+      __syncwarp();
+      base += cnt;
+      if (lane == 0) decided[0] = (uint32_t)base;
+    }
+    return;
+  }
 
+  // ---------------- consumer (warp 0) ----------------
+  const volatile CSlot* vring = ring;
+  const volatile float* vd2_32 = s_d2_32;
+  uint32_t n_fallbacks = 0;
+  int32_t prev = -1;      // material placed in the previous cell (raster order)
+  int32_t prev_u = -1;    // == prev while its usage increment is not yet reflected in the preloaded `u`
+  unsigned prev_who = 63; // lane of prev in the previous cell's slot (63: not in the slot)
+  int x = 0, y = 0;
+
+  struct CellRegs {
+    uint32_t id, cont;
+    unsigned u;   // usage[id] read BEFORE the previous cell's increment (fixed up through prev_u)
+    int32_t up;   // material above (-1: first row); warp-uniform
+  };
   auto wait_slot = [&](int c, uint32_t flag) {
-    const int s = c % RING_DEPTH;
-    while (flag != (uint32_t)c + 1u) flag = ready[s];
+    const int s = c % CH_DEPTH;
+    while (flag != (uint32_t)c + 1u) flag = readyP[s];
     asm volatile("" ::: "memory");
   };
   auto load_slot = [&](int c, CellRegs& r) {
-    const int s = c % RING_DEPTH;
+    const int s = c % CH_DEPTH;
     r.id = vring[s].id[lane];
-    r.d2 = vring[s].d2[lane];
-    r.l = vring[s].l[lane];
-    r.a = vring[s].a[lane];
-    r.b = vring[s].b[lane];
-    r.d2_32 = vd2_32[s];
+    r.cont = vring[s].cont[lane];
+  };
+  auto prev_lab = [&](int cell) -> float4 {  // Lab of the material placed in cell - 1
+    if (prev_who < 32u) {
+      const int ps = (cell - 1) % CH_DEPTH;
+      return make_float4(vring[ps].l[prev_who], vring[ps].a[prev_who], vring[ps].b[prev_who], 0.f);
+    }
+    return __ldg(&lab4[prev]);
   };
 
-  // exact multi-chunk resolution of one cell (first chunk from registers, the rest from the global lists),
-  // then the reset fallback: the reference's loop, bit for bit (main.rs:335-475)
-  auto resolve_generic = [&](int cell, const CellRegs& A, int32_t& chosen, float& ch_l, float& ch_a, float& ch_b) {
-    const int32_t up = A.up;
+  // exact multi-chunk resolution + reset fallback: the reference's loop, bit for bit (main.rs:335-475)
+  auto resolve_generic = [&](int cell, int32_t left, int32_t up, float4 left_lab) -> int32_t {
     float4 up_lab = make_float4(0.f, 0.f, 0.f, 0.f);
-    const int x = cell % gw;
-    if (up >= 0) up_lab = rowlab[x];
+    if (up >= 0) {
+      const volatile float4* ul = rowlab + x;
+      up_lab = make_float4(ul->x, ul->y, ul->z, 0.f);
+    }
     unsigned best_bits = 0xFFFFFFFFu;
     int32_t best_id = -1;
-    float4 best_lab = make_float4(0.f, 0.f, 0.f, 0.f);
     const size_t row = (size_t)cell * k;
     for (int base = 0; base < k; base += 32) {
       if (base > 0 && best_id >= 0 && __float_as_uint(cand_d2[row + base]) >= best_bits) break;  // exact early exit
       const int j = base + lane;
-      uint32_t gid = A.id;
-      float gd2 = A.d2;
-      float4 gl = make_float4(A.l, A.a, A.b, 0.f);
+      uint32_t gid = 0;
+      float gd2 = 0.f;
+      float4 gl = make_float4(0.f, 0.f, 0.f, 0.f);
       bool gok = j < k;
-      if (base > 0 && gok) {
+      if (gok) {
         gid = cand_idx[row + j];
         gd2 = cand_d2[row + j];
         gl = __ldg(&lab4[gid]);
+        gok = (unsigned)usage[gid] < max_usage && (int32_t)gid != left && (int32_t)gid != up;
       }
-      if (gok) gok = (unsigned)usage[gid] < max_usage && (int32_t)gid != left && (int32_t)gid != up;
       float gpen = 0.0f;
       if (use_penalty) {  // adjacency.rs:71-87: Up, (Down), Left, (Right)
         if (up >= 0) gpen = __fadd_rn(gpen, adjacency_term(lab_distance_rn(gl.x, gl.y, gl.z, up_lab.x, up_lab.y, up_lab.z)));
-        if (left >= 0) gpen = __fadd_rn(gpen, adjacency_term(lab_distance_rn(gl.x, gl.y, gl.z, left_l, left_a, left_b)));
+        if (left >= 0)
+          gpen = __fadd_rn(gpen, adjacency_term(lab_distance_rn(gl.x, gl.y, gl.z, left_lab.x, left_lab.y, left_lab.z)));
         gpen = __fmul_rn(gpen, weight);
       }
       const unsigned gtb = gok ? __float_as_uint(__fadd_rn(gd2, gpen)) : 0xFFFFFFFFu;
@@ -327,9 +394,6 @@ __global__ void __launch_bounds__((RING_PRODUCERS + 1) * 32, 1)
         const int who = __ffs(__ballot_sync(0xffffffffu, gtb == gmn)) - 1;
         best_bits = gmn;
         best_id = (int32_t)__shfl_sync(0xffffffffu, gid, who);
-        best_lab.x = __shfl_sync(0xffffffffu, gl.x, who);
-        best_lab.y = __shfl_sync(0xffffffffu, gl.y, who);
-        best_lab.z = __shfl_sync(0xffffffffu, gl.z, who);
       }
     }
     if (best_id < 0) {
@@ -350,101 +414,119 @@ __global__ void __launch_bounds__((RING_PRODUCERS + 1) * 32, 1)
         if (m) best_id = (int32_t)__shfl_sync(0xffffffffu, fid, __ffs(m) - 1);
       }
       if (best_id < 0) best_id = (int32_t)cand_idx[row];  // main.rs:456-474 nearest_one
-      best_lab = __ldg(&lab4[best_id]);
     }
-    chosen = best_id;
-    ch_l = best_lab.x;
-    ch_a = best_lab.y;
-    ch_b = best_lab.z;
+    usage[best_id] = (UsageT)(usage[best_id] + 1);  // main.rs:410-411 / 449 / 470
+    __syncwarp();
+    return best_id;
   };
 
-  int x = 0, y = 0;
-  // one cell: A = registers of `cell` (its t_up/up already known), B = registers of cell + 1 (slot loaded,
-  // t_up/up filled in here, in the shadow of A's Left chain).  At the end A is refilled with cell + 2.
+  // exact totals of the first chunk (main.rs:386-407); returns the winning lane, or 63 if the chunk cannot decide
+  auto resolve_exact = [&](int cell, int32_t left, int32_t up, bool valid) -> unsigned {
+    const int sA = cell % CH_DEPTH;
+    const float d2 = vring[sA].d2[lane];
+    const float l = vring[sA].l[lane], a = vring[sA].a[lane], b = vring[sA].b[lane];
+    const float d2_32 = vd2_32[sA];
+    const volatile float4* ul = rowlab + x;
+    const float ux = ul->x, uy = ul->y, uz = ul->z;
+    float4 pl = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (left >= 0) pl = prev_lab(cell);
+    bool oor_u = false, oor_l = false;
+    float pen = 0.0f;
+    if (use_penalty) {
+      float t_up = adjacency_term_fast(l, a, b, ux, uy, uz, oor_u);
+      float t_left = adjacency_term_fast(l, a, b, pl.x, pl.y, pl.z, oor_l);
+      t_up = up >= 0 ? t_up : 0.0f;  // absent terms are +0.0: x + 0.0 == x exactly
+      t_left = left >= 0 ? t_left : 0.0f;
+      pen = __fmul_rn(__fadd_rn(t_up, t_left), weight);  // adjacency.rs:71-87 order Up, Left; then * weight
+    }
+    const float total = __fadd_rn(d2, pen);  // main.rs:398
+    unsigned tb = valid ? __float_as_uint(total) : 0xFFFFFFFFu;
+    tb = ((oor_u && up >= 0) || (oor_l && left >= 0)) ? 0u : tb;  // out-of-domain arithmetic -> generic path
+    const unsigned mn = __reduce_min_sync(0xffffffffu, tb);
+    if (mn - 1u < 0xFFFFFFFEu && __float_as_uint(d2_32) >= mn)
+      return (unsigned)(__ffs(__ballot_sync(0xffffffffu, tb == mn)) - 1);  // strict <, first in order on ties
+    return 63u;
+  };
+
+  // one cell: A = registers of `cell`, B = registers of cell + 1; A is refilled with cell + 2 at the end.
+  // Everything cell + 1 needs from shared memory is requested at the top, so that the loop-carried chain
+  // (prev -> valid -> vote -> first lane -> shuffle -> prev) never waits on a load.
   auto step = [&](int cell, CellRegs& A, CellRegs& B) {
-    const uint32_t flag2 = (cell + 2 < cells) ? ready[(cell + 2) % RING_DEPTH] : 0u;
-    // ---- next cell's Up term (independent of this cell's outcome as long as gw >= 2)
+    const int sA = cell % CH_DEPTH;
+    const uint32_t flag2 = (cell + 2 < cells) ? readyP[(cell + 2) % CH_DEPTH] : 0u;
+    B.u = (unsigned)usage[B.id];  // before this cell's increment; fixed up through prev_u next iteration
     int xn = x + 1, yn = y;
     if (xn == gw) {
       xn = 0;
       yn = y + 1;
     }
-    const int32_t up_n = (yn > 0) ? rowbuf[xn] : -1;
-    const float4 upl_n = rowlab[xn];
-    const unsigned u = (unsigned)usage[A.id];
-    bool flag_n = false;
-    float t_up_n = 0.0f;
-    if (use_penalty) {
-      t_up_n = adjacency_term_fast(B.l, B.a, B.b, upl_n.x, upl_n.y, upl_n.z, flag_n);
-      t_up_n = up_n >= 0 ? t_up_n : 0.0f;
-      flag_n = flag_n && up_n >= 0;
-    }
-    // ---- this cell: the chain through the Left neighbour
-    if (x == 0) left = -1;
-    bool flag = A.flag;
-    float pen = 0.0f;
-    if (use_penalty) {
-      float t_left = adjacency_term_fast(A.l, A.a, A.b, left_l, left_a, left_b, flag);
-      t_left = left >= 0 ? t_left : 0.0f;                 // absent terms are +0.0: x + 0.0 == x exactly
-      pen = __fmul_rn(__fadd_rn(A.t_up, t_left), weight);  // adjacency.rs:71-87 order Up, Left; then * weight
-    }
-    const float total = __fadd_rn(A.d2, pen);              // main.rs:398
-    const bool ok = lane < k && u < max_usage && (int32_t)A.id != A.up && (int32_t)A.id != left;  // main.rs:375, 380
-    unsigned tb = ok ? __float_as_uint(total) : 0xFFFFFFFFu;
-    tb = flag ? 0u : tb;  // out-of-domain arithmetic forces mn == 0 -> generic path
-    const unsigned mn = __reduce_min_sync(0xffffffffu, tb);
+    uint32_t dec = decided[0];
+    int32_t up_n = *reinterpret_cast<volatile int32_t*>(rowbuf + xn);  // meaningful once cell + 1 - gw is committed
 
-    int32_t chosen;
-    float ch_l, ch_a, ch_b;
-    if (mn - 1u < 0xFFFFFFFEu && __float_as_uint(A.d2_32) >= mn) {
-      // decided by the first chunk (exact early exit: later candidates have d2 >= d2_32 >= best total);
-      // strict-< winner, first in candidate order on ties (main.rs:401-407)
-      const int who = __ffs(__ballot_sync(0xffffffffu, tb == mn)) - 1;
-      chosen = (int32_t)__shfl_sync(0xffffffffu, A.id, who);
-      ch_l = __shfl_sync(0xffffffffu, A.l, who);
-      ch_a = __shfl_sync(0xffffffffu, A.a, who);
-      ch_b = __shfl_sync(0xffffffffu, A.b, who);
+    const int32_t left = (x == 0) ? -1 : prev;
+    const unsigned ucur = A.u + ((int32_t)A.id == prev_u ? 1u : 0u);
+    const bool valid = (int32_t)A.id != A.up && (int32_t)A.id != left && ucur < max_usage;  // main.rs:375, 380
+    const unsigned m = __ballot_sync(0xffffffffu, valid);
+    const int j0 = (__ffs(m) - 1) & 31;
+    const unsigned cont0 = __shfl_sync(0xffffffffu, A.cont, j0);
+    int32_t chosen = (int32_t)__shfl_sync(0xffffffffu, A.id, j0);
+    const unsigned cnt0 = __shfl_sync(0xffffffffu, ucur, j0);
+    unsigned who = (unsigned)j0;
+    bool generic = false;
+    if (m == 0u || (m & cont0) != 0u) {  // cold
+      who = m != 0u ? resolve_exact(cell, left, A.up, valid) : 63u;
+      if (who < 32u) {
+        chosen = (int32_t)__shfl_sync(0xffffffffu, A.id, who);
+        usage[chosen] = (UsageT)(__shfl_sync(0xffffffffu, ucur, who) + 1u);
+      } else {
+        float4 pl = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (left >= 0) pl = prev_lab(cell);
+        chosen = resolve_generic(cell, left, A.up, pl);
+        generic = true;
+      }
     } else {
-      resolve_generic(cell, A, chosen, ch_l, ch_a, ch_b);
+      usage[chosen] = (UsageT)(cnt0 + 1u);  // main.rs:410-411; all lanes store the same value
     }
-    if (lane == 0) {
-      usage[chosen] = (UsageT)(usage[chosen] + 1);  // main.rs:410-411 / 449 / 470 (never exceeds max_usage)
-      placed[cell] = chosen;                        // main.rs:412
-      rowbuf[x] = chosen;
-      rowlab[x] = make_float4(ch_l, ch_a, ch_b, 0.f);
+    queue[sA] = ((unsigned long long)((uint32_t)cell + 1u) << 32) | ((unsigned long long)who << 26) | (uint32_t)chosen;
+    prev_u = chosen;
+    if (generic) {  // B.u predates a possible usage reset: re-read it (it then includes this cell's increment)
+      B.u = (unsigned)usage[B.id];
+      prev_u = -1;
     }
-    __syncwarp();
-    left = chosen;
-    left_l = ch_l;
-    left_a = ch_a;
-    left_b = ch_b;
+    prev = chosen;
+    prev_who = who;
+    // Up neighbour of cell + 1
+    if (yn > 0) {
+      if ((int)dec < cell + 2 - gw) {  // cold: the committer lags by a whole row
+        while ((int)decided[0] < cell + 2 - gw) {
+        }
+        asm volatile("" ::: "memory");
+        up_n = *reinterpret_cast<volatile int32_t*>(rowbuf + xn);
+      }
+      B.up = up_n;
+    } else {
+      B.up = -1;
+    }
     x = xn;
     y = yn;
-    B.t_up = t_up_n;
-    B.up = up_n;
-    B.flag = flag_n;
     if (cell + 2 < cells) {
       wait_slot(cell + 2, flag2);
       load_slot(cell + 2, A);
-      if (lane == 0) consumed[0] = (uint32_t)cell + 3u;
     }
   };
 
   CellRegs R0, R1;
-  R0.t_up = 0.f; R0.up = -1; R0.flag = false;
-  R1 = R0;
-  R0.id = R1.id = 0u;
-  R0.d2 = R0.l = R0.a = R0.b = R0.d2_32 = 0.f;
-  R1.d2 = R1.l = R1.a = R1.b = R1.d2_32 = 0.f;
+  R0.id = R1.id = (uint32_t)n;
+  R0.cont = R1.cont = 0u;
+  R0.u = R1.u = 0u;
+  R0.up = R1.up = -1;
   if (cells > 0) {
-    wait_slot(0, ready[0]);
+    wait_slot(0, readyP[0]);
     load_slot(0, R0);
     if (cells > 1) {
-      wait_slot(1, ready[1 % RING_DEPTH]);
+      wait_slot(1, readyP[1 % CH_DEPTH]);
       load_slot(1, R1);
     }
-    __syncwarp();
-    if (lane == 0) consumed[0] = (uint32_t)min(2, cells);
   }
   for (int cell = 0; cell < cells; cell += 2) {
     step(cell, R0, R1);
@@ -456,9 +538,9 @@ __global__ void __launch_bounds__((RING_PRODUCERS + 1) * 32, 1)
 }  // namespace
 
 template <typename UsageT>
-static int launch_ring(mosaic_ctx* ctx, unsigned cap, float weight, size_t smem) {
-  MOSAIC_CUDA(ctx, cudaFuncSetAttribute(greedy_ring_kernel<UsageT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  greedy_ring_kernel<UsageT><<<1, (RING_PRODUCERS + 1) * 32, smem, ctx->stream>>>(
+static int launch_chain(mosaic_ctx* ctx, unsigned cap, float weight, size_t smem) {
+  MOSAIC_CUDA(ctx, cudaFuncSetAttribute(greedy_chain_kernel<UsageT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  greedy_chain_kernel<UsageT><<<1, (2 + CH_PWARPS) * 32, smem, ctx->stream>>>(
       ctx->d_cand_idx, ctx->d_cand_d2, ctx->k, ctx->d_mat_lab4, ctx->n, ctx->gw, ctx->gh, cap, weight, ctx->d_placed,
       ctx->d_place_info, mosaic_ctx::kFallbackCap);
   return MOSAIC_OK;
@@ -468,16 +550,16 @@ int launch_place(mosaic_ctx* ctx, int max_usage, float weight) {
   const int n = ctx->n, gw = ctx->gw, gh = ctx->gh;
   const unsigned cap = max_usage < 0 ? 0u : (unsigned)max_usage;
   const size_t smem_limit = 220 * 1024;
-  // fast path: ring + row state + usage counters in shared memory
-  const size_t ring_fixed = sizeof(RingSlot) * RING_DEPTH + sizeof(float) * RING_DEPTH + sizeof(uint32_t) * RING_DEPTH + 16 +
-                            sizeof(float4) * (size_t)gw + sizeof(int32_t) * (size_t)((gw + 3) & ~3);
-  const size_t usage_bytes = cap <= 255u ? (size_t)n : (cap <= 65535u ? (size_t)n * 2 : (size_t)-1);
+  // fast path: rings + row state + usage counters in shared memory
+  const size_t ring_fixed = sizeof(CSlot) * CH_DEPTH + (4 + 8 + 4) * CH_DEPTH + 16 + sizeof(float4) * (size_t)gw +
+                            sizeof(int32_t) * (size_t)((gw + 3) & ~3);
+  const size_t usage_bytes = cap <= 255u ? (size_t)n + 1 : (cap <= 65535u ? ((size_t)n + 1) * 2 : (size_t)-1);
   StageTimer t(ctx, MOSAIC_STAGE_PLACE);
-  if (gw >= 2 && usage_bytes != (size_t)-1 && ring_fixed + usage_bytes + 16 <= smem_limit) {
+  if (gw >= CH_MIN_GW && ctx->n < (1 << 26) && usage_bytes != (size_t)-1 && ring_fixed + usage_bytes + 16 <= smem_limit) {
     if (cap <= 255u)
-      MOSAIC_TRY(launch_ring<uint8_t>(ctx, cap, weight, ring_fixed + usage_bytes + 16));
+      MOSAIC_TRY(launch_chain<uint8_t>(ctx, cap, weight, ring_fixed + usage_bytes + 16));
     else
-      MOSAIC_TRY(launch_ring<uint16_t>(ctx, cap, weight, ring_fixed + usage_bytes + 16));
+      MOSAIC_TRY(launch_chain<uint16_t>(ctx, cap, weight, ring_fixed + usage_bytes + 16));
   } else {
     // generic path: single warp, usage counters in shared memory when they fit, else in HBM
     const size_t row_bytes = ((size_t)gw * 4 + 15) & ~(size_t)15;

@@ -100,6 +100,16 @@ def test_candidates_ties_quantised(ctx):
     (1, 4, 4, 3, 0.3),         # single material: final nearest_one fallback
     (300, 1, 40, 2, 0.5),      # one-column grid (no Left)
     (300, 40, 1, 2, 0.5),      # one-row grid (no Up)
+    # grid_w >= 33: the three-role fast kernel (producers / consumer / committer)
+    (300, 40, 12, 3, 0.3),
+    (100, 64, 10, 3, 0.0),     # no adjacency calculator on the fast kernel
+    (40, 33, 9, 1, 1.0),       # k = n < 100, cap 1: constant resets
+    (5, 36, 4, 0, 0.3),        # max_usage 0
+    (1, 40, 3, 3, 0.3),        # single material
+    (300, 200, 3, 2, 0.5),
+    (2000, 120, 40, 3, 0.3),
+    (300, 48, 20, 300, 0.3),   # 16-bit usage counters
+    (300, 48, 20, 70000, 0.3), # cap > 65535: generic kernel with 32-bit counters
 ])
 def test_place_bit_exact(ctx, n, gw, gh, max_usage, weight):
     mat_lab = synth.lab_points(n, seed=n)
