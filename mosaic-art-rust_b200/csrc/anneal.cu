@@ -17,6 +17,8 @@
 //     degree-13 Horner, unfused) rounded once to f32 — the same operation sequence as the oracle.
 //   * initial cost: calculate_total_cost's raster-order f32 sum is evaluated in 32-pair batches
 //     (terms in parallel, accumulation in order).
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace mosaic {
@@ -72,8 +74,8 @@ struct Rng {
     const unsigned hi = next_u32(lane);
     return ((unsigned long long)hi << 32) | lo;
   }
-  __device__ unsigned long long gen_range(unsigned long long n, int lane) {  // UniformInt<usize>::sample_single
-    const unsigned long long zone = (n << __clzll((long long)n)) - 1ull;
+  __device__ unsigned long long gen_range(unsigned long long n, unsigned long long zone, int lane) {
+    // UniformInt<usize>::sample_single: zone = (n << n.leading_zeros()) - 1, hoisted by the caller
     for (;;) {
       const unsigned long long v = next_u64(lane);
       const unsigned long long hi = __umul64hi(v, n), lo = v * n;
@@ -103,57 +105,114 @@ __device__ float exp_det(float xf) {
   return __double2float_rn(__dmul_rn(p, scale));
 }
 
-__device__ __forceinline__ float pair_term(const float4* __restrict__ lab4, int a, int b) {
-  // get_similarity (similarity.rs:85-103): same index -> 0.0, else entry of (min, max)
-  if (a == b) return adjacency_term(0.0f);
-  const int lo = min(a, b), hi = max(a, b);
-  const float4 p = __ldg(&lab4[lo]), q = __ldg(&lab4[hi]);
-  return adjacency_term(lab_distance_rn(p.x, p.y, p.z, q.x, q.y, q.z));
+// ---- initial cost: all pair terms in parallel, summed later in the reference's order ----------
+// terms[2c] = right pair of cell c, terms[2c+1] = down pair (adjacency.rs:104-124); absent pairs are +0.0,
+// which the sequential f32 sum absorbs exactly (x + 0.0 == x).
+__global__ void __launch_bounds__(256) cost_terms_kernel(const float4* __restrict__ lab4, const int32_t* __restrict__ grid,
+                                                         int gw, int gh, float* __restrict__ terms) {
+  const long long pairs = 2ll * gw * gh;
+  for (long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x; s < pairs; s += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(s >> 1), x = c % gw, y = c / gw;
+    const int cur = grid[c];
+    int other = -1;
+    if (cur >= 0) {
+      if ((s & 1) == 0) {
+        if (x < gw - 1) other = grid[c + 1];
+      } else if (y < gh - 1) {
+        other = grid[c + gw];
+      }
+    }
+    float t = 0.0f;
+    if (other >= 0) {
+      // get_similarity (similarity.rs:85-103): same index -> 0.0, else the packed entry of (min, max)
+      float sim = 0.0f;
+      if (other != cur) {
+        const float4 p = __ldg(&lab4[min(cur, other)]), q = __ldg(&lab4[max(cur, other)]);
+        sim = lab_distance_rn(p.x, p.y, p.z, q.x, q.y, q.z);
+      }
+      t = adjacency_term(sim);
+    }
+    terms[s] = t;
+  }
 }
 
-template <bool GRID_SMEM>
-__global__ void __launch_bounds__(32, 1) anneal_kernel(const float4* __restrict__ lab4, int32_t* grid_gmem, int gw,
-                                                       int gh, unsigned long long iterations, float t0, float decay,
-                                                       unsigned long long seed, mosaic_opt_result* res) {
+// Where the chain's working set lives: the grid as u16 / i32 in shared memory (or in HBM when it does not
+// fit), the material Lab means as SoA in shared memory (or the float4 table in HBM/L2).
+template <typename GridT, bool GRID_SMEM, bool LAB_SMEM>
+struct AnnealMem {
+  volatile GridT* grid_s;
+  volatile int32_t* grid_g;
+  const float* lab_s;  // l[n], a[n], b[n]
+  const float4* lab_g;
+  int n;
+  __device__ __forceinline__ int get(int i) const {
+    if (GRID_SMEM) {
+      const GridT v = grid_s[i];
+      return (sizeof(GridT) == 2 && v == (GridT)0xFFFF) ? -1 : (int)v;
+    }
+    return grid_g[i];
+  }
+  __device__ __forceinline__ void set(int i, int v) const {
+    if (GRID_SMEM)
+      grid_s[i] = (GridT)v;
+    else
+      grid_g[i] = v;
+  }
+  __device__ __forceinline__ void lab(int m, float& l, float& a, float& b) const {
+    if (LAB_SMEM) {
+      l = lab_s[m];
+      a = lab_s[n + m];
+      b = lab_s[2 * n + m];
+    } else {
+      const float4 v = __ldg(&lab_g[m]);
+      l = v.x;
+      a = v.y;
+      b = v.z;
+    }
+  }
+};
+
+template <typename GridT, bool GRID_SMEM, bool LAB_SMEM>
+__global__ void __launch_bounds__(256, 1)
+    anneal_kernel(const float4* __restrict__ lab4, int n, int32_t* grid_gmem, const float* __restrict__ terms, int gw,
+                  int gh, unsigned long long iterations, float t0, float decay, unsigned long long seed,
+                  mosaic_opt_result* res) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   unsigned* ring = reinterpret_cast<unsigned*>(smem_raw);
-  volatile int32_t* grid = GRID_SMEM ? reinterpret_cast<int32_t*>(smem_raw + RNG_RING_WORDS * 4) : grid_gmem;
-  const int lane = threadIdx.x;
+  float* lab_s = reinterpret_cast<float*>(smem_raw + RNG_RING_WORDS * 4);
+  GridT* grid_s = reinterpret_cast<GridT*>(smem_raw + RNG_RING_WORDS * 4 + (LAB_SMEM ? (size_t)n * 12 : 0));
+  const int tid = threadIdx.x, lane = tid & 31;
   const int cells = gw * gh;
-  if (GRID_SMEM) {
-    for (int i = lane; i < cells; i += 32) grid[i] = grid_gmem[i];
-    __syncwarp();
-  }
+  if (GRID_SMEM)
+    for (int i = tid; i < cells; i += blockDim.x) grid_s[i] = (GridT)grid_gmem[i];  // -1 -> 0xFFFF for u16
+  if (LAB_SMEM)
+    for (int i = tid; i < n; i += blockDim.x) {
+      const float4 v = __ldg(&lab4[i]);
+      lab_s[i] = v.x;
+      lab_s[n + i] = v.y;
+      lab_s[2 * n + i] = v.z;
+    }
+  __syncthreads();
+  if (tid >= 32) return;  // the Markov chain is one warp
 
-  // ---- calculate_total_cost (adjacency.rs:91-130): raster order, right then down ----
+  AnnealMem<GridT, GRID_SMEM, LAB_SMEM> mem;
+  mem.grid_s = grid_s;
+  mem.grid_g = grid_gmem;
+  mem.lab_s = lab_s;
+  mem.lab_g = lab4;
+  mem.n = n;
+
+  // ---- calculate_total_cost (adjacency.rs:91-130): raster order, right then down, sequential f32 adds ----
   float current = 0.0f;
   {
-    const long long pairs = 2ll * cells;  // slot 2*c = right pair of cell c, 2*c+1 = down pair
+    const long long pairs = 2ll * cells;
+    float nxt = lane < pairs ? __ldg(terms + lane) : 0.0f;
     for (long long base = 0; base < pairs; base += 32) {
-      const long long s = base + lane;
-      float term = 0.0f;
-      bool present = false;
-      if (s < pairs) {
-        const int c = (int)(s >> 1), x = c % gw, y = c / gw;
-        const int cur = grid[c];
-        if (cur >= 0) {
-          if ((s & 1) == 0) {
-            if (x < gw - 1) {
-              const int r = grid[c + 1];
-              if (r >= 0) { term = pair_term(lab4, cur, r); present = true; }
-            }
-          } else if (y < gh - 1) {
-            const int d = grid[c + gw];
-            if (d >= 0) { term = pair_term(lab4, cur, d); present = true; }
-          }
-        }
-      }
-      const unsigned mask = __ballot_sync(0xffffffffu, present);
-#pragma unroll 4
-      for (int l = 0; l < 32; ++l) {
-        const float t = __shfl_sync(0xffffffffu, term, l);
-        if ((mask >> l) & 1u) current = __fadd_rn(current, t);
-      }
+      const float term = nxt;
+      const long long s = base + 32 + lane;
+      nxt = s < pairs ? __ldg(terms + s) : 0.0f;
+#pragma unroll
+      for (int l = 0; l < 32; ++l) current = __fadd_rn(current, __shfl_sync(0xffffffffu, term, l));
     }
   }
   const float initial = current;
@@ -175,15 +234,17 @@ __global__ void __launch_bounds__(32, 1) anneal_kernel(const float4* __restrict_
     rng.ring = ring;
     rng.pos = RNG_RING_WORDS;
   }
+  const unsigned long long zone_w = ((unsigned long long)gw << __clzll((long long)gw)) - 1ull;
+  const unsigned long long zone_h = ((unsigned long long)gh << __clzll((long long)gh)) - 1ull;
 
   for (unsigned long long it = 0; it < iterations; ++it) {
-    const int x1 = (int)rng.gen_range((unsigned long long)gw, lane);  // optimizer.rs:60-63: x before y
-    const int y1 = (int)rng.gen_range((unsigned long long)gh, lane);
-    const int x2 = (int)rng.gen_range((unsigned long long)gw, lane);
-    const int y2 = (int)rng.gen_range((unsigned long long)gh, lane);
+    const int x1 = (int)rng.gen_range((unsigned long long)gw, zone_w, lane);  // optimizer.rs:60-63: x before y
+    const int y1 = (int)rng.gen_range((unsigned long long)gh, zone_h, lane);
+    const int x2 = (int)rng.gen_range((unsigned long long)gw, zone_w, lane);
+    const int y2 = (int)rng.gen_range((unsigned long long)gh, zone_h, lane);
     if (x1 == x2 && y1 == y2) continue;              // optimizer.rs:66-68 (no temperature decay)
     const int i1 = y1 * gw + x1, i2 = y2 * gw + x2;
-    const int p1 = grid[i1], p2 = grid[i2];
+    const int p1 = mem.get(i1), p2 = mem.get(i2);
     if (p1 < 0 || p2 < 0) continue;                  // optimizer.rs:71-73
 
     float delta = 0.0f;
@@ -196,28 +257,37 @@ __global__ void __launch_bounds__(32, 1) anneal_kernel(const float4* __restrict_
       bool present = lane < 8 && nx >= 0 && nx < gw && ny >= 0 && ny < gh && !(nx == ox && ny == oy);
       int nb = -1;
       if (present) {
-        nb = grid[ny * gw + nx];
+        nb = mem.get(ny * gw + nx);
         present = nb >= 0;
       }
-      float t_old = 0.0f, t_new = 0.0f;
-      if (present) {
-        const int mine = side ? p2 : p1, other = side ? p1 : p2;
-        t_old = pair_term(lab4, mine, nb);   // cost with the current material at this position
-        t_new = pair_term(lab4, other, nb);  // cost after the swap
+      float l1, a1, b1, l2, a2, b2, ln = 0.f, an = 0.f, bn = 0.f;
+      mem.lab(p1, l1, a1, b1);
+      mem.lab(p2, l2, a2, b2);
+      if (nb >= 0) mem.lab(nb, ln, an, bn);
+      const float ml = side ? l2 : l1, ma = side ? a2 : a1, mb = side ? b2 : b1;  // material now at this position
+      const float ol = side ? l1 : l2, oa = side ? a1 : a2, ob = side ? b1 : b2;  // material after the swap
+      bool oor = false;
+      float t_old = adjacency_term_fast(ml, ma, mb, ln, an, bn, oor);
+      float t_new = adjacency_term_fast(ol, oa, ob, ln, an, bn, oor);
+      if (__any_sync(0xffffffffu, oor && present)) {  // outside the fast-math domain: exact builtins
+        t_old = adjacency_term(lab_distance_rn(ml, ma, mb, ln, an, bn));
+        t_new = adjacency_term(lab_distance_rn(ol, oa, ob, ln, an, bn));
       }
-      const unsigned mask = __ballot_sync(0xffffffffu, present);
+      // same material on both sides: get_similarity returns 0.0 -> term 1.0; sqrt(0) gives the same
+      t_old = present ? t_old : 0.0f;  // absent neighbours contribute +0.0 (exact identity in the sums below)
+      t_new = present ? t_new : 0.0f;
       float old_cost = 0.0f, new_cost = 0.0f;
 #pragma unroll
-      for (int l = 0; l < 8; ++l) {
-        const float to = __shfl_sync(0xffffffffu, t_old, l), tn = __shfl_sync(0xffffffffu, t_new, l);
-        if ((mask >> l) & 1u) {
-          old_cost = __fadd_rn(old_cost, to);
-          new_cost = __fadd_rn(new_cost, tn);
-        }
+      for (int l = 0; l < 8; ++l) {  // reference order: pos1 U,D,L,R then pos2 U,D,L,R (adjacency.rs:165-200)
+        old_cost = __fadd_rn(old_cost, __shfl_sync(0xffffffffu, t_old, l));
+        new_cost = __fadd_rn(new_cost, __shfl_sync(0xffffffffu, t_new, l));
       }
+      bool oor_m = false;  // warp-uniform
+      const float mutual = adjacency_term_fast(l1, a1, b1, l2, a2, b2, oor_m);
       const bool adjacent12 = (x1 == x2 && (y1 - y2 == 1 || y2 - y1 == 1)) || (y1 == y2 && (x1 - x2 == 1 || x2 - x1 == 1));
       if (adjacent12) {                              // adjacency.rs:203-211
-        const float cost = pair_term(lab4, p1, p2);
+        float cost = mutual;
+        if (oor_m) cost = adjacency_term(lab_distance_rn(l1, a1, b1, l2, a2, b2));
         old_cost = __fadd_rn(old_cost, cost);
         new_cost = __fadd_rn(new_cost, cost);
       }
@@ -228,13 +298,30 @@ __global__ void __launch_bounds__(32, 1) anneal_kernel(const float4* __restrict_
     if (delta < 0.0f) {
       accept = true;
     } else {
-      const float probability = exp_det(__fdiv_rn(-delta, temperature));  // optimizer.rs:82
-      accept = rng.gen_f32(lane) < probability;                           // optimizer.rs:83
+      const float u = rng.gen_f32(lane);  // optimizer.rs:83 (drawn only when delta >= 0)
+      // accept <=> u < exp(-delta / T).  1 - q <= exp(-q) <= 1 / (1 + q) (q >= 0) decide almost every draw
+      // without the division and the exponential; the margins (2^-18) dwarf every rounding error involved.
+      float rT;
+      asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rT) : "f"(temperature));
+      const float q = delta * rT;
+      const float lo = 1.0f - q * 1.000004f - 3.8146973e-06f;
+      float hi;
+      asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(hi) : "f"(1.0f + q * 0.999996f));
+      hi += 3.8146973e-06f;
+      const bool bounds_ok = q >= 0.0f;  // the bounds hold for q >= 0 (T > 0); NaN / negative -> exact path
+      if (bounds_ok && u < lo) {
+        accept = true;
+      } else if (bounds_ok && u > hi) {
+        accept = false;
+      } else {
+        const float probability = exp_det(__fdiv_rn(-delta, temperature));  // optimizer.rs:82
+        accept = u < probability;
+      }
     }
     if (accept) {
       if (lane == 0) {
-        grid[i1] = p2;
-        grid[i2] = p1;
+        mem.set(i1, p2);
+        mem.set(i2, p1);
       }
       __syncwarp();
       current = __fadd_rn(current, delta);
@@ -249,7 +336,7 @@ __global__ void __launch_bounds__(32, 1) anneal_kernel(const float4* __restrict_
 
   if (GRID_SMEM) {
     __syncwarp();
-    for (int i = lane; i < cells; i += 32) grid_gmem[i] = grid[i];
+    for (int i = lane; i < cells; i += 32) grid_gmem[i] = mem.get(i);
   }
   if (lane == 0) {
     res->initial_cost = initial;
@@ -263,19 +350,45 @@ __global__ void __launch_bounds__(32, 1) anneal_kernel(const float4* __restrict_
 
 }  // namespace
 
+template <typename GridT, bool GS, bool LS>
+static int launch_anneal_variant(mosaic_ctx* ctx, size_t smem, uint64_t iterations, float t0, float decay, uint64_t seed) {
+  MOSAIC_CUDA(ctx, cudaFuncSetAttribute(anneal_kernel<GridT, GS, LS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  anneal_kernel<GridT, GS, LS><<<1, 256, smem, ctx->stream>>>(ctx->d_mat_lab4, ctx->n, ctx->d_placed, ctx->d_terms,
+                                                              ctx->gw, ctx->gh, iterations, t0, decay, seed,
+                                                              (mosaic_opt_result*)ctx->d_opt_res);
+  return MOSAIC_OK;
+}
+
 int launch_anneal(mosaic_ctx* ctx, uint64_t iterations, float t0, float decay, uint64_t seed) {
   const size_t cells = (size_t)ctx->gw * ctx->gh;
+  const size_t n = (size_t)ctx->n;
   const size_t ring_bytes = RNG_RING_WORDS * 4;
-  const size_t smem_grid = ring_bytes + cells * 4;
+  const size_t limit = 220 * 1024;
+  MOSAIC_TRY(ensure(ctx, &ctx->d_terms, &ctx->terms_cap, 2 * cells));
   StageTimer t(ctx, MOSAIC_STAGE_ANNEAL);
-  if (smem_grid <= 200 * 1024) {
-    MOSAIC_CUDA(ctx, cudaFuncSetAttribute(anneal_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_grid));
-    anneal_kernel<true><<<1, 32, smem_grid, ctx->stream>>>(ctx->d_mat_lab4, ctx->d_placed, ctx->gw, ctx->gh, iterations,
-                                                           t0, decay, seed, (mosaic_opt_result*)ctx->d_opt_res);
+  {
+    int blocks = (int)std::min<size_t>((2 * cells + 255) / 256, (size_t)ctx->sm_count * 8);
+    if (blocks < 1) blocks = 1;
+    cost_terms_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->d_mat_lab4, ctx->d_placed, ctx->gw, ctx->gh, ctx->d_terms);
+    ctx->launches++;
+    MOSAIC_CUDA(ctx, cudaGetLastError());
+  }
+  const bool g16 = n <= 65534;
+  const size_t grid_bytes = cells * (g16 ? 2 : 4);
+  const size_t lab_bytes = n * 12;
+  // preference: grid + Lab in shared memory; then grid only; then everything in HBM/L2
+  if (ring_bytes + grid_bytes + lab_bytes <= limit) {
+    if (g16)
+      MOSAIC_TRY((launch_anneal_variant<uint16_t, true, true>(ctx, ring_bytes + grid_bytes + lab_bytes, iterations, t0, decay, seed)));
+    else
+      MOSAIC_TRY((launch_anneal_variant<int32_t, true, true>(ctx, ring_bytes + grid_bytes + lab_bytes, iterations, t0, decay, seed)));
+  } else if (ring_bytes + grid_bytes <= limit) {
+    if (g16)
+      MOSAIC_TRY((launch_anneal_variant<uint16_t, true, false>(ctx, ring_bytes + grid_bytes, iterations, t0, decay, seed)));
+    else
+      MOSAIC_TRY((launch_anneal_variant<int32_t, true, false>(ctx, ring_bytes + grid_bytes, iterations, t0, decay, seed)));
   } else {
-    anneal_kernel<false><<<1, 32, ring_bytes, ctx->stream>>>(ctx->d_mat_lab4, ctx->d_placed, ctx->gw, ctx->gh,
-                                                             iterations, t0, decay, seed,
-                                                             (mosaic_opt_result*)ctx->d_opt_res);
+    MOSAIC_TRY((launch_anneal_variant<int32_t, false, false>(ctx, ring_bytes, iterations, t0, decay, seed)));
   }
   ctx->launches++;
   MOSAIC_CUDA(ctx, cudaGetLastError());

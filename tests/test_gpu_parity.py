@@ -181,6 +181,57 @@ def test_anneal_bit_exact(ctx, n, gw, gh, iters, seed):
     assert res.iterations == iters
 
 
+def test_anneal_with_empty_cells_and_duplicates(ctx):
+    # empty cells are skipped without cooling (optimizer.rs:71-73); equal materials give delta 0 (adjacency.rs:156-158)
+    n, gw, gh = 6, 12, 9
+    mat_lab = synth.lab_points(n, seed=2)
+    mat_lab[4] = mat_lab[1]   # two materials with identical Lab: sim 0 between different indices
+    rng = np.random.default_rng(8)
+    grid = rng.integers(0, n, (gh, gw)).astype(np.int32)
+    grid[rng.random((gh, gw)) < 0.15] = -1
+    ctx.set_material_lab(mat_lab)
+    ctx.set_cell_lab(np.zeros((gw * gh, 3), np.float32), gw, gh)
+    for t0, decay in ((100.0, 0.99995), (0.05, 0.9995)):
+        ctx.set_placement(grid)
+        placed, res = ctx.anneal(3000, 11, t0=t0, decay=decay)
+        rgrid, rres = orc.anneal(mat_lab, grid, 3000, 11, t0=t0, decay=decay)
+        assert (placed.reshape(gh, gw) == rgrid).all()
+        assert res.accepted_count == rres.accepted_count and res.improved_count == rres.improved_count
+        for f in ("initial_cost", "final_cost", "best_cost"):
+            assert np.float32(getattr(res, f)).view(np.uint32) == np.float32(getattr(rres, f)).view(np.uint32), f
+
+
+@pytest.mark.parametrize("t0,decay", [(1.0, 0.999), (0.2, 0.9999), (0.003, 1.0), (5.0, 0.99)])
+def test_anneal_temperature_sweep(ctx, t0, decay):
+    # acceptance probabilities from ~1 down to ~0: exercises both exp bounds and the exact exp in between
+    n, gw, gh = 500, 40, 30
+    mat_lab = synth.lab_points(n, seed=21)
+    grid = np.random.default_rng(2).integers(0, n, (gh, gw)).astype(np.int32)
+    ctx.set_material_lab(mat_lab)
+    ctx.set_cell_lab(np.zeros((gw * gh, 3), np.float32), gw, gh)
+    ctx.set_placement(grid)
+    placed, res = ctx.anneal(6000, 77, t0=t0, decay=decay)
+    rgrid, rres = orc.anneal(mat_lab, grid, 6000, 77, t0=t0, decay=decay)
+    assert (placed.reshape(gh, gw) == rgrid).all()
+    assert res.accepted_count == rres.accepted_count and res.improved_count == rres.improved_count
+    assert np.float32(res.final_cost).view(np.uint32) == np.float32(rres.final_cost).view(np.uint32)
+
+
+def test_anneal_large_grid_in_hbm(ctx):
+    # 300x300 = 90,000 cells x 2 B + ring does not fit with the Lab table -> grid-only variant; 70,000 materials -> i32 grid
+    n, gw, gh = 70000, 300, 300
+    mat_lab = synth.lab_points(n, seed=5)
+    grid = np.random.default_rng(4).integers(0, n, (gh, gw)).astype(np.int32)
+    ctx.set_material_lab(mat_lab)
+    ctx.set_cell_lab(np.zeros((gw * gh, 3), np.float32), gw, gh)
+    ctx.set_placement(grid)
+    placed, res = ctx.anneal(3000, 3)
+    rgrid, rres = orc.anneal(mat_lab, grid, 3000, 3)
+    assert (placed.reshape(gh, gw) == rgrid).all()
+    assert np.float32(res.final_cost).view(np.uint32) == np.float32(rres.final_cost).view(np.uint32)
+    assert np.float32(res.initial_cost).view(np.uint32) == np.float32(rres.initial_cost).view(np.uint32)
+
+
 def test_anneal_cold_rejects(ctx):
     # low temperature: the acceptance test (exp + uniform draw) actually rejects -> exercises the RNG stream
     n, gw, gh = 200, 16, 12
