@@ -250,7 +250,11 @@ def test_anneal_cold_rejects(ctx):
 
 # ---------------------------------------------------------------- K4 render
 @pytest.mark.parametrize("w,h,gw,gh,strength", [(480, 288, 24, 16, 0.3), (480, 288, 24, 16, 0.0), (250, 130, 7, 3, 1.0),
-                                                 (512, 512, 8, 8, 0.4), (1920, 1080, 50, 28, 0.3)])
+                                                 (512, 512, 8, 8, 0.4), (1920, 1080, 50, 28, 0.3),
+                                                 (760, 432, 20, 12, 0.3),   # 38x36 tiles (the 24,000-tile shape)
+                                                 (760, 432, 20, 12, 0.0),
+                                                 (800, 450, 10, 5, 0.5),    # 80x90 tiles: upscaling, 7-tap windows
+                                                 (768, 320, 12, 10, 0.3)])  # 64x32 tiles: horizontal axis skipped
 def test_render_within_one_lsb(ctx, w, h, gw, gh, strength):
     n = 64
     mats = synth.materials(n)
