@@ -22,8 +22,8 @@ namespace mosaic {
 namespace {
 
 constexpr int TK_WARPS = 8;
-constexpr int TK_Q = 4;
-constexpr int TK_CHUNK = 2048;
+constexpr int TK_Q = 2;
+constexpr int TK_CHUNK = 1024;
 constexpr int TK_SLOTS = 128;
 constexpr int TK_FLUSH = 96;  // merge when more than this many keys are buffered (<= 128 - 32)
 
