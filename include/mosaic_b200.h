@@ -166,6 +166,12 @@ const void* mosaic_device_similarity(const mosaic_ctx* ctx);
  * packed similarity entries [tri_begin,tri_end) */
 int mosaic_shard(const mosaic_ctx* ctx, int* row_begin, int* row_end, int* mat_begin, int* mat_end,
                  uint64_t* tri_begin, uint64_t* tri_end);
+/* The same partition as a pure function (no context, no GPU): rank `rank` of `world` for a grid of
+ * grid_h rows and n materials.  Rows and materials are split into contiguous near-equal blocks;
+ * the packed similarity triangle [0, n(n-1)/2) is split into equal-size contiguous ranges with
+ * 512-entry aligned boundaries (balanced by entry count, not by row count). */
+int mosaic_shard_plan(int world, int rank, int grid_h, int n_materials, int* row_begin, int* row_end,
+                      int* mat_begin, int* mat_end, uint64_t* tri_begin, uint64_t* tri_end);
 
 #ifdef __cplusplus
 }

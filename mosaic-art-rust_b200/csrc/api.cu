@@ -690,4 +690,15 @@ int mosaic_shard(const mosaic_ctx* c, int* row_begin, int* row_end, int* mat_beg
   return MOSAIC_OK;
 }
 
+int mosaic_shard_plan(int world, int rank, int grid_h, int n_materials, int* row_begin, int* row_end, int* mat_begin,
+                      int* mat_end, uint64_t* tri_begin, uint64_t* tri_end) {
+  if (world < 1 || rank < 0 || rank >= world || grid_h < 0 || n_materials < 0) return MOSAIC_ERR_INVALID;
+  mosaic_ctx tmp;  // plain host object: only the shape fields are read
+  tmp.world = world;
+  tmp.rank = rank;
+  tmp.gh = grid_h;
+  tmp.n = n_materials;
+  return mosaic_shard(&tmp, row_begin, row_end, mat_begin, mat_end, tri_begin, tri_end);
+}
+
 }  // extern "C"

@@ -92,6 +92,7 @@ def load_library():
         "mosaic_device_placement": ([vp], vp),
         "mosaic_device_similarity": ([vp], vp),
         "mosaic_shard": ([vp] + [C.POINTER(C.c_int)] * 4 + [u64p, u64p], C.c_int),
+        "mosaic_shard_plan": ([C.c_int] * 4 + [C.POINTER(C.c_int)] * 4 + [u64p, u64p], C.c_int),
     }
     for name, (args, res) in sig.items():
         fn = getattr(L, name)  # AttributeError here = the library does not export what the header declares
@@ -109,7 +110,19 @@ EXPORTED_SYMBOLS = (
     "mosaic_cell_lab", "mosaic_similarity_tri", "mosaic_candidates", "mosaic_place", "mosaic_fallback_cells",
     "mosaic_set_placement", "mosaic_anneal", "mosaic_render", "mosaic_generate", "mosaic_selftest", "mosaic_dims",
     "mosaic_device_output", "mosaic_device_placement", "mosaic_device_similarity", "mosaic_shard",
+    "mosaic_shard_plan",
 )
+
+
+def shard_plan(world, rank, grid_h, n_materials):
+    """Partition of rows / materials / packed similarity entries for one rank (pure host function)."""
+    L = load_library()
+    v = [C.c_int() for _ in range(4)]
+    t = [C.c_uint64(), C.c_uint64()]
+    rc = L.mosaic_shard_plan(world, rank, grid_h, n_materials, *[C.byref(x) for x in v], C.byref(t[0]), C.byref(t[1]))
+    if rc != 0:
+        raise MosaicError(rc, "mosaic_shard_plan: invalid arguments")
+    return dict(rows=(v[0].value, v[1].value), materials=(v[2].value, v[3].value), tri=(t[0].value, t[1].value))
 
 
 def _ptr(a):
