@@ -361,6 +361,9 @@ def run_gpu(args, cfg):
                        "accepted": int(rep.opt.accepted_count)},
         }
     ctx.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
     return result, rank, world
 
 
