@@ -156,6 +156,14 @@ int mosaic_generate(mosaic_ctx* ctx, const mosaic_params* params, int32_t* place
  * correctly rounded builtins over all 2^32 float bit patterns.  mismatches[0] = sqrt, [1] = rcp. */
 int mosaic_selftest(mosaic_ctx* ctx, uint64_t mismatches[2]);
 
+/* ---- diagnostics ------------------------------------------------------------------------------ */
+/* Placement-chain profile.  `enable` != 0 makes later mosaic_place calls launch the instrumented
+ * instantiation of the chain kernel (same results, clock64 reads on the consumer warp); counters (may
+ * be NULL) receives the numbers of the last instrumented launch: [0..3] consumer cycles spent in cells
+ * resolved by the bound-only / exact-first-chunk / generic / generic+reset path, [4..7] the cell counts
+ * per path, [8] cycles waiting for producers, [9] cycles waiting for the committer, [10] total cycles. */
+int mosaic_debug_chain_profile(mosaic_ctx* ctx, int enable, uint64_t counters[16]);
+
 /* ---- introspection -------------------------------------------------------------------------- */
 int mosaic_dims(const mosaic_ctx* ctx, int* n_materials, int* grid_w, int* grid_h, int* tile_w, int* tile_h);
 /* device pointers of resident results (NULL if absent): for zero-copy consumers */

@@ -390,7 +390,7 @@ void mosaic_ctx_destroy(mosaic_ctx* c) {
   if (c->stream) cudaStreamSynchronize(c->stream);
   dist_destroy(c);
   void* bufs[] = {c->d_materials_owned, c->d_mat_lab, c->d_mat_lab4, c->d_mat_soa, c->d_target_owned, c->d_cell_lab,
-                  c->d_cell_rgbsum,     c->d_cand_idx, c->d_cand_d2, c->d_placed,  c->d_usage,        c->d_place_info,
+                  c->d_cell_rgbsum,     c->d_cand_idx, c->d_cand_d2, c->d_placed,  c->d_usage,        c->d_place_info, c->d_place_rec,
                   c->d_sim,             c->d_opt_res,  c->d_rng_ring, c->d_terms, c->d_out,    c->axis_h.start,   c->axis_h.size,
                   c->axis_h.w,          c->axis_v.start, c->axis_v.size, c->axis_v.w};
   for (void* p : bufs)
@@ -656,6 +656,18 @@ int mosaic_selftest(mosaic_ctx* c, uint64_t mismatches[2]) {
   MOSAIC_TRY(launch_selftest(c, m));
   mismatches[0] = m[0];
   mismatches[1] = m[1];
+  return MOSAIC_OK;
+}
+
+int mosaic_debug_chain_profile(mosaic_ctx* c, int enable, uint64_t counters[16]) {
+  if (!c) return MOSAIC_ERR_INVALID;
+  MOSAIC_CUDA(c, cudaSetDevice(c->device));
+  if (counters) {
+    unsigned long long v[16] = {};
+    MOSAIC_TRY(read_chain_profile(c, v));
+    for (int i = 0; i < 16; ++i) counters[i] = v[i];
+  }
+  c->profile_chain = enable != 0;
   return MOSAIC_OK;
 }
 

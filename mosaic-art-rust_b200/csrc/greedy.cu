@@ -29,7 +29,7 @@ __global__ void __launch_bounds__(32, 1) greedy_generic_kernel(const uint32_t* _
                                                              unsigned max_usage, float weight,
                                                              int32_t* __restrict__ placed, uint32_t* usage_gmem,
                                                              uint32_t* __restrict__ info, uint32_t fallback_cap) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   // smem: rowbuf[gw] (material id of the row above / current row), then usage[n] when it fits
   int32_t* rowbuf = reinterpret_cast<int32_t*>(smem_raw);
   uint32_t* usage = USAGE_SMEM ? reinterpret_cast<uint32_t*>(smem_raw + (((size_t)gw * 4 + 15) & ~(size_t)15))
@@ -171,128 +171,141 @@ __global__ void __launch_bounds__(32, 1) greedy_generic_kernel(const uint32_t* _
 
 
 // ------------------------------------------------------------------------------------------------
-// Fast path: one CTA, three warp roles around shared-memory rings.
+// Fast path: a fully parallel preparation kernel + ONE CTA with two warps around a TMA-fed ring.
 //
-//   producers (6 warps)  stream the state-independent data of each cell — ids, d2 and Lab of its first 32
-//                        candidates, d2 of candidate 32 — from HBM/L2 into a 64-slot ring, far ahead, and
-//                        derive per candidate j the CONTENDER MASK
-//                            cont[j] = { j' > j : d2[j'] < hi[j] },  hi[j] = fl(d2[j] + fl(2 * w))
-//                        (all ones if d2 of candidate 32 < hi[j]).  hi[j] bounds the candidate's total from
-//                        above: total = fl(d2 + fl(fl(t_up + t_left) * w)) with t_up, t_left in [0, 1] and
-//                        IEEE rounding monotone; and every total is bounded from below by its d2.
-//   consumer   (1 warp)   walks the cells in raster order.  Its loop-carried chain is integer-only in the
-//                        common case: valid = (id != Up) & (id != Left) & (usage < cap); j0 = first valid
-//                        lane; if no other valid lane is a contender of j0 then no candidate can be
-//                        STRICTLY better than j0 (total_j' >= d2_j' >= hi_j0 >= total_j0), so j0 is exactly
-//                        the reference's winner — without evaluating a single penalty (91 % of the cells
-//                        of the 24,000-tile config).  Otherwise the exact totals of the chunk are evaluated
-//                        (sqrt / reciprocal sequences bit-identical to IEEE), and cells the first chunk
-//                        cannot decide (all 32 rejected, or the early-exit bound fails) take the generic
-//                        multi-chunk + reset-fallback path.  Every shortcut is an exact bound: placements
-//                        are bit-identical to the serial loop of main.rs:335-475.
-//   committer  (1 warp)   drains the consumer's decisions, up to 32 cells at a time (one per lane): row
-//                        buffers (material id + Lab of the row above), the placement array in HBM, and
-//                        the `decided` counter that frees ring slots.
-constexpr int CH_DEPTH = 64;
-constexpr int CH_GUARD = 3;   // slots of the last decided cells stay intact (the exact path re-reads them)
-constexpr int CH_BATCH = 4;
-constexpr int CH_PWARPS = 6;
+//   place_prep_kernel     (whole GPU, one warp per cell) gathers the state-independent data of the cell's
+//                        first 32 candidates — id, d2, Lab — into one contiguous 720-byte record, and derives
+//                        per candidate i the THREAT WINDOW  [lo_i, i):
+//                            lo_i = #{ j : hi[j] <= d2[i] },   hi[j] = fl(d2[j] + fl(2 * w)).
+//                        hi[j] bounds candidate j's total from above: total = fl(d2 + fl(fl(t_up + t_left) * w))
+//                        with t_up, t_left in [0, 1] and IEEE rounding monotone; every total is bounded from
+//                        below by its d2.  So if j0 is the first valid candidate, a later valid candidate i can
+//                        be STRICTLY better than j0 only if d2[i] < hi[j0], i.e. lo_i <= j0 < i.  Lane 0 (which
+//                        can never threaten anybody) carries the window of candidate 32, the first one beyond
+//                        the record: [lo_32, 64).
+//   consumer  (warp 0)    walks the cells in raster order; records arrive in a 64-slot shared-memory ring by
+//                        1-D TMA bulk copies (8 records per copy, one mbarrier per batch).  Its loop-carried
+//                        chain is four instructions: compare (id == previous winner) -> select one of two
+//                        precomputed keys -> REDUX.MIN -> mask.  key = valid ? (lane << 26 | id) : ~0, so the
+//                        minimum IS the first valid candidate and its id; validity (id != Up, id != Left,
+//                        usage < cap) is precomputed one cell ahead for both outcomes of the comparison.  If no
+//                        lane is inside its threat window the first valid candidate is exactly the reference's
+//                        winner — no penalty is evaluated (91 % of the cells of the 24,000-tile config).
+//                        Otherwise the exact totals of the first 32 are evaluated (sqrt / reciprocal sequences
+//                        bit-identical to IEEE), and cells the record cannot decide (all 32 rejected, or the
+//                        early-exit bound fails) take the generic multi-chunk + reset-fallback path.  Every
+//                        shortcut is an exact bound: placements are bit-identical to main.rs:335-475.
+//   committer (warp 1)    drains the consumer's decisions, up to 32 cells at a time (one per lane): Lab of the
+//                        row above, the placement array in HBM, the `decided` counter; lane 0 re-arms the
+//                        mbarrier of every ring batch that has been fully consumed and issues its next TMA copy.
+constexpr int CH_DEPTH = 64;   // ring slots (records)
+constexpr int CH_BATCH = 8;    // records per TMA copy / mbarrier
+constexpr int CH_NBATCH = CH_DEPTH / CH_BATCH;
+constexpr int CH_GUARD = 3;    // slots of the last decided cells stay intact (the exact path re-reads them)
 constexpr int CH_MIN_GW = 33;  // the committer handles up to 32 consecutive cells at once: one per column
+constexpr uint32_t CH_IDMASK = 0x03FFFFFFu;
 
-struct CSlot {
-  uint32_t id[32];  // material id, or the dummy id `n` (usage pinned at the cap) for lanes >= k
+struct __align__(16) CRec {
+  uint32_t word[32];  // lane << 26 | material id; the dummy id `n` (usage pinned at the cap) for lanes >= k
+  uint16_t meta[32];  // lo | span << 8: the lane threatens j0 iff (j0 - lo) <u span
   float d2[32], l[32], a[32], b[32];
-  uint32_t cont[32];
+  float d2_32;        // d2 of candidate 32 (+inf if k <= 32)
+  uint32_t pad[3];
 };
+static_assert(sizeof(CRec) == 720, "record layout");
 
-template <typename UsageT>
-__global__ void __launch_bounds__((2 + CH_PWARPS) * 32, 1)
-    greedy_chain_kernel(const uint32_t* __restrict__ cand_idx, const float* __restrict__ cand_d2, int k,
-                        const float4* __restrict__ lab4, int n, int gw, int gh, unsigned max_usage, float weight,
-                        int32_t* __restrict__ placed, uint32_t* __restrict__ info, uint32_t fallback_cap) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  CSlot* ring = reinterpret_cast<CSlot*>(smem_raw);
-  float* s_d2_32 = reinterpret_cast<float*>(smem_raw + sizeof(CSlot) * CH_DEPTH);
-  volatile unsigned long long* queue = reinterpret_cast<volatile unsigned long long*>(s_d2_32 + CH_DEPTH);
-  volatile uint32_t* readyP = reinterpret_cast<volatile uint32_t*>(const_cast<unsigned long long*>(queue) + CH_DEPTH);
-  volatile uint32_t* decided = readyP + CH_DEPTH;  // [0] = number of cells committed
+__global__ void __launch_bounds__(256) place_prep_kernel(const uint32_t* __restrict__ cand_idx,
+                                                         const float* __restrict__ cand_d2, int k,
+                                                         const float4* __restrict__ lab4, int n, int cells, float weight,
+                                                         CRec* __restrict__ rec) {
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  const bool use_penalty = weight > 0.0f;
+  const float two_w = __fmul_rn(2.0f, weight);
+  const float inf = __int_as_float(0x7f800000);
+  for (int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; c < cells; c += warps) {
+    uint32_t id = (uint32_t)n;
+    float d2 = inf;
+    float4 lab = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (lane < k) {
+      id = __ldg(cand_idx + (size_t)c * k + lane);
+      d2 = __ldg(cand_d2 + (size_t)c * k + lane);
+      lab = __ldg(&lab4[id]);
+    }
+    const float d32 = k > 32 ? __ldg(cand_d2 + (size_t)c * k + 32) : inf;
+    const float hi = use_penalty ? __fadd_rn(d2, two_w) : d2;
+    unsigned lo = 0, lo32 = 0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {  // hi is ascending: {j : hi[j] <= v} is a prefix
+      const float hj = __shfl_sync(0xffffffffu, hi, j);
+      lo += hj <= d2 ? 1u : 0u;
+      lo32 += hj <= d32 ? 1u : 0u;
+    }
+    unsigned span = (unsigned)lane > lo ? (unsigned)lane - lo : 0u;
+    if (lane == 0) {
+      lo = lo32;
+      span = 64u - lo32;  // j0 = 63 (no valid candidate) is always inside
+    }
+    CRec& r = rec[c];
+    r.word[lane] = ((uint32_t)lane << 26) | id;
+    r.meta[lane] = (uint16_t)(lo | (span << 8));
+    r.d2[lane] = d2;
+    r.l[lane] = lab.x;
+    r.a[lane] = lab.y;
+    r.b[lane] = lab.z;
+    if (lane == 0) r.d2_32 = d32;
+  }
+}
+
+// diagnostics (mosaic_debug_chain_profile): consumer-warp cycles and cell counts per path of the last
+// PROFILED launch: [0..3] cycles fast / exact / generic / generic+fallback, [4..7] the cell counts,
+// [8] cycles waiting for a TMA batch, [9] cycles waiting for the committer (row above), [10] total cycles
+__device__ unsigned long long g_chain_prof[16];
+
+template <typename UsageT, bool PROF>
+__global__ void __launch_bounds__(64, 1)
+    greedy_chain_kernel(const CRec* __restrict__ rec, const uint32_t* __restrict__ cand_idx,
+                        const float* __restrict__ cand_d2, int k, const float4* __restrict__ lab4, int n, int gw, int gh,
+                        unsigned max_usage, float weight, int32_t* __restrict__ placed, uint32_t* __restrict__ info,
+                        uint32_t fallback_cap) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  CRec* ring = reinterpret_cast<CRec*>(smem_raw);
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem_raw + sizeof(CRec) * CH_DEPTH);
+  volatile unsigned long long* queue = bars + CH_NBATCH;
+  volatile uint32_t* decided = reinterpret_cast<volatile uint32_t*>(const_cast<unsigned long long*>(queue) + CH_DEPTH);
   float4* rowlab = reinterpret_cast<float4*>(const_cast<uint32_t*>(decided) + 4);
   int32_t* rowbuf = reinterpret_cast<int32_t*>(rowlab + gw);
   UsageT* usage = reinterpret_cast<UsageT*>(rowbuf + ((gw + 3) & ~3));
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int cells = gw * gh;
+  const int nbatches = (cells + CH_BATCH - 1) / CH_BATCH;
   const bool use_penalty = weight > 0.0f;  // main.rs:355-362
   for (int i = tid; i < n; i += blockDim.x) usage[i] = 0;
   for (int i = tid; i < gw; i += blockDim.x) rowbuf[i] = -1;
-  for (int i = tid; i < CH_DEPTH; i += blockDim.x) {
-    readyP[i] = 0u;
-    queue[i] = 0ull;
-  }
+  for (int i = tid; i < CH_DEPTH; i += blockDim.x) queue[i] = 0ull;
   if (tid == 0) {
     decided[0] = 0u;
     usage[n] = (UsageT)~(UsageT)0;  // dummy material: never usable
+    for (int b = 0; b < CH_NBATCH; ++b) mbar_init(&bars[b], 1);
+    mbar_fence_init();
   }
   __syncthreads();
 
-  if (warp >= 2) {
-    // ---------------- producers ----------------
-    const int pw = warp - 2;
-    const float two_w = __fmul_rn(2.0f, weight);
-    for (int c0 = pw * CH_BATCH; c0 < cells; c0 += CH_PWARPS * CH_BATCH) {
-      const int last = min(c0 + CH_BATCH, cells) - 1;
-      while ((int)decided[0] + (CH_DEPTH - CH_GUARD) <= last) __nanosleep(64);  // slot still in use
-      uint32_t id[CH_BATCH];
-      float d2[CH_BATCH], d32[CH_BATCH];
-      float4 lab[CH_BATCH];
-#pragma unroll
-      for (int b = 0; b < CH_BATCH; ++b) {
-        const int c = min(c0 + b, cells - 1);
-        id[b] = (uint32_t)n;
-        d2[b] = __int_as_float(0x7f800000);
-        if (lane < k) {
-          id[b] = __ldg(cand_idx + (size_t)c * k + lane);
-          d2[b] = __ldg(cand_d2 + (size_t)c * k + lane);
-        }
-        d32[b] = k > 32 ? __ldg(cand_d2 + (size_t)c * k + 32) : __int_as_float(0x7f800000);
-      }
-#pragma unroll
-      for (int b = 0; b < CH_BATCH; ++b)
-        lab[b] = lane < k ? __ldg(&lab4[id[b]]) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-      for (int b = 0; b < CH_BATCH; ++b) {
-        const int c = c0 + b;
-        if (c < cells) {  // warp-uniform
-          CSlot& s = ring[c % CH_DEPTH];
-          s.id[lane] = id[b];
-          s.d2[lane] = d2[b];
-          s.l[lane] = lab[b].x;
-          s.a[lane] = lab[b].y;
-          s.b[lane] = lab[b].z;
-          __syncwarp();
-          const float hi = use_penalty ? __fadd_rn(d2[b], two_w) : d2[b];
-          int r = lane + 1;
-          while (r < 32 && s.d2[r] < hi) ++r;  // d2 ascending: contenders are the lanes (lane, r)
-          uint32_t cont = (r >= 32 ? 0xFFFFFFFFu : ((1u << r) - 1u)) & ~((2u << lane) - 1u);
-          if (r >= 32 && d32[b] < hi) cont = 0xFFFFFFFFu;  // the next chunk may hold a contender
-          s.cont[lane] = cont;
-          if (lane == 0) s_d2_32[c % CH_DEPTH] = d32[b];
-        }
-      }
-      __threadfence_block();
-      __syncwarp();
-      if (lane == 0) {
-#pragma unroll
-        for (int b = 0; b < CH_BATCH; ++b)
-          if (c0 + b < cells) readyP[(c0 + b) % CH_DEPTH] = (uint32_t)(c0 + b) + 1u;
-      }
-    }
-    return;
-  }
+  auto issue_batch = [&](int batch) {  // records [batch*8, batch*8+8) -> ring position batch % 8
+    const int first = batch * CH_BATCH;
+    const unsigned bytes = (unsigned)(min(CH_BATCH, cells - first) * (int)sizeof(CRec));
+    unsigned long long* bar = &bars[batch % CH_NBATCH];
+    mbar_expect_tx(bar, bytes);
+    tma_load_1d(ring + (first % CH_DEPTH), rec + first, bytes, bar);
+  };
 
   if (warp == 1) {
     // ---------------- committer ----------------
-    const volatile CSlot* vring = ring;
+    const volatile CRec* vring = ring;
+    int next_batch = 0;
+    if (lane == 0)
+      for (; next_batch < min(CH_NBATCH, nbatches); ++next_batch) issue_batch(next_batch);
     int base = 0;
     while (base < cells) {
       const int cell = base + lane;
@@ -300,55 +313,73 @@ __global__ void __launch_bounds__((2 + CH_PWARPS) * 32, 1)
       const unsigned long long e = queue[s];
       const bool have = cell < cells && (uint32_t)(e >> 32) == (uint32_t)cell + 1u;
       const unsigned ready_mask = __ballot_sync(0xffffffffu, have);
-      const int cnt = __ffs(~ready_mask) - 1 < 0 ? 32 : __ffs(~ready_mask) - 1;  // consecutive from lane 0
+      const int cnt = ready_mask == 0xFFFFFFFFu ? 32 : __ffs(~ready_mask) - 1;  // consecutive from lane 0
       if (cnt == 0) {
         __nanosleep(20);
         continue;
       }
       if (lane < cnt) {
-        const int32_t chosen = (int32_t)((uint32_t)e & 0x03FFFFFFu);
+        const int32_t chosen = (int32_t)((uint32_t)e & CH_IDMASK);
         const unsigned who = ((uint32_t)e >> 26) & 63u;
         float4 lab;
         if (who < 32u)
           lab = make_float4(vring[s].l[who], vring[s].a[who], vring[s].b[who], 0.f);
         else
           lab = __ldg(&lab4[chosen]);
-        const int x = cell % gw;
-        rowbuf[x] = chosen;
-        rowlab[x] = lab;
+        rowlab[cell % gw] = lab;
         placed[cell] = chosen;  // main.rs:412
       }
       __threadfence_block();
       __syncwarp();
       base += cnt;
-      if (lane == 0) decided[0] = (uint32_t)base;
+      if (lane == 0) {
+        decided[0] = (uint32_t)base;
+        // ring batches whose 8 cells are all older than the guard window are free: fetch their successors
+        while (next_batch < nbatches && (next_batch - CH_NBATCH + 1) * CH_BATCH + CH_GUARD <= base) {
+          issue_batch(next_batch);
+          ++next_batch;
+        }
+      }
     }
     return;
   }
 
   // ---------------- consumer (warp 0) ----------------
-  const volatile CSlot* vring = ring;
-  const volatile float* vd2_32 = s_d2_32;
+  const volatile CRec* vring = ring;
   uint32_t n_fallbacks = 0;
-  int32_t prev = -1;      // material placed in the previous cell (raster order)
-  int32_t prev_u = -1;    // == prev while its usage increment is not yet reflected in the preloaded `u`
-  unsigned prev_who = 63; // lane of prev in the previous cell's slot (63: not in the slot)
-  int x = 0, y = 0;
+  int32_t prev = -1;       // material placed in the previous cell (raster order)
+  unsigned prev_who = 63;  // lane of prev in the previous cell's record (63: not in the record)
+  int x = 0;
+  unsigned long long prof[11] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 
   struct CellRegs {
-    uint32_t id, cont;
-    unsigned u;   // usage[id] read BEFORE the previous cell's increment (fixed up through prev_u)
-    int32_t up;   // material above (-1: first row); warp-uniform
+    uint32_t word, id, lo, span;
+    uint32_t k0, k1;  // redux key if id != / == the previous winner
+    unsigned u;       // usage[id] EXCLUDING the increment of the previous cell
+    int32_t up;       // material above (-1: first row); warp-uniform
   };
-  auto wait_slot = [&](int c, uint32_t flag) {
-    const int s = c % CH_DEPTH;
-    while (flag != (uint32_t)c + 1u) flag = readyP[s];
-    asm volatile("" ::: "memory");
+  auto wait_batch = [&](int c) {  // c is the first cell of its batch
+    unsigned long long* bar = &bars[(c / CH_BATCH) % CH_NBATCH];
+    const unsigned parity = (unsigned)((c / CH_DEPTH) & 1);
+    if (!mbar_test(bar, parity)) {
+      long long tw = 0;
+      if (PROF) tw = clock64();
+      mbar_wait(bar, parity);
+      if (PROF) prof[8] += (unsigned long long)(clock64() - tw);
+    }
   };
   auto load_slot = [&](int c, CellRegs& r) {
     const int s = c % CH_DEPTH;
-    r.id = vring[s].id[lane];
-    r.cont = vring[s].cont[lane];
+    r.word = vring[s].word[lane];
+    const uint32_t meta = vring[s].meta[lane];
+    r.id = r.word & CH_IDMASK;
+    r.lo = meta & 255u;
+    r.span = meta >> 8;
+  };
+  auto make_keys = [&](CellRegs& r, int xc) {
+    const bool ok = (int32_t)r.id != r.up;                          // main.rs:380 (Up)
+    r.k0 = (ok && r.u < max_usage) ? r.word : 0xFFFFFFFFu;          // main.rs:375
+    r.k1 = (ok && xc == 0 && r.u + 1u < max_usage) ? r.word : 0xFFFFFFFFu;  // == Left unless the row starts here
   };
   auto prev_lab = [&](int cell) -> float4 {  // Lab of the material placed in cell - 1
     if (prev_who < 32u) {
@@ -357,43 +388,66 @@ __global__ void __launch_bounds__((2 + CH_PWARPS) * 32, 1)
     }
     return __ldg(&lab4[prev]);
   };
+  auto wait_row_above = [&](int cell) {  // rowlab[x] holds the Lab of cell - gw once it has been committed
+    if ((int)decided[0] <= cell - gw) {
+      long long tw = 0;
+      if (PROF) tw = clock64();
+      while ((int)decided[0] <= cell - gw) {
+      }
+      if (PROF) prof[9] += (unsigned long long)(clock64() - tw);
+    }
+    asm volatile("" ::: "memory");
+  };
 
   // exact multi-chunk resolution + reset fallback: the reference's loop, bit for bit (main.rs:335-475)
   auto resolve_generic = [&](int cell, int32_t left, int32_t up, float4 left_lab) -> int32_t {
     float4 up_lab = make_float4(0.f, 0.f, 0.f, 0.f);
     if (up >= 0) {
+      wait_row_above(cell);
       const volatile float4* ul = rowlab + x;
       up_lab = make_float4(ul->x, ul->y, ul->z, 0.f);
     }
+    const size_t row = (size_t)cell * k;
+    // all chunks are requested up front: two dependent global round trips in total
+    uint32_t gid[4];
+    float gd2[4];
+    float4 gl[4];
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch) {
+      const int j = ch * 32 + lane;
+      gid[ch] = 0u;
+      gd2[ch] = 0.f;
+      if (j < k) {
+        gid[ch] = __ldg(cand_idx + row + j);
+        gd2[ch] = __ldg(cand_d2 + row + j);
+      }
+    }
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch) gl[ch] = (ch * 32 + lane < k) ? __ldg(&lab4[gid[ch]]) : make_float4(0.f, 0.f, 0.f, 0.f);
     unsigned best_bits = 0xFFFFFFFFu;
     int32_t best_id = -1;
-    const size_t row = (size_t)cell * k;
-    for (int base = 0; base < k; base += 32) {
-      if (base > 0 && best_id >= 0 && __float_as_uint(cand_d2[row + base]) >= best_bits) break;  // exact early exit
-      const int j = base + lane;
-      uint32_t gid = 0;
-      float gd2 = 0.f;
-      float4 gl = make_float4(0.f, 0.f, 0.f, 0.f);
-      bool gok = j < k;
-      if (gok) {
-        gid = cand_idx[row + j];
-        gd2 = cand_d2[row + j];
-        gl = __ldg(&lab4[gid]);
-        gok = (unsigned)usage[gid] < max_usage && (int32_t)gid != left && (int32_t)gid != up;
-      }
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch) {
+      const int base = ch * 32;
+      if (base >= k) break;
+      if (base > 0 && best_id >= 0 && __float_as_uint(__shfl_sync(0xffffffffu, gd2[ch], 0)) >= best_bits) break;  // exact early exit
+      bool gok = base + lane < k;
+      if (gok) gok = (unsigned)usage[gid[ch]] < max_usage && (int32_t)gid[ch] != left && (int32_t)gid[ch] != up;
       float gpen = 0.0f;
       if (use_penalty) {  // adjacency.rs:71-87: Up, (Down), Left, (Right)
-        if (up >= 0) gpen = __fadd_rn(gpen, adjacency_term(lab_distance_rn(gl.x, gl.y, gl.z, up_lab.x, up_lab.y, up_lab.z)));
+        if (up >= 0)
+          gpen = __fadd_rn(gpen, adjacency_term(lab_distance_rn(gl[ch].x, gl[ch].y, gl[ch].z, up_lab.x, up_lab.y, up_lab.z)));
         if (left >= 0)
-          gpen = __fadd_rn(gpen, adjacency_term(lab_distance_rn(gl.x, gl.y, gl.z, left_lab.x, left_lab.y, left_lab.z)));
+          gpen = __fadd_rn(gpen, adjacency_term(lab_distance_rn(gl[ch].x, gl[ch].y, gl[ch].z, left_lab.x, left_lab.y,
+                                                                left_lab.z)));
         gpen = __fmul_rn(gpen, weight);
       }
-      const unsigned gtb = gok ? __float_as_uint(__fadd_rn(gd2, gpen)) : 0xFFFFFFFFu;
+      const unsigned gtb = gok ? __float_as_uint(__fadd_rn(gd2[ch], gpen)) : 0xFFFFFFFFu;
       const unsigned gmn = __reduce_min_sync(0xffffffffu, gtb);
       if (gmn < best_bits) {  // strict <: earlier chunks / earlier lanes win ties (main.rs:401-407)
         const int who = __ffs(__ballot_sync(0xffffffffu, gtb == gmn)) - 1;
         best_bits = gmn;
-        best_id = (int32_t)__shfl_sync(0xffffffffu, gid, who);
+        best_id = (int32_t)__shfl_sync(0xffffffffu, gid[ch], who);
       }
     }
     if (best_id < 0) {
@@ -402,32 +456,33 @@ __global__ void __launch_bounds__((2 + CH_PWARPS) * 32, 1)
       ++n_fallbacks;
       for (int i = lane; i < n; i += 32) usage[i] = 0;  // lib.rs:86-88
       __syncwarp();
-      for (int base = 0; base < k && best_id < 0; base += 32) {
-        const int j = base + lane;
-        uint32_t fid = 0;
-        bool fok = false;
-        if (j < k) {
-          fid = cand_idx[row + j];
-          fok = (int32_t)fid != left && (int32_t)fid != up;  // main.rs:448
-        }
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) {
+        if (ch * 32 >= k || best_id >= 0) break;
+        const bool fok = ch * 32 + lane < k && (int32_t)gid[ch] != left && (int32_t)gid[ch] != up;  // main.rs:448
         const unsigned m = __ballot_sync(0xffffffffu, fok);
-        if (m) best_id = (int32_t)__shfl_sync(0xffffffffu, fid, __ffs(m) - 1);
+        if (m) best_id = (int32_t)__shfl_sync(0xffffffffu, gid[ch], __ffs(m) - 1);
       }
-      if (best_id < 0) best_id = (int32_t)cand_idx[row];  // main.rs:456-474 nearest_one
+      if (best_id < 0) best_id = (int32_t)__shfl_sync(0xffffffffu, gid[0], 0);  // main.rs:456-474 nearest_one
     }
-    usage[best_id] = (UsageT)(usage[best_id] + 1);  // main.rs:410-411 / 449 / 470
+    __syncwarp();
+    if (lane == 0) usage[best_id] = (UsageT)(usage[best_id] + 1);  // main.rs:410-411 / 449 / 470
     __syncwarp();
     return best_id;
   };
 
-  // exact totals of the first chunk (main.rs:386-407); returns the winning lane, or 63 if the chunk cannot decide
+  // exact totals of the record's 32 candidates (main.rs:386-407); returns the winning lane, or 63 if they cannot decide
   auto resolve_exact = [&](int cell, int32_t left, int32_t up, bool valid) -> unsigned {
     const int sA = cell % CH_DEPTH;
     const float d2 = vring[sA].d2[lane];
     const float l = vring[sA].l[lane], a = vring[sA].a[lane], b = vring[sA].b[lane];
-    const float d2_32 = vd2_32[sA];
-    const volatile float4* ul = rowlab + x;
-    const float ux = ul->x, uy = ul->y, uz = ul->z;
+    const float d2_32 = vring[sA].d2_32;
+    float ux = 0.f, uy = 0.f, uz = 0.f;
+    if (up >= 0) {
+      wait_row_above(cell);
+      const volatile float4* ul = rowlab + x;
+      ux = ul->x, uy = ul->y, uz = ul->z;
+    }
     float4 pl = make_float4(0.f, 0.f, 0.f, 0.f);
     if (left >= 0) pl = prev_lab(cell);
     bool oor_u = false, oor_l = false;
@@ -448,101 +503,120 @@ __global__ void __launch_bounds__((2 + CH_PWARPS) * 32, 1)
     return 63u;
   };
 
-  // one cell: A = registers of `cell`, B = registers of cell + 1; A is refilled with cell + 2 at the end.
-  // Everything cell + 1 needs from shared memory is requested at the top, so that the loop-carried chain
-  // (prev -> valid -> vote -> first lane -> shuffle -> prev) never waits on a load.
+  // one cell: A = registers of `cell` (keys ready), B = registers of cell + 1 (record loaded); A is refilled with
+  // cell + 2 at the end.  Loop-carried chain: prev -> compare -> select -> REDUX.MIN -> mask -> prev.
   auto step = [&](int cell, CellRegs& A, CellRegs& B) {
-    const int sA = cell % CH_DEPTH;
-    const uint32_t flag2 = (cell + 2 < cells) ? readyP[(cell + 2) % CH_DEPTH] : 0u;
-    B.u = (unsigned)usage[B.id];  // before this cell's increment; fixed up through prev_u next iteration
-    int xn = x + 1, yn = y;
-    if (xn == gw) {
-      xn = 0;
-      yn = y + 1;
+    long long t_begin = 0;
+    unsigned long long w0 = 0;
+    if (PROF) {
+      t_begin = clock64();
+      w0 = prof[8] + prof[9];
     }
-    uint32_t dec = decided[0];
-    int32_t up_n = *reinterpret_cast<volatile int32_t*>(rowbuf + xn);  // meaningful once cell + 1 - gw is committed
-
-    const int32_t left = (x == 0) ? -1 : prev;
-    const unsigned ucur = A.u + ((int32_t)A.id == prev_u ? 1u : 0u);
-    const bool valid = (int32_t)A.id != A.up && (int32_t)A.id != left && ucur < max_usage;  // main.rs:375, 380
-    const unsigned m = __ballot_sync(0xffffffffu, valid);
-    const int j0 = (__ffs(m) - 1) & 31;
-    const unsigned cont0 = __shfl_sync(0xffffffffu, A.cont, j0);
-    int32_t chosen = (int32_t)__shfl_sync(0xffffffffu, A.id, j0);
-    const unsigned cnt0 = __shfl_sync(0xffffffffu, ucur, j0);
-    unsigned who = (unsigned)j0;
-    bool generic = false;
-    if (m == 0u || (m & cont0) != 0u) {  // cold
-      who = m != 0u ? resolve_exact(cell, left, A.up, valid) : 63u;
+    int path = 0;
+    const bool same = A.id == (uint32_t)prev;
+    const uint32_t key = same ? A.k1 : A.k0;
+    uint32_t r = __reduce_min_sync(0xffffffffu, key);  // first valid lane << 26 | its material id
+    // cell + 1: usage before this cell's increment, material above
+    const int xn = (x + 1 == gw) ? 0 : x + 1;
+    B.u = (unsigned)usage[B.id];
+    B.up = *reinterpret_cast<volatile int32_t*>(rowbuf + xn);
+    const uint32_t j0 = r >> 26;
+    const bool threat = (j0 - A.lo) < A.span && (key != 0xFFFFFFFFu || lane == 0);
+    if (__any_sync(0xffffffffu, threat)) {  // cold: (possibly) more than one contender, or no valid candidate
+      const bool valid = key != 0xFFFFFFFFu;
+      const int32_t left = (x == 0) ? -1 : prev;
+      unsigned who = 63u;
+      path = 1;
+      if (j0 < 32u) who = resolve_exact(cell, left, A.up, valid);
       if (who < 32u) {
-        chosen = (int32_t)__shfl_sync(0xffffffffu, A.id, who);
-        usage[chosen] = (UsageT)(__shfl_sync(0xffffffffu, ucur, who) + 1u);
+        r = __shfl_sync(0xffffffffu, A.word, who);
       } else {
         float4 pl = make_float4(0.f, 0.f, 0.f, 0.f);
         if (left >= 0) pl = prev_lab(cell);
-        chosen = resolve_generic(cell, left, A.up, pl);
-        generic = true;
+        const uint32_t nfb0 = n_fallbacks;
+        const int32_t g = resolve_generic(cell, left, A.up, pl);
+        path = n_fallbacks != nfb0 ? 3 : 2;
+        r = (63u << 26) | (uint32_t)g;
+        // the generic path updated (possibly reset) the counters itself: re-read, excluding this cell's increment
+        B.u = (unsigned)usage[B.id];
+        if (B.id == (uint32_t)g) B.u -= 1u;
       }
-    } else {
-      usage[chosen] = (UsageT)(cnt0 + 1u);  // main.rs:410-411; all lanes store the same value
     }
-    queue[sA] = ((unsigned long long)((uint32_t)cell + 1u) << 32) | ((unsigned long long)who << 26) | (uint32_t)chosen;
-    prev_u = chosen;
-    if (generic) {  // B.u predates a possible usage reset: re-read it (it then includes this cell's increment)
-      B.u = (unsigned)usage[B.id];
-      prev_u = -1;
+    const int32_t chosen = (int32_t)(r & CH_IDMASK);
+    if ((uint32_t)lane == (r >> 26)) usage[A.id] = (UsageT)(A.u + (same ? 1u : 0u) + 1u);  // main.rs:410-411
+    if (lane == 0) {
+      *reinterpret_cast<volatile int32_t*>(rowbuf + x) = chosen;
+      queue[cell % CH_DEPTH] = ((unsigned long long)((uint32_t)cell + 1u) << 32) | r;
     }
+    __syncwarp();
     prev = chosen;
-    prev_who = who;
-    // Up neighbour of cell + 1
-    if (yn > 0) {
-      if ((int)dec < cell + 2 - gw) {  // cold: the committer lags by a whole row
-        while ((int)decided[0] < cell + 2 - gw) {
-        }
-        asm volatile("" ::: "memory");
-        up_n = *reinterpret_cast<volatile int32_t*>(rowbuf + xn);
-      }
-      B.up = up_n;
-    } else {
-      B.up = -1;
-    }
+    prev_who = r >> 26;
+    make_keys(B, xn);
     x = xn;
-    y = yn;
     if (cell + 2 < cells) {
-      wait_slot(cell + 2, flag2);
+      if (((cell + 2) % CH_BATCH) == 0) wait_batch(cell + 2);
       load_slot(cell + 2, A);
+    }
+    if (PROF) {
+      prof[path] += (unsigned long long)(clock64() - t_begin) - (prof[8] + prof[9] - w0);
+      prof[4 + path] += 1ull;
     }
   };
 
   CellRegs R0, R1;
+  R0.word = R1.word = 0xFFFFFFFFu;
   R0.id = R1.id = (uint32_t)n;
-  R0.cont = R1.cont = 0u;
+  R0.lo = R1.lo = R0.span = R1.span = 0u;
+  R0.k0 = R0.k1 = R1.k0 = R1.k1 = 0xFFFFFFFFu;
   R0.u = R1.u = 0u;
   R0.up = R1.up = -1;
   if (cells > 0) {
-    wait_slot(0, readyP[0]);
+    wait_batch(0);
     load_slot(0, R0);
-    if (cells > 1) {
-      wait_slot(1, readyP[1 % CH_DEPTH]);
-      load_slot(1, R1);
-    }
+    make_keys(R0, 0);
+    if (cells > 1) load_slot(1, R1);
   }
+  long long t_all = 0;
+  if (PROF) t_all = clock64();
   for (int cell = 0; cell < cells; cell += 2) {
     step(cell, R0, R1);
     if (cell + 1 < cells) step(cell + 1, R1, R0);
   }
   if (lane == 0) info[0] = n_fallbacks;
+  if (PROF && lane == 0) {
+    prof[10] = (unsigned long long)(clock64() - t_all);
+    for (int i = 0; i < 11; ++i) g_chain_prof[i] = prof[i];
+  }
 }
 
 }  // namespace
 
+template <typename UsageT, bool PROF>
+static int launch_chain_impl(mosaic_ctx* ctx, unsigned cap, float weight, size_t smem) {
+  MOSAIC_CUDA(ctx, cudaFuncSetAttribute(greedy_chain_kernel<UsageT, PROF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)smem));
+  greedy_chain_kernel<UsageT, PROF><<<1, 64, smem, ctx->stream>>>(
+      reinterpret_cast<const CRec*>(ctx->d_place_rec), ctx->d_cand_idx, ctx->d_cand_d2, ctx->k, ctx->d_mat_lab4, ctx->n,
+      ctx->gw, ctx->gh, cap, weight, ctx->d_placed, ctx->d_place_info, mosaic_ctx::kFallbackCap);
+  return MOSAIC_OK;
+}
 template <typename UsageT>
 static int launch_chain(mosaic_ctx* ctx, unsigned cap, float weight, size_t smem) {
-  MOSAIC_CUDA(ctx, cudaFuncSetAttribute(greedy_chain_kernel<UsageT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  greedy_chain_kernel<UsageT><<<1, (2 + CH_PWARPS) * 32, smem, ctx->stream>>>(
-      ctx->d_cand_idx, ctx->d_cand_d2, ctx->k, ctx->d_mat_lab4, ctx->n, ctx->gw, ctx->gh, cap, weight, ctx->d_placed,
-      ctx->d_place_info, mosaic_ctx::kFallbackCap);
+  const int cells = ctx->gw * ctx->gh;
+  MOSAIC_TRY(ensure(ctx, &ctx->d_place_rec, &ctx->place_rec_cap, (size_t)cells * sizeof(CRec)));
+  int blocks = (cells + 7) / 8;
+  if (blocks > ctx->sm_count * 8) blocks = ctx->sm_count * 8;
+  place_prep_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->d_cand_idx, ctx->d_cand_d2, ctx->k, ctx->d_mat_lab4, ctx->n, cells,
+                                                     weight, reinterpret_cast<CRec*>(ctx->d_place_rec));
+  ctx->launches++;
+  MOSAIC_CUDA(ctx, cudaGetLastError());
+  return ctx->profile_chain ? launch_chain_impl<UsageT, true>(ctx, cap, weight, smem)
+                            : launch_chain_impl<UsageT, false>(ctx, cap, weight, smem);
+}
+
+int read_chain_profile(mosaic_ctx* ctx, unsigned long long* out16) {
+  MOSAIC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  MOSAIC_CUDA(ctx, cudaMemcpyFromSymbol(out16, g_chain_prof, sizeof(unsigned long long) * 16));
   return MOSAIC_OK;
 }
 
@@ -550,8 +624,8 @@ int launch_place(mosaic_ctx* ctx, int max_usage, float weight) {
   const int n = ctx->n, gw = ctx->gw, gh = ctx->gh;
   const unsigned cap = max_usage < 0 ? 0u : (unsigned)max_usage;
   const size_t smem_limit = 220 * 1024;
-  // fast path: rings + row state + usage counters in shared memory
-  const size_t ring_fixed = sizeof(CSlot) * CH_DEPTH + (4 + 8 + 4) * CH_DEPTH + 16 + sizeof(float4) * (size_t)gw +
+  // fast path: record ring + row state + usage counters in shared memory
+  const size_t ring_fixed = sizeof(CRec) * CH_DEPTH + 8 * CH_NBATCH + 8 * CH_DEPTH + 16 + sizeof(float4) * (size_t)gw +
                             sizeof(int32_t) * (size_t)((gw + 3) & ~3);
   const size_t usage_bytes = cap <= 255u ? (size_t)n + 1 : (cap <= 65535u ? ((size_t)n + 1) * 2 : (size_t)-1);
   StageTimer t(ctx, MOSAIC_STAGE_PLACE);

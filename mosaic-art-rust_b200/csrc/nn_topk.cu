@@ -96,39 +96,6 @@ __device__ __forceinline__ void merge_buffer(QueryState& st, int& cnt, unsigned&
   cnt = 0;
 }
 
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(
-                   (unsigned)__cvta_generic_to_shared(bar)),
-               "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
-  const unsigned addr = (unsigned)__cvta_generic_to_shared(bar);
-  unsigned done;
-  do {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(done)
-        : "r"(addr), "r"(parity)
-        : "memory");
-  } while (!done);
-}
-__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, unsigned bytes,
-                                            unsigned long long* bar) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-          (unsigned)__cvta_generic_to_shared(smem_dst)),
-      "l"(gmem_src), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
-      : "memory");
-}
-
 __global__ void __launch_bounds__(TK_WARPS * 32) nn_topk_kernel(const float* __restrict__ soa, int n, int n_pad,
                                                                 const float* __restrict__ cell_lab, int cell_begin,
                                                                 int cell_end, int k, uint32_t* __restrict__ out_idx,

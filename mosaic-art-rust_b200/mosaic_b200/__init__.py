@@ -87,6 +87,7 @@ def load_library():
         "mosaic_render": ([vp, C.c_float, vp], C.c_int),
         "mosaic_generate": ([vp, C.POINTER(Params), vp, vp, C.POINTER(Report)], C.c_int),
         "mosaic_selftest": ([vp, u64p], C.c_int),
+        "mosaic_debug_chain_profile": ([vp, C.c_int, u64p], C.c_int),
         "mosaic_dims": ([vp] + [C.POINTER(C.c_int)] * 5, C.c_int),
         "mosaic_device_output": ([vp], vp),
         "mosaic_device_placement": ([vp], vp),
@@ -109,6 +110,7 @@ EXPORTED_SYMBOLS = (
     "mosaic_set_target_device", "mosaic_set_material_lab", "mosaic_set_cell_lab", "mosaic_material_lab",
     "mosaic_cell_lab", "mosaic_similarity_tri", "mosaic_candidates", "mosaic_place", "mosaic_fallback_cells",
     "mosaic_set_placement", "mosaic_anneal", "mosaic_render", "mosaic_generate", "mosaic_selftest", "mosaic_dims",
+    "mosaic_debug_chain_profile",
     "mosaic_device_output", "mosaic_device_placement", "mosaic_device_similarity", "mosaic_shard",
     "mosaic_shard_plan",
 )
@@ -318,6 +320,14 @@ class Context:
         m = (C.c_uint64 * 2)()
         self._check(self._L.mosaic_selftest(self._h, m))
         return int(m[0]), int(m[1])
+
+    def chain_profile(self, enable=True):
+        """Enable/disable the instrumented placement kernel and return the counters of its last launch."""
+        m = (C.c_uint64 * 16)()
+        self._check(self._L.mosaic_debug_chain_profile(self._h, 1 if enable else 0, m))
+        keys = ("cyc_fast", "cyc_exact", "cyc_generic", "cyc_fallback", "n_fast", "n_exact", "n_generic",
+                "n_fallback", "cyc_wait_producer", "cyc_wait_committer", "cyc_total")
+        return dict(zip(keys, (int(x) for x in m)))
 
     def output_shape(self):
         d = self.dims()
