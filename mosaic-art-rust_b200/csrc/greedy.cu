@@ -345,18 +345,30 @@ __global__ void __launch_bounds__(64, 1)
   }
 
   // ---------------- consumer (warp 0) ----------------
+  // Software pipeline over five register sets (cells c .. c+4):
+  //   c+4  record words requested from the ring
+  //   c+3  usage counter + material above requested (AFTER the commit of c, so the counter covers cells <= c)
+  //   c+2  keys computed (counter += [id == winner of c]; k1 covers the winner of c+1)
+  //   c+1  REDUX.MIN issued speculatively with the presumed winner of c, BEFORE the threat vote of c resolves
+  //   c    threat vote -> (cold path) -> commit
+  // so that on the hot path no instruction consumes a shared-memory load issued in the same iteration, and
+  // the vote/branch of cell c overlaps the reduction of cell c+1.
   const volatile CRec* vring = ring;
+  constexpr uint32_t NOKEY = 0xFFFFFFFFu;
   uint32_t n_fallbacks = 0;
   int32_t prev = -1;       // material placed in the previous cell (raster order)
   unsigned prev_who = 63;  // lane of prev in the previous cell's record (63: not in the record)
-  int x = 0;
   unsigned long long prof[11] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 
-  struct CellRegs {
-    uint32_t word, id, lo, span;
-    uint32_t k0, k1;  // redux key if id != / == the previous winner
-    unsigned u;       // usage[id] EXCLUDING the increment of the previous cell
-    int32_t up;       // material above (-1: first row); warp-uniform
+  struct CellSet {
+    uint32_t word, meta;  // as loaded from the record
+    uint32_t id, lo, span;
+    uint32_t k0, k1;      // redux key if id != / == the winner of the previous cell
+    uint32_t key;         // the key that went into the reduction
+    unsigned u;           // usage[id]; see the pipeline comment for which cells it covers at each stage
+    unsigned ucur;        // usage[id] covering every earlier cell (valid once the reduction has been issued)
+    int32_t up;           // material above (-1: first row); warp-uniform
+    int x;                // column
   };
   auto wait_batch = [&](int c) {  // c is the first cell of its batch
     unsigned long long* bar = &bars[(c / CH_BATCH) % CH_NBATCH];
@@ -368,18 +380,20 @@ __global__ void __launch_bounds__(64, 1)
       if (PROF) prof[8] += (unsigned long long)(clock64() - tw);
     }
   };
-  auto load_slot = [&](int c, CellRegs& r) {
+  auto load_rec = [&](int c, CellSet& r) {
     const int s = c % CH_DEPTH;
     r.word = vring[s].word[lane];
-    const uint32_t meta = vring[s].meta[lane];
-    r.id = r.word & CH_IDMASK;
-    r.lo = meta & 255u;
-    r.span = meta >> 8;
+    r.meta = vring[s].meta[lane];
   };
-  auto make_keys = [&](CellRegs& r, int xc) {
-    const bool ok = (int32_t)r.id != r.up;                          // main.rs:380 (Up)
-    r.k0 = (ok && r.u < max_usage) ? r.word : 0xFFFFFFFFu;          // main.rs:375
-    r.k1 = (ok && xc == 0 && r.u + 1u < max_usage) ? r.word : 0xFFFFFFFFu;  // == Left unless the row starts here
+  auto unpack = [&](CellSet& r) {
+    r.id = r.word & CH_IDMASK;
+    r.lo = r.meta & 255u;
+    r.span = r.meta >> 8;
+  };
+  auto make_keys = [&](CellSet& r) {
+    const bool ok = (int32_t)r.id != r.up;                                      // main.rs:380 (Up)
+    r.k0 = (ok && r.u < max_usage) ? r.word : NOKEY;                            // main.rs:375
+    r.k1 = (ok && r.x == 0 && r.u + 1u < max_usage) ? r.word : NOKEY;           // == Left unless the row starts here
   };
   auto prev_lab = [&](int cell) -> float4 {  // Lab of the material placed in cell - 1
     if (prev_who < 32u) {
@@ -388,25 +402,23 @@ __global__ void __launch_bounds__(64, 1)
     }
     return __ldg(&lab4[prev]);
   };
-  auto wait_row_above = [&](int cell) {  // rowlab[x] holds the Lab of cell - gw once it has been committed
-    if ((int)decided[0] <= cell - gw) {
+  auto row_above_lab = [&](int cell, int x) -> float4 {  // rowlab[x] holds the Lab of cell - gw once it is committed
+    const volatile float4* ul = rowlab + x;
+    float4 v = make_float4(ul->x, ul->y, ul->z, 0.f);
+    if ((int)decided[0] <= cell - gw) {  // cold: the committer lags by a whole row
       long long tw = 0;
       if (PROF) tw = clock64();
       while ((int)decided[0] <= cell - gw) {
       }
       if (PROF) prof[9] += (unsigned long long)(clock64() - tw);
+      asm volatile("" ::: "memory");
+      v = make_float4(ul->x, ul->y, ul->z, 0.f);
     }
-    asm volatile("" ::: "memory");
+    return v;
   };
 
   // exact multi-chunk resolution + reset fallback: the reference's loop, bit for bit (main.rs:335-475)
-  auto resolve_generic = [&](int cell, int32_t left, int32_t up, float4 left_lab) -> int32_t {
-    float4 up_lab = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (up >= 0) {
-      wait_row_above(cell);
-      const volatile float4* ul = rowlab + x;
-      up_lab = make_float4(ul->x, ul->y, ul->z, 0.f);
-    }
+  auto resolve_generic = [&](int cell, int x, int32_t left, int32_t up, float4 left_lab) -> int32_t {
     const size_t row = (size_t)cell * k;
     // all chunks are requested up front: two dependent global round trips in total
     uint32_t gid[4];
@@ -424,6 +436,8 @@ __global__ void __launch_bounds__(64, 1)
     }
 #pragma unroll
     for (int ch = 0; ch < 4; ++ch) gl[ch] = (ch * 32 + lane < k) ? __ldg(&lab4[gid[ch]]) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 up_lab = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (up >= 0) up_lab = row_above_lab(cell, x);
     unsigned best_bits = 0xFFFFFFFFu;
     int32_t best_id = -1;
 #pragma unroll
@@ -472,23 +486,20 @@ __global__ void __launch_bounds__(64, 1)
   };
 
   // exact totals of the record's 32 candidates (main.rs:386-407); returns the winning lane, or 63 if they cannot decide
-  auto resolve_exact = [&](int cell, int32_t left, int32_t up, bool valid) -> unsigned {
+  auto resolve_exact = [&](int cell, int x, int32_t left, int32_t up, bool valid) -> unsigned {
     const int sA = cell % CH_DEPTH;
+    // every load is requested before the first one is consumed
     const float d2 = vring[sA].d2[lane];
     const float l = vring[sA].l[lane], a = vring[sA].a[lane], b = vring[sA].b[lane];
     const float d2_32 = vring[sA].d2_32;
-    float ux = 0.f, uy = 0.f, uz = 0.f;
-    if (up >= 0) {
-      wait_row_above(cell);
-      const volatile float4* ul = rowlab + x;
-      ux = ul->x, uy = ul->y, uz = ul->z;
-    }
     float4 pl = make_float4(0.f, 0.f, 0.f, 0.f);
     if (left >= 0) pl = prev_lab(cell);
+    float4 ul = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (up >= 0) ul = row_above_lab(cell, x);
     bool oor_u = false, oor_l = false;
     float pen = 0.0f;
     if (use_penalty) {
-      float t_up = adjacency_term_fast(l, a, b, ux, uy, uz, oor_u);
+      float t_up = adjacency_term_fast(l, a, b, ul.x, ul.y, ul.z, oor_u);
       float t_left = adjacency_term_fast(l, a, b, pl.x, pl.y, pl.z, oor_l);
       t_up = up >= 0 ? t_up : 0.0f;  // absent terms are +0.0: x + 0.0 == x exactly
       t_left = left >= 0 ? t_left : 0.0f;
@@ -503,9 +514,12 @@ __global__ void __launch_bounds__(64, 1)
     return 63u;
   };
 
-  // one cell: A = registers of `cell` (keys ready), B = registers of cell + 1 (record loaded); A is refilled with
-  // cell + 2 at the end.  Loop-carried chain: prev -> compare -> select -> REDUX.MIN -> mask -> prev.
-  auto step = [&](int cell, CellRegs& A, CellRegs& B) {
+  uint32_t r = NOKEY;  // REDUX.MIN of the current cell: first valid lane << 26 | its material id
+
+  // One cell with every path (vote -> exact totals -> generic multi-chunk / reset fallback).  ONE copy of this code
+  // exists: the hot loop below leaves through it whenever a cell is (possibly) contended, and the last cells of
+  // the grid run through it.
+  auto full_step = [&](int cell, CellSet& A, CellSet& B, CellSet& C, CellSet& D, CellSet& E) {
     long long t_begin = 0;
     unsigned long long w0 = 0;
     if (PROF) {
@@ -513,78 +527,178 @@ __global__ void __launch_bounds__(64, 1)
       w0 = prof[8] + prof[9];
     }
     int path = 0;
-    const bool same = A.id == (uint32_t)prev;
-    const uint32_t key = same ? A.k1 : A.k0;
-    uint32_t r = __reduce_min_sync(0xffffffffu, key);  // first valid lane << 26 | its material id
-    // cell + 1: usage before this cell's increment, material above
-    const int xn = (x + 1 == gw) ? 0 : x + 1;
-    B.u = (unsigned)usage[B.id];
-    B.up = *reinterpret_cast<volatile int32_t*>(rowbuf + xn);
+    // (1) threat vote of `cell`; reduction of cell + 1 with the presumed winner
     const uint32_t j0 = r >> 26;
-    const bool threat = (j0 - A.lo) < A.span && (key != 0xFFFFFFFFu || lane == 0);
-    if (__any_sync(0xffffffffu, threat)) {  // cold: (possibly) more than one contender, or no valid candidate
-      const bool valid = key != 0xFFFFFFFFu;
-      const int32_t left = (x == 0) ? -1 : prev;
+    const bool threat = (j0 - A.lo) < A.span && (A.key != NOKEY || lane == 0);
+    const bool any_threat = __any_sync(0xffffffffu, threat);
+    int32_t chosen = (int32_t)(r & CH_IDMASK);
+    bool same_b = B.id == (uint32_t)chosen;
+    uint32_t key_b = same_b ? B.k1 : B.k0;
+    uint32_t r_next = __reduce_min_sync(0xffffffffu, key_b);
+    if (__builtin_expect(any_threat, 0)) {  // cold: (possibly) more than one contender, or no valid candidate
+      const bool valid = A.key != NOKEY;
+      const int32_t left = (A.x == 0) ? -1 : prev;
       unsigned who = 63u;
       path = 1;
-      if (j0 < 32u) who = resolve_exact(cell, left, A.up, valid);
+      if (j0 < 32u) who = resolve_exact(cell, A.x, left, A.up, valid);
       if (who < 32u) {
         r = __shfl_sync(0xffffffffu, A.word, who);
       } else {
         float4 pl = make_float4(0.f, 0.f, 0.f, 0.f);
         if (left >= 0) pl = prev_lab(cell);
         const uint32_t nfb0 = n_fallbacks;
-        const int32_t g = resolve_generic(cell, left, A.up, pl);
+        const int32_t g = resolve_generic(cell, A.x, left, A.up, pl);
         path = n_fallbacks != nfb0 ? 3 : 2;
         r = (63u << 26) | (uint32_t)g;
-        // the generic path updated (possibly reset) the counters itself: re-read, excluding this cell's increment
-        B.u = (unsigned)usage[B.id];
-        if (B.id == (uint32_t)g) B.u -= 1u;
+        // the generic path updated (possibly reset) the counters itself: re-read the counters in flight so
+        // that they cover exactly the cells they are supposed to cover (all of them exclude this cell)
+        B.u = (unsigned)usage[B.id] - (B.id == (uint32_t)g ? 1u : 0u);
+        make_keys(B);
+        C.u = (unsigned)usage[C.id] - (C.id == (uint32_t)g ? 1u : 0u);
       }
+      chosen = (int32_t)(r & CH_IDMASK);
+      same_b = B.id == (uint32_t)chosen;
+      key_b = same_b ? B.k1 : B.k0;
+      r_next = __reduce_min_sync(0xffffffffu, key_b);
     }
-    const int32_t chosen = (int32_t)(r & CH_IDMASK);
-    if ((uint32_t)lane == (r >> 26)) usage[A.id] = (UsageT)(A.u + (same ? 1u : 0u) + 1u);  // main.rs:410-411
+    // (2) commit
+    if ((uint32_t)lane == (r >> 26)) usage[A.id] = (UsageT)(A.ucur + 1u);  // main.rs:410-411
     if (lane == 0) {
-      *reinterpret_cast<volatile int32_t*>(rowbuf + x) = chosen;
+      *reinterpret_cast<volatile int32_t*>(rowbuf + A.x) = chosen;
       queue[cell % CH_DEPTH] = ((unsigned long long)((uint32_t)cell + 1u) << 32) | r;
     }
     __syncwarp();
+    // (3) cell + 3: unpack the record requested one step ago; usage counter (covers cells <= cell), material above
+    unpack(D);
+    D.u = (unsigned)usage[D.id];
+    D.up = *reinterpret_cast<volatile int32_t*>(rowbuf + D.x);
+    // (4) cell + 2: keys (counter now covers cells <= cell; k1 covers the winner of cell + 1)
+    C.u += C.id == (uint32_t)chosen ? 1u : 0u;
+    make_keys(C);
+    // (5) cell + 4: record
+    E.x = D.x + 1 == gw ? 0 : D.x + 1;
+    if (cell + 4 < cells) {
+      if (((cell + 4) % CH_BATCH) == 0) wait_batch(cell + 4);
+      load_rec(cell + 4, E);
+    }
+    // rotate
+    B.key = key_b;
+    B.ucur = B.u + (same_b ? 1u : 0u);
     prev = chosen;
     prev_who = r >> 26;
-    make_keys(B, xn);
-    x = xn;
-    if (cell + 2 < cells) {
-      if (((cell + 2) % CH_BATCH) == 0) wait_batch(cell + 2);
-      load_slot(cell + 2, A);
-    }
+    r = r_next;
     if (PROF) {
       prof[path] += (unsigned long long)(clock64() - t_begin) - (prof[8] + prof[9] - w0);
       prof[4 + path] += 1ull;
     }
   };
 
-  CellRegs R0, R1;
-  R0.word = R1.word = 0xFFFFFFFFu;
-  R0.id = R1.id = (uint32_t)n;
-  R0.lo = R1.lo = R0.span = R1.span = 0u;
-  R0.k0 = R0.k1 = R1.k0 = R1.k1 = 0xFFFFFFFFu;
-  R0.u = R1.u = 0u;
-  R0.up = R1.up = -1;
-  if (cells > 0) {
-    wait_batch(0);
-    load_slot(0, R0);
-    make_keys(R0, 0);
-    if (cells > 1) load_slot(1, R1);
+  // The hot step: a cell whose first valid candidate is provably the reference's winner.  No cold code inside: the
+  // five unrolled copies must stay well inside the ~6 KB L0 instruction cache of the SM sub-partition (a far
+  // jump per cell to out-of-line code costs more than the whole dependency chain).  Returns true — WITHOUT
+  // side effects — if the cell is (possibly) contended; the caller then re-runs it through full_step.
+  // Requires cell + 4 < cells.
+  auto hot_step = [&](uint32_t cell, CellSet& A, CellSet& B, CellSet& C, CellSet& D, CellSet& E) -> bool {
+    const uint32_t j0 = r >> 26;
+    const bool threat = (j0 - A.lo) < A.span && (A.key != NOKEY || lane == 0);
+    const bool any_threat = __any_sync(0xffffffffu, threat);
+    const uint32_t chosen = r & CH_IDMASK;
+    const bool same_b = B.id == chosen;
+    const uint32_t key_b = same_b ? B.k1 : B.k0;
+    const uint32_t r_next = __reduce_min_sync(0xffffffffu, key_b);  // speculative: the winner of `cell` is presumed
+    if (any_threat) return true;
+    // commit
+    if ((uint32_t)lane == j0) usage[A.id] = (UsageT)(A.ucur + 1u);  // main.rs:410-411
+    if (lane == 0) {
+      *reinterpret_cast<volatile int32_t*>(rowbuf + A.x) = (int32_t)chosen;
+      queue[cell % CH_DEPTH] = ((unsigned long long)(cell + 1u) << 32) | r;
+    }
+    __syncwarp();
+    // cell + 3: usage counter (covers cells <= cell), material above
+    unpack(D);
+    D.u = (unsigned)usage[D.id];
+    D.up = *reinterpret_cast<volatile int32_t*>(rowbuf + D.x);
+    // cell + 2: keys
+    C.u += C.id == chosen ? 1u : 0u;
+    make_keys(C);
+    // cell + 4: record
+    E.x = D.x + 1 == gw ? 0 : D.x + 1;
+    const uint32_t s4 = (cell + 4u) % CH_DEPTH;  // its batch has been waited for at the head of the hot block
+    E.word = vring[s4].word[lane];
+    E.meta = vring[s4].meta[lane];
+    B.key = key_b;
+    B.ucur = B.u + (same_b ? 1u : 0u);
+    prev = (int32_t)chosen;
+    prev_who = j0;
+    r = r_next;
+    return false;
+  };
+
+  CellSet S[5];
+#pragma unroll
+  for (int t = 0; t < 5; ++t) {
+    S[t].word = NOKEY;
+    S[t].meta = 0u;
+    S[t].id = (uint32_t)n;
+    S[t].lo = S[t].span = 0u;
+    S[t].k0 = S[t].k1 = S[t].key = NOKEY;
+    S[t].u = S[t].ucur = 0u;
+    S[t].up = -1;
+    S[t].x = t;  // gw >= CH_MIN_GW: the first cells are in the first row
   }
+  // prologue (gw >= 33 => cells >= 33): records of cells 0..3; cells 0..2 see the initial counters and no row above
+  wait_batch(0);
+#pragma unroll
+  for (int t = 0; t < 4; ++t) load_rec(t, S[t]);
+#pragma unroll
+  for (int t = 0; t < 3; ++t) {
+    unpack(S[t]);
+    S[t].u = (unsigned)usage[S[t].id];  // zero, except for the dummy material of lanes >= k (pinned at the cap)
+  }
+  make_keys(S[0]);
+  make_keys(S[1]);
+  S[0].key = S[0].k0;
+  S[0].ucur = S[0].u;
+  r = __reduce_min_sync(0xffffffffu, S[0].key);
   long long t_all = 0;
   if (PROF) t_all = clock64();
-  for (int cell = 0; cell < cells; cell += 2) {
-    step(cell, R0, R1);
-    if (cell + 1 < cells) step(cell + 1, R1, R0);
+  auto rotate = [&](int by) {  // S[i] <- S[(i + by) % 5]: the set of the current cell moves to S[0] (cold)
+    for (int t = 0; t < by; ++t) {
+      const CellSet s0 = S[0];
+      S[0] = S[1];
+      S[1] = S[2];
+      S[2] = S[3];
+      S[3] = S[4];
+      S[4] = s0;
+    }
+  };
+  int cell = 0;
+  while (cell < cells) {
+    int p = 0;
+    if (cell + 9 <= cells) {  // five hot steps: records up to cell + 8 are requested
+      wait_batch(cell + 8);   // the block reads records cell + 4 .. cell + 8: this batch, or the one already waited for
+      if (hot_step(cell, S[0], S[1], S[2], S[3], S[4])) p = 0;
+      else if (hot_step(cell + 1, S[1], S[2], S[3], S[4], S[0])) p = 1;
+      else if (hot_step(cell + 2, S[2], S[3], S[4], S[0], S[1])) p = 2;
+      else if (hot_step(cell + 3, S[3], S[4], S[0], S[1], S[2])) p = 3;
+      else if (hot_step(cell + 4, S[4], S[0], S[1], S[2], S[3])) p = 4;
+      else {
+        cell += 5;
+        continue;
+      }
+    }
+    rotate(p);
+    cell += p;
+    full_step(cell, S[0], S[1], S[2], S[3], S[4]);
+    rotate(1);
+    cell += 1;
   }
   if (lane == 0) info[0] = n_fallbacks;
   if (PROF && lane == 0) {
     prof[10] = (unsigned long long)(clock64() - t_all);
+    // the hot steps carry no instrumentation: their share is what the other paths and the waits leave
+    prof[4] = (unsigned long long)cells - prof[5] - prof[6] - prof[7];
+    prof[0] = prof[10] - prof[1] - prof[2] - prof[3] - prof[8] - prof[9];
     for (int i = 0; i < 11; ++i) g_chain_prof[i] = prof[i];
   }
 }
