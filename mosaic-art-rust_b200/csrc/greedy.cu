@@ -174,50 +174,59 @@ __global__ void __launch_bounds__(32, 1) greedy_generic_kernel(const uint32_t* _
 // Fast path: a fully parallel preparation kernel + ONE CTA with two warps around a TMA-fed ring.
 //
 //   place_prep_kernel     (whole GPU, one warp per cell) gathers the state-independent data of the cell's
-//                        first 32 candidates — id, d2, Lab — into one contiguous 720-byte record, and derives
-//                        per candidate i the THREAT WINDOW  [lo_i, i):
+//                        first 32 candidates — id, d2, Lab — into two contiguous records (a 256-byte hot one,
+//                        a 528-byte cold one) and derives per candidate i the THREAT WINDOW  [lo_i, i):
 //                            lo_i = #{ j : hi[j] <= d2[i] },   hi[j] = fl(d2[j] + fl(2 * w)).
 //                        hi[j] bounds candidate j's total from above: total = fl(d2 + fl(fl(t_up + t_left) * w))
 //                        with t_up, t_left in [0, 1] and IEEE rounding monotone; every total is bounded from
 //                        below by its d2.  So if j0 is the first valid candidate, a later valid candidate i can
-//                        be STRICTLY better than j0 only if d2[i] < hi[j0], i.e. lo_i <= j0 < i.  Lane 0 (which
-//                        can never threaten anybody) carries the window of candidate 32, the first one beyond
-//                        the record: [lo_32, 64).
+//                        be STRICTLY better than j0 only if d2[i] < hi[j0], i.e. lo_i <= j0 < i.  The window is
+//                        stored as a 32-bit mask (bit j set: i threatens j).  Lane 0 (which can never threaten
+//                        anybody) carries the window of candidate 32, the first one beyond the record:
+//                        bits [lo_32, 32) — and all ones for the first cell of every grid row, which sends those
+//                        cells (the only ones where the material of the previous cell is NOT a neighbour) to
+//                        the full step.
 //   consumer  (warp 0)    walks the cells in raster order; records arrive in a 64-slot shared-memory ring by
 //                        1-D TMA bulk copies (8 records per copy, one mbarrier per batch).  Its loop-carried
-//                        chain is four instructions: compare (id == previous winner) -> select one of two
-//                        precomputed keys -> REDUX.MIN -> mask.  key = valid ? (lane << 26 | id) : ~0, so the
-//                        minimum IS the first valid candidate and its id; validity (id != Up, id != Left,
-//                        usage < cap) is precomputed one cell ahead for both outcomes of the comparison.  If no
-//                        lane is inside its threat window the first valid candidate is exactly the reference's
-//                        winner — no penalty is evaluated (91 % of the cells of the 24,000-tile config).
-//                        Otherwise the exact totals of the first 32 are evaluated (sqrt / reciprocal sequences
-//                        bit-identical to IEEE), and cells the record cannot decide (all 32 rejected, or the
-//                        early-exit bound fails) take the generic multi-chunk + reset-fallback path.  Every
-//                        shortcut is an exact bound: placements are bit-identical to main.rs:335-475.
+//                        chain is four instructions: compare (id == previous winner) -> select -> REDUX.MIN ->
+//                        mask.  key = valid ? (lane << 26 | id) : ~0, so the minimum IS the first valid
+//                        candidate and its id; validity (id != Up, usage < cap) is precomputed two cells ahead.
+//                        A second reduction, REDUX.OR over the window masks of the valid lanes, is issued next to
+//                        it — it does not depend on the winner — and one funnel shift by j0 tells whether any
+//                        valid candidate threatens the first valid one.  If none does, the first valid candidate
+//                        is exactly the reference's winner and no penalty is evaluated (91 % of the cells of the
+//                        24,000-tile config).  Otherwise the exact totals of the first 32 are evaluated (sqrt /
+//                        reciprocal sequences bit-identical to IEEE), and cells the record cannot decide (all 32
+//                        rejected, or the early-exit bound fails) take the generic multi-chunk + reset-fallback
+//                        path.  Every shortcut is an exact bound: placements are bit-identical to
+//                        main.rs:335-475.
 //   committer (warp 1)    drains the consumer's decisions, up to 32 cells at a time (one per lane): Lab of the
 //                        row above, the placement array in HBM, the `decided` counter; lane 0 re-arms the
-//                        mbarrier of every ring batch that has been fully consumed and issues its next TMA copy.
+//                        mbarrier of every ring batch that has been fully consumed and issues its next TMA copies.
 constexpr int CH_DEPTH = 64;   // ring slots (records)
 constexpr int CH_BATCH = 8;    // records per TMA copy / mbarrier
 constexpr int CH_NBATCH = CH_DEPTH / CH_BATCH;
+constexpr int CH_SHADOW = 4;   // hot slots 64..67 mirror slots 0..3: a hot block reads five consecutive slots
 constexpr int CH_GUARD = 3;    // slots of the last decided cells stay intact (the exact path re-reads them)
 constexpr int CH_MIN_GW = 33;  // the committer handles up to 32 consecutive cells at once: one per column
 constexpr uint32_t CH_IDMASK = 0x03FFFFFFu;
 
-struct __align__(16) CRec {
-  uint32_t word[32];  // lane << 26 | material id; the dummy id `n` (usage pinned at the cap) for lanes >= k
-  uint16_t meta[32];  // lo | span << 8: the lane threatens j0 iff (j0 - lo) <u span
-  float d2[32], l[32], a[32], b[32];
-  float d2_32;        // d2 of candidate 32 (+inf if k <= 32)
-  uint32_t pad[3];
+struct __align__(16) HRec {  // what every cell needs
+  uint2 wm[32];  // .x = lane << 26 | material id (the dummy id `n`, usage pinned at the cap, for lanes >= k)
+                 // .y = threat window mask
 };
-static_assert(sizeof(CRec) == 720, "record layout");
+struct __align__(16) XRec {  // what only contended cells need
+  float d2[32], l[32], a[32], b[32];
+  float d2_32;          // d2 of candidate 32 (+inf if k <= 32)
+  uint32_t win32;       // window mask of candidate 32 (lane 0 of HRec carries all ones in the first column)
+  uint32_t pad[2];
+};
+static_assert(sizeof(HRec) == 256 && sizeof(XRec) == 528, "record layout");
 
 __global__ void __launch_bounds__(256) place_prep_kernel(const uint32_t* __restrict__ cand_idx,
                                                          const float* __restrict__ cand_d2, int k,
-                                                         const float4* __restrict__ lab4, int n, int cells, float weight,
-                                                         CRec* __restrict__ rec) {
+                                                         const float4* __restrict__ lab4, int n, int cells, int gw,
+                                                         float weight, HRec* __restrict__ hrec, XRec* __restrict__ xrec) {
   const int lane = threadIdx.x & 31;
   const int warps = (gridDim.x * blockDim.x) >> 5;
   const bool use_penalty = weight > 0.0f;
@@ -241,19 +250,21 @@ __global__ void __launch_bounds__(256) place_prep_kernel(const uint32_t* __restr
       lo += hj <= d2 ? 1u : 0u;
       lo32 += hj <= d32 ? 1u : 0u;
     }
-    unsigned span = (unsigned)lane > lo ? (unsigned)lane - lo : 0u;
+    const uint32_t below_lane = (1u << lane) - 1u;                       // bits [0, lane)
+    const uint32_t below_lo = lo >= 32u ? 0xFFFFFFFFu : (1u << lo) - 1u;  // bits [0, lo)
+    uint32_t win = below_lane & ~below_lo;                                // bits [lo, lane)
+    const uint32_t win32 = lo32 >= 32u ? 0u : ~((1u << lo32) - 1u);       // bits [lo32, 32)
+    if (lane == 0) win = (c % gw == 0) ? 0xFFFFFFFFu : win32;
+    hrec[c].wm[lane] = make_uint2(((uint32_t)lane << 26) | id, win);
+    XRec& x = xrec[c];
+    x.d2[lane] = d2;
+    x.l[lane] = lab.x;
+    x.a[lane] = lab.y;
+    x.b[lane] = lab.z;
     if (lane == 0) {
-      lo = lo32;
-      span = 64u - lo32;  // j0 = 63 (no valid candidate) is always inside
+      x.d2_32 = d32;
+      x.win32 = win32;
     }
-    CRec& r = rec[c];
-    r.word[lane] = ((uint32_t)lane << 26) | id;
-    r.meta[lane] = (uint16_t)(lo | (span << 8));
-    r.d2[lane] = d2;
-    r.l[lane] = lab.x;
-    r.a[lane] = lab.y;
-    r.b[lane] = lab.z;
-    if (lane == 0) r.d2_32 = d32;
   }
 }
 
@@ -264,13 +275,14 @@ __device__ unsigned long long g_chain_prof[16];
 
 template <typename UsageT, bool PROF>
 __global__ void __launch_bounds__(64, 1)
-    greedy_chain_kernel(const CRec* __restrict__ rec, const uint32_t* __restrict__ cand_idx,
+    greedy_chain_kernel(const HRec* __restrict__ hrec, const XRec* __restrict__ xrec, const uint32_t* __restrict__ cand_idx,
                         const float* __restrict__ cand_d2, int k, const float4* __restrict__ lab4, int n, int gw, int gh,
                         unsigned max_usage, float weight, int32_t* __restrict__ placed, uint32_t* __restrict__ info,
                         uint32_t fallback_cap) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  CRec* ring = reinterpret_cast<CRec*>(smem_raw);
-  unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem_raw + sizeof(CRec) * CH_DEPTH);
+  HRec* hring = reinterpret_cast<HRec*>(smem_raw);
+  XRec* xring = reinterpret_cast<XRec*>(smem_raw + sizeof(HRec) * (CH_DEPTH + CH_SHADOW));
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(xring + CH_DEPTH);
   volatile unsigned long long* queue = bars + CH_NBATCH;
   volatile uint32_t* decided = reinterpret_cast<volatile uint32_t*>(const_cast<unsigned long long*>(queue) + CH_DEPTH);
   float4* rowlab = reinterpret_cast<float4*>(const_cast<uint32_t*>(decided) + 4);
@@ -294,15 +306,19 @@ __global__ void __launch_bounds__(64, 1)
 
   auto issue_batch = [&](int batch) {  // records [batch*8, batch*8+8) -> ring position batch % 8
     const int first = batch * CH_BATCH;
-    const unsigned bytes = (unsigned)(min(CH_BATCH, cells - first) * (int)sizeof(CRec));
+    const int cnt = min(CH_BATCH, cells - first);
+    const int slot = first % CH_DEPTH;
+    const int shadow = slot == 0 ? min(cnt, CH_SHADOW) : 0;
     unsigned long long* bar = &bars[batch % CH_NBATCH];
-    mbar_expect_tx(bar, bytes);
-    tma_load_1d(ring + (first % CH_DEPTH), rec + first, bytes, bar);
+    mbar_expect_tx(bar, (unsigned)((cnt + shadow) * (int)sizeof(HRec) + cnt * (int)sizeof(XRec)));
+    tma_load_1d(hring + slot, hrec + first, (unsigned)(cnt * (int)sizeof(HRec)), bar);
+    tma_load_1d(xring + slot, xrec + first, (unsigned)(cnt * (int)sizeof(XRec)), bar);
+    if (shadow) tma_load_1d(hring + CH_DEPTH, hrec + first, (unsigned)(shadow * (int)sizeof(HRec)), bar);
   };
 
   if (warp == 1) {
     // ---------------- committer ----------------
-    const volatile CRec* vring = ring;
+    const volatile XRec* vx = xring;
     int next_batch = 0;
     if (lane == 0)
       for (; next_batch < min(CH_NBATCH, nbatches); ++next_batch) issue_batch(next_batch);
@@ -323,7 +339,7 @@ __global__ void __launch_bounds__(64, 1)
         const unsigned who = ((uint32_t)e >> 26) & 63u;
         float4 lab;
         if (who < 32u)
-          lab = make_float4(vring[s].l[who], vring[s].a[who], vring[s].b[who], 0.f);
+          lab = make_float4(vx[s].l[who], vx[s].a[who], vx[s].b[who], 0.f);
         else
           lab = __ldg(&lab4[chosen]);
         rowlab[cell % gw] = lab;
@@ -348,29 +364,28 @@ __global__ void __launch_bounds__(64, 1)
   // Software pipeline over five register sets (cells c .. c+4):
   //   c+4  record words requested from the ring
   //   c+3  usage counter + material above requested (AFTER the commit of c, so the counter covers cells <= c)
-  //   c+2  keys computed (counter += [id == winner of c]; k1 covers the winner of c+1)
-  //   c+1  REDUX.MIN issued speculatively with the presumed winner of c, BEFORE the threat vote of c resolves
-  //   c    threat vote -> (cold path) -> commit
-  // so that on the hot path no instruction consumes a shared-memory load issued in the same iteration, and
-  // the vote/branch of cell c overlaps the reduction of cell c+1.
-  const volatile CRec* vring = ring;
+  //   c+2  key + window mask computed (counter += [id == winner of c])
+  //   c+1  REDUX.MIN / REDUX.OR issued with the presumed winner of c, BEFORE the threat test of c resolves
+  //   c    threat test -> (cold path) -> commit
+  // so that on the hot path no instruction consumes a shared-memory load issued in the same step, and the
+  // test/branch of cell c overlaps the reductions of cell c+1.
+  const volatile HRec* vh = hring;
+  const volatile XRec* vx = xring;
   constexpr uint32_t NOKEY = 0xFFFFFFFFu;
+  const bool l0 = lane == 0;
   uint32_t n_fallbacks = 0;
-  int32_t prev = -1;       // material placed in the previous cell (raster order)
-  unsigned prev_who = 63;  // lane of prev in the previous cell's record (63: not in the record)
   unsigned long long prof[11] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 
   struct CellSet {
-    uint32_t word, meta;  // as loaded from the record
-    uint32_t id, lo, span;
-    uint32_t k0, k1;      // redux key if id != / == the winner of the previous cell
-    uint32_t key;         // the key that went into the reduction
-    unsigned u;           // usage[id]; see the pipeline comment for which cells it covers at each stage
-    unsigned ucur;        // usage[id] covering every earlier cell (valid once the reduction has been issued)
-    int32_t up;           // material above (-1: first row); warp-uniform
-    int x;                // column
+    uint32_t w, m;  // record words: lane << 26 | id, window mask
+    uint32_t id;
+    unsigned u;     // usage[id]; see the pipeline comment for which cells it covers at each stage
+    int32_t up;     // material above (-1: first row); warp-uniform
+    int x;          // column
+    uint32_t k0;    // redux key if id is not the winner of the previous cell (else: NOKEY, except in column 0)
+    uint32_t km;    // window mask that goes into the OR reduction in that case
   };
-  auto wait_batch = [&](int c) {  // c is the first cell of its batch
+  auto wait_batch = [&](int c) {  // the batch of cell c
     unsigned long long* bar = &bars[(c / CH_BATCH) % CH_NBATCH];
     const unsigned parity = (unsigned)((c / CH_DEPTH) & 1);
     if (!mbar_test(bar, parity)) {
@@ -380,27 +395,15 @@ __global__ void __launch_bounds__(64, 1)
       if (PROF) prof[8] += (unsigned long long)(clock64() - tw);
     }
   };
-  auto load_rec = [&](int c, CellSet& r) {
-    const int s = c % CH_DEPTH;
-    r.word = vring[s].word[lane];
-    r.meta = vring[s].meta[lane];
+  auto load_rec = [&](int c, CellSet& s) {
+    const int slot = c % CH_DEPTH;
+    s.w = vh[slot].wm[lane].x;
+    s.m = vh[slot].wm[lane].y;
   };
-  auto unpack = [&](CellSet& r) {
-    r.id = r.word & CH_IDMASK;
-    r.lo = r.meta & 255u;
-    r.span = r.meta >> 8;
-  };
-  auto make_keys = [&](CellSet& r) {
-    const bool ok = (int32_t)r.id != r.up;                                      // main.rs:380 (Up)
-    r.k0 = (ok && r.u < max_usage) ? r.word : NOKEY;                            // main.rs:375
-    r.k1 = (ok && r.x == 0 && r.u + 1u < max_usage) ? r.word : NOKEY;           // == Left unless the row starts here
-  };
-  auto prev_lab = [&](int cell) -> float4 {  // Lab of the material placed in cell - 1
-    if (prev_who < 32u) {
-      const int ps = (cell - 1) % CH_DEPTH;
-      return make_float4(vring[ps].l[prev_who], vring[ps].a[prev_who], vring[ps].b[prev_who], 0.f);
-    }
-    return __ldg(&lab4[prev]);
+  auto make_keys = [&](CellSet& s) {
+    const bool ok = (int32_t)s.id != s.up && s.u < max_usage;  // main.rs:380 (Up), main.rs:375
+    s.k0 = ok ? s.w : NOKEY;
+    s.km = (ok || l0) ? s.m : 0u;
   };
   auto row_above_lab = [&](int cell, int x) -> float4 {  // rowlab[x] holds the Lab of cell - gw once it is committed
     const volatile float4* ul = rowlab + x;
@@ -415,6 +418,19 @@ __global__ void __launch_bounds__(64, 1)
       v = make_float4(ul->x, ul->y, ul->z, 0.f);
     }
     return v;
+  };
+
+  uint32_t r = NOKEY;      // REDUX.MIN of the current cell: first valid lane << 26 | its material id
+  uint32_t T = NOKEY;      // REDUX.OR of the current cell: bit j set <=> some valid candidate threatens candidate j
+  uint32_t rprev = NOKEY;  // r of the previous cell after its resolution (lane 63 = not in the record)
+
+  auto prev_lab = [&](int cell) -> float4 {  // Lab of the material placed in cell - 1
+    const unsigned prev_who = rprev >> 26;
+    if (prev_who < 32u) {
+      const int ps = (cell - 1) % CH_DEPTH;
+      return make_float4(vx[ps].l[prev_who], vx[ps].a[prev_who], vx[ps].b[prev_who], 0.f);
+    }
+    return __ldg(&lab4[rprev & CH_IDMASK]);
   };
 
   // exact multi-chunk resolution + reset fallback: the reference's loop, bit for bit (main.rs:335-475)
@@ -489,9 +505,9 @@ __global__ void __launch_bounds__(64, 1)
   auto resolve_exact = [&](int cell, int x, int32_t left, int32_t up, bool valid) -> unsigned {
     const int sA = cell % CH_DEPTH;
     // every load is requested before the first one is consumed
-    const float d2 = vring[sA].d2[lane];
-    const float l = vring[sA].l[lane], a = vring[sA].a[lane], b = vring[sA].b[lane];
-    const float d2_32 = vring[sA].d2_32;
+    const float d2 = vx[sA].d2[lane];
+    const float l = vx[sA].l[lane], a = vx[sA].a[lane], b = vx[sA].b[lane];
+    const float d2_32 = vx[sA].d2_32;
     float4 pl = make_float4(0.f, 0.f, 0.f, 0.f);
     if (left >= 0) pl = prev_lab(cell);
     float4 ul = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -514,11 +530,9 @@ __global__ void __launch_bounds__(64, 1)
     return 63u;
   };
 
-  uint32_t r = NOKEY;  // REDUX.MIN of the current cell: first valid lane << 26 | its material id
-
-  // One cell with every path (vote -> exact totals -> generic multi-chunk / reset fallback).  ONE copy of this code
-  // exists: the hot loop below leaves through it whenever a cell is (possibly) contended, and the last cells of
-  // the grid run through it.
+  // One cell with every path (threat test -> exact totals -> generic multi-chunk / reset fallback).  ONE copy of
+  // this code exists: the hot loop below leaves through it whenever a cell is (possibly) contended or starts a
+  // grid row, and the last cells of the grid run through it.
   auto full_step = [&](int cell, CellSet& A, CellSet& B, CellSet& C, CellSet& D, CellSet& E) {
     long long t_begin = 0;
     unsigned long long w0 = 0;
@@ -527,22 +541,28 @@ __global__ void __launch_bounds__(64, 1)
       w0 = prof[8] + prof[9];
     }
     int path = 0;
-    // (1) threat vote of `cell`; reduction of cell + 1 with the presumed winner
+    // (1) the key of this cell, for real: in column 0 the previous winner is not a neighbour (main.rs:309-333)
+    const int32_t prev = cell > 0 ? (int32_t)(rprev & CH_IDMASK) : -1;
+    const bool same = cell > 0 && A.id == (uint32_t)prev;
+    const unsigned ucur = A.u + (same ? 1u : 0u);  // usage[id] over every earlier cell
+    uint32_t key = same ? NOKEY : A.k0;
+    uint32_t tm = (same && !l0) ? 0u : A.km;
+    if (A.x == 0) {
+      const bool ok = (int32_t)A.id != A.up && ucur < max_usage;
+      key = ok ? A.w : NOKEY;
+      tm = l0 ? vx[cell % CH_DEPTH].win32 : (ok ? A.m : 0u);  // (lane 0 of the hot record carries all ones here)
+    }
+    r = __reduce_min_sync(0xffffffffu, key);  // (a dead hot block leaves r and T undefined)
+    T = __reduce_or_sync(0xffffffffu, tm);
     const uint32_t j0 = r >> 26;
-    const bool threat = (j0 - A.lo) < A.span && (A.key != NOKEY || lane == 0);
-    const bool any_threat = __any_sync(0xffffffffu, threat);
-    int32_t chosen = (int32_t)(r & CH_IDMASK);
-    bool same_b = B.id == (uint32_t)chosen;
-    uint32_t key_b = same_b ? B.k1 : B.k0;
-    uint32_t r_next = __reduce_min_sync(0xffffffffu, key_b);
-    if (__builtin_expect(any_threat, 0)) {  // cold: (possibly) more than one contender, or no valid candidate
-      const bool valid = A.key != NOKEY;
+    if (__funnelshift_rc(T, 0xFFFFFFFFu, j0) & 1u) {  // (possibly) more than one contender, or no valid candidate
+      const bool valid = key != NOKEY;
       const int32_t left = (A.x == 0) ? -1 : prev;
       unsigned who = 63u;
       path = 1;
       if (j0 < 32u) who = resolve_exact(cell, A.x, left, A.up, valid);
       if (who < 32u) {
-        r = __shfl_sync(0xffffffffu, A.word, who);
+        r = __shfl_sync(0xffffffffu, A.w, who);
       } else {
         float4 pl = make_float4(0.f, 0.f, 0.f, 0.f);
         if (left >= 0) pl = prev_lab(cell);
@@ -556,95 +576,98 @@ __global__ void __launch_bounds__(64, 1)
         make_keys(B);
         C.u = (unsigned)usage[C.id] - (C.id == (uint32_t)g ? 1u : 0u);
       }
-      chosen = (int32_t)(r & CH_IDMASK);
-      same_b = B.id == (uint32_t)chosen;
-      key_b = same_b ? B.k1 : B.k0;
-      r_next = __reduce_min_sync(0xffffffffu, key_b);
     }
     // (2) commit
-    if ((uint32_t)lane == (r >> 26)) usage[A.id] = (UsageT)(A.ucur + 1u);  // main.rs:410-411
+    const uint32_t chosen = r & CH_IDMASK;
+    if ((uint32_t)lane == (r >> 26)) usage[A.id] = (UsageT)(ucur + 1u);  // main.rs:410-411
     if (lane == 0) {
-      *reinterpret_cast<volatile int32_t*>(rowbuf + A.x) = chosen;
+      *reinterpret_cast<volatile int32_t*>(rowbuf + A.x) = (int32_t)chosen;
       queue[cell % CH_DEPTH] = ((unsigned long long)((uint32_t)cell + 1u) << 32) | r;
     }
     __syncwarp();
-    // (3) cell + 3: unpack the record requested one step ago; usage counter (covers cells <= cell), material above
-    unpack(D);
+    // (3) reductions of cell + 1
+    const bool same_b = B.id == chosen;
+    const uint32_t r_next = __reduce_min_sync(0xffffffffu, same_b ? NOKEY : B.k0);
+    const uint32_t T_next = __reduce_or_sync(0xffffffffu, (same_b && !l0) ? 0u : B.km);
+    // (4) cell + 3: unpack the record requested one step ago; usage counter (covers cells <= cell), material above
+    D.id = D.w & CH_IDMASK;
     D.u = (unsigned)usage[D.id];
     D.up = *reinterpret_cast<volatile int32_t*>(rowbuf + D.x);
-    // (4) cell + 2: keys (counter now covers cells <= cell; k1 covers the winner of cell + 1)
-    C.u += C.id == (uint32_t)chosen ? 1u : 0u;
+    // (5) cell + 2: key + mask (counter now covers cells <= cell)
+    C.u += C.id == chosen ? 1u : 0u;
     make_keys(C);
-    // (5) cell + 4: record
+    // (6) cell + 4: record
     E.x = D.x + 1 == gw ? 0 : D.x + 1;
     if (cell + 4 < cells) {
       if (((cell + 4) % CH_BATCH) == 0) wait_batch(cell + 4);
       load_rec(cell + 4, E);
     }
-    // rotate
-    B.key = key_b;
-    B.ucur = B.u + (same_b ? 1u : 0u);
-    prev = chosen;
-    prev_who = r >> 26;
+    rprev = r;
     r = r_next;
+    T = T_next;
     if (PROF) {
       prof[path] += (unsigned long long)(clock64() - t_begin) - (prof[8] + prof[9] - w0);
       prof[4 + path] += 1ull;
     }
   };
 
-  // The hot step: a cell whose first valid candidate is provably the reference's winner.  No cold code inside: the
-  // five unrolled copies must stay well inside the ~6 KB L0 instruction cache of the SM sub-partition (a far
-  // jump per cell to out-of-line code costs more than the whole dependency chain).  Returns true — WITHOUT
-  // side effects — if the cell is (possibly) contended; the caller then re-runs it through full_step.
-  // Requires cell + 4 < cells.
-  auto hot_step = [&](uint32_t cell, CellSet& A, CellSet& B, CellSet& C, CellSet& D, CellSet& E) -> bool {
-    const uint32_t j0 = r >> 26;
-    const bool threat = (j0 - A.lo) < A.span && (A.key != NOKEY || lane == 0);
-    const bool any_threat = __any_sync(0xffffffffu, threat);
-    const uint32_t chosen = r & CH_IDMASK;
+  // The hot block: five cells whose first valid candidates are provably the reference's winners.  It is ONE
+  // basic block — no branch between the steps — so that ptxas can park the reductions of cell c+1 behind the
+  // bookkeeping of cell c: once a cell is (possibly) contended the block goes `dead` and every later state
+  // update in it is predicated off; the caller re-runs that cell through full_step.  No cold code inside: the
+  // unrolled steps must stay inside the ~6 KB L0 instruction cache of the SM sub-partition (a far jump per cell
+  // to out-of-line code costs more than the whole dependency chain).  Each decision is parked in lane STEP's
+  // `myr`; the block's decisions go to the row buffer and the committer's queue with one store per lane.
+  // `hb`: this lane's pair in the hot record of the block's first cell + 4 (five consecutive slots).
+  uint32_t myr = 0u;
+  bool dead = false;
+  int done = 0;
+  auto hot_step = [&](const int STEP, const uint2* hb, CellSet& A, CellSet& B, CellSet& C, CellSet& D, CellSet& E) {
+    const uint32_t rc = r;
+    const uint32_t chosen = rc & CH_IDMASK;
+    const uint32_t j0 = rc >> 26;
+    dead = dead || (__funnelshift_rc(T, 0xFFFFFFFFu, j0) & 1u) != 0u;  // j0 = 63 (no valid candidate) shifts the ones in
+    const bool live = !dead;
     const bool same_b = B.id == chosen;
-    const uint32_t key_b = same_b ? B.k1 : B.k0;
-    const uint32_t r_next = __reduce_min_sync(0xffffffffu, key_b);  // speculative: the winner of `cell` is presumed
-    if (any_threat) return true;
-    // commit
-    if ((uint32_t)lane == j0) usage[A.id] = (UsageT)(A.ucur + 1u);  // main.rs:410-411
-    if (lane == 0) {
-      *reinterpret_cast<volatile int32_t*>(rowbuf + A.x) = (int32_t)chosen;
-      queue[cell % CH_DEPTH] = ((unsigned long long)(cell + 1u) << 32) | r;
-    }
-    __syncwarp();
+    r = __reduce_min_sync(0xffffffffu, same_b ? NOKEY : B.k0);  // the winner of this cell is presumed
+    T = __reduce_or_sync(0xffffffffu, (same_b && !l0) ? 0u : B.km);
+    // commit: the winner is not the previous winner (that lane's key is NOKEY), so A.u covers every earlier cell
+    // (a predicated store, not a branch: the step must stay one basic block.  The warp is converged and its
+    // shared-memory accesses execute in program order, so the counter reads below see the store.)
+    st_shared_if(live && (uint32_t)lane == j0, &usage[A.id], (UsageT)(A.u + 1u));  // main.rs:410-411
+    myr = (live && lane == STEP) ? rc : myr;
+    done += live ? 1 : 0;
     // cell + 3: usage counter (covers cells <= cell), material above
-    unpack(D);
-    D.u = (unsigned)usage[D.id];
-    D.up = *reinterpret_cast<volatile int32_t*>(rowbuf + D.x);
-    // cell + 2: keys
-    C.u += C.id == chosen ? 1u : 0u;
-    make_keys(C);
-    // cell + 4: record
-    E.x = D.x + 1 == gw ? 0 : D.x + 1;
-    const uint32_t s4 = (cell + 4u) % CH_DEPTH;  // its batch has been waited for at the head of the hot block
-    E.word = vring[s4].word[lane];
-    E.meta = vring[s4].meta[lane];
-    B.key = key_b;
-    B.ucur = B.u + (same_b ? 1u : 0u);
-    prev = (int32_t)chosen;
-    prev_who = j0;
-    r = r_next;
-    return false;
+    const uint32_t did = D.w & CH_IDMASK;
+    const unsigned du = (unsigned)usage[did];
+    const int32_t dup = rowbuf[D.x];
+    D.id = live ? did : D.id;
+    D.u = live ? du : D.u;
+    D.up = live ? dup : D.up;
+    // cell + 2: key + mask
+    C.u += (live && C.id == chosen) ? 1u : 0u;
+    const bool ok = (int32_t)C.id != C.up && C.u < max_usage;  // main.rs:380 (Up), main.rs:375
+    C.k0 = live ? (ok ? C.w : NOKEY) : C.k0;
+    C.km = live ? ((ok || l0) ? C.m : 0u) : C.km;
+    // cell + 4: record (its batch has been waited for)
+    const uint2 e = hb[STEP * 32];
+    const int ex = D.x + 1 == gw ? 0 : D.x + 1;
+    E.x = live ? ex : E.x;
+    E.w = live ? e.x : E.w;
+    E.m = live ? e.y : E.m;
   };
 
   CellSet S[5];
 #pragma unroll
   for (int t = 0; t < 5; ++t) {
-    S[t].word = NOKEY;
-    S[t].meta = 0u;
+    S[t].w = (uint32_t)n;  // (a dead hot step may look up the counter of a set that has not been loaded yet)
+    S[t].m = 0u;
     S[t].id = (uint32_t)n;
-    S[t].lo = S[t].span = 0u;
-    S[t].k0 = S[t].k1 = S[t].key = NOKEY;
-    S[t].u = S[t].ucur = 0u;
+    S[t].u = 0u;
     S[t].up = -1;
     S[t].x = t;  // gw >= CH_MIN_GW: the first cells are in the first row
+    S[t].k0 = NOKEY;
+    S[t].km = 0u;
   }
   // prologue (gw >= 33 => cells >= 33): records of cells 0..3; cells 0..2 see the initial counters and no row above
   wait_batch(0);
@@ -652,14 +675,13 @@ __global__ void __launch_bounds__(64, 1)
   for (int t = 0; t < 4; ++t) load_rec(t, S[t]);
 #pragma unroll
   for (int t = 0; t < 3; ++t) {
-    unpack(S[t]);
+    S[t].id = S[t].w & CH_IDMASK;
     S[t].u = (unsigned)usage[S[t].id];  // zero, except for the dummy material of lanes >= k (pinned at the cap)
   }
   make_keys(S[0]);
   make_keys(S[1]);
-  S[0].key = S[0].k0;
-  S[0].ucur = S[0].u;
-  r = __reduce_min_sync(0xffffffffu, S[0].key);
+  r = __reduce_min_sync(0xffffffffu, S[0].k0);
+  T = __reduce_or_sync(0xffffffffu, S[0].km);
   long long t_all = 0;
   if (PROF) t_all = clock64();
   auto rotate = [&](int by) {  // S[i] <- S[(i + by) % 5]: the set of the current cell moves to S[0] (cold)
@@ -672,26 +694,48 @@ __global__ void __launch_bounds__(64, 1)
       S[4] = s0;
     }
   };
-  int cell = 0;
-  while (cell < cells) {
-    int p = 0;
-    if (cell + 9 <= cells) {  // five hot steps: records up to cell + 8 are requested
-      wait_batch(cell + 8);   // the block reads records cell + 4 .. cell + 8: this batch, or the one already waited for
-      if (hot_step(cell, S[0], S[1], S[2], S[3], S[4])) p = 0;
-      else if (hot_step(cell + 1, S[1], S[2], S[3], S[4], S[0])) p = 1;
-      else if (hot_step(cell + 2, S[2], S[3], S[4], S[0], S[1])) p = 2;
-      else if (hot_step(cell + 3, S[3], S[4], S[0], S[1], S[2])) p = 3;
-      else if (hot_step(cell + 4, S[4], S[0], S[1], S[2], S[3])) p = 4;
-      else {
-        cell += 5;
-        continue;
+  const uint32_t ucells = (uint32_t)cells;
+  uint32_t cell = 0;
+  while (cell < ucells) {
+    if (cell + 9u <= ucells) {  // hot blocks: records up to cell + 8 are requested
+      wait_batch((int)cell + 8);  // a block reads records cell + 4 .. cell + 8: this batch, or one already waited for
+      bool ran_block = false;
+      for (;;) {
+        // probe the batch the NEXT block needs now, look at the answer after this block
+        bool next_ready = true;
+        if (cell + 14u <= ucells) {
+          const uint32_t c13 = cell + 13u;
+          next_ready = mbar_test(&bars[(c13 / CH_BATCH) % CH_NBATCH], (c13 / CH_DEPTH) & 1u);
+        }
+        const uint2* hb = reinterpret_cast<const uint2*>(hring) + ((cell + 4u) % CH_DEPTH) * 32u + lane;
+        const int x0 = S[0].x;
+        dead = false;
+        done = 0;
+        hot_step(0, hb, S[0], S[1], S[2], S[3], S[4]);
+        hot_step(1, hb, S[1], S[2], S[3], S[4], S[0]);
+        hot_step(2, hb, S[2], S[3], S[4], S[0], S[1]);
+        hot_step(3, hb, S[3], S[4], S[0], S[1], S[2]);
+        hot_step(4, hb, S[4], S[0], S[1], S[2], S[3]);
+        if (lane < done) {  // flush the parked decisions: lane t holds the one of cell + t
+          int xs = x0 + lane;
+          xs = xs >= gw ? xs - gw : xs;
+          *reinterpret_cast<volatile int32_t*>(rowbuf + xs) = (int32_t)(myr & CH_IDMASK);
+          queue[(cell + (uint32_t)lane) % CH_DEPTH] = ((unsigned long long)(cell + (uint32_t)lane + 1u) << 32) | myr;
+        }
+        __syncwarp();
+        cell += (uint32_t)done;
+        if (done < 5 || cell + 9u > ucells) break;
+        ran_block = true;
+        if (!next_ready) wait_batch((int)cell + 8);
       }
+      // the decision of the last cell that went through: lane done-1 of this block, else lane 4 of the one before
+      if (done > 0 || ran_block) rprev = __shfl_sync(0xffffffffu, myr, done > 0 ? done - 1 : 4);
+      rotate(done % 5);
+      if (cell >= ucells) break;
     }
-    rotate(p);
-    cell += p;
-    full_step(cell, S[0], S[1], S[2], S[3], S[4]);
+    full_step((int)cell, S[0], S[1], S[2], S[3], S[4]);
     rotate(1);
-    cell += 1;
+    cell += 1u;
   }
   if (lane == 0) info[0] = n_fallbacks;
   if (PROF && lane == 0) {
@@ -707,21 +751,24 @@ __global__ void __launch_bounds__(64, 1)
 
 template <typename UsageT, bool PROF>
 static int launch_chain_impl(mosaic_ctx* ctx, unsigned cap, float weight, size_t smem) {
+  const size_t cells = (size_t)ctx->gw * ctx->gh;
   MOSAIC_CUDA(ctx, cudaFuncSetAttribute(greedy_chain_kernel<UsageT, PROF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)smem));
   greedy_chain_kernel<UsageT, PROF><<<1, 64, smem, ctx->stream>>>(
-      reinterpret_cast<const CRec*>(ctx->d_place_rec), ctx->d_cand_idx, ctx->d_cand_d2, ctx->k, ctx->d_mat_lab4, ctx->n,
-      ctx->gw, ctx->gh, cap, weight, ctx->d_placed, ctx->d_place_info, mosaic_ctx::kFallbackCap);
+      reinterpret_cast<const HRec*>(ctx->d_place_rec), reinterpret_cast<const XRec*>(ctx->d_place_rec + cells * sizeof(HRec)),
+      ctx->d_cand_idx, ctx->d_cand_d2, ctx->k, ctx->d_mat_lab4, ctx->n, ctx->gw, ctx->gh, cap, weight, ctx->d_placed,
+      ctx->d_place_info, mosaic_ctx::kFallbackCap);
   return MOSAIC_OK;
 }
 template <typename UsageT>
 static int launch_chain(mosaic_ctx* ctx, unsigned cap, float weight, size_t smem) {
   const int cells = ctx->gw * ctx->gh;
-  MOSAIC_TRY(ensure(ctx, &ctx->d_place_rec, &ctx->place_rec_cap, (size_t)cells * sizeof(CRec)));
+  MOSAIC_TRY(ensure(ctx, &ctx->d_place_rec, &ctx->place_rec_cap, (size_t)cells * (sizeof(HRec) + sizeof(XRec))));
   int blocks = (cells + 7) / 8;
   if (blocks > ctx->sm_count * 8) blocks = ctx->sm_count * 8;
   place_prep_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->d_cand_idx, ctx->d_cand_d2, ctx->k, ctx->d_mat_lab4, ctx->n, cells,
-                                                     weight, reinterpret_cast<CRec*>(ctx->d_place_rec));
+                                                     ctx->gw, weight, reinterpret_cast<HRec*>(ctx->d_place_rec),
+                                                     reinterpret_cast<XRec*>(ctx->d_place_rec + (size_t)cells * sizeof(HRec)));
   ctx->launches++;
   MOSAIC_CUDA(ctx, cudaGetLastError());
   return ctx->profile_chain ? launch_chain_impl<UsageT, true>(ctx, cap, weight, smem)
@@ -739,8 +786,8 @@ int launch_place(mosaic_ctx* ctx, int max_usage, float weight) {
   const unsigned cap = max_usage < 0 ? 0u : (unsigned)max_usage;
   const size_t smem_limit = 220 * 1024;
   // fast path: record ring + row state + usage counters in shared memory
-  const size_t ring_fixed = sizeof(CRec) * CH_DEPTH + 8 * CH_NBATCH + 8 * CH_DEPTH + 16 + sizeof(float4) * (size_t)gw +
-                            sizeof(int32_t) * (size_t)((gw + 3) & ~3);
+  const size_t ring_fixed = sizeof(HRec) * (CH_DEPTH + CH_SHADOW) + sizeof(XRec) * CH_DEPTH + 8 * CH_NBATCH + 8 * CH_DEPTH + 16 +
+                            sizeof(float4) * (size_t)gw + sizeof(int32_t) * (size_t)((gw + 3) & ~3);
   const size_t usage_bytes = cap <= 255u ? (size_t)n + 1 : (cap <= 65535u ? ((size_t)n + 1) * 2 : (size_t)-1);
   StageTimer t(ctx, MOSAIC_STAGE_PLACE);
   if (gw >= CH_MIN_GW && ctx->n < (1 << 26) && usage_bytes != (size_t)-1 && ring_fixed + usage_bytes + 16 <= smem_limit) {
