@@ -175,17 +175,18 @@ __global__ void __launch_bounds__(32, 1) greedy_generic_kernel(const uint32_t* _
 //
 //   place_prep_kernel     (whole GPU, one warp per cell) gathers the state-independent data of the cell's
 //                        first 32 candidates — id, d2, Lab — into two contiguous records (a 256-byte hot one,
-//                        a 528-byte cold one) and derives per candidate i the THREAT WINDOW  [lo_i, i):
-//                            lo_i = #{ j : hi[j] <= d2[i] },   hi[j] = fl(d2[j] + fl(2 * w)).
-//                        hi[j] bounds candidate j's total from above: total = fl(d2 + fl(fl(t_up + t_left) * w))
-//                        with t_up, t_left in [0, 1] and IEEE rounding monotone; every total is bounded from
-//                        below by its d2.  So if j0 is the first valid candidate, a later valid candidate i can
-//                        be STRICTLY better than j0 only if d2[i] < hi[j0], i.e. lo_i <= j0 < i.  The window is
-//                        stored as a 32-bit mask (bit j set: i threatens j).  Lane 0 (which can never threaten
-//                        anybody) carries the window of candidate 32, the first one beyond the record:
-//                        bits [lo_32, 32) — and all ones for the first cell of every grid row, which sends those
-//                        cells (the only ones where the material of the previous cell is NOT a neighbour) to
-//                        the full step.
+//                        a 528-byte cold one) and derives per candidate i its THREAT WINDOW: the set of earlier
+//                        candidates j < i with  d2[i] < hi[j],  where
+//                            hi[j] = fl(d2[j] + fl(fl(M_up[j] + M_left[j]) * w))
+//                        bounds candidate j's total from above: M_x[j] is the adjacency term of j against the
+//                        nearest OTHER material among the (<= 100) candidates of the neighbour cell — the
+//                        neighbour's material is always one of them, IEEE rounding is monotone, and every total
+//                        is bounded from below by its d2.  So if j0 is the first valid candidate, a later valid
+//                        candidate i can be STRICTLY better than j0 only if bit j0 of its window is set.  The
+//                        window is a 32-bit mask.  Lane 0 (which can never threaten anybody) carries the window
+//                        of candidate 32, the first one beyond the record — and all ones for the first cell of
+//                        every grid row, which sends those cells (the only ones where the material of the
+//                        previous cell is NOT a neighbour) to the full step.
 //   consumer  (warp 0)    walks the cells in raster order; records arrive in a 64-slot shared-memory ring by
 //                        1-D TMA bulk copies (8 records per copy, one mbarrier per batch).  Its loop-carried
 //                        chain is four instructions: compare (id == previous winner) -> select -> REDUX.MIN ->
@@ -227,11 +228,12 @@ __global__ void __launch_bounds__(256) place_prep_kernel(const uint32_t* __restr
                                                          const float* __restrict__ cand_d2, int k,
                                                          const float4* __restrict__ lab4, int n, int cells, int gw,
                                                          float weight, HRec* __restrict__ hrec, XRec* __restrict__ xrec) {
+  __shared__ float4 nb_s[8][2][kMaxK];  // per warp: (Lab, id) of every candidate of the cell above / to the left
   const int lane = threadIdx.x & 31;
   const int warps = (gridDim.x * blockDim.x) >> 5;
   const bool use_penalty = weight > 0.0f;
-  const float two_w = __fmul_rn(2.0f, weight);
   const float inf = __int_as_float(0x7f800000);
+  float4(*nb)[kMaxK] = nb_s[threadIdx.x >> 5];
   for (int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; c < cells; c += warps) {
     uint32_t id = (uint32_t)n;
     float d2 = inf;
@@ -242,18 +244,48 @@ __global__ void __launch_bounds__(256) place_prep_kernel(const uint32_t* __restr
       lab = __ldg(&lab4[id]);
     }
     const float d32 = k > 32 ? __ldg(cand_d2 + (size_t)c * k + 32) : inf;
-    const float hi = use_penalty ? __fadd_rn(d2, two_w) : d2;
-    unsigned lo = 0, lo32 = 0;
+    // Upper bound of each candidate's penalty.  Whatever the replay decides, the material above / to the left is
+    // one of the <= 100 candidates of that cell (main.rs:349-413; the fallback picks among the same list,
+    // main.rs:436-470), and it is not this candidate (a candidate equal to a neighbour is rejected,
+    // main.rs:380).  1/(sqrt(d2)+1) decreases with d2 and every rounding is monotone, so the term of the nearest
+    // OTHER candidate of the neighbour cell bounds the real one from above.
+    float m_sum = 0.0f;
+    if (use_penalty) {
+      const int nbc[2] = {c >= gw ? c - gw : -1, c % gw != 0 ? c - 1 : -1};  // adjacency.rs:71-87 order: Up, Left
+      __syncwarp();
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {  // hi is ascending: {j : hi[j] <= v} is a prefix
-      const float hj = __shfl_sync(0xffffffffu, hi, j);
-      lo += hj <= d2 ? 1u : 0u;
-      lo32 += hj <= d32 ? 1u : 0u;
+      for (int s = 0; s < 2; ++s)
+        if (nbc[s] >= 0)
+          for (int u = lane; u < k; u += 32) {
+            const uint32_t idu = __ldg(cand_idx + (size_t)nbc[s] * k + u);
+            const float4 q = __ldg(&lab4[idu]);
+            nb[s][u] = make_float4(q.x, q.y, q.z, __uint_as_float(idu));
+          }
+      __syncwarp();
+      float m[2] = {0.0f, 0.0f};
+#pragma unroll
+      for (int s = 0; s < 2; ++s)
+        if (nbc[s] >= 0) {
+          float dmin = inf;
+          for (int u = 0; u < k; ++u) {
+            const float4 q = nb[s][u];
+            const float dl = __fsub_rn(lab.x, q.x), da = __fsub_rn(lab.y, q.y), db = __fsub_rn(lab.z, q.z);
+            const float dd = __fadd_rn(__fadd_rn(__fmul_rn(dl, dl), __fmul_rn(da, da)), __fmul_rn(db, db));
+            dmin = (__float_as_uint(q.w) != id && dd < dmin) ? dd : dmin;
+          }
+          m[s] = dmin < inf ? adjacency_term(__fsqrt_rn(dmin)) : 0.0f;
+        }
+      m_sum = __fadd_rn(m[0], m[1]);
     }
-    const uint32_t below_lane = (1u << lane) - 1u;                       // bits [0, lane)
-    const uint32_t below_lo = lo >= 32u ? 0xFFFFFFFFu : (1u << lo) - 1u;  // bits [0, lo)
-    uint32_t win = below_lane & ~below_lo;                                // bits [lo, lane)
-    const uint32_t win32 = lo32 >= 32u ? 0u : ~((1u << lo32) - 1u);       // bits [lo32, 32)
+    // hi >= the candidate's total  fl(d2 + fl(fl(t_up + t_left) * w))  (main.rs:386-398); every total >= its d2
+    const float hi = use_penalty ? __fadd_rn(d2, __fmul_rn(m_sum, weight)) : d2;
+    uint32_t win = 0u, win32 = 0u;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float hj = __shfl_sync(0xffffffffu, hi, j);
+      win |= (j < lane && d2 < hj) ? (1u << j) : 0u;   // this candidate can be STRICTLY better than candidate j
+      win32 |= d32 < hj ? (1u << j) : 0u;              // so can candidate 32 (and only then anyone behind it)
+    }
     if (lane == 0) win = (c % gw == 0) ? 0xFFFFFFFFu : win32;
     hrec[c].wm[lane] = make_uint2(((uint32_t)lane << 26) | id, win);
     XRec& x = xrec[c];
