@@ -25,7 +25,10 @@ namespace mosaic {
 
 namespace {
 
-constexpr int RNG_RING_WORDS = 512;  // 32 ChaCha blocks
+constexpr int RNG_HALF_WORDS = 512;   // 32 ChaCha blocks: one refill
+constexpr int RNG_RING_WORDS = 1024;  // two halves
+constexpr int RNG_SLACK = 16;         // words one iteration may look ahead (8 for the positions + 1 for the f32)
+constexpr int RNG_SMEM_WORDS = RNG_RING_WORDS + 16;  // + the key (8 words), padded
 
 __device__ __forceinline__ unsigned rotl32(unsigned v, int c) { return __funnelshift_l(v, v, c); }
 
@@ -35,13 +38,19 @@ __device__ __forceinline__ unsigned rotl32(unsigned v, int c) { return __funnels
   a += b; d ^= a; d = rotl32(d, 8);  \
   c += d; b ^= c; b = rotl32(b, 7);
 
-__device__ void chacha12_block(const unsigned* key, unsigned long long counter, unsigned* out /* 16 words, stride 1 */) {
+// 32 ChaCha12 blocks (one per lane) -> ring[0 .. 512); the key sits behind the ring (ring[512 .. 520)).
+// Out of line on purpose: inlined at every draw it made the kernel 190 KB of code, and the chain's loop
+// has to live in the instruction caches (L0 ~6 KB, L1.5 32 KB).
+__device__ __noinline__ void chacha12_refill(unsigned* half, const unsigned* key, unsigned long long first_block, int lane) {
+  const unsigned long long counter = first_block + (unsigned long long)lane;
+  unsigned* out = half + 16 * lane;
   unsigned s0 = 0x61707865u, s1 = 0x3320646eu, s2 = 0x79622d32u, s3 = 0x6b206574u;
   unsigned s4 = key[0], s5 = key[1], s6 = key[2], s7 = key[3], s8 = key[4], s9 = key[5], s10 = key[6], s11 = key[7];
   unsigned s12 = (unsigned)counter, s13 = (unsigned)(counter >> 32), s14 = 0u, s15 = 0u;
   unsigned x0 = s0, x1 = s1, x2 = s2, x3 = s3, x4 = s4, x5 = s5, x6 = s6, x7 = s7, x8 = s8, x9 = s9, x10 = s10,
            x11 = s11, x12 = s12, x13 = s13, x14 = s14, x15 = s15;
-#pragma unroll
+  __syncwarp();
+#pragma unroll 1
   for (int r = 0; r < 6; ++r) {
     MOSAIC_QR(x0, x4, x8, x12) MOSAIC_QR(x1, x5, x9, x13) MOSAIC_QR(x2, x6, x10, x14) MOSAIC_QR(x3, x7, x11, x15)
     MOSAIC_QR(x0, x5, x10, x15) MOSAIC_QR(x1, x6, x11, x12) MOSAIC_QR(x2, x7, x8, x13) MOSAIC_QR(x3, x4, x9, x14)
@@ -50,31 +59,38 @@ __device__ void chacha12_block(const unsigned* key, unsigned long long counter, 
   out[4] = x4 + s4;   out[5] = x5 + s5;   out[6] = x6 + s6;    out[7] = x7 + s7;
   out[8] = x8 + s8;   out[9] = x9 + s9;   out[10] = x10 + s10; out[11] = x11 + s11;
   out[12] = x12 + s12; out[13] = x13 + s13; out[14] = x14 + s14; out[15] = x15 + s15;
+  __syncwarp();
 }
 
+// The word stream of rand 0.8.5 StdRng (BlockRng over ChaCha12): words are consumed strictly in order; a u64 is
+// two consecutive words, low first.  The ring holds two halves of 32 blocks; `pos` / `filled` are stream word
+// indices (mod 2^32), and a half is regenerated only when every word in it lies >= 512 - RNG_SLACK words behind `pos`.
 struct Rng {
-  unsigned key[8];
   unsigned long long next_block;  // counter of the first block of the next refill
-  unsigned* ring;                 // shared memory, RNG_RING_WORDS
-  int pos;                        // next unread word; RNG_RING_WORDS = empty
+  unsigned* ring;                 // shared memory: RNG_RING_WORDS words, then the key (8 words)
+  unsigned pos, filled;
 
-  __device__ void refill(int lane) {
-    __syncwarp();
-    chacha12_block(key, next_block + (unsigned long long)lane, ring + 16 * lane);
-    next_block += 32ull;
-    pos = 0;
-    __syncwarp();
+  __device__ __forceinline__ void ensure(int words, int lane) {  // words <= RNG_HALF_WORDS
+    if ((int)(filled - pos) < words) {
+      chacha12_refill(ring + (filled & (RNG_RING_WORDS - 1)), ring + RNG_RING_WORDS, next_block, lane);
+      next_block += 32ull;
+      filled += RNG_HALF_WORDS;
+    }
   }
-  __device__ unsigned next_u32(int lane) {
-    if (pos >= RNG_RING_WORDS) refill(lane);
-    return ring[pos++];
+  __device__ __forceinline__ unsigned peek(int i) const { return ring[(pos + (unsigned)i) & (RNG_RING_WORDS - 1)]; }
+  // the general (sequential, rejection-aware) draws: only the cold paths use them
+  __device__ __forceinline__ unsigned next_u32(int lane) {
+    ensure(1, lane);
+    const unsigned v = peek(0);
+    pos += 1u;
+    return v;
   }
-  __device__ unsigned long long next_u64(int lane) {  // BlockRng::next_u64: two consecutive words, low first
+  __device__ __forceinline__ unsigned long long next_u64(int lane) {
     const unsigned lo = next_u32(lane);
     const unsigned hi = next_u32(lane);
     return ((unsigned long long)hi << 32) | lo;
   }
-  __device__ unsigned long long gen_range(unsigned long long n, unsigned long long zone, int lane) {
+  __device__ __forceinline__ unsigned long long gen_range_slow(unsigned long long n, unsigned long long zone, int lane) {
     // UniformInt<usize>::sample_single: zone = (n << n.leading_zeros()) - 1, hoisted by the caller
     for (;;) {
       const unsigned long long v = next_u64(lane);
@@ -82,11 +98,10 @@ struct Rng {
       if (lo <= zone) return hi;
     }
   }
-  __device__ float gen_f32(int lane) { return __fmul_rn((float)(next_u32(lane) >> 8), 1.0f / 16777216.0f); }
 };
 
 // deterministic f32 exp: identical operation sequence to the oracle (all IEEE double, unfused)
-__device__ float exp_det(float xf) {
+__device__ __forceinline__ float exp_det(float xf) {
   if (xf != xf) return xf;
   if (xf > 88.8f) return __int_as_float(0x7f800000);
   if (xf < -104.0f) return 0.0f;
@@ -103,6 +118,43 @@ __device__ float exp_det(float xf) {
   const int k = (int)kd;
   const double scale = __longlong_as_double((long long)(k + 1023) << 52);
   return __double2float_rn(__dmul_rn(p, scale));
+}
+
+// ---- cold paths, out of line so that the chain's loop stays contiguous in the instruction cache ----------
+struct SlowPositions {
+  int x1, y1, x2, y2;
+  unsigned pos, filled;
+  unsigned long long next_block;
+};
+// the four position draws when one of them is rejected (UniformInt<usize>::sample_single's loop, optimizer.rs:60-63)
+__device__ __noinline__ SlowPositions positions_slow(unsigned* ring, unsigned pos, unsigned filled,
+                                                     unsigned long long next_block, unsigned long long gw,
+                                                     unsigned long long gh, unsigned long long zone_w,
+                                                     unsigned long long zone_h, int lane) {
+  Rng rng;
+  rng.next_block = next_block;
+  rng.ring = ring;
+  rng.pos = pos;
+  rng.filled = filled;
+  SlowPositions o;
+  o.x1 = (int)rng.gen_range_slow(gw, zone_w, lane);
+  o.y1 = (int)rng.gen_range_slow(gh, zone_h, lane);
+  o.x2 = (int)rng.gen_range_slow(gw, zone_w, lane);
+  o.y2 = (int)rng.gen_range_slow(gh, zone_h, lane);
+  rng.ensure(1, lane);  // the f32 the caller may draw next
+  o.pos = rng.pos;
+  o.filled = rng.filled;
+  o.next_block = rng.next_block;
+  return o;
+}
+// u < exp(-delta / T) with the deterministic exponential (optimizer.rs:82-83)
+__device__ __noinline__ bool accept_exact(float delta, float temperature, float u) {
+  return u < exp_det(__fdiv_rn(-delta, temperature));
+}
+
+// exact builtins for inputs outside the domain of the branch-free sequences (out of line: cold)
+__device__ __noinline__ float adjacency_term_exact(float l1, float a1, float b1, float l2, float a2, float b2) {
+  return adjacency_term(lab_distance_rn(l1, a1, b1, l2, a2, b2));
 }
 
 // ---- initial cost: all pair terms in parallel, summed later in the reference's order ----------
@@ -179,8 +231,8 @@ __global__ void __launch_bounds__(256, 1)
                   mosaic_opt_result* res) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   unsigned* ring = reinterpret_cast<unsigned*>(smem_raw);
-  float* lab_s = reinterpret_cast<float*>(smem_raw + RNG_RING_WORDS * 4);
-  GridT* grid_s = reinterpret_cast<GridT*>(smem_raw + RNG_RING_WORDS * 4 + (LAB_SMEM ? (size_t)n * 12 : 0));
+  float* lab_s = reinterpret_cast<float*>(smem_raw + RNG_SMEM_WORDS * 4);
+  GridT* grid_s = reinterpret_cast<GridT*>(smem_raw + RNG_SMEM_WORDS * 4 + (LAB_SMEM ? (size_t)n * 12 : 0));
   const int tid = threadIdx.x, lane = tid & 31;
   const int cells = gw * gh;
   if (GRID_SMEM)
@@ -203,17 +255,29 @@ __global__ void __launch_bounds__(256, 1)
   mem.n = n;
 
   // ---- calculate_total_cost (adjacency.rs:91-130): raster order, right then down, sequential f32 adds ----
+  // The chain is one FADD per term (4 cycles).  Each lane fetches four consecutive terms (LDG.128, two batches
+  // of 128 terms in flight to cover the L2 latency); they are handed to the chain in order by shuffles.
   float current = 0.0f;
   {
     const long long pairs = 2ll * cells;
-    float nxt = lane < pairs ? __ldg(terms + lane) : 0.0f;
-    for (long long base = 0; base < pairs; base += 32) {
-      const float term = nxt;
-      const long long s = base + 32 + lane;
-      nxt = s < pairs ? __ldg(terms + s) : 0.0f;
+    const long long nvec = pairs >> 2;  // `terms` is 16-byte aligned (cudaMalloc)
+    const float4* t4 = reinterpret_cast<const float4*>(terms);
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);  // absent terms are +0.0: x + 0.0 == x exactly
+    float4 n0 = lane < nvec ? __ldg(t4 + lane) : zero4;
+    float4 n1 = 32 + lane < nvec ? __ldg(t4 + 32 + lane) : zero4;
+    for (long long base = 0; base < nvec; base += 32) {
+      const float4 cur = n0;
+      n0 = n1;
+      n1 = base + 64 + lane < nvec ? __ldg(t4 + base + 64 + lane) : zero4;
 #pragma unroll
-      for (int l = 0; l < 32; ++l) current = __fadd_rn(current, __shfl_sync(0xffffffffu, term, l));
+      for (int l = 0; l < 32; ++l) {
+        current = __fadd_rn(current, __shfl_sync(0xffffffffu, cur.x, l));
+        current = __fadd_rn(current, __shfl_sync(0xffffffffu, cur.y, l));
+        current = __fadd_rn(current, __shfl_sync(0xffffffffu, cur.z, l));
+        current = __fadd_rn(current, __shfl_sync(0xffffffffu, cur.w, l));
+      }
     }
+    for (long long s = nvec << 2; s < pairs; ++s) current = __fadd_rn(current, __ldg(terms + s));
   }
   const float initial = current;
   float best = current;
@@ -228,109 +292,117 @@ __global__ void __launch_bounds__(256, 1)
       state = state * 6364136223846793005ull + 11634580027462260723ull;
       const unsigned xorshifted = (unsigned)(((state >> 18) ^ state) >> 27);
       const unsigned rot = (unsigned)(state >> 59);
-      rng.key[i] = __funnelshift_r(xorshifted, xorshifted, rot);
+      ring[RNG_RING_WORDS + i] = __funnelshift_r(xorshifted, xorshifted, rot);  // (every lane writes the same words)
     }
+    __syncwarp();
     rng.next_block = 0ull;
     rng.ring = ring;
-    rng.pos = RNG_RING_WORDS;
+    rng.pos = 0u;
+    rng.filled = 0u;
   }
-  const unsigned long long zone_w = ((unsigned long long)gw << __clzll((long long)gw)) - 1ull;
-  const unsigned long long zone_h = ((unsigned long long)gh << __clzll((long long)gh)) - 1ull;
+  const unsigned long long ugw = (unsigned long long)gw, ugh = (unsigned long long)gh;
+  const unsigned long long zone_w = (ugw << __clzll((long long)gw)) - 1ull;
+  const unsigned long long zone_h = (ugh << __clzll((long long)gh)) - 1ull;
 
+  // The loop is written for ONE warp on its own: a branch costs it about as much as the arithmetic of a whole
+  // swap delta, so everything that can be a select is a select and the rare cases leave through cold paths.
   for (unsigned long long it = 0; it < iterations; ++it) {
-    const int x1 = (int)rng.gen_range((unsigned long long)gw, zone_w, lane);  // optimizer.rs:60-63: x before y
-    const int y1 = (int)rng.gen_range((unsigned long long)gh, zone_h, lane);
-    const int x2 = (int)rng.gen_range((unsigned long long)gw, zone_w, lane);
-    const int y2 = (int)rng.gen_range((unsigned long long)gh, zone_h, lane);
-    if (x1 == x2 && y1 == y2) continue;              // optimizer.rs:66-68 (no temperature decay)
+    rng.ensure(RNG_SLACK, lane);
+    // optimizer.rs:60-63: x1, y1, x2, y2 — four u64 draws, no rejection in all but ~n/2^64 of the cases.
+    // gen_range(0..n): (hi, lo) = v * n (128-bit), accepted iff lo <= zone, result hi.  n < 2^31, so the product
+    // is two 32x32->64 multiplies.
+    int xy[4];
+    bool no_reject = true;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const unsigned nq = (q & 1) ? (unsigned)gh : (unsigned)gw;
+      const unsigned long long zq = (q & 1) ? zone_h : zone_w;
+      const unsigned long long t0 = (unsigned long long)rng.peek(2 * q) * nq;
+      const unsigned long long t1 = (unsigned long long)rng.peek(2 * q + 1) * nq + (t0 >> 32);
+      const unsigned long long lo = (t1 << 32) | (t0 & 0xFFFFFFFFull);
+      xy[q] = (int)(t1 >> 32);
+      no_reject = no_reject && lo <= zq;
+    }
+    int x1 = xy[0], y1 = xy[1], x2 = xy[2], y2 = xy[3];
+    if (__builtin_expect(!no_reject, 0)) {
+      const SlowPositions sp = positions_slow(ring, rng.pos, rng.filled, rng.next_block, ugw, ugh, zone_w, zone_h, lane);
+      x1 = sp.x1, y1 = sp.y1, x2 = sp.x2, y2 = sp.y2;
+      rng.pos = sp.pos;
+      rng.filled = sp.filled;
+      rng.next_block = sp.next_block;
+    } else {
+      rng.pos += 8u;
+    }
     const int i1 = y1 * gw + x1, i2 = y2 * gw + x2;
     const int p1 = mem.get(i1), p2 = mem.get(i2);
-    if (p1 < 0 || p2 < 0) continue;                  // optimizer.rs:71-73
+    // lanes 0-3: neighbours of pos1 (Up, Down, Left, Right); lanes 4-7: neighbours of pos2
+    const int side = (lane >> 2) & 1, dir = lane & 3;
+    const int cx = side ? x2 : x1, cy = side ? y2 : y1;
+    const int ox = side ? x1 : x2, oy = side ? y1 : y2;  // the other swap position (skipped)
+    const int nx = cx + (dir == 3) - (dir == 2), ny = cy + (dir == 1) - (dir == 0);
+    const bool inside = lane < 8 && nx >= 0 && nx < gw && ny >= 0 && ny < gh && !(nx == ox && ny == oy);
+    const int nb = mem.get(inside ? ny * gw + nx : i1);  // (a valid address either way; ignored when !inside)
+    // optimizer.rs:66-68 (same position: no temperature decay) and 71-73 (an empty cell)
+    if (__builtin_expect((x1 == x2 && y1 == y2) || p1 < 0 || p2 < 0, 0)) continue;
 
-    float delta = 0.0f;
-    if (p1 != p2) {                                  // adjacency.rs:156-158
-      // lanes 0-3: neighbours of pos1 (Up, Down, Left, Right); lanes 4-7: neighbours of pos2
-      const int side = (lane >> 2) & 1, dir = lane & 3;
-      const int cx = side ? x2 : x1, cy = side ? y2 : y1;
-      const int ox = side ? x1 : x2, oy = side ? y1 : y2;  // the other swap position (skipped)
-      const int nx = cx + (dir == 3) - (dir == 2), ny = cy + (dir == 1) - (dir == 0);
-      bool present = lane < 8 && nx >= 0 && nx < gw && ny >= 0 && ny < gh && !(nx == ox && ny == oy);
-      int nb = -1;
-      if (present) {
-        nb = mem.get(ny * gw + nx);
-        present = nb >= 0;
-      }
-      float l1, a1, b1, l2, a2, b2, ln = 0.f, an = 0.f, bn = 0.f;
-      mem.lab(p1, l1, a1, b1);
-      mem.lab(p2, l2, a2, b2);
-      if (nb >= 0) mem.lab(nb, ln, an, bn);
-      const float ml = side ? l2 : l1, ma = side ? a2 : a1, mb = side ? b2 : b1;  // material now at this position
-      const float ol = side ? l1 : l2, oa = side ? a1 : a2, ob = side ? b1 : b2;  // material after the swap
-      bool oor = false;
-      float t_old = adjacency_term_fast(ml, ma, mb, ln, an, bn, oor);
-      float t_new = adjacency_term_fast(ol, oa, ob, ln, an, bn, oor);
-      if (__any_sync(0xffffffffu, oor && present)) {  // outside the fast-math domain: exact builtins
-        t_old = adjacency_term(lab_distance_rn(ml, ma, mb, ln, an, bn));
-        t_new = adjacency_term(lab_distance_rn(ol, oa, ob, ln, an, bn));
-      }
-      // same material on both sides: get_similarity returns 0.0 -> term 1.0; sqrt(0) gives the same
-      t_old = present ? t_old : 0.0f;  // absent neighbours contribute +0.0 (exact identity in the sums below)
-      t_new = present ? t_new : 0.0f;
-      float old_cost = 0.0f, new_cost = 0.0f;
+    const bool present = inside && nb >= 0;
+    float l1, a1, b1, l2, a2, b2, ln, an, bn;
+    mem.lab(p1, l1, a1, b1);
+    mem.lab(p2, l2, a2, b2);
+    mem.lab(present ? nb : p1, ln, an, bn);
+    const float ml = side ? l2 : l1, ma = side ? a2 : a1, mb = side ? b2 : b1;  // material now at this position
+    const float ol = side ? l1 : l2, oa = side ? a1 : a2, ob = side ? b1 : b2;  // material after the swap
+    bool oor = false, oor_m = false;
+    float t_old = adjacency_term_fast(ml, ma, mb, ln, an, bn, oor);
+    float t_new = adjacency_term_fast(ol, oa, ob, ln, an, bn, oor);
+    float mutual = adjacency_term_fast(l1, a1, b1, l2, a2, b2, oor_m);  // warp-uniform
+    const bool adjacent12 = (x1 == x2 && (y1 - y2 == 1 || y2 - y1 == 1)) || (y1 == y2 && (x1 - x2 == 1 || x2 - x1 == 1));
+    if (__builtin_expect(__any_sync(0xffffffffu, (oor && present) || (oor_m && adjacent12)), 0)) {
+      // outside the domain of the branch-free sequences: the exact builtins
+      t_old = adjacency_term_exact(ml, ma, mb, ln, an, bn);
+      t_new = adjacency_term_exact(ol, oa, ob, ln, an, bn);
+      mutual = adjacency_term_exact(l1, a1, b1, l2, a2, b2);
+    }
+    // same material on both sides: get_similarity returns 0.0 -> term 1.0; sqrt(0) gives the same
+    t_old = present ? t_old : 0.0f;  // absent neighbours contribute +0.0 (exact identity in the sums below)
+    t_new = present ? t_new : 0.0f;
+    float old_cost = 0.0f, new_cost = 0.0f;
 #pragma unroll
-      for (int l = 0; l < 8; ++l) {  // reference order: pos1 U,D,L,R then pos2 U,D,L,R (adjacency.rs:165-200)
-        old_cost = __fadd_rn(old_cost, __shfl_sync(0xffffffffu, t_old, l));
-        new_cost = __fadd_rn(new_cost, __shfl_sync(0xffffffffu, t_new, l));
-      }
-      bool oor_m = false;  // warp-uniform
-      const float mutual = adjacency_term_fast(l1, a1, b1, l2, a2, b2, oor_m);
-      const bool adjacent12 = (x1 == x2 && (y1 - y2 == 1 || y2 - y1 == 1)) || (y1 == y2 && (x1 - x2 == 1 || x2 - x1 == 1));
-      if (adjacent12) {                              // adjacency.rs:203-211
-        float cost = mutual;
-        if (oor_m) cost = adjacency_term(lab_distance_rn(l1, a1, b1, l2, a2, b2));
-        old_cost = __fadd_rn(old_cost, cost);
-        new_cost = __fadd_rn(new_cost, cost);
-      }
-      delta = __fsub_rn(new_cost, old_cost);
+    for (int l = 0; l < 8; ++l) {  // reference order: pos1 U,D,L,R then pos2 U,D,L,R (adjacency.rs:165-200)
+      old_cost = __fadd_rn(old_cost, __shfl_sync(0xffffffffu, t_old, l));
+      new_cost = __fadd_rn(new_cost, __shfl_sync(0xffffffffu, t_new, l));
     }
+    mutual = adjacent12 ? mutual : 0.0f;       // adjacency.rs:203-211 (x + 0.0 == x: the sums are >= +0.0)
+    old_cost = __fadd_rn(old_cost, mutual);
+    new_cost = __fadd_rn(new_cost, mutual);
+    const float delta = p1 != p2 ? __fsub_rn(new_cost, old_cost) : 0.0f;  // adjacency.rs:156-158
 
-    bool accept;
-    if (delta < 0.0f) {
-      accept = true;
-    } else {
-      const float u = rng.gen_f32(lane);  // optimizer.rs:83 (drawn only when delta >= 0)
-      // accept <=> u < exp(-delta / T).  1 - q <= exp(-q) <= 1 / (1 + q) (q >= 0) decide almost every draw
-      // without the division and the exponential; the margins (2^-18) dwarf every rounding error involved.
-      float rT;
-      asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rT) : "f"(temperature));
-      const float q = delta * rT;
-      const float lo = 1.0f - q * 1.000004f - 3.8146973e-06f;
-      float hi;
-      asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(hi) : "f"(1.0f + q * 0.999996f));
-      hi += 3.8146973e-06f;
-      const bool bounds_ok = q >= 0.0f;  // the bounds hold for q >= 0 (T > 0); NaN / negative -> exact path
-      if (bounds_ok && u < lo) {
-        accept = true;
-      } else if (bounds_ok && u > hi) {
-        accept = false;
-      } else {
-        const float probability = exp_det(__fdiv_rn(-delta, temperature));  // optimizer.rs:82
-        accept = u < probability;
-      }
+    // accept <=> delta < 0 || u < exp(-delta / T), u drawn only when delta >= 0 (optimizer.rs:80-84).
+    // 1 - q <= exp(-q) <= 1 / (1 + q) (q >= 0) decide almost every draw without the division and the
+    // exponential; the margins (2^-18) dwarf every rounding error involved.
+    const bool downhill = delta < 0.0f;
+    const float u = __fmul_rn((float)(rng.peek(0) >> 8), 1.0f / 16777216.0f);
+    rng.pos += downhill ? 0u : 1u;
+    float rT, hi;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rT) : "f"(temperature));
+    const float q = delta * rT;
+    const float lo = 1.0f - q * 1.000004f - 3.8146973e-06f;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(hi) : "f"(1.0f + q * 0.999996f));
+    hi += 3.8146973e-06f;
+    const bool bounds_ok = q >= 0.0f;  // the bounds hold for q >= 0 (T > 0); NaN / negative -> exact path
+    bool accept = downhill || (bounds_ok && u < lo);
+    if (__builtin_expect(!accept && !(bounds_ok && u > hi), 0)) {
+      accept = accept_exact(delta, temperature, u);
     }
-    if (accept) {
-      if (lane == 0) {
-        mem.set(i1, p2);
-        mem.set(i2, p1);
-      }
-      __syncwarp();
-      current = __fadd_rn(current, delta);
-      accepted += 1;
-      if (current < best) {
-        best = current;
-        improved += 1;
-      }
-    }
+    // (every lane stores the same values: no branch, no divergence)
+    mem.set(i1, accept ? p2 : p1);
+    mem.set(i2, accept ? p1 : p2);
+    __syncwarp();
+    current = accept ? __fadd_rn(current, delta) : current;
+    accepted += accept ? 1ull : 0ull;
+    const bool better = accept && current < best;
+    best = better ? current : best;
+    improved += better ? 1ull : 0ull;
     temperature = __fmul_rn(temperature, decay);     // optimizer.rs:102
   }
 
@@ -362,7 +434,7 @@ static int launch_anneal_variant(mosaic_ctx* ctx, size_t smem, uint64_t iteratio
 int launch_anneal(mosaic_ctx* ctx, uint64_t iterations, float t0, float decay, uint64_t seed) {
   const size_t cells = (size_t)ctx->gw * ctx->gh;
   const size_t n = (size_t)ctx->n;
-  const size_t ring_bytes = RNG_RING_WORDS * 4;
+  const size_t ring_bytes = RNG_SMEM_WORDS * 4;
   const size_t limit = 220 * 1024;
   MOSAIC_TRY(ensure(ctx, &ctx->d_terms, &ctx->terms_cap, 2 * cells));
   StageTimer t(ctx, MOSAIC_STAGE_ANNEAL);
