@@ -26,6 +26,7 @@ constexpr int TK_Q = 2;
 constexpr int TK_CHUNK = 1024;
 constexpr int TK_SLOTS = 128;
 constexpr int TK_FLUSH = 96;  // merge when more than this many keys are buffered (<= 128 - 32)
+constexpr int TK_ROUNDS = 4;  // consecutive cell groups per warp: the second one starts from the first one's answer
 
 struct __align__(16) QueryState {
   unsigned long long topk[TK_SLOTS];
@@ -92,14 +93,14 @@ __device__ __forceinline__ void merge_buffer(QueryState& st, int& cnt, unsigned&
 #pragma unroll
   for (int r = 0; r < 4; ++r) st.topk[lane * 4 + r] = v[r];
   __syncwarp();
-  tau = (unsigned)(st.topk[k - 1] >> 32);  // 0xFFFFFFFF until k keys have been seen
+  tau = min(tau, (unsigned)(st.topk[k - 1] >> 32));  // (the list holds ~0 until k keys have been seen)
   cnt = 0;
 }
 
-__global__ void __launch_bounds__(TK_WARPS * 32) nn_topk_kernel(const float* __restrict__ soa, int n, int n_pad,
-                                                                const float* __restrict__ cell_lab, int cell_begin,
-                                                                int cell_end, int k, uint32_t* __restrict__ out_idx,
-                                                                float* __restrict__ out_d2) {
+__global__ void __launch_bounds__(TK_WARPS * 32) nn_topk_kernel(const float* __restrict__ soa, const float4* __restrict__ lab4,
+                                                                int n, int n_pad, const float* __restrict__ cell_lab,
+                                                                int cell_begin, int cell_end, int k,
+                                                                uint32_t* __restrict__ out_idx, float* __restrict__ out_d2) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* mats = reinterpret_cast<float*>(smem_raw);  // [2][3][TK_CHUNK]
   QueryState* states = reinterpret_cast<QueryState*>(smem_raw + 2 * 3 * TK_CHUNK * sizeof(float));
@@ -109,9 +110,10 @@ __global__ void __launch_bounds__(TK_WARPS * 32) nn_topk_kernel(const float* __r
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nchunks = (n + TK_CHUNK - 1) / TK_CHUNK;
+  const int total_chunks = nchunks * TK_ROUNDS;  // the materials are streamed once per round
 
-  auto issue = [&](int c) {
-    const int s = c & 1;
+  auto issue = [&](int g) {
+    const int s = g & 1, c = g % nchunks;
     const int cnt = min(TK_CHUNK, n_pad - c * TK_CHUNK);  // n_pad is a multiple of 4 floats -> 16-byte sizes
     const unsigned bytes = (unsigned)cnt * sizeof(float);
     mbar_expect_tx(&bars[s], 3 * bytes);
@@ -129,76 +131,106 @@ __global__ void __launch_bounds__(TK_WARPS * 32) nn_topk_kernel(const float* __r
   __syncthreads();
   if (tid == 0) {
     issue(0);
-    if (nchunks > 1) issue(1);
+    if (total_chunks > 1) issue(1);
   }
 
-  // this warp's cells
-  const int first_cell = cell_begin + (blockIdx.x * TK_WARPS + warp) * TK_Q;
-  float ql[TK_Q], qa[TK_Q], qb[TK_Q];
-  int cnt[TK_Q];
-  unsigned tau[TK_Q];
   QueryState* st = states + warp * TK_Q;
-#pragma unroll
-  for (int qi = 0; qi < TK_Q; ++qi) {
-    int cell = min(first_cell + qi, cell_end - 1);
-    ql[qi] = __ldg(cell_lab + 3 * (size_t)cell);
-    qa[qi] = __ldg(cell_lab + 3 * (size_t)cell + 1);
-    qb[qi] = __ldg(cell_lab + 3 * (size_t)cell + 2);
-    cnt[qi] = 0;
-    tau[qi] = 0xFFFFFFFFu;
-#pragma unroll
-    for (int r = 0; r < 4; ++r) st[qi].topk[lane * 4 + r] = ~0ull;
-  }
-  __syncwarp();
-  const bool warp_active = first_cell < cell_end;  // warp-uniform
   const unsigned lt_mask = (1u << lane) - 1u;
-
-  for (int c = 0; c < nchunks; ++c) {
-    const int s = c & 1;
-    mbar_wait(&bars[s], (unsigned)((c >> 1) & 1));
-    if (warp_active) {
-      const float* sl = mats + (s * 3 + 0) * TK_CHUNK;
-      const float* sa = mats + (s * 3 + 1) * TK_CHUNK;
-      const float* sb = mats + (s * 3 + 2) * TK_CHUNK;
-      const int count = min(TK_CHUNK, n - c * TK_CHUNK);
-      const unsigned base_idx = (unsigned)(c * TK_CHUNK);
-      for (int j0 = 0; j0 < count; j0 += 32) {
-        const int j = j0 + lane;
-        const bool in_range = j < count;
-        const float ml = sl[j], ma = sa[j], mb = sb[j];
+  int g = 0;  // running chunk number across the rounds
+  for (int round = 0; round < TK_ROUNDS; ++round) {
+    // this warp's cells of this round: TK_ROUNDS * TK_Q consecutive raster cells per warp
+    const int first_cell = cell_begin + ((blockIdx.x * TK_WARPS + warp) * TK_ROUNDS + round) * TK_Q;
+    const bool warp_active = first_cell < cell_end;  // warp-uniform
+    float ql[TK_Q], qa[TK_Q], qb[TK_Q];
+    int cnt[TK_Q];
+    unsigned tau[TK_Q];
+#pragma unroll
+    for (int qi = 0; qi < TK_Q; ++qi) {
+      const int cell = min(first_cell + qi, cell_end - 1);
+      ql[qi] = __ldg(cell_lab + 3 * (size_t)cell);
+      qa[qi] = __ldg(cell_lab + 3 * (size_t)cell + 1);
+      qb[qi] = __ldg(cell_lab + 3 * (size_t)cell + 2);
+      cnt[qi] = 0;
+      tau[qi] = 0xFFFFFFFFu;
+    }
+    if (round > 0 && warp_active) {
+      // Seed the threshold from the answer of the previous cell (raster neighbour, almost the same colour): its
+      // k materials are k materials whose distance to THIS cell is <= the largest of them, so that value bounds
+      // this cell's k-th smallest distance from above — same arithmetic as the scan, hence an exact bound.
+      float far_[TK_Q];
+#pragma unroll
+      for (int qi = 0; qi < TK_Q; ++qi) far_[qi] = 0.0f;
+      for (int e = lane; e < k; e += 32) {
+        const float4 m = __ldg(&lab4[(uint32_t)st[TK_Q - 1].topk[e]]);
 #pragma unroll
         for (int qi = 0; qi < TK_Q; ++qi) {
-          const float dl = __fsub_rn(ql[qi], ml), da = __fsub_rn(qa[qi], ma), db = __fsub_rn(qb[qi], mb);
-          const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dl, dl), __fmul_rn(da, da)), __fmul_rn(db, db));
-          const unsigned bits = __float_as_uint(d2);
-          const bool pass = in_range && bits <= tau[qi];
-          const unsigned mask = __ballot_sync(0xffffffffu, pass);
-          if (mask) {
-            if (pass)
-              st[qi].buf[cnt[qi] + __popc(mask & lt_mask)] = ((unsigned long long)bits << 32) | (base_idx + j);
-            cnt[qi] += __popc(mask);
-            if (cnt[qi] > TK_FLUSH) merge_buffer(st[qi], cnt[qi], tau[qi], k, lane);
+          const float dl = __fsub_rn(ql[qi], m.x), da = __fsub_rn(qa[qi], m.y), db = __fsub_rn(qb[qi], m.z);
+          far_[qi] = fmaxf(far_[qi], __fadd_rn(__fadd_rn(__fmul_rn(dl, dl), __fmul_rn(da, da)), __fmul_rn(db, db)));
+        }
+      }
+#pragma unroll
+      for (int qi = 0; qi < TK_Q; ++qi) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) far_[qi] = fmaxf(far_[qi], __shfl_xor_sync(0xffffffffu, far_[qi], o));
+        tau[qi] = __float_as_uint(far_[qi]);  // d2 >= 0: the bit patterns order like the values
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int qi = 0; qi < TK_Q; ++qi) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) st[qi].topk[lane * 4 + r] = ~0ull;
+    }
+    __syncwarp();
+
+    for (int c = 0; c < nchunks; ++c, ++g) {
+      const int s = g & 1;
+      mbar_wait(&bars[s], (unsigned)((g >> 1) & 1));
+      if (warp_active) {
+        const float* sl = mats + (s * 3 + 0) * TK_CHUNK;
+        const float* sa = mats + (s * 3 + 1) * TK_CHUNK;
+        const float* sb = mats + (s * 3 + 2) * TK_CHUNK;
+        const int count = min(TK_CHUNK, n - c * TK_CHUNK);
+        const unsigned base_idx = (unsigned)(c * TK_CHUNK);
+        for (int j0 = 0; j0 < count; j0 += 32) {
+          const int j = j0 + lane;
+          const bool in_range = j < count;
+          const float ml = sl[j], ma = sa[j], mb = sb[j];
+#pragma unroll
+          for (int qi = 0; qi < TK_Q; ++qi) {
+            const float dl = __fsub_rn(ql[qi], ml), da = __fsub_rn(qa[qi], ma), db = __fsub_rn(qb[qi], mb);
+            const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dl, dl), __fmul_rn(da, da)), __fmul_rn(db, db));
+            const unsigned bits = __float_as_uint(d2);
+            const bool pass = in_range && bits <= tau[qi];
+            const unsigned mask = __ballot_sync(0xffffffffu, pass);
+            if (mask) {
+              if (pass)
+                st[qi].buf[cnt[qi] + __popc(mask & lt_mask)] = ((unsigned long long)bits << 32) | (base_idx + j);
+              cnt[qi] += __popc(mask);
+              if (cnt[qi] > TK_FLUSH) merge_buffer(st[qi], cnt[qi], tau[qi], k, lane);
+            }
+          }
+        }
+      }
+      __syncthreads();  // every warp is done with stage s
+      if (tid == 0 && g + 2 < total_chunks) issue(g + 2);
+    }
+
+    if (warp_active) {
+#pragma unroll
+      for (int qi = 0; qi < TK_Q; ++qi) {
+        if (cnt[qi] > 0) merge_buffer(st[qi], cnt[qi], tau[qi], k, lane);
+        const int cell = first_cell + qi;
+        if (cell < cell_end) {
+          for (int e = lane; e < k; e += 32) {
+            unsigned long long key = st[qi].topk[e];
+            out_idx[(size_t)cell * k + e] = (uint32_t)key;
+            out_d2[(size_t)cell * k + e] = __uint_as_float((unsigned)(key >> 32));
           }
         }
       }
     }
-    __syncthreads();  // every warp is done with stage s
-    if (tid == 0 && c + 2 < nchunks) issue(c + 2);
-  }
-
-  if (warp_active) {
-#pragma unroll
-    for (int qi = 0; qi < TK_Q; ++qi) {
-      if (cnt[qi] > 0) merge_buffer(st[qi], cnt[qi], tau[qi], k, lane);
-      const int cell = first_cell + qi;
-      if (cell < cell_end) {
-        for (int e = lane; e < k; e += 32) {
-          unsigned long long key = st[qi].topk[e];
-          out_idx[(size_t)cell * k + e] = (uint32_t)key;
-          out_d2[(size_t)cell * k + e] = __uint_as_float((unsigned)(key >> 32));
-        }
-      }
-    }
+    __syncwarp();
   }
 }
 
@@ -215,11 +247,11 @@ int launch_topk_range(mosaic_ctx* ctx, int k, int cell_begin, int cell_end) {
     MOSAIC_CUDA(ctx, cudaFuncSetAttribute(nn_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTopkSmem));
     if (ctx->device < 64) attr_set[ctx->device] = true;
   }
-  const int per_cta = TK_WARPS * TK_Q;
+  const int per_cta = TK_WARPS * TK_Q * TK_ROUNDS;
   const int blocks = (cells + per_cta - 1) / per_cta;
   {
     StageTimer t(ctx, MOSAIC_STAGE_TOPK);
-    nn_topk_kernel<<<blocks, TK_WARPS * 32, kTopkSmem, ctx->stream>>>(ctx->d_mat_soa, ctx->n, ctx->n_pad,
+    nn_topk_kernel<<<blocks, TK_WARPS * 32, kTopkSmem, ctx->stream>>>(ctx->d_mat_soa, ctx->d_mat_lab4, ctx->n, ctx->n_pad,
                                                                       ctx->d_cell_lab, cell_begin, cell_end, k,
                                                                       ctx->d_cand_idx, ctx->d_cand_d2);
     ctx->launches++;
