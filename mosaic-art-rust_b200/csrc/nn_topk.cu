@@ -14,7 +14,11 @@
 // FMA contraction would change the bits) + compare + vote.  Selection: a 64-bit key
 // (d2 bits << 32 | index) is appended to a per-cell shared-memory buffer when d2 <= tau (the current
 // K-th smallest d2); when the buffer holds > 96 keys the warp bitonic-sorts it in registers and
-// merges it with the sorted top list (128 slots), tightening tau.
+// merges it with the sorted top list (128 slots), tightening tau.  A warp handles TK_ROUNDS consecutive groups
+// of raster cells; from the second group on, tau starts at the largest distance from the new cell to the k
+// materials of the previous cell's answer (k materials within that distance exist, so it bounds the k-th
+// smallest from above): raster neighbours have almost the same colour, which removes most of the k*ln(n/k)
+// early insertions and their sorts.
 #include "common.cuh"
 
 namespace mosaic {
