@@ -21,20 +21,27 @@ __constant__ float c_srgb_lin[256];
 
 constexpr int kLutRep = 8;
 
+#ifndef MOSAIC_LABF_VARIANT
+#define MOSAIC_LABF_VARIANT 2
+#endif
 __device__ __forceinline__ float lab_f(float t) {
   // palette lab.rs: epsilon = (6/29)^3, kappa = 841/108, delta = 4/29
   const float eps = 0.008856452f, kappa = 7.787037f, delta = 0.13793103f;
-  float lg, y;
+  float lg, z;
   asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(t));
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(lg * 0.33333334f));  // MUFU seed, ~2^-21 relative
-  // one Newton step on y^3 = t:  y += (t - y^3) / (3 y^2)
-  float y2 = y * y;
-  float e = fmaf(-y2, y, t);
-  float r;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(y2 * 3.0f));
-  y = fmaf(e, r, y);
-  float lin = fmaf(kappa, t, delta);
-  return t > eps ? y : lin;
+#if MOSAIC_LABF_VARIANT == 2
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(z) : "f"(lg * 0.33333334f));  // MUFU only, ~2^-21 relative
+  const float y = z;
+#else
+  // z ~ t^(-1/3) from two MUFUs (~2^-21 relative), one division-free Newton step on z^-3 = t, then cbrt = t z^2
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(z) : "f"(lg * -0.33333334f));
+  const float z2 = z * z;
+  const float e = fmaf(-(t * z2), z, 1.0f);
+  z = fmaf(z * e, 0.33333334f, z);
+  const float y = t * z * z;
+#endif
+  const float lin = fmaf(kappa, t, delta);
+  return t > eps ? y : lin;  // (t == 0: the MUFU path produces inf/NaN, which the select discards)
 }
 
 struct LabAcc {
