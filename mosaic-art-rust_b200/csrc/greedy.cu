@@ -496,13 +496,17 @@ __global__ void __launch_bounds__(64, 1)
       bool gok = base + lane < k;
       if (gok) gok = (unsigned)usage[gid[ch]] < max_usage && (int32_t)gid[ch] != left && (int32_t)gid[ch] != up;
       float gpen = 0.0f;
-      if (use_penalty) {  // adjacency.rs:71-87: Up, (Down), Left, (Right)
-        if (up >= 0)
-          gpen = __fadd_rn(gpen, adjacency_term(lab_distance_rn(gl[ch].x, gl[ch].y, gl[ch].z, up_lab.x, up_lab.y, up_lab.z)));
-        if (left >= 0)
-          gpen = __fadd_rn(gpen, adjacency_term(lab_distance_rn(gl[ch].x, gl[ch].y, gl[ch].z, left_lab.x, left_lab.y,
-                                                                left_lab.z)));
-        gpen = __fmul_rn(gpen, weight);
+      if (use_penalty) {  // adjacency.rs:71-87: Up, (Down), Left, (Right); absent terms are +0.0 (x + 0.0 == x)
+        bool oor_u = false, oor_l = false;
+        float t_up = adjacency_term_fast(gl[ch].x, gl[ch].y, gl[ch].z, up_lab.x, up_lab.y, up_lab.z, oor_u);
+        float t_left = adjacency_term_fast(gl[ch].x, gl[ch].y, gl[ch].z, left_lab.x, left_lab.y, left_lab.z, oor_l);
+        if (__any_sync(0xffffffffu, (oor_u && up >= 0) || (oor_l && left >= 0))) {  // outside the fast domain
+          t_up = adjacency_term(lab_distance_rn(gl[ch].x, gl[ch].y, gl[ch].z, up_lab.x, up_lab.y, up_lab.z));
+          t_left = adjacency_term(lab_distance_rn(gl[ch].x, gl[ch].y, gl[ch].z, left_lab.x, left_lab.y, left_lab.z));
+        }
+        t_up = up >= 0 ? t_up : 0.0f;
+        t_left = left >= 0 ? t_left : 0.0f;
+        gpen = __fmul_rn(__fadd_rn(t_up, t_left), weight);
       }
       const unsigned gtb = gok ? __float_as_uint(__fadd_rn(gd2[ch], gpen)) : 0xFFFFFFFFu;
       const unsigned gmn = __reduce_min_sync(0xffffffffu, gtb);
