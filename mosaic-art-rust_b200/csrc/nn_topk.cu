@@ -94,6 +94,7 @@ __device__ __forceinline__ void merge_buffer(QueryState& st, int& cnt, unsigned&
     v[r] = v[r] < t ? v[r] : t;
   }
   bitonic128<128>(v, lane);
+  __syncwarp();  // every lane has read its (mirrored) slots of the old list before anybody overwrites them
 #pragma unroll
   for (int r = 0; r < 4; ++r) st.topk[lane * 4 + r] = v[r];
   __syncwarp();
