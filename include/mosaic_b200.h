@@ -151,6 +151,26 @@ typedef struct {
 int mosaic_generate(mosaic_ctx* ctx, const mosaic_params* params, int32_t* placed_out,
                     uint8_t* out_rgb, mosaic_report* report);
 
+/* ---- similarity-database file ------------------------------------------ */
+/* The JSON file of SimilarityDatabase::save_to_file / load_from_file (similarity.rs:31-42, 112-123):
+ * {"path_to_index": {path: idx}, "index_to_path": {"idx": path}, "lab_colors": [{"l","a","b"}],
+ *  "similarities": [packed upper triangle]} in serde_json's pretty layout, f32 in shortest round-trip form.
+ * Host-only: no CUDA device is needed for these calls (except mosaic_simdb_save_ctx). */
+typedef struct mosaic_simdb mosaic_simdb;
+/* paths[i] = path of material i (UTF-8), lab = n*3, sim = n(n-1)/2 (NULL allowed when n < 2). */
+int mosaic_simdb_save_json(const char* file, const char* const* paths, int n, const float* lab, const float* sim);
+/* Lab means + freshly computed packed matrix of a context -> file (main.rs:122-131). */
+int mosaic_simdb_save_ctx(mosaic_ctx* ctx, const char* file, const char* const* paths);
+int mosaic_simdb_load_json(const char* file, mosaic_simdb** out); /* SimilarityDatabase::load_from_file */
+void mosaic_simdb_free(mosaic_simdb* db);
+/* rows of lab_colors, entries of similarities, entries of path_to_index (they differ in GUI-touched files) */
+int mosaic_simdb_info(const mosaic_simdb* db, int* n_rows, uint64_t* n_similarities, int* n_paths);
+const char* mosaic_simdb_path(const mosaic_simdb* db, int index);       /* index_to_path; "" if absent */
+int64_t mosaic_simdb_index_of(const mosaic_simdb* db, const char* path); /* path_to_index; -1 if absent */
+int mosaic_simdb_copy(const mosaic_simdb* db, float* lab_out, float* sim_out); /* either may be NULL */
+/* SimilarityDatabase::get_similarity (similarity.rs:85-103); MOSAIC_ERR_STATE where the reference returns None */
+int mosaic_simdb_get_similarity(const mosaic_simdb* db, const char* path1, const char* path2, float* out);
+
 /* ---- self test ------------------------------------------------------------------------------ */
 /* Checks the branch-free IEEE sqrt / reciprocal sequences used on the serial chains against the
  * correctly rounded builtins over all 2^32 float bit patterns.  mismatches[0] = sqrt, [1] = rcp. */

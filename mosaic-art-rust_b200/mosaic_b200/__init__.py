@@ -94,6 +94,15 @@ def load_library():
         "mosaic_device_similarity": ([vp], vp),
         "mosaic_shard": ([vp] + [C.POINTER(C.c_int)] * 4 + [u64p, u64p], C.c_int),
         "mosaic_shard_plan": ([C.c_int] * 4 + [C.POINTER(C.c_int)] * 4 + [u64p, u64p], C.c_int),
+        "mosaic_simdb_save_json": ([C.c_char_p, C.POINTER(C.c_char_p), C.c_int, f32p, f32p], C.c_int),
+        "mosaic_simdb_save_ctx": ([vp, C.c_char_p, C.POINTER(C.c_char_p)], C.c_int),
+        "mosaic_simdb_load_json": ([C.c_char_p, C.POINTER(vp)], C.c_int),
+        "mosaic_simdb_free": ([vp], None),
+        "mosaic_simdb_info": ([vp, C.POINTER(C.c_int), u64p, C.POINTER(C.c_int)], C.c_int),
+        "mosaic_simdb_path": ([vp, C.c_int], C.c_char_p),
+        "mosaic_simdb_index_of": ([vp, C.c_char_p], C.c_int64),
+        "mosaic_simdb_copy": ([vp, f32p, f32p], C.c_int),
+        "mosaic_simdb_get_similarity": ([vp, C.c_char_p, C.c_char_p, f32p], C.c_int),
     }
     for name, (args, res) in sig.items():
         fn = getattr(L, name)  # AttributeError here = the library does not export what the header declares
@@ -113,6 +122,9 @@ EXPORTED_SYMBOLS = (
     "mosaic_debug_chain_profile",
     "mosaic_device_output", "mosaic_device_placement", "mosaic_device_similarity", "mosaic_shard",
     "mosaic_shard_plan",
+    "mosaic_simdb_save_json", "mosaic_simdb_save_ctx", "mosaic_simdb_load_json", "mosaic_simdb_free",
+    "mosaic_simdb_info", "mosaic_simdb_path", "mosaic_simdb_index_of", "mosaic_simdb_copy",
+    "mosaic_simdb_get_similarity",
 )
 
 
@@ -125,6 +137,79 @@ def shard_plan(world, rank, grid_h, n_materials):
     if rc != 0:
         raise MosaicError(rc, "mosaic_shard_plan: invalid arguments")
     return dict(rows=(v[0].value, v[1].value), materials=(v[2].value, v[3].value), tri=(t[0].value, t[1].value))
+
+
+class SimilarityDb:
+    """The reference's similarity-database FILE (SimilarityDatabase, src/similarity.rs:31-138): JSON with
+    path_to_index / index_to_path / lab_colors / similarities.  Host-only, no GPU needed."""
+
+    def __init__(self, handle):
+        self._L = load_library()
+        self._h = handle
+
+    @staticmethod
+    def _paths(paths):
+        arr = (C.c_char_p * len(paths))(*[p.encode("utf-8") for p in paths])
+        return arr
+
+    @classmethod
+    def save(cls, file, paths, lab, sim):
+        """SimilarityDatabase::save_to_file (similarity.rs:112-116)."""
+        L = load_library()
+        lab = np.ascontiguousarray(lab, np.float32).reshape(-1, 3)
+        sim = np.ascontiguousarray(sim, np.float32).ravel()
+        n = len(paths)
+        assert lab.shape[0] == n and sim.shape[0] == (n * (n - 1) // 2 if n > 1 else 0)
+        rc = L.mosaic_simdb_save_json(os.fsencode(file), cls._paths(paths), n,
+                                      lab.ctypes.data_as(C.POINTER(C.c_float)), sim.ctypes.data_as(C.POINTER(C.c_float)))
+        if rc != 0:
+            raise MosaicError(rc, (L.mosaic_last_error(None) or b"").decode())
+
+    @classmethod
+    def load(cls, file):
+        """SimilarityDatabase::load_from_file (similarity.rs:119-123)."""
+        L = load_library()
+        h = C.c_void_p()
+        rc = L.mosaic_simdb_load_json(os.fsencode(file), C.byref(h))
+        if rc != 0:
+            raise MosaicError(rc, (L.mosaic_last_error(None) or b"").decode())
+        return cls(h)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.mosaic_simdb_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def info(self):
+        n, ns, npth = C.c_int(), C.c_uint64(), C.c_int()
+        self._L.mosaic_simdb_info(self._h, C.byref(n), C.byref(ns), C.byref(npth))
+        return dict(rows=n.value, similarities=ns.value, paths=npth.value)
+
+    def path(self, index):
+        p = self._L.mosaic_simdb_path(self._h, index)
+        return None if p is None else p.decode("utf-8")
+
+    def index_of(self, path):
+        return int(self._L.mosaic_simdb_index_of(self._h, path.encode("utf-8")))
+
+    def arrays(self):
+        i = self.info()
+        lab = np.empty((i["rows"], 3), np.float32)
+        sim = np.empty(i["similarities"], np.float32)
+        self._L.mosaic_simdb_copy(self._h, lab.ctypes.data_as(C.POINTER(C.c_float)), sim.ctypes.data_as(C.POINTER(C.c_float)))
+        return lab, sim
+
+    def get_similarity(self, path1, path2):
+        """SimilarityDatabase::get_similarity (similarity.rs:85-103): None where the reference returns None."""
+        out = C.c_float()
+        rc = self._L.mosaic_simdb_get_similarity(self._h, path1.encode("utf-8"), path2.encode("utf-8"), C.byref(out))
+        return out.value if rc == 0 else None
 
 
 def _ptr(a):
@@ -315,6 +400,11 @@ class Context:
         rep = Report()
         self._check(self._L.mosaic_generate(self._h, C.byref(p), _ptr(placed_out), _ptr(image_out), C.byref(rep)))
         return rep
+
+    def save_similarity_db(self, file, paths):
+        """Lab means + freshly built packed matrix -> the reference's JSON file (main.rs:122-131)."""
+        assert len(paths) == self.dims()["n"]
+        self._check(self._L.mosaic_simdb_save_ctx(self._h, os.fsencode(file), SimilarityDb._paths(paths)))
 
     def selftest(self):
         m = (C.c_uint64 * 2)()
