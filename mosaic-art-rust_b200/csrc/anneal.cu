@@ -228,7 +228,9 @@ template <typename GridT, bool GRID_SMEM, bool LAB_SMEM>
 __global__ void __launch_bounds__(256, 1)
     anneal_kernel(const float4* __restrict__ lab4, int n, int32_t* grid_gmem, const float* __restrict__ terms, int gw,
                   int gh, unsigned long long iterations, float t0, float decay, unsigned long long seed,
-                  mosaic_opt_result* res) {
+                  mosaic_opt_result* res, float* __restrict__ deltas /* one slot per iteration, or NULL */) {
+  __shared__ float s_initial;
+  __shared__ volatile int s_initial_ready;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   unsigned* ring = reinterpret_cast<unsigned*>(smem_raw);
   float* lab_s = reinterpret_cast<float*>(smem_raw + RNG_SMEM_WORDS * 4);
@@ -244,21 +246,14 @@ __global__ void __launch_bounds__(256, 1)
       lab_s[n + i] = v.y;
       lab_s[2 * n + i] = v.z;
     }
+  if (tid == 0) s_initial_ready = 0;
   __syncthreads();
-  if (tid >= 32) return;  // the Markov chain is one warp
-
-  AnnealMem<GridT, GRID_SMEM, LAB_SMEM> mem;
-  mem.grid_s = grid_s;
-  mem.grid_g = grid_gmem;
-  mem.lab_s = lab_s;
-  mem.lab_g = lab4;
-  mem.n = n;
 
   // ---- calculate_total_cost (adjacency.rs:91-130): raster order, right then down, sequential f32 adds ----
   // The chain is one FADD per term (4 cycles).  Each lane fetches four consecutive terms (LDG.128, two batches
   // of 128 terms in flight to cover the L2 latency); they are handed to the chain in order by shuffles.
-  float current = 0.0f;
-  {
+  auto total_cost = [&]() -> float {
+    float acc = 0.0f;
     const long long pairs = 2ll * cells;
     const long long nvec = pairs >> 2;  // `terms` is 16-byte aligned (cudaMalloc)
     const float4* t4 = reinterpret_cast<const float4*>(terms);
@@ -271,15 +266,40 @@ __global__ void __launch_bounds__(256, 1)
       n1 = base + 64 + lane < nvec ? __ldg(t4 + base + 64 + lane) : zero4;
 #pragma unroll
       for (int l = 0; l < 32; ++l) {
-        current = __fadd_rn(current, __shfl_sync(0xffffffffu, cur.x, l));
-        current = __fadd_rn(current, __shfl_sync(0xffffffffu, cur.y, l));
-        current = __fadd_rn(current, __shfl_sync(0xffffffffu, cur.z, l));
-        current = __fadd_rn(current, __shfl_sync(0xffffffffu, cur.w, l));
+        acc = __fadd_rn(acc, __shfl_sync(0xffffffffu, cur.x, l));
+        acc = __fadd_rn(acc, __shfl_sync(0xffffffffu, cur.y, l));
+        acc = __fadd_rn(acc, __shfl_sync(0xffffffffu, cur.z, l));
+        acc = __fadd_rn(acc, __shfl_sync(0xffffffffu, cur.w, l));
       }
     }
-    for (long long s = nvec << 2; s < pairs; ++s) current = __fadd_rn(current, __ldg(terms + s));
+    for (long long s = nvec << 2; s < pairs; ++s) acc = __fadd_rn(acc, __ldg(terms + s));
+    return acc;
+  };
+  // The acceptance rule never looks at the running cost (optimizer.rs:80-84), only the bookkeeping does
+  // (optimizer.rs:86-99).  So, given a delta log, the 2*cells-term serial sum runs on warp 1 WHILE warp 0 walks the
+  // Markov chain; warp 0 replays `current += delta` / best / improved afterwards, in the original order.
+  const bool deferred = deltas != nullptr;
+  if (tid >= 32) {
+    if (deferred && tid < 64) {
+      const float v = total_cost();
+      if (lane == 0) {
+        s_initial = v;
+        __threadfence_block();
+        s_initial_ready = 1;
+      }
+    }
+    return;  // the Markov chain is one warp
   }
-  const float initial = current;
+
+  AnnealMem<GridT, GRID_SMEM, LAB_SMEM> mem;
+  mem.grid_s = grid_s;
+  mem.grid_g = grid_gmem;
+  mem.lab_s = lab_s;
+  mem.lab_g = lab4;
+  mem.n = n;
+
+  float current = deferred ? 0.0f : total_cost();
+  float initial = current;
   float best = current;
   unsigned long long improved = 0, accepted = 0;
   float temperature = t0;
@@ -398,17 +418,41 @@ __global__ void __launch_bounds__(256, 1)
     mem.set(i1, accept ? p2 : p1);
     mem.set(i2, accept ? p1 : p2);
     __syncwarp();
-    current = accept ? __fadd_rn(current, delta) : current;
+    if (deferred) {
+      if (accept) deltas[accepted] = delta;  // (every lane: same address, same value)
+    } else {
+      current = accept ? __fadd_rn(current, delta) : current;
+      const bool better = accept && current < best;
+      best = better ? current : best;
+      improved += better ? 1ull : 0ull;
+    }
     accepted += accept ? 1ull : 0ull;
-    const bool better = accept && current < best;
-    best = better ? current : best;
-    improved += better ? 1ull : 0ull;
     temperature = __fmul_rn(temperature, decay);     // optimizer.rs:102
   }
 
   if (GRID_SMEM) {
     __syncwarp();
     for (int i = lane; i < cells; i += 32) grid_gmem[i] = mem.get(i);
+  }
+  if (deferred) {  // optimizer.rs:86-99 replayed over the logged deltas
+    while (s_initial_ready == 0) {
+    }
+    __threadfence_block();
+    initial = s_initial;
+    current = initial;
+    best = initial;
+    __syncwarp();
+    for (unsigned long long base = 0; base < accepted; base += 32) {
+      const float d = base + lane < accepted ? deltas[base + lane] : 0.0f;
+      const int cnt = (int)min(32ull, accepted - base);
+      for (int l = 0; l < cnt; ++l) {
+        current = __fadd_rn(current, __shfl_sync(0xffffffffu, d, l));
+        if (current < best) {
+          best = current;
+          improved += 1ull;
+        }
+      }
+    }
   }
   if (lane == 0) {
     res->initial_cost = initial;
@@ -425,9 +469,15 @@ __global__ void __launch_bounds__(256, 1)
 template <typename GridT, bool GS, bool LS>
 static int launch_anneal_variant(mosaic_ctx* ctx, size_t smem, uint64_t iterations, float t0, float decay, uint64_t seed) {
   MOSAIC_CUDA(ctx, cudaFuncSetAttribute(anneal_kernel<GridT, GS, LS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // delta log: one float per iteration (up to 256 MB); beyond that the bookkeeping stays inside the loop
+  float* deltas = nullptr;
+  if (iterations > 0 && iterations <= (1ull << 26)) {
+    MOSAIC_TRY(ensure(ctx, &ctx->d_deltas, &ctx->deltas_cap, (size_t)iterations));
+    deltas = ctx->d_deltas;
+  }
   anneal_kernel<GridT, GS, LS><<<1, 256, smem, ctx->stream>>>(ctx->d_mat_lab4, ctx->n, ctx->d_placed, ctx->d_terms,
                                                               ctx->gw, ctx->gh, iterations, t0, decay, seed,
-                                                              (mosaic_opt_result*)ctx->d_opt_res);
+                                                              (mosaic_opt_result*)ctx->d_opt_res, deltas);
   return MOSAIC_OK;
 }
 
