@@ -227,7 +227,8 @@ static_assert(sizeof(HRec) == 256 && sizeof(XRec) == 528, "record layout");
 __global__ void __launch_bounds__(256) place_prep_kernel(const uint32_t* __restrict__ cand_idx,
                                                          const float* __restrict__ cand_d2, int k,
                                                          const float4* __restrict__ lab4, int n, int cells, int gw,
-                                                         float weight, HRec* __restrict__ hrec, XRec* __restrict__ xrec) {
+                                                         float weight, HRec* __restrict__ hrec, XRec* __restrict__ xrec,
+                                                         float* __restrict__ glab /* cells x 3 x 128 */) {
   __shared__ float4 nb_s[8][2][kMaxK];  // per warp: (Lab, id) of every candidate of the cell above / to the left
   const int lane = threadIdx.x & 31;
   const int warps = (gridDim.x * blockDim.x) >> 5;
@@ -244,6 +245,20 @@ __global__ void __launch_bounds__(256) place_prep_kernel(const uint32_t* __restr
       lab = __ldg(&lab4[id]);
     }
     const float d32 = k > 32 ? __ldg(cand_d2 + (size_t)c * k + 32) : inf;
+    // Lab of ALL k candidates, gathered once here (in parallel, off the chain) so that the rare cells that need the
+    // candidates behind the first 32 fetch ids, distances and colours in ONE round trip instead of two dependent ones
+    {
+      float* g = glab + (size_t)c * (3 * kKPad);
+      g[lane] = lab.x;
+      g[kKPad + lane] = lab.y;
+      g[2 * kKPad + lane] = lab.z;
+      for (int r = 32 + lane; r < k; r += 32) {
+        const float4 q = __ldg(&lab4[__ldg(cand_idx + (size_t)c * k + r)]);
+        g[r] = q.x;
+        g[kKPad + r] = q.y;
+        g[2 * kKPad + r] = q.z;
+      }
+    }
     // Upper bound of each candidate's penalty.  Whatever the replay decides, the material above / to the left is
     // one of the <= 100 candidates of that cell (main.rs:349-413; the fallback picks among the same list,
     // main.rs:436-470), and it is not this candidate (a candidate equal to a neighbour is rejected,
@@ -307,8 +322,9 @@ __device__ unsigned long long g_chain_prof[16];
 
 template <typename UsageT, bool PROF>
 __global__ void __launch_bounds__(64, 1)
-    greedy_chain_kernel(const HRec* __restrict__ hrec, const XRec* __restrict__ xrec, const uint32_t* __restrict__ cand_idx,
-                        const float* __restrict__ cand_d2, int k, const float4* __restrict__ lab4, int n, int gw, int gh,
+    greedy_chain_kernel(const HRec* __restrict__ hrec, const XRec* __restrict__ xrec, const float* __restrict__ glab,
+                        const uint32_t* __restrict__ cand_idx, const float* __restrict__ cand_d2, int k,
+                        const float4* __restrict__ lab4, int n, int gw, int gh,
                         unsigned max_usage, float weight, int32_t* __restrict__ placed, uint32_t* __restrict__ info,
                         uint32_t fallback_cap) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -468,22 +484,23 @@ __global__ void __launch_bounds__(64, 1)
   // exact multi-chunk resolution + reset fallback: the reference's loop, bit for bit (main.rs:335-475)
   auto resolve_generic = [&](int cell, int x, int32_t left, int32_t up, float4 left_lab) -> int32_t {
     const size_t row = (size_t)cell * k;
-    // all chunks are requested up front: two dependent global round trips in total
+    // all chunks are requested up front, colours from the table the preparation kernel gathered: ONE global round trip
     uint32_t gid[4];
     float gd2[4];
     float4 gl[4];
+    const float* g = glab + (size_t)cell * (3 * kKPad);
 #pragma unroll
     for (int ch = 0; ch < 4; ++ch) {
       const int j = ch * 32 + lane;
       gid[ch] = 0u;
       gd2[ch] = 0.f;
+      gl[ch] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (j < k) {
         gid[ch] = __ldg(cand_idx + row + j);
         gd2[ch] = __ldg(cand_d2 + row + j);
+        gl[ch] = make_float4(__ldg(g + j), __ldg(g + kKPad + j), __ldg(g + 2 * kKPad + j), 0.f);
       }
     }
-#pragma unroll
-    for (int ch = 0; ch < 4; ++ch) gl[ch] = (ch * 32 + lane < k) ? __ldg(&lab4[gid[ch]]) : make_float4(0.f, 0.f, 0.f, 0.f);
     float4 up_lab = make_float4(0.f, 0.f, 0.f, 0.f);
     if (up >= 0) up_lab = row_above_lab(cell, x);
     unsigned best_bits = 0xFFFFFFFFu;
@@ -792,19 +809,21 @@ static int launch_chain_impl(mosaic_ctx* ctx, unsigned cap, float weight, size_t
                                         (int)smem));
   greedy_chain_kernel<UsageT, PROF><<<1, 64, smem, ctx->stream>>>(
       reinterpret_cast<const HRec*>(ctx->d_place_rec), reinterpret_cast<const XRec*>(ctx->d_place_rec + cells * sizeof(HRec)),
-      ctx->d_cand_idx, ctx->d_cand_d2, ctx->k, ctx->d_mat_lab4, ctx->n, ctx->gw, ctx->gh, cap, weight, ctx->d_placed,
+      reinterpret_cast<const float*>(ctx->d_place_rec + cells * (sizeof(HRec) + sizeof(XRec))), ctx->d_cand_idx, ctx->d_cand_d2, ctx->k, ctx->d_mat_lab4, ctx->n, ctx->gw, ctx->gh, cap, weight, ctx->d_placed,
       ctx->d_place_info, mosaic_ctx::kFallbackCap);
   return MOSAIC_OK;
 }
 template <typename UsageT>
 static int launch_chain(mosaic_ctx* ctx, unsigned cap, float weight, size_t smem) {
   const int cells = ctx->gw * ctx->gh;
-  MOSAIC_TRY(ensure(ctx, &ctx->d_place_rec, &ctx->place_rec_cap, (size_t)cells * (sizeof(HRec) + sizeof(XRec))));
+  MOSAIC_TRY(ensure(ctx, &ctx->d_place_rec, &ctx->place_rec_cap,
+                    (size_t)cells * (sizeof(HRec) + sizeof(XRec) + 3 * kKPad * sizeof(float))));
   int blocks = (cells + 7) / 8;
   if (blocks > ctx->sm_count * 8) blocks = ctx->sm_count * 8;
   place_prep_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->d_cand_idx, ctx->d_cand_d2, ctx->k, ctx->d_mat_lab4, ctx->n, cells,
                                                      ctx->gw, weight, reinterpret_cast<HRec*>(ctx->d_place_rec),
-                                                     reinterpret_cast<XRec*>(ctx->d_place_rec + (size_t)cells * sizeof(HRec)));
+                                                     reinterpret_cast<XRec*>(ctx->d_place_rec + (size_t)cells * sizeof(HRec)),
+                                                     reinterpret_cast<float*>(ctx->d_place_rec + (size_t)cells * (sizeof(HRec) + sizeof(XRec))));
   ctx->launches++;
   MOSAIC_CUDA(ctx, cudaGetLastError());
   return ctx->profile_chain ? launch_chain_impl<UsageT, true>(ctx, cap, weight, smem)
