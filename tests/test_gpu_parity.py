@@ -254,7 +254,9 @@ def test_anneal_cold_rejects(ctx):
                                                  (760, 432, 20, 12, 0.3),   # 38x36 tiles (the 24,000-tile shape)
                                                  (760, 432, 20, 12, 0.0),
                                                  (800, 450, 10, 5, 0.5),    # 80x90 tiles: upscaling, 7-tap windows
-                                                 (768, 320, 12, 10, 0.3)])  # 64x32 tiles: horizontal axis skipped
+                                                 (768, 320, 12, 10, 0.3),   # 64x32 tiles: horizontal axis skipped
+                                                 (900, 510, 30, 30, 0.3),   # 30x17 tiles (the giant-mosaic shape): 15/25 taps
+                                                 (640, 640, 40, 32, 0.6)])  # 16x20 tiles: 25/21 taps
 def test_render_within_one_lsb(ctx, w, h, gw, gh, strength):
     n = 64
     mats = synth.materials(n)
