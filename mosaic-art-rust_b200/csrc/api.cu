@@ -295,6 +295,7 @@ int run_render(mosaic_ctx* c, float strength, uint8_t* out_rgb) {
   int bands = out_rgb ? std::min(mosaic_ctx::kBands, rows) : 1;
   if ((size_t)rows * row_bytes < ((size_t)8 << 20)) bands = std::min(bands, 1);  // small images: one copy
   StageTimer t(c, MOSAIC_STAGE_RENDER);
+  MOSAIC_TRY(render_reset_cache(c));
   for (int b = 0; b < std::max(bands, 1); ++b) {
     const int b0 = rb + (int)((long long)rows * b / std::max(bands, 1)), b1 = rb + (int)((long long)rows * (b + 1) / std::max(bands, 1));
     if (b1 <= b0) continue;
@@ -408,7 +409,7 @@ void mosaic_ctx_destroy(mosaic_ctx* c) {
   dist_destroy(c);
   void* bufs[] = {c->d_materials_owned, c->d_mat_lab, c->d_mat_lab4, c->d_mat_soa, c->d_target_owned, c->d_cell_lab,
                   c->d_cell_rgbsum,     c->d_cand_idx, c->d_cand_d2, c->d_placed,  c->d_usage,        c->d_place_info, c->d_place_rec,
-                  c->d_sim,             c->d_sim_counter, c->d_opt_res,  c->d_rng_ring, c->d_terms, c->d_deltas, c->d_out,    c->axis_h.start,   c->axis_h.size,
+                  c->d_sim,             c->d_sim_counter, c->d_opt_res,  c->d_rng_ring, c->d_terms, c->d_deltas, c->d_thumbs, c->d_thumb_sums, c->d_thumb_state, c->d_out,    c->axis_h.start,   c->axis_h.size,
                   c->axis_h.w,          c->axis_v.start, c->axis_v.size, c->axis_v.w};
   for (void* p : bufs)
     if (p) cudaFree(p);
