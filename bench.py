@@ -52,6 +52,18 @@ def workload_config(name):
     return cfg
 
 
+def config_block(cfg, world):
+    """The `config` object of the JSON line — identical for both arms (the driver compares them)."""
+    return {"workload": describe(cfg), "grid": [cfg["grid_w"], cfg["grid_h"]], "materials": cfg["n_materials"],
+            "max_usage": cfg["max_usage"], "adjacency_weight": cfg["adjacency_weight"],
+            "color_strength": cfg["color_strength"], "sa_iterations": cfg["sa_iterations"],
+            "seed": cfg["seed"], "similarity_matrix_built": True,
+            "l2": "inputs (222 MB of RGB8 at C3) are larger than the 126 MB L2; no explicit flush",
+            "parallelism": ("1 GPU" if world == 1 else
+                            f"grid rows / material indices / similarity ranges sharded over {world} GPUs, "
+                            "NCCL allgather of Lab means + candidate lists, greedy + annealing on rank 0")}
+
+
 def describe(cfg):
     return (f"{cfg['name']}: {cfg['grid_w']}x{cfg['grid_h']} grid ({cfg['grid_w'] * cfg['grid_h']} cells) from a synthetic "
             f"{cfg['target_w']}x{cfg['target_h']} target vs {cfg['n_materials']} synthetic 64x64 materials")
@@ -340,14 +352,7 @@ def run_gpu(args, cfg):
             "metric": METRIC, "value": cells / (ms_value * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_value, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": describe(cfg), "grid": [gw, gh], "materials": n,
-                       "max_usage": cfg["max_usage"], "adjacency_weight": cfg["adjacency_weight"],
-                       "color_strength": cfg["color_strength"], "sa_iterations": cfg["sa_iterations"],
-                       "seed": cfg["seed"], "similarity_matrix_built": True,
-                       "l2": "inputs (222 MB of RGB8) are larger than the 126 MB L2; no explicit flush",
-                       "parallelism": ("1 GPU" if world == 1 else
-                                       f"grid rows / material indices / similarity ranges sharded over {world} GPUs, "
-                                       "NCCL allgather of Lab means + candidate lists, greedy + annealing on rank 0")},
+            "config": config_block(cfg, world),
             "e2e": {"value": cells / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e, "wall_ms_per_step": wall_ms,
                     "h2d_bytes_per_step": int(h2d_total), "d2h_bytes_per_step": int(d2h_total)},
             "gpu_launches": int(launches),
@@ -388,7 +393,7 @@ def main():
         line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-                "data": "synthetic", "config": {"workload": describe(cfg)},
+                "data": "synthetic", "config": config_block(cfg, max(args.gpus, 1)),
                 "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
                                  "sample": r["sample"], "stage_ms": r["stage_ms"],
                                  "note": "C++ restatement of the reference CPU path (Rust toolchain unavailable); "

@@ -166,6 +166,96 @@ __global__ void __launch_bounds__(256) lab_mean_cells_kernel(const uint8_t* __re
   }
 }
 
+// TMA-staged variant of the cell kernel.  One warp per cell; the tile is brought into shared memory by 1-D bulk
+// copies — one per tile row, issued in parallel by the lanes (lane r copies the 16-byte-aligned span that covers
+// row r of the crop), all completing on one mbarrier — and the NEXT cell of the warp is already in flight while
+// the current one is reduced (two buffers per warp).  Pixels are then read from shared memory in the crop's
+// row-major order, lane-strided, exactly like the direct kernel, so both produce identical sums.
+__global__ void __launch_bounds__(256) lab_mean_cells_tma_kernel(const uint8_t* __restrict__ img, int img_w, int gw,
+                                                                 int cell_begin, int cell_end, int tile_w, int tile_h,
+                                                                 int row_pitch /* bytes per staged row, multiple of 16 */,
+                                                                 float* __restrict__ lab_out,
+                                                                 unsigned long long* __restrict__ rgbsum_out) {
+  extern __shared__ __align__(128) unsigned char stage_raw[];
+  __shared__ float lut_s[256 * kLutRep];
+  __shared__ unsigned long long bars[8][2];
+  load_lut(lut_s);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float* lut = lut_s + (lane & (kLutRep - 1));
+  const int warps_per_grid = (gridDim.x * blockDim.x) >> 5;
+  const int pixels = tile_w * tile_h;
+  const size_t buf_bytes = (size_t)row_pitch * tile_h;
+  unsigned char* buf0 = stage_raw + (size_t)warp * 2 * buf_bytes;
+  if (lane == 0) {
+    mbar_init(&bars[warp][0], 1);
+    mbar_init(&bars[warp][1], 1);
+    mbar_fence_init();
+  }
+  __syncwarp();
+  const size_t img_row_bytes = (size_t)img_w * 3;
+  auto issue = [&](int cell, int b) {  // stage the crop of `cell` into buffer b
+    const int cx = cell % gw, cy = cell / gw;
+    const size_t first = ((size_t)cy * tile_h) * img_row_bytes + (size_t)cx * tile_w * 3;  // byte offset of the crop
+    unsigned total = 0;  // the barrier must expect every byte BEFORE its single arrival
+    for (int r = lane; r < tile_h; r += 32) {
+      const size_t start = first + (size_t)r * img_row_bytes;
+      total += (unsigned)(((start + (size_t)tile_w * 3 + 15) & ~(size_t)15) - (start & ~(size_t)15));
+    }
+    total = warp_sum_u32(total);
+    if (lane == 0) mbar_expect_tx(&bars[warp][b], total);
+    __syncwarp();
+    for (int r = lane; r < tile_h; r += 32) {
+      const size_t start = first + (size_t)r * img_row_bytes;
+      const size_t a0 = start & ~(size_t)15, a1 = (start + (size_t)tile_w * 3 + 15) & ~(size_t)15;
+      tma_load_1d(buf0 + (size_t)b * buf_bytes + (size_t)r * row_pitch, img + a0, (unsigned)(a1 - a0), &bars[warp][b]);
+    }
+  };
+  int cell = cell_begin + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  int it = 0;
+  if (cell < cell_end) issue(cell, 0);
+  for (; cell < cell_end; cell += warps_per_grid, ++it) {
+    const int b = it & 1;
+    const int next = cell + warps_per_grid;
+    if (next < cell_end) issue(next, b ^ 1);
+    mbar_wait(&bars[warp][b], (unsigned)((it >> 1) & 1));
+    const int cx = cell % gw, cy = cell / gw;
+    const size_t first = ((size_t)cy * tile_h) * img_row_bytes + (size_t)cx * tile_w * 3;
+    const unsigned char* base = buf0 + (size_t)b * buf_bytes;
+    LabAcc acc;
+    int py = lane / tile_w, px = lane - py * tile_w;
+    const int step_y = 32 / tile_w, step_x = 32 - step_y * tile_w;
+    for (int p = lane; p < pixels; p += 32) {
+      const unsigned off = (unsigned)((first + (size_t)py * img_row_bytes) & 15);  // the row's offset inside its aligned span
+      const unsigned char* q = base + (size_t)py * row_pitch + off + 3 * px;
+      const unsigned r8 = q[0], g8 = q[1], b8 = q[2];
+      accumulate_pixel(lut, r8, g8, b8, acc);
+      acc.r += r8;
+      acc.g += g8;
+      acc.b += b8;
+      px += step_x;
+      py += step_y;
+      if (px >= tile_w) {
+        px -= tile_w;
+        py += 1;
+      }
+    }
+    finish(acc, (float)pixels, lab_out + 3 * (size_t)cell);
+    unsigned long long sr = acc.r, sg = acc.g, sb = acc.b;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      sr += __shfl_xor_sync(0xffffffffu, sr, o);
+      sg += __shfl_xor_sync(0xffffffffu, sg, o);
+      sb += __shfl_xor_sync(0xffffffffu, sb, o);
+    }
+    if (lane == 0) {
+      rgbsum_out[3 * (size_t)cell] = sr;
+      rgbsum_out[3 * (size_t)cell + 1] = sg;
+      rgbsum_out[3 * (size_t)cell + 2] = sb;
+    }
+    __syncwarp();  // every lane is done with buffer b before it is refilled two iterations later
+  }
+}
+
 // n*3 packed Lab -> float4 gather table + SoA (l[], a[], b[]; padded with +inf so that padding can
 // never rank among the nearest).
 __global__ void pack_lab_kernel(const float* __restrict__ lab, int n, int n_pad, float4* __restrict__ lab4,
@@ -235,11 +325,27 @@ int launch_cell_lab_range(mosaic_ctx* ctx, int cell_begin, int cell_end) {
   int blocks = (cells + 7) / 8;
   int max_blocks = ctx->sm_count * 8;
   if (blocks > max_blocks) blocks = max_blocks;
+  // TMA-staged path: the aligned spans must stay inside the allocation (owned buffers are cudaMalloc'ed, i.e. padded
+  // to 256 B; a caller-owned image qualifies when its size is a multiple of 16) and two tiles per warp must fit
+  const size_t row_pitch = (((size_t)ctx->tile_w * 3 + 15 + 15) & ~(size_t)15);
+  const size_t stage = 8 * 2 * row_pitch * (size_t)ctx->tile_h;
+  const bool owned = ctx->d_target == ctx->d_target_owned;
+  const bool tma_ok = ((uintptr_t)ctx->d_target % 16 == 0) && (owned || ((size_t)ctx->tw_img * ctx->th_img * 3) % 16 == 0) &&
+                      stage <= 96 * 1024;
   {
     StageTimer t(ctx, MOSAIC_STAGE_CELL_LAB);
-    lab_mean_cells_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->d_target, ctx->tw_img, ctx->gw, cell_begin, cell_end,
-                                                           ctx->tile_w, ctx->tile_h, ctx->d_cell_lab,
-                                                           ctx->d_cell_rgbsum);
+    if (tma_ok) {
+      MOSAIC_CUDA(ctx, cudaFuncSetAttribute(lab_mean_cells_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage));
+      int tblocks = (cells + 7) / 8;
+      if (tblocks > ctx->sm_count * 2) tblocks = ctx->sm_count * 2;  // two resident CTAs per SM, several cells per warp
+      lab_mean_cells_tma_kernel<<<tblocks, 256, stage, ctx->stream>>>(ctx->d_target, ctx->tw_img, ctx->gw, cell_begin,
+                                                                       cell_end, ctx->tile_w, ctx->tile_h, (int)row_pitch,
+                                                                       ctx->d_cell_lab, ctx->d_cell_rgbsum);
+    } else {
+      lab_mean_cells_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->d_target, ctx->tw_img, ctx->gw, cell_begin, cell_end,
+                                                             ctx->tile_w, ctx->tile_h, ctx->d_cell_lab,
+                                                             ctx->d_cell_rgbsum);
+    }
     ctx->launches++;
   }
   MOSAIC_CUDA(ctx, cudaGetLastError());
