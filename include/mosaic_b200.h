@@ -140,7 +140,9 @@ typedef struct {
   uint64_t optimization_iterations; /* --optimization-iterations (1000) */
   uint64_t seed;             /* extension: annealer seed */
   int build_similarity;      /* materialise the packed matrix (main.rs:126,143); it is never read by
-                                the kernels (they recompute entries bit-identically from Lab) */
+                                the kernels (they recompute entries bit-identically from Lab).  A sharded
+                                context computes its own range here; mosaic_similarity_tri gathers the
+                                whole matrix on every rank */
 } mosaic_params;
 typedef struct {
   uint32_t n_fallbacks;

@@ -256,7 +256,16 @@ int run_anneal(mosaic_ctx* c, uint64_t iterations, float t0, float decay, uint64
   return MOSAIC_OK;
 }
 
-int run_similarity(mosaic_ctx* c) {
+int gather_similarity(mosaic_ctx* c) {
+  if (c->world == 1 || c->sim_gathered) return MOSAIC_OK;
+  MOSAIC_TRY(allgather_slices(c, c->d_sim, sizeof(float), [&](int r, uint64_t* sb, uint64_t* se) { shard_tri(c, r, sb, se); }));
+  c->sim_gathered = true;
+  return MOSAIC_OK;
+}
+
+// gather = false (the fused path): a sharded context computes its own range and leaves the all-gather to the first
+// caller that wants the whole matrix — no kernel reads it (they recompute entries from the Lab means)
+int run_similarity(mosaic_ctx* c, bool gather = true) {
   if (!c->have_mat_lab) MOSAIC_TRY(run_material_lab(c));
   const uint64_t n = (uint64_t)c->n;
   const uint64_t total = n > 1 ? n * (n - 1) / 2 : 0;  // similarity.rs:71 (n == 0 underflows in the reference)
@@ -271,7 +280,8 @@ int run_similarity(mosaic_ctx* c) {
     int rc = launch_similarity(c, b, e);
     c->d_sim = full;
     MOSAIC_TRY(rc);
-    MOSAIC_TRY(allgather_slices(c, c->d_sim, sizeof(float), [&](int r, uint64_t* sb, uint64_t* se) { shard_tri(c, r, sb, se); }));
+    c->sim_gathered = false;
+    if (gather) MOSAIC_TRY(gather_similarity(c));
   }
   c->have_sim = true;
   return MOSAIC_OK;
@@ -654,7 +664,7 @@ int mosaic_generate(mosaic_ctx* c, const mosaic_params* p, int32_t* placed_out, 
   MOSAIC_TRY(require(c, c->have_target, "target"));
   // main.rs:105-164 (MosaicGenerator::new) ...
   MOSAIC_TRY(run_material_lab(c));
-  if (p->build_similarity) MOSAIC_TRY(run_similarity(c));
+  if (p->build_similarity) MOSAIC_TRY(run_similarity(c, /*gather=*/false));
   // ... main.rs:477-685 (generate_mosaic)
   MOSAIC_TRY(run_cell_lab(c));
   MOSAIC_TRY(run_candidates(c, kMaxK));
@@ -706,7 +716,9 @@ int mosaic_dims(const mosaic_ctx* c, int* n_materials, int* grid_w, int* grid_h,
 
 const void* mosaic_device_output(const mosaic_ctx* c) { return c && c->have_out ? c->d_out : nullptr; }
 const void* mosaic_device_placement(const mosaic_ctx* c) { return c && c->have_placed ? c->d_placed : nullptr; }
-const void* mosaic_device_similarity(const mosaic_ctx* c) { return c && c->have_sim ? c->d_sim : nullptr; }
+const void* mosaic_device_similarity(const mosaic_ctx* c) {
+  return c && c->have_sim && (c->world == 1 || c->sim_gathered) ? c->d_sim : nullptr;
+}
 
 int mosaic_shard(const mosaic_ctx* c, int* row_begin, int* row_end, int* mat_begin, int* mat_end, uint64_t* tri_begin,
                  uint64_t* tri_end) {

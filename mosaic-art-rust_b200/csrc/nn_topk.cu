@@ -14,7 +14,7 @@
 // FMA contraction would change the bits) + compare + vote.  Selection: a 64-bit key
 // (d2 bits << 32 | index) is appended to a per-cell shared-memory buffer when d2 <= tau (the current
 // K-th smallest d2); when the buffer holds > 96 keys the warp bitonic-sorts it in registers and
-// merges it with the sorted top list (128 slots), tightening tau.  A warp handles TK_ROUNDS consecutive groups
+// merges it with the sorted top list (128 slots), tightening tau.  A warp handles up to four consecutive groups
 // of raster cells; from the second group on, tau starts at the largest distance from the new cell to the k
 // materials of the previous cell's answer (k materials within that distance exist, so it bounds the k-th
 // smallest from above): raster neighbours have almost the same colour, which removes most of the k*ln(n/k)
@@ -30,7 +30,7 @@ constexpr int TK_Q = 2;
 constexpr int TK_CHUNK = 1024;
 constexpr int TK_SLOTS = 128;
 constexpr int TK_FLUSH = 96;  // merge when more than this many keys are buffered (<= 128 - 32)
-constexpr int TK_ROUNDS = 4;  // consecutive cell groups per warp: the second one starts from the first one's answer
+constexpr int TK_MAX_ROUNDS = 4;  // consecutive cell groups per warp: every group after the first starts from its predecessor's answer
 
 struct __align__(16) QueryState {
   unsigned long long topk[TK_SLOTS];
@@ -104,7 +104,7 @@ __device__ __forceinline__ void merge_buffer(QueryState& st, int& cnt, unsigned&
 
 __global__ void __launch_bounds__(TK_WARPS * 32) nn_topk_kernel(const float* __restrict__ soa, const float4* __restrict__ lab4,
                                                                 int n, int n_pad, const float* __restrict__ cell_lab,
-                                                                int cell_begin, int cell_end, int k,
+                                                                int cell_begin, int cell_end, int k, int rounds,
                                                                 uint32_t* __restrict__ out_idx, float* __restrict__ out_d2) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* mats = reinterpret_cast<float*>(smem_raw);  // [2][3][TK_CHUNK]
@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(TK_WARPS * 32) nn_topk_kernel(const float* __r
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nchunks = (n + TK_CHUNK - 1) / TK_CHUNK;
-  const int total_chunks = nchunks * TK_ROUNDS;  // the materials are streamed once per round
+  const int total_chunks = nchunks * rounds;  // the materials are streamed once per round
 
   auto issue = [&](int g) {
     const int s = g & 1, c = g % nchunks;
@@ -142,9 +142,9 @@ __global__ void __launch_bounds__(TK_WARPS * 32) nn_topk_kernel(const float* __r
   QueryState* st = states + warp * TK_Q;
   const unsigned lt_mask = (1u << lane) - 1u;
   int g = 0;  // running chunk number across the rounds
-  for (int round = 0; round < TK_ROUNDS; ++round) {
-    // this warp's cells of this round: TK_ROUNDS * TK_Q consecutive raster cells per warp
-    const int first_cell = cell_begin + ((blockIdx.x * TK_WARPS + warp) * TK_ROUNDS + round) * TK_Q;
+  for (int round = 0; round < rounds; ++round) {
+    // this warp's cells of this round: rounds * TK_Q consecutive raster cells per warp
+    const int first_cell = cell_begin + ((blockIdx.x * TK_WARPS + warp) * rounds + round) * TK_Q;
     const bool warp_active = first_cell < cell_end;  // warp-uniform
     float ql[TK_Q], qa[TK_Q], qb[TK_Q];
     int cnt[TK_Q];
@@ -252,12 +252,15 @@ int launch_topk_range(mosaic_ctx* ctx, int k, int cell_begin, int cell_end) {
     MOSAIC_CUDA(ctx, cudaFuncSetAttribute(nn_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTopkSmem));
     if (ctx->device < 64) attr_set[ctx->device] = true;
   }
-  const int per_cta = TK_WARPS * TK_Q * TK_ROUNDS;
+  // rounds per warp: as many as keep at least two CTAs per SM in flight (a sharded context has fewer cells per GPU)
+  int rounds = TK_MAX_ROUNDS;
+  while (rounds > 1 && (cells + TK_WARPS * TK_Q * rounds - 1) / (TK_WARPS * TK_Q * rounds) < 2 * ctx->sm_count) rounds >>= 1;
+  const int per_cta = TK_WARPS * TK_Q * rounds;
   const int blocks = (cells + per_cta - 1) / per_cta;
   {
     StageTimer t(ctx, MOSAIC_STAGE_TOPK);
     nn_topk_kernel<<<blocks, TK_WARPS * 32, kTopkSmem, ctx->stream>>>(ctx->d_mat_soa, ctx->d_mat_lab4, ctx->n, ctx->n_pad,
-                                                                      ctx->d_cell_lab, cell_begin, cell_end, k,
+                                                                      ctx->d_cell_lab, cell_begin, cell_end, k, rounds,
                                                                       ctx->d_cand_idx, ctx->d_cand_d2);
     ctx->launches++;
   }
