@@ -127,6 +127,34 @@ def test_place_bit_exact(ctx, n, gw, gh, max_usage, weight):
     assert (placed == rplaced).all()
 
 
+def test_place_randomized_against_the_replay(ctx):
+    """Random shapes, caps, weights and colour fields through the chain kernel (hot blocks, contended cells, the
+    multi-chunk path, usage resets, narrow-grid kernel) against the oracle's replay of main.rs:335-475."""
+    rng = np.random.default_rng(20261017)
+    for trial in range(120):
+        n = int(rng.choice([1, 2, 7, 31, 33, 64, 100, 150, 400, 1200]))
+        gw = int(rng.integers(1, 90))
+        gh = int(rng.integers(1, 14))
+        max_usage = int(rng.choice([0, 1, 1, 2, 3, 3, 5, 40, 300]))
+        weight = float(rng.choice([0.0, 0.05, 0.3, 0.3, 1.0, 2.5]))
+        mat_lab = synth.lab_points(n, seed=1000 + trial)
+        if trial % 4 == 0:    # clustered materials: many near-ties and contended cells
+            mat_lab = (mat_lab[rng.integers(0, max(1, n // 8), n)] + rng.normal(0, 0.05, (n, 3))).astype(np.float32)
+        yy, xx = np.mgrid[0:gh, 0:gw]
+        smooth = np.stack([50 + 30 * np.sin(xx / 5.0 + trial), 40 * np.cos(yy / 4.0), 30 * np.sin((xx + yy) / 6.0)], -1)
+        noise = rng.normal(0, float(rng.choice([0.0, 0.5, 20.0])), smooth.shape)
+        cell_lab = (smooth + noise).reshape(-1, 3).astype(np.float32)
+        ctx.set_material_lab(mat_lab)
+        ctx.set_cell_lab(cell_lab, gw, gh)
+        idx, d2 = ctx.candidates()
+        placed, nfb = ctx.place(max_usage, weight)
+        rplaced, rnfb, rfb, _ = orc.place(idx, d2, mat_lab, gw, gh, max_usage, weight)
+        tag = f"trial {trial}: n={n} grid={gw}x{gh} cap={max_usage} w={weight}"
+        assert nfb == rnfb, tag
+        assert (placed == rplaced).all(), tag
+        assert (ctx.fallback_cells() == rfb[:4096]).all(), tag
+
+
 def test_place_full_pipeline_c1(ctx):
     cfg = synth.CONFIGS["C1"]
     mats = synth.materials(cfg["n_materials"])
@@ -248,6 +276,32 @@ def test_anneal_cold_rejects(ctx):
     assert np.float32(res.final_cost).view(np.uint32) == np.float32(rres.final_cost).view(np.uint32)
 
 
+def test_anneal_randomized(ctx):
+    """Random grids, material counts, temperatures and seeds: grid, counters and cost bits against the oracle."""
+    rng = np.random.default_rng(7)
+    for trial in range(40):
+        n = int(rng.choice([2, 3, 17, 64, 300, 2000]))
+        gw, gh = int(rng.integers(1, 70)), int(rng.integers(1, 40))
+        iters = int(rng.choice([0, 1, 50, 700, 3000]))
+        t0 = float(rng.choice([100.0, 1.0, 0.05, 0.002]))
+        decay = float(rng.choice([0.99995, 0.999, 0.9]))
+        seed = int(rng.integers(0, 2**62))
+        mat_lab = synth.lab_points(n, seed=trial)
+        grid = rng.integers(0, n, (gh, gw)).astype(np.int32)
+        if trial % 3 == 0:
+            grid[rng.random((gh, gw)) < 0.1] = -1            # empty cells (optimizer.rs:71-73)
+        ctx.set_material_lab(mat_lab)
+        ctx.set_cell_lab(np.zeros((gw * gh, 3), np.float32), gw, gh)
+        ctx.set_placement(grid)
+        placed, res = ctx.anneal(iters, seed, t0=t0, decay=decay)
+        rgrid, rres = orc.anneal(mat_lab, grid, iters, seed, t0=t0, decay=decay)
+        tag = f"trial {trial}: n={n} grid={gw}x{gh} iters={iters} t0={t0} decay={decay}"
+        assert (placed.reshape(gh, gw) == rgrid).all(), tag
+        assert (res.accepted_count, res.improved_count) == (rres.accepted_count, rres.improved_count), tag
+        for a, b in ((res.initial_cost, rres.initial_cost), (res.final_cost, rres.final_cost), (res.best_cost, rres.best_cost)):
+            assert np.float32(a).view(np.uint32) == np.float32(b).view(np.uint32), tag
+
+
 # ---------------------------------------------------------------- K4 render
 @pytest.mark.parametrize("w,h,gw,gh,strength", [(480, 288, 24, 16, 0.3), (480, 288, 24, 16, 0.0), (250, 130, 7, 3, 1.0),
                                                  (512, 512, 8, 8, 0.4), (1920, 1080, 50, 28, 0.3),
@@ -274,6 +328,32 @@ def test_render_within_one_lsb(ctx, w, h, gw, gh, strength):
     assert diff.max() <= 1, f"max diff {diff.max()}"
     # tighter: the arithmetic is restated operation by operation, so in practice it is bit-exact
     assert (diff > 0).mean() < 1e-3
+
+
+def test_render_randomized_shapes(ctx):
+    """Random material and tile sizes (all kernel paths: dot-product with 4/5/7-word windows, per-cell fast and
+    generic kernels, skipped axes) and strengths, <= 1 LSB against the oracle."""
+    rng = np.random.default_rng(11)
+    for trial in range(24):
+        mw, mh = int(rng.choice([16, 20, 32, 48, 64, 64, 96])), int(rng.choice([16, 24, 32, 64, 64, 80]))
+        tw, th = int(rng.integers(4, 72)), int(rng.integers(4, 72))
+        gw, gh = int(rng.integers(1, 9)), int(rng.integers(1, 7))
+        strength = float(rng.choice([0.0, 0.3, 0.7, 1.0]))
+        n = 24
+        mats = synth.materials(n, w=mw, h=mh, seed=100 + trial)
+        tgt = synth.target(gw * tw + int(rng.integers(0, 3)), gh * th + int(rng.integers(0, 3)), seed=200 + trial)
+        gw_, gh_ = gw, gh
+        if tgt.shape[1] // gw_ != tw or tgt.shape[0] // gh_ != th:
+            continue
+        placed = rng.integers(-1, n, gw * gh).astype(np.int32)
+        ctx.set_materials(mats)
+        ctx.set_target(tgt, gw, gh)
+        ctx.cell_lab(fetch=False)
+        ctx.set_placement(placed)
+        out = ctx.render(strength)
+        ref = orc.render(tgt, gw, gh, mats, placed, strength, threads=8)
+        diff = np.abs(out.astype(np.int16) - ref.astype(np.int16))
+        assert diff.max() <= 1, f"trial {trial}: {mw}x{mh} -> {tw}x{th}, strength {strength}: max diff {diff.max()}"
 
 
 def test_render_identity_resize(ctx):
