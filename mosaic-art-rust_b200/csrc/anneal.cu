@@ -27,7 +27,7 @@ namespace {
 
 constexpr int RNG_HALF_WORDS = 512;   // 32 ChaCha blocks: one refill
 constexpr int RNG_RING_WORDS = 1024;  // two halves
-constexpr int RNG_SLACK = 16;         // words one iteration may look ahead (8 for the positions + 1 for the f32)
+constexpr int RNG_SLACK = 128;        // words one round may look ahead (a 65-word sampling window + an acceptance sample behind each iteration)
 constexpr int RNG_SMEM_WORDS = RNG_RING_WORDS + 16;  // + the key (8 words), padded
 
 __device__ __forceinline__ unsigned rotl32(unsigned v, int c) { return __funnelshift_l(v, v, c); }
@@ -210,6 +210,17 @@ struct AnnealMem {
     else
       grid_g[i] = v;
   }
+  // predicated store (no branch): the loop of the chain must stay free of them
+  __device__ __forceinline__ void set_if(bool pred, int i, int v) const {
+    if (GRID_SMEM) {
+      if (sizeof(GridT) == 2)
+        st_shared_if(pred, reinterpret_cast<unsigned short*>(const_cast<GridT*>(grid_s)) + i, (unsigned short)v);
+      else
+        st_shared_if(pred, reinterpret_cast<unsigned*>(const_cast<GridT*>(grid_s)) + i, (unsigned)v);
+    } else {
+      st_global_if(pred, reinterpret_cast<unsigned*>(const_cast<int32_t*>(grid_g)) + i, (unsigned)v);
+    }
+  }
   __device__ __forceinline__ void lab(int m, float& l, float& a, float& b) const {
     if (LAB_SMEM) {
       l = lab_s[m];
@@ -326,58 +337,137 @@ __global__ void __launch_bounds__(256, 1)
 
   // The loop is written for ONE warp on its own: a branch costs it about as much as the arithmetic of a whole
   // swap delta, so everything that can be a select is a select and the rare cases leave through cold paths.
-  for (unsigned long long it = 0; it < iterations; ++it) {
+  //
+  // A swap delta only occupies 8 lanes (one per neighbour term), and the chain is pure latency.  So the warp runs
+  // THREE slots of 8 lanes per round: slot 0 evaluates the next iteration at its known stream position; slots 1 and
+  // 2 evaluate the iteration after it at the two positions it can start from (right behind this one's position
+  // draws if this one draws no acceptance sample, one word later if it does).  The round then retires the two
+  // iterations strictly in order: each one's acceptance uses the real temperature and the real stream position,
+  // and the speculated delta is used only if no swap accepted by the first iteration touched a cell the second one
+  // read (the two swapped cells against its two cells and their neighbours).  Every retired iteration is therefore
+  // computed from exactly the state the serial loop would have seen — same arithmetic, same order — and a round
+  // retires two iterations for the latency of one.  The retirement is straight-line code (selects and predicated
+  // stores): a branch costs this lone warp ~50 cycles.
+  //
+  // Position draws (optimizer.rs:60-63): gen_range(0..n) = Lemire's widening multiply with rejection, (hi, lo) =
+  // v * n accepted iff lo <= zone — for n = 200 more than a fifth of the samples are rejected, so rejection is the
+  // normal case, not a cold path.  Each lane takes the u64 at an even and at an odd word offset of a 65-word
+  // window and evaluates both for both ranges (n < 2^31: two 32x32->64 multiplies each); four ballots later, the
+  // sequential x1, y1, x2, y2 sampling of this iteration and of both candidates for the next one is a walk over
+  // bit masks.  A window that runs out (never, in practice) takes the general sampler.
+  const int slot = lane >> 3, sl = lane & 7, slot_base = lane & 24;
+  const int side = (sl >> 2) & 1, dir = sl & 3;  // lanes 0-3 of a slot: neighbours of pos1 (U, D, L, R); 4-7: of pos2
+  struct Walk {
+    int j0, j1, j2, j3;
+    bool ok;
+  };
+  auto walk = [](unsigned mw, unsigned mh, unsigned startbit) -> Walk {  // x1 (w), y1 (h), x2 (w), y2 (h), in stream order
+    Walk k;
+    unsigned m = startbit < 32u ? mw & ~((1u << startbit) - 1u) : 0u;
+    k.ok = m != 0u;
+    k.j0 = m ? __ffs(m) - 1 : 0;
+    m = mh & ~((2u << k.j0) - 1u);
+    k.ok = k.ok && m != 0u;
+    k.j1 = m ? __ffs(m) - 1 : 0;
+    m = mw & ~((2u << k.j1) - 1u);
+    k.ok = k.ok && m != 0u;
+    k.j2 = m ? __ffs(m) - 1 : 0;
+    m = mh & ~((2u << k.j2) - 1u);
+    k.ok = k.ok && m != 0u;
+    k.j3 = m ? __ffs(m) - 1 : 0;
+    return k;
+  };
+  auto near = [](int ax, int ay, int bx, int by) { return abs(ax - bx) + abs(ay - by) <= 1; };
+  auto accept_bounds = [](float delta, float temperature, float u, bool& undecided) -> bool {
+    // accept <=> delta < 0 || u < exp(-delta / T) (optimizer.rs:80-84).  1 - q <= exp(-q) <= 1 / (1 + q) (q >= 0)
+    // decide almost every draw without the division and the exponential; the margins (2^-18) dwarf every
+    // rounding error involved.  `undecided`: the sliver in between (or q < 0 / NaN) needs the exact exponential.
+    float rT, hi;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rT) : "f"(temperature));
+    const float q = delta * rT;
+    const float lo = 1.0f - q * 1.000004f - 3.8146973e-06f;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(hi) : "f"(1.0f + q * 0.999996f));
+    hi += 3.8146973e-06f;
+    const bool bounds_ok = q >= 0.0f;
+    const bool acc = delta < 0.0f || (bounds_ok && u < lo);
+    undecided = !acc && !(bounds_ok && u > hi);
+    return acc;
+  };
+  unsigned long long it = 0;
+  while (it < iterations) {
     rng.ensure(RNG_SLACK, lane);
-    // optimizer.rs:60-63: x1, y1, x2, y2 — four u64 draws, no rejection in all but ~n/2^64 of the cases.
-    // gen_range(0..n): (hi, lo) = v * n (128-bit), accepted iff lo <= zone, result hi.  n < 2^31, so the product
-    // is two 32x32->64 multiplies.
-    int xy[4];
-    bool no_reject = true;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const unsigned nq = (q & 1) ? (unsigned)gh : (unsigned)gw;
-      const unsigned long long zq = (q & 1) ? zone_h : zone_w;
-      const unsigned long long t0 = (unsigned long long)rng.peek(2 * q) * nq;
-      const unsigned long long t1 = (unsigned long long)rng.peek(2 * q + 1) * nq + (t0 >> 32);
-      const unsigned long long lo = (t1 << 32) | (t0 & 0xFFFFFFFFull);
-      xy[q] = (int)(t1 >> 32);
-      no_reject = no_reject && lo <= zq;
+    const unsigned basepos = rng.pos;
+    // ---- candidate samples of the window: lane j holds the u64 at words 2j (even set) and 2j+1 (odd set) ----
+    const unsigned w0 = ring[(basepos + 2u * lane) & (RNG_RING_WORDS - 1)], w1 = ring[(basepos + 2u * lane + 1u) & (RNG_RING_WORDS - 1)],
+                   w2 = ring[(basepos + 2u * lane + 2u) & (RNG_RING_WORDS - 1)];
+    int hiw_e, hih_e, hiw_o, hih_o;
+    bool okw_e, okh_e, okw_o, okh_o;
+    {
+      const unsigned long long a0 = (unsigned long long)w0 * (unsigned)gw, a1 = (unsigned long long)w1 * (unsigned)gw + (a0 >> 32);
+      const unsigned long long b0 = (unsigned long long)w0 * (unsigned)gh, b1 = (unsigned long long)w1 * (unsigned)gh + (b0 >> 32);
+      okw_e = ((a1 << 32) | (a0 & 0xFFFFFFFFull)) <= zone_w;
+      okh_e = ((b1 << 32) | (b0 & 0xFFFFFFFFull)) <= zone_h;
+      hiw_e = (int)(a1 >> 32);
+      hih_e = (int)(b1 >> 32);
+      const unsigned long long c0 = (unsigned long long)w1 * (unsigned)gw, c1 = (unsigned long long)w2 * (unsigned)gw + (c0 >> 32);
+      const unsigned long long d0 = (unsigned long long)w1 * (unsigned)gh, d1 = (unsigned long long)w2 * (unsigned)gh + (d0 >> 32);
+      okw_o = ((c1 << 32) | (c0 & 0xFFFFFFFFull)) <= zone_w;
+      okh_o = ((d1 << 32) | (d0 & 0xFFFFFFFFull)) <= zone_h;
+      hiw_o = (int)(c1 >> 32);
+      hih_o = (int)(d1 >> 32);
     }
-    int x1 = xy[0], y1 = xy[1], x2 = xy[2], y2 = xy[3];
-    if (__builtin_expect(!no_reject, 0)) {
-      const SlowPositions sp = positions_slow(ring, rng.pos, rng.filled, rng.next_block, ugw, ugh, zone_w, zone_h, lane);
-      x1 = sp.x1, y1 = sp.y1, x2 = sp.x2, y2 = sp.y2;
-      rng.pos = sp.pos;
+    const unsigned EW = __ballot_sync(0xffffffffu, okw_e), EH = __ballot_sync(0xffffffffu, okh_e);
+    const unsigned OW = __ballot_sync(0xffffffffu, okw_o), OH = __ballot_sync(0xffffffffu, okh_o);
+    const Walk k0 = walk(EW, EH, 0u);                       // this iteration
+    unsigned adv0 = 2u * (unsigned)(k0.j3 + 1);              // words its position draws consume
+    const unsigned sb = (unsigned)(k0.j3 + 1);               // the next iteration starts at word adv0 (even set, bit sb) ...
+    const Walk ka = walk(EW, EH, sb), kb = walk(OW, OH, sb);  // ... or at word adv0 + 1 (odd set, bit sb)
+    // every lane fetches the positions of ITS slot: slot 0 <- k0 (even set), slot 1 <- ka (even), slot 2 <- kb (odd)
+    const Walk& mine = slot == 0 ? k0 : (slot == 1 ? ka : kb);
+    const int e1 = __shfl_sync(0xffffffffu, hiw_e, mine.j0), o1 = __shfl_sync(0xffffffffu, hiw_o, mine.j0);
+    const int e2 = __shfl_sync(0xffffffffu, hih_e, mine.j1), o2 = __shfl_sync(0xffffffffu, hih_o, mine.j1);
+    const int e3 = __shfl_sync(0xffffffffu, hiw_e, mine.j2), o3 = __shfl_sync(0xffffffffu, hiw_o, mine.j2);
+    const int e4 = __shfl_sync(0xffffffffu, hih_e, mine.j3), o4 = __shfl_sync(0xffffffffu, hih_o, mine.j3);
+    int x1 = slot == 2 ? o1 : e1, y1 = slot == 2 ? o2 : e2, x2 = slot == 2 ? o3 : e3, y2 = slot == 2 ? o4 : e4;
+    unsigned my_adv = slot == 0 ? adv0 : 2u * (unsigned)(mine.j3 + 1) - adv0;
+    bool inval = slot == 3 || (slot != 0 && !mine.ok);  // this slot's speculation cannot be used (slot 3 is idle)
+    if (__builtin_expect(!k0.ok, 0)) {  // the window ran out: the general sampler for this iteration, no speculation
+      const SlowPositions sp = positions_slow(ring, basepos, rng.filled, rng.next_block, ugw, ugh, zone_w, zone_h, lane);
+      if (slot == 0) x1 = sp.x1, y1 = sp.y1, x2 = sp.x2, y2 = sp.y2;
+      adv0 = sp.pos - basepos;
+      if (slot == 0) my_adv = adv0;
+      inval = slot != 0;
       rng.filled = sp.filled;
       rng.next_block = sp.next_block;
-    } else {
-      rng.pos += 8u;
+      rng.pos = sp.pos;
+      rng.ensure(RNG_SLACK, lane);
+      rng.pos = basepos;
     }
+
+    // ---- the swap deltas of the three slots ----
     const int i1 = y1 * gw + x1, i2 = y2 * gw + x2;
     const int p1 = mem.get(i1), p2 = mem.get(i2);
-    // lanes 0-3: neighbours of pos1 (Up, Down, Left, Right); lanes 4-7: neighbours of pos2
-    const int side = (lane >> 2) & 1, dir = lane & 3;
     const int cx = side ? x2 : x1, cy = side ? y2 : y1;
     const int ox = side ? x1 : x2, oy = side ? y1 : y2;  // the other swap position (skipped)
     const int nx = cx + (dir == 3) - (dir == 2), ny = cy + (dir == 1) - (dir == 0);
-    const bool inside = lane < 8 && nx >= 0 && nx < gw && ny >= 0 && ny < gh && !(nx == ox && ny == oy);
+    const bool inside = nx >= 0 && nx < gw && ny >= 0 && ny < gh && !(nx == ox && ny == oy);
     const int nb = mem.get(inside ? ny * gw + nx : i1);  // (a valid address either way; ignored when !inside)
     // optimizer.rs:66-68 (same position: no temperature decay) and 71-73 (an empty cell)
-    if (__builtin_expect((x1 == x2 && y1 == y2) || p1 < 0 || p2 < 0, 0)) continue;
-
+    const bool skip = (x1 == x2 && y1 == y2) || p1 < 0 || p2 < 0;
+    const int q1 = skip ? 0 : p1, q2 = skip ? 0 : p2;  // (a skipped iteration evaluates nothing; keep the loads in range)
     const bool present = inside && nb >= 0;
     float l1, a1, b1, l2, a2, b2, ln, an, bn;
-    mem.lab(p1, l1, a1, b1);
-    mem.lab(p2, l2, a2, b2);
-    mem.lab(present ? nb : p1, ln, an, bn);
+    mem.lab(q1, l1, a1, b1);
+    mem.lab(q2, l2, a2, b2);
+    mem.lab(present ? nb : q1, ln, an, bn);
     const float ml = side ? l2 : l1, ma = side ? a2 : a1, mb = side ? b2 : b1;  // material now at this position
     const float ol = side ? l1 : l2, oa = side ? a1 : a2, ob = side ? b1 : b2;  // material after the swap
     bool oor = false, oor_m = false;
     float t_old = adjacency_term_fast(ml, ma, mb, ln, an, bn, oor);
     float t_new = adjacency_term_fast(ol, oa, ob, ln, an, bn, oor);
-    float mutual = adjacency_term_fast(l1, a1, b1, l2, a2, b2, oor_m);  // warp-uniform
+    float mutual = adjacency_term_fast(l1, a1, b1, l2, a2, b2, oor_m);  // slot-uniform
     const bool adjacent12 = (x1 == x2 && (y1 - y2 == 1 || y2 - y1 == 1)) || (y1 == y2 && (x1 - x2 == 1 || x2 - x1 == 1));
-    if (__builtin_expect(__any_sync(0xffffffffu, (oor && present) || (oor_m && adjacent12)), 0)) {
+    if (__builtin_expect(__any_sync(0xffffffffu, !skip && ((oor && present) || (oor_m && adjacent12))), 0)) {
       // outside the domain of the branch-free sequences: the exact builtins
       t_old = adjacency_term_exact(ml, ma, mb, ln, an, bn);
       t_new = adjacency_term_exact(ol, oa, ob, ln, an, bn);
@@ -389,45 +479,73 @@ __global__ void __launch_bounds__(256, 1)
     float old_cost = 0.0f, new_cost = 0.0f;
 #pragma unroll
     for (int l = 0; l < 8; ++l) {  // reference order: pos1 U,D,L,R then pos2 U,D,L,R (adjacency.rs:165-200)
-      old_cost = __fadd_rn(old_cost, __shfl_sync(0xffffffffu, t_old, l));
-      new_cost = __fadd_rn(new_cost, __shfl_sync(0xffffffffu, t_new, l));
+      old_cost = __fadd_rn(old_cost, __shfl_sync(0xffffffffu, t_old, slot_base + l));
+      new_cost = __fadd_rn(new_cost, __shfl_sync(0xffffffffu, t_new, slot_base + l));
     }
     mutual = adjacent12 ? mutual : 0.0f;       // adjacency.rs:203-211 (x + 0.0 == x: the sums are >= +0.0)
     old_cost = __fadd_rn(old_cost, mutual);
     new_cost = __fadd_rn(new_cost, mutual);
-    const float delta = p1 != p2 ? __fsub_rn(new_cost, old_cost) : 0.0f;  // adjacency.rs:156-158
+    const float my_delta = p1 != p2 ? __fsub_rn(new_cost, old_cost) : 0.0f;  // adjacency.rs:156-158
 
-    // accept <=> delta < 0 || u < exp(-delta / T), u drawn only when delta >= 0 (optimizer.rs:80-84).
-    // 1 - q <= exp(-q) <= 1 / (1 + q) (q >= 0) decide almost every draw without the division and the
-    // exponential; the margins (2^-18) dwarf every rounding error involved.
-    const bool downhill = delta < 0.0f;
-    const float u = __fmul_rn((float)(rng.peek(0) >> 8), 1.0f / 16777216.0f);
-    rng.pos += downhill ? 0u : 1u;
-    float rT, hi;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rT) : "f"(temperature));
-    const float q = delta * rT;
-    const float lo = 1.0f - q * 1.000004f - 3.8146973e-06f;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(hi) : "f"(1.0f + q * 0.999996f));
-    hi += 3.8146973e-06f;
-    const bool bounds_ok = q >= 0.0f;  // the bounds hold for q >= 0 (T > 0); NaN / negative -> exact path
-    bool accept = downhill || (bounds_ok && u < lo);
-    if (__builtin_expect(!accept && !(bounds_ok && u > hi), 0)) {
-      accept = accept_exact(delta, temperature, u);
+    // ---- retire iteration `it` (slot 0) ----
+    const int ax1 = __shfl_sync(0xffffffffu, x1, 0), ay1 = __shfl_sync(0xffffffffu, y1, 0);
+    const int ax2 = __shfl_sync(0xffffffffu, x2, 0), ay2 = __shfl_sync(0xffffffffu, y2, 0);
+    const int ap1 = __shfl_sync(0xffffffffu, p1, 0), ap2 = __shfl_sync(0xffffffffu, p2, 0);
+    const float delta0 = __shfl_sync(0xffffffffu, my_delta, 0);
+    const bool skip0 = __shfl_sync(0xffffffffu, skip, 0);
+    const float u0 = __fmul_rn((float)(ring[(basepos + adv0) & (RNG_RING_WORDS - 1)] >> 8), 1.0f / 16777216.0f);
+    bool und0, und1;
+    bool accept0 = accept_bounds(delta0, temperature, u0, und0) && !skip0;
+    und0 = und0 && !skip0;
+    const bool nodraw0 = skip0 || delta0 < 0.0f;  // u drawn only when delta >= 0 (optimizer.rs:80-84)
+    const float temperature1 = skip0 ? temperature : __fmul_rn(temperature, decay);  // optimizer.rs:102 (not on skips)
+    const unsigned cur1 = basepos + adv0 + (nodraw0 ? 0u : 1u);
+    // ---- iteration `it + 1`: the slot that sits at cur1 ----
+    const int src1 = nodraw0 ? 8 : 16;
+    const int bx1 = __shfl_sync(0xffffffffu, x1, src1), by1 = __shfl_sync(0xffffffffu, y1, src1);
+    const int bx2 = __shfl_sync(0xffffffffu, x2, src1), by2 = __shfl_sync(0xffffffffu, y2, src1);
+    const int bp1 = __shfl_sync(0xffffffffu, p1, src1), bp2 = __shfl_sync(0xffffffffu, p2, src1);
+    const float delta1 = __shfl_sync(0xffffffffu, my_delta, src1);
+    const bool skip1 = __shfl_sync(0xffffffffu, skip, src1);
+    const unsigned adv1 = __shfl_sync(0xffffffffu, my_adv, src1);
+    const bool usable1 = !__shfl_sync(0xffffffffu, inval, src1) && it + 1ull < iterations;
+    // stale if the first swap changed a cell the second one read (its two cells or one of their neighbours)
+    const bool touch01 = near(bx1, by1, ax1, ay1) || near(bx1, by1, ax2, ay2) || near(bx2, by2, ax1, ay1) || near(bx2, by2, ax2, ay2);
+    const float u1 = __fmul_rn((float)(ring[(cur1 + adv1) & (RNG_RING_WORDS - 1)] >> 8), 1.0f / 16777216.0f);
+    bool accept1 = accept_bounds(delta1, temperature1, u1, und1) && !skip1;
+    und1 = und1 && !skip1;
+    if (__builtin_expect(und0 || (usable1 && und1), 0)) {  // the exact exponential, in order
+      if (und0) accept0 = accept_exact(delta0, temperature, u0);
+      if (usable1 && !(accept0 && touch01) && und1) accept1 = accept_exact(delta1, temperature1, u1);
     }
-    // (every lane stores the same values: no branch, no divergence)
-    mem.set(i1, accept ? p2 : p1);
-    mem.set(i2, accept ? p1 : p2);
+    const bool go1 = usable1 && !(accept0 && touch01);
+    accept1 = accept1 && go1;
+    // apply (every lane stores the same values; a rejected or skipped first iteration stores the cells' own values back)
+    const int ai1 = ay1 * gw + ax1, ai2 = ay2 * gw + ax2, bi1 = by1 * gw + bx1, bi2 = by2 * gw + bx2;
+    mem.set(ai1, accept0 ? ap2 : ap1);
+    mem.set(ai2, accept0 ? ap1 : ap2);
+    mem.set_if(accept1, bi1, bp2);
+    mem.set_if(accept1, bi2, bp1);
     __syncwarp();
     if (deferred) {
-      if (accept) deltas[accepted] = delta;  // (every lane: same address, same value)
+      st_global_if(accept0, reinterpret_cast<unsigned*>(deltas + accepted), __float_as_uint(delta0));
+      st_global_if(accept1, reinterpret_cast<unsigned*>(deltas + accepted + (accept0 ? 1ull : 0ull)), __float_as_uint(delta1));
     } else {
-      current = accept ? __fadd_rn(current, delta) : current;
-      const bool better = accept && current < best;
-      best = better ? current : best;
-      improved += better ? 1ull : 0ull;
+      current = accept0 ? __fadd_rn(current, delta0) : current;
+      const bool better0 = accept0 && current < best;
+      best = better0 ? current : best;
+      improved += better0 ? 1ull : 0ull;
+      current = accept1 ? __fadd_rn(current, delta1) : current;
+      const bool better1 = accept1 && current < best;
+      best = better1 ? current : best;
+      improved += better1 ? 1ull : 0ull;
     }
-    accepted += accept ? 1ull : 0ull;
-    temperature = __fmul_rn(temperature, decay);     // optimizer.rs:102
+    accepted += (accept0 ? 1ull : 0ull) + (accept1 ? 1ull : 0ull);
+    const bool decay1 = go1 && !skip1;
+    temperature = decay1 ? __fmul_rn(temperature1, decay) : temperature1;
+    const bool nodraw1 = skip1 || delta1 < 0.0f;
+    rng.pos = go1 ? cur1 + adv1 + (nodraw1 ? 0u : 1u) : cur1;
+    it += go1 ? 2ull : 1ull;
   }
 
   if (GRID_SMEM) {
