@@ -754,12 +754,10 @@ __global__ void __launch_bounds__(64, 1)
       wait_batch((int)cell + 8);  // a block reads records cell + 4 .. cell + 8: this batch, or one already waited for
       bool ran_block = false;
       for (;;) {
-        // probe the batch the NEXT block needs now, look at the answer after this block
-        bool next_ready = true;
-        if (cell + 14u <= ucells) {
-          const uint32_t c13 = cell + 13u;
-          next_ready = mbar_test(&bars[(c13 / CH_BATCH) % CH_NBATCH], (c13 / CH_DEPTH) & 1u);
-        }
+        // probe the batch the NEXT block needs now, look at the answer after this block (near the end of the grid
+        // the probe looks at a batch that is certainly there: branches are what this loop cannot afford)
+        const uint32_t c13 = min(cell + 13u, ucells - 1u);
+        const bool next_ready = mbar_test(&bars[(c13 / CH_BATCH) % CH_NBATCH], (c13 / CH_DEPTH) & 1u);
         const uint2* hb = reinterpret_cast<const uint2*>(hring) + ((cell + 4u) % CH_DEPTH) * 32u + lane;
         const int x0 = S[0].x;
         dead = false;
@@ -769,22 +767,25 @@ __global__ void __launch_bounds__(64, 1)
         hot_step(2, hb, S[2], S[3], S[4], S[0], S[1]);
         hot_step(3, hb, S[3], S[4], S[0], S[1], S[2]);
         hot_step(4, hb, S[4], S[0], S[1], S[2], S[3]);
-        if (lane < done) {  // flush the parked decisions: lane t holds the one of cell + t
+        {  // flush the parked decisions (predicated stores): lane t holds the one of cell + t
           int xs = x0 + lane;
           xs = xs >= gw ? xs - gw : xs;
-          *reinterpret_cast<volatile int32_t*>(rowbuf + xs) = (int32_t)(myr & CH_IDMASK);
-          queue[(cell + (uint32_t)lane) % CH_DEPTH] = ((unsigned long long)(cell + (uint32_t)lane + 1u) << 32) | myr;
+          xs = lane < done ? xs : 0;
+          st_shared_if(lane < done, reinterpret_cast<unsigned*>(rowbuf) + xs, myr & CH_IDMASK);
+          st_shared_if(lane < done, const_cast<unsigned long long*>(queue) + ((cell + (uint32_t)lane) % CH_DEPTH),
+                       ((unsigned long long)(cell + (uint32_t)lane + 1u) << 32) | myr);
         }
-        __syncwarp();
         cell += (uint32_t)done;
-        if (done < 5 || cell + 9u > ucells) break;
+        // one exit test per block: a contended cell, the end of the grid, or records that have not arrived yet
+        if (done < 5 || cell + 9u > ucells || !next_ready) break;
         ran_block = true;
-        if (!next_ready) wait_batch((int)cell + 8);
       }
+      __syncwarp();
       // the decision of the last cell that went through: lane done-1 of this block, else lane 4 of the one before
       if (done > 0 || ran_block) rprev = __shfl_sync(0xffffffffu, myr, done > 0 ? done - 1 : 4);
       rotate(done % 5);
       if (cell >= ucells) break;
+      if (done == 5) continue;  // only the next records were missing (or the grid is about to end): wait and go on
     }
     full_step((int)cell, S[0], S[1], S[2], S[3], S[4]);
     rotate(1);
