@@ -148,56 +148,76 @@ def run_cpu(cfg, steps, warmup, budget_s):
 
 # --------------------------------------------------------------------------- clocks
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons DURING the timed region.  NVML polled from a thread of this process every few
+    milliseconds (the timed region of a 24,000-tile mosaic is tens of milliseconds: an `nvidia-smi -lms` child does not
+    even start that fast); `nvidia-smi` is the fallback when the NVML binding is missing."""
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown"}
 
     def __init__(self, gpu_index):
         self.gpu_index = gpu_index
-        self.proc = None
-        self.path = f"/tmp/mosaic_clocks_{os.getpid()}.csv"
+        self.samples, self.reason_bits = [], 0
+        self.smax = None
+        self._stop = False
+        self._thread = None
+        self._nvml = None
+
+    def _physical_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if self.gpu_index < len(ids) and ids[self.gpu_index].isdigit():
+                return int(ids[self.gpu_index])
+        return self.gpu_index
 
     def start(self):
         try:
-            self.f = open(self.path, "w")
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.gpu_index), "-lms", "20"], stdout=self.f,
-                                         stderr=subprocess.DEVNULL)
+            import pynvml
+            pynvml.nvmlInit()
+            self._nvml = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index())
+            self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
         except Exception:
-            self.proc = None
+            self._nvml = None
+            return
+        import threading
+
+        def loop():
+            nv = self._nvml
+            while not self._stop:
+                try:
+                    self.samples.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+                    self.reason_bits |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h))
+                except Exception:
+                    pass
+                time.sleep(0.003)
+
+        self._thread = threading.Thread(target=loop, daemon=True)
+        self._thread.start()
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
+        if self._nvml is None:
+            return self._smi_once()
+        self._stop = True
+        self._thread.join(timeout=2)
+        if not self.samples:
+            return self._smi_once()
+        reasons = sorted(name for bit, name in self.REASONS.items() if self.reason_bits & bit)
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.smax, "reasons": reasons,
+                "samples": len(self.samples), "source": "nvml, polled during the timed region"}
+
+    def _smi_once(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
-            self.proc.wait(timeout=5)
+            out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i",
+                                  str(self._physical_index())], capture_output=True, text=True, timeout=20).stdout
+            parts = [x.strip() for x in out.strip().splitlines()[0].split(",")]
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            reasons = sorted(n for n, v in zip(names, parts[2:6]) if v.lower().startswith("active"))
+            return {"sm_mhz": float(parts[0]), "sm_max_mhz": float(parts[1]), "reasons": reasons, "samples": 1,
+                    "source": "nvidia-smi, one sample right after the timed region"}
         except Exception:
-            self.proc.kill()
-        self.f.close()
-        sm, smax, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        with open(self.path) as f:
-            for line in f:
-                parts = [p.strip() for p in line.split(",")]
-                if len(parts) < 9:
-                    continue
-                try:
-                    sm.append(float(parts[1]))
-                    smax.append(float(parts[2]))
-                except ValueError:
-                    continue
-                for nm, val in zip(names, parts[5:9]):
-                    if val.lower().startswith("active"):
-                        reasons.add(nm)
-        try:
-            os.remove(self.path)
-        except OSError:
-            pass
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(smax), "reasons": sorted(reasons),
-                "samples": len(sm)}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
 
 
 # --------------------------------------------------------------------------- GPU arm
@@ -375,7 +395,7 @@ def run_gpu(args, cfg):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="C3")
