@@ -90,6 +90,13 @@ int mosaic_set_target_device(mosaic_ctx* ctx, const void* dev_rgb, int w, int h,
  * tests): n*3 / (grid_w*grid_h)*3 floats, host memory. */
 int mosaic_set_material_lab(mosaic_ctx* ctx, const float* lab, int n);
 int mosaic_set_cell_lab(mosaic_ctx* ctx, const float* lab, int grid_w, int grid_h);
+/* Lab colours the similarity database holds for the materials (SimilarityDatabase::get_lab_color,
+ * similarity.rs:106-109), when they are not the tiles' own means: MosaicGenerator::new keeps the colours of a
+ * database loaded from a file and only adds the tiles it does not know (main.rs:120-143), so similarities
+ * (adjacency penalty, annealing energy, the matrix itself) come from the file's colours while matching uses
+ * the tiles' colours.  n*3 floats in material order; NULL = back to the materials' Lab means (the state
+ * after every mosaic_set_materials_*). */
+int mosaic_set_similarity_lab(mosaic_ctx* ctx, const float* lab, int n);
 
 /* ---- B1/B2: Lab means  (MosaicGeneratorImpl::calculate_average_lab, lib.rs:94-119) ---------- */
 /* B1: all materials (call sites main.rs:280, 294).  lab_out: n*3 floats or NULL (keep on device). */

@@ -1,0 +1,443 @@
+// mosaic_b200.hpp — C++17 host-side mirror of the reference's interface for the matching path, over the C ABI
+// of mosaic_b200.h (header-only; link libmosaic_b200.so).
+//
+// The reference is a Rust crate and there is no rustc in this image, so the host side that would live in Rust
+//  is mirrored here in C++ with the reference's names, argument meaning and error behaviour:
+//
+//   SimilarityDatabase           src/similarity.rs:31-138   add_tile, build_similarities, get_similarity,
+//                                                           get_lab_color, save_to_file, load_from_file, load_or_new
+//   AdjacencyPenaltyCalculator   src/adjacency.rs:49-130    new(db, weight), calculate_total_cost(grid)
+//   OptimizationConfig/Result,
+//   MosaicOptimizer              src/optimizer.rs:7-129,203-220   new(calculator, config), optimize(grid)
+//   MosaicGeneratorImpl          src/lib.rs:91-119          calculate_average_lab(image)
+//   MosaicGenerator              src/main.rs:92-685         new(...), generate_mosaic(...)  (the CLI's private struct,
+//                                                           minus directory scan and codecs: images come in memory)
+//
+// `Option<PathBuf>` grids are std::vector<std::vector<std::optional<std::string>>>; `anyhow::Result` errors are
+// exceptions (mosaic_b200::Error carries the status code and mosaic_last_error's text).  Every computation of the
+// hot path is forwarded to the GPU library; what stays here is bookkeeping (path <-> index maps) and the single-cell
+// calculate_penalty query (≤4 terms over GPU-built similarities; the placement kernel has its own fused copy).
+// The reference's signatures carry no device handle, so SimilarityDatabase / AdjacencyPenaltyCalculator /
+// MosaicOptimizer run on a lazily created process-wide scratch Context (device MOSAIC_B200_DEVICE, default 0);
+// MosaicGenerator owns the Context that holds its materials.  Without an sm_100a device every compute call throws
+// Error(MOSAIC_ERR_CUDA): there is no CPU fallback.
+// Differences from the reference are the ones listed in INTEGRATION.md: the annealer takes a seed (the reference
+// draws from the unseedable thread_rng, optimizer.rs:48), materials are uniform-size RGB8 buffers.
+#ifndef MOSAIC_B200_HPP
+#define MOSAIC_B200_HPP
+#include <algorithm>
+#include <cstdint>
+#include <cstdlib>
+#include <fstream>
+#include <map>
+#include <memory>
+#include <optional>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "mosaic_b200.h"
+
+namespace mosaic_b200 {
+
+struct Error : std::runtime_error {
+  int code;
+  Error(int c, const std::string& what) : std::runtime_error(what), code(c) {}
+};
+
+struct Lab {  // palette::Lab<D65, f32>
+  float l = 0, a = 0, b = 0;
+};
+
+using PathGrid = std::vector<std::vector<std::optional<std::string>>>;  // Vec<Vec<Option<PathBuf>>>, [y][x]
+
+// RAII mosaic_ctx
+class Context {
+ public:
+  explicit Context(int device = 0) {
+    const int rc = mosaic_ctx_create(&ctx_, device);
+    if (rc != MOSAIC_OK) throw Error(rc, mosaic_last_error(nullptr));
+  }
+  ~Context() { mosaic_ctx_destroy(ctx_); }
+  Context(const Context&) = delete;
+  Context& operator=(const Context&) = delete;
+  mosaic_ctx* get() const { return ctx_; }
+  void check(int rc) const {
+    if (rc != MOSAIC_OK) throw Error(rc, mosaic_last_error(ctx_));
+  }
+
+ private:
+  mosaic_ctx* ctx_ = nullptr;
+};
+
+namespace detail {
+inline Context& scratch_context() {  // created on first use; throws Error when there is no sm_100a GPU
+  static std::unique_ptr<Context> ctx;
+  if (!ctx) {
+    const char* dev = std::getenv("MOSAIC_B200_DEVICE");
+    ctx = std::make_unique<Context>(dev ? std::atoi(dev) : 0);
+  }
+  return *ctx;
+}
+}  // namespace detail
+
+// ---- src/similarity.rs -----------------------------------------------------------------------------------
+class SimilarityDatabase {
+ public:
+  SimilarityDatabase() = default;  // SimilarityDatabase::new()
+
+  void add_tile(const std::string& path, Lab lab_color) {  // similarity.rs:60-66
+    const size_t index = lab_.size() / 3;
+    path_to_index_[path] = index;
+    if (index_to_path_.size() <= index) index_to_path_.resize(index + 1);
+    index_to_path_[index] = path;
+    lab_.insert(lab_.end(), {lab_color.l, lab_color.a, lab_color.b});
+  }
+
+  // similarity.rs:69-82: the packed upper-triangular matrix of all current tiles, on the GPU (K3)
+  void build_similarities() { build_similarities(detail::scratch_context()); }
+  void build_similarities(Context& ctx) {
+    const int n = (int)(lab_.size() / 3);
+    sim_.assign(n > 1 ? (size_t)n * (n - 1) / 2 : 0, 0.0f);
+    if (n == 0) return;  // (the reference underflows n * (n - 1) here, similarity.rs:71)
+    ctx.check(mosaic_set_material_lab(ctx.get(), lab_.data(), n));
+    ctx.check(mosaic_similarity_tri(ctx.get(), sim_.empty() ? nullptr : sim_.data()));
+  }
+
+  std::optional<float> get_similarity(const std::string& path1, const std::string& path2) const {  // similarity.rs:85-103
+    const auto a = path_to_index_.find(path1), b = path_to_index_.find(path2);
+    if (a == path_to_index_.end() || b == path_to_index_.end()) return std::nullopt;
+    if (a->second == b->second) return 0.0f;
+    const uint64_t i = std::min(a->second, b->second), j = std::max(a->second, b->second), n = lab_.size() / 3;
+    const uint64_t pos = i * n - i * (i + 1) / 2 + j - i - 1;
+    if (pos >= sim_.size()) return std::nullopt;
+    return sim_[pos];
+  }
+
+  std::optional<Lab> get_lab_color(const std::string& path) const {  // similarity.rs:106-109
+    const auto it = path_to_index_.find(path);
+    if (it == path_to_index_.end() || it->second * 3 + 2 >= lab_.size()) return std::nullopt;
+    return Lab{lab_[3 * it->second], lab_[3 * it->second + 1], lab_[3 * it->second + 2]};
+  }
+
+  void save_to_file(const std::string& file) const {  // similarity.rs:112-116
+    const size_t n = lab_.size() / 3;
+    // the C entry point writes the whole packed matrix: a database whose matrix is out of date (tiles added after the
+    // last build — the reference would write the stale, shorter list) must be rebuilt first
+    if (sim_.size() != (n > 1 ? n * (n - 1) / 2 : 0)) throw Error(MOSAIC_ERR_STATE, "save_to_file: call build_similarities() first");
+    std::vector<const char*> paths;
+    for (const auto& p : index_to_path_) paths.push_back(p.c_str());
+    const int rc = mosaic_simdb_save_json(file.c_str(), paths.data(), (int)paths.size(), lab_.data(), sim_.data());
+    if (rc != MOSAIC_OK) throw Error(rc, mosaic_last_error(nullptr));
+  }
+
+  static SimilarityDatabase load_from_file(const std::string& file) {  // similarity.rs:119-123
+    mosaic_simdb* h = nullptr;
+    const int rc = mosaic_simdb_load_json(file.c_str(), &h);
+    if (rc != MOSAIC_OK) throw Error(rc, mosaic_last_error(nullptr));
+    SimilarityDatabase db;
+    int rows = 0, npaths = 0;
+    uint64_t nsim = 0;
+    mosaic_simdb_info(h, &rows, &nsim, &npaths);
+    db.lab_.resize((size_t)rows * 3);
+    db.sim_.resize(nsim);
+    mosaic_simdb_copy(h, db.lab_.data(), db.sim_.data());
+    db.index_to_path_.resize(rows);
+    for (int i = 0; i < rows; ++i) {
+      const char* p = mosaic_simdb_path(h, i);
+      db.index_to_path_[i] = p ? p : "";
+      if (p && *p) db.path_to_index_[p] = (size_t)mosaic_simdb_index_of(h, p);
+    }
+    mosaic_simdb_free(h);
+    return db;
+  }
+
+  static SimilarityDatabase load_or_new(const std::string& file) {  // similarity.rs:126-137
+    try {
+      return load_from_file(file);
+    } catch (const Error&) {
+      return SimilarityDatabase();
+    }
+  }
+
+  size_t len() const { return lab_.size() / 3; }
+  const std::vector<float>& lab_colors() const { return lab_; }
+  int64_t index_of(const std::string& path) const {
+    const auto it = path_to_index_.find(path);
+    return it == path_to_index_.end() ? -1 : (int64_t)it->second;
+  }
+
+ private:
+  std::map<std::string, size_t> path_to_index_;
+  std::vector<std::string> index_to_path_;
+  std::vector<float> lab_, sim_;
+};
+
+namespace detail {
+// grid of paths -> material indices of `db` (-1 = empty cell or unknown path: get_similarity would return None and
+// the reference skips the pair, adjacency.rs:104-124)
+inline std::vector<int32_t> grid_ids(const SimilarityDatabase& db, const PathGrid& grid, int* gw, int* gh) {
+  *gh = (int)grid.size();
+  *gw = *gh ? (int)grid[0].size() : 0;
+  std::vector<int32_t> ids;
+  ids.reserve((size_t)*gw * *gh);
+  for (const auto& row : grid)
+    for (const auto& cell : row) ids.push_back(cell ? (int32_t)db.index_of(*cell) : -1);
+  return ids;
+}
+}  // namespace detail
+
+// ---- src/adjacency.rs -------------------------------------------------------------------------------------
+struct GridPosition {  // adjacency.rs:4-47
+  size_t x = 0, y = 0;
+  GridPosition() = default;
+  GridPosition(size_t x_, size_t y_) : x(x_), y(y_) {}
+  bool operator==(const GridPosition& o) const { return x == o.x && y == o.y; }
+  bool operator!=(const GridPosition& o) const { return !(*this == o); }
+  // up, down, left, right — the order the penalty terms are added in (adjacency.rs:17-45)
+  std::vector<GridPosition> get_adjacent_positions(size_t grid_width, size_t grid_height) const {
+    std::vector<GridPosition> adjacent;
+    if (y > 0) adjacent.emplace_back(x, y - 1);
+    if (y + 1 < grid_height) adjacent.emplace_back(x, y + 1);
+    if (x > 0) adjacent.emplace_back(x - 1, y);
+    if (x + 1 < grid_width) adjacent.emplace_back(x + 1, y);
+    return adjacent;
+  }
+};
+
+class AdjacencyPenaltyCalculator {
+ public:
+  AdjacencyPenaltyCalculator(const SimilarityDatabase& similarity_db, float penalty_weight)  // adjacency.rs:55-60
+      : db_(similarity_db), weight_(penalty_weight) {}
+
+  // adjacency.rs:63-88: weight * sum over the placed up/down/left/right neighbours of 1 / (similarity + 1).  A one-cell
+  // query over the GPU-built matrix (the placement kernel evaluates the same expression fused, greedy.cu).
+  float calculate_penalty(const std::string& candidate_path, GridPosition position, const PathGrid& grid, size_t grid_width,
+                          size_t grid_height) const {
+    float penalty = 0.0f;
+    for (const GridPosition& adj : position.get_adjacent_positions(grid_width, grid_height)) {
+      const auto& neighbor = grid[adj.y][adj.x];
+      if (!neighbor) continue;
+      if (const auto similarity = db_.get_similarity(candidate_path, *neighbor)) penalty += 1.0f / (*similarity + 1.0f);
+    }
+    return penalty * weight_;
+  }
+
+  // adjacency.rs:91-130: sum over right / down pairs of 1 / (similarity + 1), raster order, f32
+  float calculate_total_cost(const PathGrid& grid) const {
+    if (grid.empty() || grid[0].empty()) return 0.0f;
+    return calculate_total_cost(detail::scratch_context(), grid);
+  }
+  float calculate_total_cost(Context& ctx, const PathGrid& grid) const {
+    int gw, gh;
+    const std::vector<int32_t> ids = detail::grid_ids(db_, grid, &gw, &gh);
+    if (gw == 0 || gh == 0) return 0.0f;
+    load(ctx, ids, gw, gh);
+    mosaic_opt_result res{};
+    ctx.check(mosaic_anneal(ctx.get(), 0, 100.0f, 0.99995f, 0, nullptr, &res));  // 0 iterations: the cost only
+    return res.initial_cost;
+  }
+
+  const SimilarityDatabase& database() const { return db_; }
+  float penalty_weight() const { return weight_; }
+
+  void load(Context& ctx, const std::vector<int32_t>& ids, int gw, int gh) const {
+    ctx.check(mosaic_set_material_lab(ctx.get(), db_.lab_colors().data(), (int)db_.len()));
+    const std::vector<float> zeros((size_t)gw * gh * 3, 0.0f);  // cell colours play no role in the energy
+    ctx.check(mosaic_set_cell_lab(ctx.get(), zeros.data(), gw, gh));
+    ctx.check(mosaic_set_placement(ctx.get(), ids.data()));
+  }
+
+ private:
+  const SimilarityDatabase& db_;
+  float weight_;
+};
+
+// ---- src/optimizer.rs -------------------------------------------------------------------------------------
+struct OptimizationConfig {  // optimizer.rs:7-27
+  size_t max_iterations = 1000;
+  float initial_temperature = 100.0f;
+  float temperature_decay = 0.99995f;
+  size_t report_interval = 100;
+  uint64_t seed = 0;  // extension: the reference's thread_rng cannot be seeded (optimizer.rs:48)
+};
+
+struct OptimizationResult {  // optimizer.rs:203-220
+  float initial_cost = 0, final_cost = 0, best_cost = 0;
+  size_t improved_count = 0, accepted_count = 0, iterations = 0;
+  float improvement_percentage() const {
+    return initial_cost > 0.0f ? (initial_cost - final_cost) / initial_cost * 100.0f : 0.0f;
+  }
+};
+
+class MosaicOptimizer {
+ public:
+  MosaicOptimizer(const AdjacencyPenaltyCalculator& calculator, OptimizationConfig config)  // optimizer.rs:36-38
+      : calc_(calculator), config_(config) {}
+
+  OptimizationResult optimize(PathGrid& grid) const {
+    if (grid.empty() || grid[0].empty()) return OptimizationResult();  // optimizer.rs:43-45, before any device work
+    return optimize(detail::scratch_context(), grid);
+  }
+  OptimizationResult optimize(Context& ctx, PathGrid& grid) const {  // optimizer.rs:41-129
+    int gw, gh;
+    const std::vector<int32_t> ids = detail::grid_ids(calc_.database(), grid, &gw, &gh);
+    if (gh == 0 || gw == 0) return OptimizationResult();  // optimizer.rs:43-45
+    calc_.load(ctx, ids, gw, gh);
+    std::vector<int32_t> out(ids.size());
+    mosaic_opt_result r{};
+    ctx.check(mosaic_anneal(ctx.get(), config_.max_iterations, config_.initial_temperature, config_.temperature_decay,
+                            config_.seed, out.data(), &r));
+    // the kernel swaps material indices; cells whose path is unknown to the database carry -1 and never move
+    // (they are "empty" for the optimiser exactly as for get_similarity)
+    std::vector<std::string> path_of(calc_.database().len());
+    for (const auto& row : grid)
+      for (const auto& c : row)
+        if (c && calc_.database().index_of(*c) >= 0) path_of[(size_t)calc_.database().index_of(*c)] = *c;
+    for (int y = 0; y < gh; ++y)
+      for (int x = 0; x < gw; ++x) {
+        const int32_t id = out[(size_t)y * gw + x];
+        if (id >= 0) grid[y][x] = path_of[(size_t)id];
+      }
+    OptimizationResult res;
+    res.initial_cost = r.initial_cost;
+    res.final_cost = r.final_cost;
+    res.best_cost = r.best_cost;
+    res.improved_count = (size_t)r.improved_count;
+    res.accepted_count = (size_t)r.accepted_count;
+    res.iterations = (size_t)r.iterations;
+    return res;
+  }
+
+ private:
+  const AdjacencyPenaltyCalculator& calc_;
+  OptimizationConfig config_;
+};
+
+// ---- src/lib.rs ---------------------------------------------------------------------------------------------
+struct RgbImage {  // image::RgbImage: interleaved RGB8, row-major
+  int width = 0, height = 0;
+  std::vector<uint8_t> data;
+  RgbImage() = default;
+  RgbImage(int w, int h) : width(w), height(h), data((size_t)w * h * 3, 0) {}
+};
+
+struct MosaicGeneratorImpl {
+  // MosaicGenerator::calculate_average_lab (lib.rs:94-119)
+  // is_aspect_ratio_match (lib.rs:121-123) is the directory scan's filter: control plane, not mirrored
+  static Lab calculate_average_lab(const RgbImage& img) { return calculate_average_lab(detail::scratch_context(), img); }
+  static Lab calculate_average_lab(Context& ctx, const RgbImage& img) {
+    float lab[3];
+    ctx.check(mosaic_set_materials_rgb8(ctx.get(), img.data.data(), 1, img.width, img.height));
+    ctx.check(mosaic_material_lab(ctx.get(), lab));
+    return Lab{lab[0], lab[1], lab[2]};
+  }
+};
+
+struct Tile {  // lib.rs:45-49
+  std::string path;
+  Lab lab_color;
+};
+
+// ---- src/main.rs: struct MosaicGenerator (private to the CLI binary) ------------------------------------------
+class MosaicGenerator {
+ public:
+  // MosaicGenerator::new (main.rs:105-164) with the materials already decoded and filtered (load_tiles, main.rs:166-261,
+  // is the control plane): `paths[i]` names material i, `rgb` holds n uniform-size RGB8 images.  Tile Lab means on the
+  // GPU (B1); the similarity database is built + saved, or loaded from `similarity_db_path` and topped up with the
+  // tiles it does not know, then rebuilt (main.rs:120-143).  Similarities always come from the database's colours:
+  // when a loaded file disagrees with the tiles' own means they are handed to the library separately
+  // (mosaic_set_similarity_lab).  An empty `similarity_db_path` skips the file (in-memory use).
+  MosaicGenerator(const std::vector<std::string>& paths, const uint8_t* rgb, int mat_w, int mat_h,
+                  size_t max_usage_per_image, const std::string& similarity_db_path, bool rebuild_similarity,
+                  float adjacency_penalty_weight, float color_adjustment_strength, int device = 0)
+      : ctx_(device),
+        max_usage_(max_usage_per_image),
+        weight_(adjacency_penalty_weight),
+        strength_(std::min(std::max(color_adjustment_strength, 0.0f), 1.0f)) {  // main.rs:162
+    const int n = (int)paths.size();
+    ctx_.check(mosaic_set_materials_rgb8(ctx_.get(), rgb, n, mat_w, mat_h));
+    std::vector<float> lab((size_t)n * 3);
+    ctx_.check(mosaic_material_lab(ctx_.get(), lab.data()));
+    for (int i = 0; i < n; ++i) tiles_.push_back(Tile{paths[i], Lab{lab[3 * i], lab[3 * i + 1], lab[3 * i + 2]}});
+
+    const bool exists = !similarity_db_path.empty() && std::ifstream(similarity_db_path).good();
+    if (rebuild_similarity || !exists) {  // main.rs:120-134
+      for (const Tile& t : tiles_) similarity_db_.add_tile(t.path, t.lab_color);
+      similarity_db_.build_similarities(ctx_);
+      if (!similarity_db_path.empty()) {
+        try {
+          similarity_db_.save_to_file(similarity_db_path);
+        } catch (const Error& e) {
+          save_warning_ = std::string("Warning: Failed to save similarity database: ") + e.what();
+        }
+      }
+    } else {
+      similarity_db_ = SimilarityDatabase::load_or_new(similarity_db_path);  // main.rs:135-137
+    }
+    bool topped_up = false;
+    for (const Tile& t : tiles_)  // main.rs:139-143
+      if (!similarity_db_.get_lab_color(t.path)) {
+        similarity_db_.add_tile(t.path, t.lab_color);
+        topped_up = true;
+      }
+    if (topped_up || !(rebuild_similarity || !exists)) {
+      // the database may now hold other paths too: its matrix is built on the scratch context, the generator's context
+      // keeps the tiles
+      similarity_db_.build_similarities();
+    }
+    std::vector<float> db_lab((size_t)n * 3);
+    bool differs = false;
+    for (int i = 0; i < n; ++i) {
+      const Lab c = *similarity_db_.get_lab_color(tiles_[i].path);
+      db_lab[3 * i] = c.l, db_lab[3 * i + 1] = c.a, db_lab[3 * i + 2] = c.b;
+      differs |= c.l != lab[3 * i] || c.a != lab[3 * i + 1] || c.b != lab[3 * i + 2];
+    }
+    if (differs) ctx_.check(mosaic_set_similarity_lab(ctx_.get(), db_lab.data(), n));
+  }
+
+  // generate_mosaic (main.rs:477-685) minus file I/O: returns the mosaic image; `placed` (optional) receives the grid
+  RgbImage generate_mosaic(const RgbImage& target, int grid_w, int grid_h, bool enable_optimization,
+                           size_t optimization_iterations, uint64_t seed = 0, PathGrid* placed = nullptr,
+                           mosaic_report* report = nullptr) {
+    ctx_.check(mosaic_set_target_rgb8(ctx_.get(), target.data.data(), target.width, target.height, grid_w, grid_h));
+    mosaic_params p{};
+    p.max_usage = (int)max_usage_;
+    p.adjacency_weight = weight_;
+    p.color_strength = strength_;
+    p.enable_optimization = enable_optimization ? 1 : 0;
+    p.optimization_iterations = optimization_iterations;
+    p.seed = seed;
+    p.build_similarity = 0;  // the matrix belongs to the database and was built by the constructor (main.rs:126, 143)
+    int n, gw, gh, tw, th;
+    mosaic_dims(ctx_.get(), &n, &gw, &gh, &tw, &th);
+    RgbImage out(gw * tw, gh * th);  // main.rs:499-503
+    std::vector<int32_t> ids((size_t)gw * gh);
+    mosaic_report rep{};
+    ctx_.check(mosaic_generate(ctx_.get(), &p, ids.data(), out.data.data(), &rep));
+    if (report) *report = rep;
+    if (placed) {
+      placed->assign(gh, std::vector<std::optional<std::string>>(gw));
+      for (int y = 0; y < gh; ++y)
+        for (int x = 0; x < gw; ++x)
+          if (ids[(size_t)y * gw + x] >= 0) (*placed)[y][x] = tiles_[(size_t)ids[(size_t)y * gw + x]].path;
+    }
+    return out;
+  }
+
+  const std::vector<Tile>& tiles() const { return tiles_; }
+  SimilarityDatabase& similarity_db() { return similarity_db_; }
+  Context& context() { return ctx_; }
+  const std::string& save_warning() const { return save_warning_; }  // the reference prints it to stderr (main.rs:131)
+
+ private:
+  Context ctx_;
+  std::string save_warning_;
+  std::vector<Tile> tiles_;
+  SimilarityDatabase similarity_db_;
+  size_t max_usage_;
+  float weight_, strength_;
+};
+
+}  // namespace mosaic_b200
+#endif

@@ -593,7 +593,7 @@ static int launch_anneal_variant(mosaic_ctx* ctx, size_t smem, uint64_t iteratio
     MOSAIC_TRY(ensure(ctx, &ctx->d_deltas, &ctx->deltas_cap, (size_t)iterations));
     deltas = ctx->d_deltas;
   }
-  anneal_kernel<GridT, GS, LS><<<1, 256, smem, ctx->stream>>>(ctx->d_mat_lab4, ctx->n, ctx->d_placed, ctx->d_terms,
+  anneal_kernel<GridT, GS, LS><<<1, 256, smem, ctx->stream>>>(ctx->sim_lab4(), ctx->n, ctx->d_placed, ctx->d_terms,
                                                               ctx->gw, ctx->gh, iterations, t0, decay, seed,
                                                               (mosaic_opt_result*)ctx->d_opt_res, deltas);
   return MOSAIC_OK;
@@ -609,7 +609,7 @@ int launch_anneal(mosaic_ctx* ctx, uint64_t iterations, float t0, float decay, u
   {
     int blocks = (int)std::min<size_t>((2 * cells + 255) / 256, (size_t)ctx->sm_count * 8);
     if (blocks < 1) blocks = 1;
-    cost_terms_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->d_mat_lab4, ctx->d_placed, ctx->gw, ctx->gh, ctx->d_terms);
+    cost_terms_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->sim_lab4(), ctx->d_placed, ctx->gw, ctx->gh, ctx->d_terms);
     ctx->launches++;
     MOSAIC_CUDA(ctx, cudaGetLastError());
   }

@@ -810,7 +810,7 @@ static int launch_chain_impl(mosaic_ctx* ctx, unsigned cap, float weight, size_t
                                         (int)smem));
   greedy_chain_kernel<UsageT, PROF><<<1, 64, smem, ctx->stream>>>(
       reinterpret_cast<const HRec*>(ctx->d_place_rec), reinterpret_cast<const XRec*>(ctx->d_place_rec + cells * sizeof(HRec)),
-      reinterpret_cast<const float*>(ctx->d_place_rec + cells * (sizeof(HRec) + sizeof(XRec))), ctx->d_cand_idx, ctx->d_cand_d2, ctx->k, ctx->d_mat_lab4, ctx->n, ctx->gw, ctx->gh, cap, weight, ctx->d_placed,
+      reinterpret_cast<const float*>(ctx->d_place_rec + cells * (sizeof(HRec) + sizeof(XRec))), ctx->d_cand_idx, ctx->d_cand_d2, ctx->k, ctx->sim_lab4(), ctx->n, ctx->gw, ctx->gh, cap, weight, ctx->d_placed,
       ctx->d_place_info, mosaic_ctx::kFallbackCap);
   return MOSAIC_OK;
 }
@@ -821,7 +821,7 @@ static int launch_chain(mosaic_ctx* ctx, unsigned cap, float weight, size_t smem
                     (size_t)cells * (sizeof(HRec) + sizeof(XRec) + 3 * kKPad * sizeof(float))));
   int blocks = (cells + 7) / 8;
   if (blocks > ctx->sm_count * 8) blocks = ctx->sm_count * 8;
-  place_prep_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->d_cand_idx, ctx->d_cand_d2, ctx->k, ctx->d_mat_lab4, ctx->n, cells,
+  place_prep_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->d_cand_idx, ctx->d_cand_d2, ctx->k, ctx->sim_lab4(), ctx->n, cells,
                                                      ctx->gw, weight, reinterpret_cast<HRec*>(ctx->d_place_rec),
                                                      reinterpret_cast<XRec*>(ctx->d_place_rec + (size_t)cells * sizeof(HRec)),
                                                      reinterpret_cast<float*>(ctx->d_place_rec + (size_t)cells * (sizeof(HRec) + sizeof(XRec))));
@@ -860,14 +860,14 @@ int launch_place(mosaic_ctx* ctx, int max_usage, float weight) {
       MOSAIC_CUDA(ctx, cudaFuncSetAttribute(greedy_generic_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)smem_with_usage));
       greedy_generic_kernel<true><<<1, 32, smem_with_usage, ctx->stream>>>(
-          ctx->d_cand_idx, ctx->d_cand_d2, ctx->k, ctx->d_mat_lab4, n, gw, gh, cap, weight, ctx->d_placed, nullptr,
+          ctx->d_cand_idx, ctx->d_cand_d2, ctx->k, ctx->sim_lab4(), n, gw, gh, cap, weight, ctx->d_placed, nullptr,
           ctx->d_place_info, mosaic_ctx::kFallbackCap);
     } else {
       MOSAIC_TRY(ensure(ctx, &ctx->d_usage, &ctx->usage_cap, (size_t)n));
       MOSAIC_CUDA(ctx, cudaFuncSetAttribute(greedy_generic_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)row_bytes));
       greedy_generic_kernel<false><<<1, 32, row_bytes, ctx->stream>>>(
-          ctx->d_cand_idx, ctx->d_cand_d2, ctx->k, ctx->d_mat_lab4, n, gw, gh, cap, weight, ctx->d_placed, ctx->d_usage,
+          ctx->d_cand_idx, ctx->d_cand_d2, ctx->k, ctx->sim_lab4(), n, gw, gh, cap, weight, ctx->d_placed, ctx->d_usage,
           ctx->d_place_info, mosaic_ctx::kFallbackCap);
     }
   }

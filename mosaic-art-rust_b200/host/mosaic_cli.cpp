@@ -1,0 +1,217 @@
+// mosaic-b200 — a small C++ host over the C ABI with the reference CLI's flag names (struct Args, main.rs:20-88) and
+// main()'s sequence (main.rs:741-779): target aspect -> MosaicGenerator::new -> generate_mosaic -> save.
+//
+// Out of scope here (the reference's control plane): image codecs.  Images are binary PPM
+// (P6, maxval 255); --material-src is a directory of *.ppm of ONE size (the reference decodes png/jpg/webp of any size;
+// the variable-size material path is not built).  The material selection follows load_tiles (main.rs:166-261): aspect
+// filter (lib.rs:121-123), no-match fallback to the first min(len, 2*max) files, truncate to --max-materials; files are
+// taken in sorted order (read_dir order is unspecified in the reference).
+//
+//   g++ -std=c++17 -O2 -I../../include mosaic_cli.cpp -L.. -lmosaic_b200 -Wl,-rpath,'$ORIGIN/..' -o mosaic-b200
+#include <dirent.h>
+#include <sys/stat.h>
+
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+
+#include "mosaic_b200.hpp"
+
+using namespace mosaic_b200;
+
+struct Args {  // main.rs:23-88, same defaults
+  std::string target, material_src, output;
+  unsigned grid_w = 50, grid_h = 28;
+  size_t max_materials = 500;
+  float aspect_tolerance = 0.1f;
+  size_t max_usage_per_image = 3;
+  float adjacency_penalty_weight = 0.3f;
+  bool enable_optimization = true;
+  size_t optimization_iterations = 1000;
+  std::string similarity_db = "similarity_db.json";
+  bool rebuild_similarity_db = false;
+  float color_adjustment_strength = 0.3f;
+  bool show_time = true, show_grid = true;
+  unsigned long long seed = 0;  // extension: the reference's annealer is OS-seeded (optimizer.rs:48)
+};
+
+static bool parse_bool(const std::string& v) { return v == "true" || v == "1"; }
+
+static bool parse(int argc, char** argv, Args* a) {
+  for (int i = 1; i < argc; ++i) {
+    std::string k = argv[i], v;
+    const size_t eq = k.find('=');
+    const bool flag_only = k == "--rebuild-similarity-db";
+    if (eq != std::string::npos) {
+      v = k.substr(eq + 1);
+      k = k.substr(0, eq);
+    } else if (!flag_only) {
+      if (i + 1 >= argc) {
+        std::fprintf(stderr, "error: a value is required for '%s'\n", k.c_str());
+        return false;
+      }
+      v = argv[++i];
+    }
+    if (k == "-t" || k == "--target") a->target = v;
+    else if (k == "-m" || k == "--material-src") a->material_src = v;
+    else if (k == "-o" || k == "--output") a->output = v;
+    else if (k == "--grid-w") a->grid_w = (unsigned)std::stoul(v);
+    else if (k == "--grid-h") a->grid_h = (unsigned)std::stoul(v);
+    else if (k == "--max-materials") a->max_materials = std::stoul(v);
+    else if (k == "--aspect-tolerance") a->aspect_tolerance = std::stof(v);
+    else if (k == "--max-usage-per-image") a->max_usage_per_image = std::stoul(v);
+    else if (k == "--adjacency-penalty-weight") a->adjacency_penalty_weight = std::stof(v);
+    else if (k == "--enable-optimization") a->enable_optimization = parse_bool(v);
+    else if (k == "--optimization-iterations") a->optimization_iterations = std::stoul(v);
+    else if (k == "--similarity-db") a->similarity_db = v;
+    else if (k == "--rebuild-similarity-db") a->rebuild_similarity_db = true;
+    else if (k == "--color-adjustment-strength") a->color_adjustment_strength = std::stof(v);
+    else if (k == "--show-time") a->show_time = parse_bool(v);
+    else if (k == "--show-grid") a->show_grid = parse_bool(v);
+    else if (k == "--seed") a->seed = std::stoull(v);
+    else {
+      std::fprintf(stderr, "error: unexpected argument '%s'\n", k.c_str());
+      return false;
+    }
+  }
+  if (a->target.empty() || a->material_src.empty() || a->output.empty()) {
+    std::fprintf(stderr, "error: the following required arguments were not provided: --target --material-src --output\n");
+    return false;
+  }
+  return true;
+}
+
+static bool read_ppm(const std::string& file, RgbImage* img, bool header_only = false) {
+  std::ifstream in(file, std::ios::binary);
+  std::string magic;
+  int w = 0, h = 0, maxv = 0;
+  auto token = [&](std::string* t) {
+    t->clear();
+    int c;
+    while ((c = in.get()) != EOF) {
+      if (c == '#') {
+        while ((c = in.get()) != EOF && c != '\n') {
+        }
+      } else if (!std::isspace(c)) {
+        t->push_back((char)c);
+        break;
+      }
+    }
+    while ((c = in.peek()) != EOF && !std::isspace(c)) t->push_back((char)in.get());
+  };
+  std::string t;
+  token(&magic);
+  token(&t), w = std::atoi(t.c_str());
+  token(&t), h = std::atoi(t.c_str());
+  token(&t), maxv = std::atoi(t.c_str());
+  if (magic != "P6" || w <= 0 || h <= 0 || maxv != 255) return false;
+  in.get();  // the single whitespace after maxval
+  img->width = w;
+  img->height = h;
+  if (header_only) return true;
+  img->data.resize((size_t)w * h * 3);
+  in.read((char*)img->data.data(), (std::streamsize)img->data.size());
+  return (size_t)in.gcount() == img->data.size();
+}
+
+static bool write_ppm(const std::string& file, const RgbImage& img) {
+  std::ofstream out(file, std::ios::binary);
+  out << "P6\n" << img.width << " " << img.height << "\n255\n";
+  out.write((const char*)img.data.data(), (std::streamsize)img.data.size());
+  return (bool)out;
+}
+
+int main(int argc, char** argv) {
+  Args args;
+  if (!parse(argc, argv, &args)) return 2;
+  try {
+    const auto t0 = std::chrono::steady_clock::now();
+    RgbImage target;
+    if (!read_ppm(args.target, &target)) throw std::runtime_error("cannot read target (binary PPM expected): " + args.target);
+    const float target_aspect = (float)target.width / (float)target.height;  // main.rs:745-747
+    std::printf("Target aspect ratio: %.3f\n", target_aspect);
+
+    // ---- load_tiles (main.rs:166-261)
+    std::printf("Collecting material images...\n");
+    std::vector<std::string> entries;
+    if (DIR* d = opendir(args.material_src.c_str())) {
+      while (dirent* e = readdir(d)) {
+        const std::string name = e->d_name, path = args.material_src + "/" + name;
+        struct stat st;
+        if (name.size() > 4 && name.substr(name.size() - 4) == ".ppm" && stat(path.c_str(), &st) == 0 && S_ISREG(st.st_mode))
+          entries.push_back(path);
+      }
+      closedir(d);
+    } else {
+      throw std::runtime_error("cannot read directory " + args.material_src);
+    }
+    std::sort(entries.begin(), entries.end());
+    std::vector<std::string> chosen;
+    std::vector<RgbImage> headers(entries.size());
+    for (size_t i = 0; i < entries.size(); ++i) {
+      if (!read_ppm(entries[i], &headers[i], true)) {
+        std::fprintf(stderr, "Error processing \"%s\": not a binary PPM\n", entries[i].c_str());
+        continue;
+      }
+      const float aspect = (float)headers[i].width / (float)headers[i].height;
+      if (std::fabs(aspect - target_aspect) <= args.aspect_tolerance) chosen.push_back(entries[i]);  // lib.rs:121-123
+    }
+    if (chosen.empty()) {  // main.rs:211-253
+      std::printf("No tiles matched target aspect ratio %.3f, loading tiles without aspect filtering...\n", target_aspect);
+      const size_t take = std::min(entries.size(), args.max_materials * 2);
+      chosen.assign(entries.begin(), entries.begin() + (std::ptrdiff_t)take);
+    }
+    if (chosen.size() > args.max_materials) chosen.resize(args.max_materials);  // main.rs:255-257
+    if (chosen.empty()) throw std::runtime_error("no material images found in " + args.material_src);
+    std::vector<uint8_t> rgb;
+    int mw = 0, mh = 0;
+    std::vector<std::string> paths;
+    for (const std::string& p : chosen) {
+      RgbImage m;
+      if (!read_ppm(p, &m)) {
+        std::fprintf(stderr, "Error processing \"%s\": truncated PPM\n", p.c_str());
+        continue;
+      }
+      if (paths.empty()) mw = m.width, mh = m.height;
+      if (m.width != mw || m.height != mh)
+        throw std::runtime_error("materials of different sizes are not supported (" + p + " is " + std::to_string(m.width) + "x" +
+                                 std::to_string(m.height) + ", expected " + std::to_string(mw) + "x" + std::to_string(mh) + ")");
+      rgb.insert(rgb.end(), m.data.begin(), m.data.end());
+      paths.push_back(p);
+    }
+    std::printf("Loaded %zu tiles (aspect ratio matched)\n", paths.size());
+    const auto t1 = std::chrono::steady_clock::now();
+
+    MosaicGenerator generator(paths, rgb.data(), mw, mh, args.max_usage_per_image, args.similarity_db, args.rebuild_similarity_db,
+                              args.adjacency_penalty_weight, args.color_adjustment_strength);
+    if (!generator.save_warning().empty()) std::fprintf(stderr, "%s\n", generator.save_warning().c_str());
+    const auto t2 = std::chrono::steady_clock::now();
+
+    std::printf("Target image: %dx%d\n", target.width, target.height);
+    std::printf("Grid: %ux%u, Tile size: %ux%u\n", args.grid_w, args.grid_h, target.width / args.grid_w, target.height / args.grid_h);
+    mosaic_report rep{};
+    const RgbImage out = generator.generate_mosaic(target, (int)args.grid_w, (int)args.grid_h, args.enable_optimization,
+                                                   args.optimization_iterations, args.seed, nullptr, &rep);
+    const auto t3 = std::chrono::steady_clock::now();
+    if (rep.annealed)
+      std::printf("Optimization complete: cost %.3f -> %.3f, improved %llu, accepted %llu of %llu\n", rep.opt.initial_cost,
+                  rep.opt.final_cost, (unsigned long long)rep.opt.improved_count, (unsigned long long)rep.opt.accepted_count,
+                  (unsigned long long)rep.opt.iterations);
+    if (rep.n_fallbacks) std::printf("Fallback selections: %u\n", rep.n_fallbacks);
+    if (!write_ppm(args.output, out)) throw std::runtime_error("cannot write " + args.output);
+    const auto t4 = std::chrono::steady_clock::now();
+    if (args.show_time) {
+      auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+      std::printf("Time: load %.1f ms, materials + similarity database %.1f ms, mosaic %.1f ms, save %.1f ms\n", ms(t0, t1), ms(t1, t2),
+                  ms(t2, t3), ms(t3, t4));
+    }
+    std::printf("Mosaic saved to \"%s\"\n", args.output.c_str());
+  } catch (const std::exception& e) {
+    std::fprintf(stderr, "Error: %s\n", e.what());
+    return 1;
+  }
+  return 0;
+}

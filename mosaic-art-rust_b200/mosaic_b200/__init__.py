@@ -75,6 +75,7 @@ def load_library():
         "mosaic_set_target_rgb8": ([vp, vp, C.c_int, C.c_int, C.c_int, C.c_int], C.c_int),
         "mosaic_set_target_device": ([vp, vp, C.c_int, C.c_int, C.c_int, C.c_int], C.c_int),
         "mosaic_set_material_lab": ([vp, f32p, C.c_int], C.c_int),
+        "mosaic_set_similarity_lab": ([vp, f32p, C.c_int], C.c_int),
         "mosaic_set_cell_lab": ([vp, f32p, C.c_int, C.c_int], C.c_int),
         "mosaic_material_lab": ([vp, vp], C.c_int),
         "mosaic_cell_lab": ([vp, vp], C.c_int),
@@ -116,7 +117,7 @@ EXPORTED_SYMBOLS = (
     "mosaic_ctx_create", "mosaic_ctx_create_sharded", "mosaic_nccl_unique_id", "mosaic_ctx_destroy",
     "mosaic_last_error", "mosaic_ctx_set_stream", "mosaic_ctx_sync", "mosaic_stage_ms", "mosaic_kernel_launches",
     "mosaic_set_materials_rgb8", "mosaic_set_materials_device", "mosaic_set_target_rgb8",
-    "mosaic_set_target_device", "mosaic_set_material_lab", "mosaic_set_cell_lab", "mosaic_material_lab",
+    "mosaic_set_target_device", "mosaic_set_material_lab", "mosaic_set_similarity_lab", "mosaic_set_cell_lab", "mosaic_material_lab",
     "mosaic_cell_lab", "mosaic_similarity_tri", "mosaic_candidates", "mosaic_place", "mosaic_fallback_cells",
     "mosaic_set_placement", "mosaic_anneal", "mosaic_render", "mosaic_generate", "mosaic_selftest", "mosaic_dims",
     "mosaic_debug_chain_profile",
@@ -326,6 +327,14 @@ class Context:
     def set_material_lab(self, lab):
         lab = np.ascontiguousarray(lab, np.float32)
         self._check(self._L.mosaic_set_material_lab(self._h, lab.ctypes.data_as(C.POINTER(C.c_float)), lab.shape[0]))
+
+    def set_similarity_lab(self, lab):
+        """Lab colours of the similarity database (main.rs:120-143) when they differ from the tiles'; None clears."""
+        if lab is None:
+            self._check(self._L.mosaic_set_similarity_lab(self._h, None, 0))
+            return
+        lab = np.ascontiguousarray(lab, np.float32)
+        self._check(self._L.mosaic_set_similarity_lab(self._h, lab.ctypes.data_as(C.POINTER(C.c_float)), lab.shape[0]))
 
     def set_cell_lab(self, lab, grid_w, grid_h):
         lab = np.ascontiguousarray(lab, np.float32)

@@ -1,0 +1,479 @@
+// The reference's own unit tests for the matching path, restated against the C++ host mirror
+// (include/mosaic_b200.hpp) — same fixtures, same assertions, citing the Rust test each one follows.
+//
+//   test_host_mirror --cpu            tests that need no GPU (bookkeeping, file format, loud failure without a device)
+//   test_host_mirror                  everything (needs an sm_100a GPU)
+//   test_host_mirror --generate DIR   MosaicGenerator end to end on DIR/{materials.bin,target.bin,meta.txt}; writes
+//                                     DIR/placed.bin, DIR/image.bin, DIR/report.txt for the Python parity test
+//
+// Built and driven by tests/test_host_mirror.py.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <sstream>
+
+#include "mosaic_b200.hpp"
+
+using namespace mosaic_b200;
+
+static int g_failed = 0, g_run = 0;
+#define CHECK(cond)                                                              \
+  do {                                                                           \
+    if (!(cond)) {                                                               \
+      std::printf("  FAILED %s:%d: %s\n", __FILE__, __LINE__, #cond);            \
+      ++g_failed;                                                                \
+    }                                                                            \
+  } while (0)
+#define RUN(fn)                          \
+  do {                                   \
+    std::printf("%s\n", #fn);            \
+    ++g_run;                             \
+    try {                                \
+      fn();                              \
+    } catch (const std::exception& e) {  \
+      std::printf("  EXCEPTION %s\n", e.what()); \
+      ++g_failed;                        \
+    }                                    \
+  } while (0)
+
+static std::string tmp_path(const char* name) {
+  const char* d = std::getenv("TMPDIR");
+  return std::string(d ? d : "/tmp") + "/mosaic_b200_" + name;
+}
+
+// ---------------------------------------------------------------- no GPU needed
+static void test_similarity_database_get_lab_color() {  // similarity.rs:235-252
+  SimilarityDatabase db;
+  db.add_tile("test.png", Lab{50.0f, 25.0f, -15.0f});
+  const auto got = db.get_lab_color("test.png");
+  CHECK(got.has_value());
+  CHECK(got->l == 50.0f && got->a == 25.0f && got->b == -15.0f);
+  CHECK(!db.get_lab_color("nonexistent.png").has_value());
+}
+
+static void test_similarity_database_empty() {  // similarity.rs:308-318
+  SimilarityDatabase db;
+  CHECK(!db.get_similarity("tile1.png", "tile2.png").has_value());
+  CHECK(!db.get_lab_color("tile1.png").has_value());
+}
+
+static void test_similarity_database_load_or_new() {  // similarity.rs:281-296
+  CHECK(SimilarityDatabase::load_or_new("nonexistent_db.json").len() == 0);
+  SimilarityDatabase original;
+  original.add_tile("test.png", Lab{50.0f, 0.0f, 0.0f});
+  const std::string f = tmp_path("load_or_new.json");
+  original.save_to_file(f);
+  CHECK(SimilarityDatabase::load_or_new(f).len() == 1);
+  std::remove(f.c_str());
+}
+
+static void test_similarity_database_load_from_invalid_file() {  // similarity.rs:299-305
+  const std::string f = tmp_path("invalid.json");
+  std::ofstream(f) << "invalid json";
+  bool threw = false;
+  try {
+    SimilarityDatabase::load_from_file(f);
+  } catch (const Error&) {
+    threw = true;
+  }
+  CHECK(threw);
+  std::remove(f.c_str());
+}
+
+static void test_grid_position_adjacent() {  // adjacency.rs:225-241
+  const auto adj = GridPosition(1, 1).get_adjacent_positions(3, 3);
+  CHECK(adj.size() == 4);
+  CHECK(adj[0] == GridPosition(1, 0) && adj[1] == GridPosition(1, 2) && adj[2] == GridPosition(0, 1) && adj[3] == GridPosition(2, 1));
+  const auto corner = GridPosition(0, 0).get_adjacent_positions(3, 3);
+  CHECK(corner.size() == 2);
+  CHECK(corner[0] == GridPosition(0, 1) && corner[1] == GridPosition(1, 0));
+}
+
+static void test_optimization_result_improvement() {  // optimizer.rs:280-292, 550-586
+  OptimizationResult r;
+  r.initial_cost = 100.0f, r.final_cost = 75.0f, r.best_cost = 75.0f;
+  CHECK(r.improvement_percentage() == 25.0f);
+  OptimizationResult zero;
+  CHECK(zero.improvement_percentage() == 0.0f);
+  OptimizationResult worse;
+  worse.initial_cost = 50.0f, worse.final_cost = 75.0f;
+  CHECK(worse.improvement_percentage() == -50.0f);
+  OptimizationResult perfect;
+  perfect.initial_cost = 100.0f, perfect.final_cost = 0.0f;
+  CHECK(perfect.improvement_percentage() == 100.0f);
+}
+
+static void test_optimization_config_defaults() {  // optimizer.rs:621-628
+  OptimizationConfig c;
+  CHECK(c.max_iterations == 1000 && c.initial_temperature == 100.0f && c.temperature_decay == 0.99995f && c.report_interval == 100);
+}
+
+static void test_optimization_empty_grid() {  // optimizer.rs:295-307 — returns before any device work
+  PathGrid empty;
+  SimilarityDatabase db;
+  AdjacencyPenaltyCalculator calc(db, 1.0f);
+  MosaicOptimizer opt(calc, OptimizationConfig());
+  const OptimizationResult r = opt.optimize(empty);
+  CHECK(r.initial_cost == 0.0f && r.final_cost == 0.0f && r.improved_count == 0);
+}
+
+static void test_no_gpu_is_loud() {  // there is no CPU fallback behind the mirror: without a device the call throws
+  SimilarityDatabase db;
+  db.add_tile("a.png", Lab{50.0f, 0.0f, 0.0f});
+  db.add_tile("b.png", Lab{60.0f, 10.0f, 10.0f});
+  try {
+    db.build_similarities();
+    CHECK(db.get_similarity("a.png", "b.png") == std::optional<float>(std::sqrt(300.0f)));  // a GPU was there after all
+    std::printf("  (device present: computed on the GPU)\n");
+  } catch (const Error& e) {
+    CHECK(e.code == MOSAIC_ERR_CUDA);
+    CHECK(!db.get_similarity("a.png", "b.png").has_value() || *db.get_similarity("a.png", "b.png") == 0.0f);
+    std::printf("  (no device: %s)\n", e.what());
+  }
+}
+
+// ---------------------------------------------------------------- GPU
+static SimilarityDatabase three_tiles() {
+  SimilarityDatabase db;
+  db.add_tile("tile1.png", Lab{50.0f, 0.0f, 0.0f});
+  db.add_tile("tile2.png", Lab{60.0f, 10.0f, 10.0f});
+  db.add_tile("tile3.png", Lab{40.0f, -10.0f, -10.0f});
+  db.build_similarities();
+  return db;
+}
+
+static void test_similarity_database_basic() {  // similarity.rs:186-204
+  const SimilarityDatabase db = three_tiles();
+  CHECK(db.get_similarity("tile1.png", "tile2.png").has_value());
+  CHECK(db.get_similarity("tile1.png", "tile1.png") == std::optional<float>(0.0f));
+}
+
+static void test_similarity_database_multiple_tiles() {  // similarity.rs:336-361 + the fixture's values (√300, √1200)
+  const SimilarityDatabase db = three_tiles();
+  const auto s12 = db.get_similarity("tile1.png", "tile2.png"), s21 = db.get_similarity("tile2.png", "tile1.png");
+  const auto s13 = db.get_similarity("tile1.png", "tile3.png"), s23 = db.get_similarity("tile2.png", "tile3.png");
+  CHECK(s12 && s21 && s13 && s23);
+  CHECK(s12 == s21);
+  CHECK(*s12 > 0.0f && *s13 > 0.0f && *s23 > 0.0f);
+  CHECK(*s12 == std::sqrt(300.0f) && *s13 == std::sqrt(300.0f) && *s23 == std::sqrt(1200.0f));
+}
+
+static void test_similarity_database_single_tile() {  // similarity.rs:321-333
+  SimilarityDatabase db;
+  db.add_tile("tile1.png", Lab{50.0f, 0.0f, 0.0f});
+  db.build_similarities();
+  CHECK(db.get_similarity("tile1.png", "tile1.png") == std::optional<float>(0.0f));
+  CHECK(!db.get_similarity("tile1.png", "nonexistent.png").has_value());
+}
+
+static void test_similarity_database_save_load() {  // similarity.rs:255-278
+  SimilarityDatabase db;
+  db.add_tile("tile1.png", Lab{50.0f, 0.0f, 0.0f});
+  db.add_tile("tile2.png", Lab{60.0f, 10.0f, 10.0f});
+  db.build_similarities();
+  const std::string f = tmp_path("save_load.json");
+  db.save_to_file(f);
+  const SimilarityDatabase loaded = SimilarityDatabase::load_from_file(f);
+  CHECK(loaded.len() == 2);
+  const auto sim = loaded.get_similarity("tile1.png", "tile2.png");
+  CHECK(sim && *sim > 0.0f && *sim == *db.get_similarity("tile1.png", "tile2.png"));
+  std::remove(f.c_str());
+}
+
+static void test_adjacency_penalty_calculation() {  // adjacency.rs:243-271; value from SURVEY Appendix B
+  const SimilarityDatabase db = three_tiles();
+  AdjacencyPenaltyCalculator calc(db, 1.0f);
+  PathGrid grid(3, std::vector<std::optional<std::string>>(3));
+  grid[0][0] = "tile1.png";
+  grid[0][1] = "tile2.png";
+  const float penalty = calc.calculate_penalty("tile3.png", GridPosition(1, 0), grid, 3, 3);
+  CHECK(penalty > 0.0f);
+  // neighbours of (1,0): down (empty), left tile1 (√300), right (empty) -> 1 / (17.320509 + 1)
+  CHECK(penalty == 1.0f / (std::sqrt(300.0f) + 1.0f));
+}
+
+static void test_total_cost_calculation() {  // adjacency.rs:273-290
+  SimilarityDatabase db;
+  db.add_tile("tile1.png", Lab{50.0f, 0.0f, 0.0f});
+  db.add_tile("tile2.png", Lab{50.0f, 0.0f, 0.0f});
+  db.build_similarities();
+  AdjacencyPenaltyCalculator calc(db, 1.0f);
+  PathGrid grid(2, std::vector<std::optional<std::string>>(2));
+  grid[0][0] = "tile1.png";
+  grid[0][1] = "tile2.png";
+  const float total = calc.calculate_total_cost(grid);
+  CHECK(total > 0.5f);
+  CHECK(total == 1.0f);  // identical colours: similarity 0 -> 1 / (0 + 1)
+}
+
+static SimilarityDatabase four_tiles() {  // optimizer.rs:230-245
+  SimilarityDatabase db;
+  db.add_tile("tile1.png", Lab{50.0f, 0.0f, 0.0f});
+  db.add_tile("tile2.png", Lab{60.0f, 10.0f, 10.0f});
+  db.add_tile("tile3.png", Lab{40.0f, -10.0f, -10.0f});
+  db.add_tile("tile4.png", Lab{55.0f, 5.0f, 5.0f});
+  db.build_similarities();
+  return db;
+}
+static PathGrid four_grid() {
+  PathGrid grid(2, std::vector<std::optional<std::string>>(2));
+  grid[0][0] = "tile1.png", grid[0][1] = "tile2.png", grid[1][0] = "tile3.png", grid[1][1] = "tile4.png";
+  return grid;
+}
+
+static bool same_multiset(const PathGrid& a, const PathGrid& b) {
+  std::vector<std::string> va, vb;
+  for (const auto& r : a)
+    for (const auto& c : r) va.push_back(c ? *c : "<none>");
+  for (const auto& r : b)
+    for (const auto& c : r) vb.push_back(c ? *c : "<none>");
+  std::sort(va.begin(), va.end());
+  std::sort(vb.begin(), vb.end());
+  return va == vb;
+}
+
+static void test_optimization_basic() {  // optimizer.rs:247-264
+  const SimilarityDatabase db = four_tiles();
+  PathGrid grid = four_grid();
+  AdjacencyPenaltyCalculator calc(db, 1.0f);
+  OptimizationConfig cfg;
+  cfg.max_iterations = 10;
+  const OptimizationResult r = MosaicOptimizer(calc, cfg).optimize(grid);
+  CHECK(r.iterations == 10);
+  CHECK(r.final_cost >= 0.0f);
+  CHECK(same_multiset(grid, four_grid()));  // swaps only permute the tiles
+  // the energy the optimiser reports is the energy of the grid it returns (up to the f32 drift of summed deltas)
+  CHECK(std::fabs(calc.calculate_total_cost(grid) - r.final_cost) < 1e-4f);
+  // the fixture's initial energy, SURVEY Appendix B: 0x3E7FBDDA
+  uint32_t bits;
+  std::memcpy(&bits, &r.initial_cost, 4);
+  CHECK(bits == 0x3E7FBDDAu);
+}
+
+static void test_optimization_single_tile_grid() {  // optimizer.rs:310-331
+  SimilarityDatabase db;
+  db.add_tile("single.png", Lab{50.0f, 0.0f, 0.0f});
+  db.build_similarities();
+  PathGrid grid(1, std::vector<std::optional<std::string>>(1));
+  grid[0][0] = "single.png";
+  AdjacencyPenaltyCalculator calc(db, 1.0f);
+  OptimizationConfig cfg;
+  cfg.max_iterations = 100;
+  const OptimizationResult r = MosaicOptimizer(calc, cfg).optimize(grid);
+  CHECK(r.initial_cost == 0.0f && r.final_cost == 0.0f && r.improved_count == 0 && r.accepted_count == 0);
+  CHECK(grid[0][0] == std::optional<std::string>("single.png"));
+}
+
+static void test_optimization_grid_with_empty_cells() {  // optimizer.rs:334-358
+  SimilarityDatabase db;
+  db.add_tile("tile1.png", Lab{50.0f, 0.0f, 0.0f});
+  db.add_tile("tile2.png", Lab{60.0f, 10.0f, 10.0f});
+  db.build_similarities();
+  PathGrid grid(3, std::vector<std::optional<std::string>>(3));
+  grid[0][0] = "tile1.png";
+  grid[2][2] = "tile2.png";
+  AdjacencyPenaltyCalculator calc(db, 1.0f);
+  OptimizationConfig cfg;
+  cfg.max_iterations = 50;
+  const OptimizationResult r = MosaicOptimizer(calc, cfg).optimize(grid);
+  CHECK(r.final_cost >= 0.0f);
+  CHECK(r.initial_cost == 0.0f);
+  int placed = 0;
+  for (const auto& row : grid)
+    for (const auto& c : row) placed += c.has_value();
+  CHECK(placed == 2);
+}
+
+static void test_optimization_extreme_temperature_values() {  // optimizer.rs:361-397
+  const SimilarityDatabase db = four_tiles();
+  AdjacencyPenaltyCalculator calc(db, 1.0f);
+  PathGrid g1 = four_grid(), g2 = four_grid();
+  OptimizationConfig hi;
+  hi.max_iterations = 20, hi.initial_temperature = 10000.0f, hi.temperature_decay = 0.95f;
+  const OptimizationResult rh = MosaicOptimizer(calc, hi).optimize(g1);
+  CHECK(rh.iterations == 20 && rh.final_cost >= 0.0f);
+  OptimizationConfig lo;
+  lo.max_iterations = 20, lo.initial_temperature = 0.001f, lo.temperature_decay = 0.99f;
+  const OptimizationResult rl = MosaicOptimizer(calc, lo).optimize(g2);
+  CHECK(rl.iterations == 20);
+  CHECK(rl.final_cost <= rl.initial_cost || std::isfinite(rl.final_cost));
+}
+
+static void test_optimization_decay_edge_cases() {  // optimizer.rs:400-437
+  const SimilarityDatabase db = four_tiles();
+  AdjacencyPenaltyCalculator calc(db, 1.0f);
+  PathGrid g = four_grid();
+  OptimizationConfig zero;
+  zero.max_iterations = 10, zero.temperature_decay = 0.0f;
+  const OptimizationResult rz = MosaicOptimizer(calc, zero).optimize(g);
+  CHECK(rz.iterations == 10 && std::isfinite(rz.final_cost));
+  PathGrid g2 = four_grid();
+  OptimizationConfig fast;
+  fast.max_iterations = 50, fast.initial_temperature = 1000.0f, fast.temperature_decay = 0.5f;
+  const OptimizationResult rf = MosaicOptimizer(calc, fast).optimize(g2);
+  CHECK(rf.iterations == 50 && rf.final_cost >= 0.0f);
+}
+
+static void test_optimization_zero_and_single_iteration() {  // optimizer.rs:440-475
+  const SimilarityDatabase db = four_tiles();
+  AdjacencyPenaltyCalculator calc(db, 1.0f);
+  PathGrid g = four_grid();
+  OptimizationConfig c0;
+  c0.max_iterations = 0;
+  const OptimizationResult r0 = MosaicOptimizer(calc, c0).optimize(g);
+  CHECK(r0.iterations == 0 && r0.improved_count == 0 && r0.accepted_count == 0 && r0.initial_cost == r0.final_cost);
+  CHECK(g == four_grid());
+  OptimizationConfig c1;
+  c1.max_iterations = 1;
+  const OptimizationResult r1 = MosaicOptimizer(calc, c1).optimize(g);
+  CHECK(r1.iterations == 1 && std::isfinite(r1.final_cost));
+}
+
+static void test_optimization_large_grid() {  // optimizer.rs:478-518
+  SimilarityDatabase db;
+  for (int i = 0; i < 25; ++i)
+    db.add_tile("tile_" + std::to_string(i) + ".png", Lab{50.0f + (float)i, ((float)i - 12.0f) * 2.0f, ((float)i - 12.0f) * 3.0f});
+  db.build_similarities();
+  PathGrid grid(5, std::vector<std::optional<std::string>>(5));
+  for (int y = 0, t = 0; y < 5; ++y)
+    for (int x = 0; x < 5; ++x) grid[y][x] = "tile_" + std::to_string(t++) + ".png";
+  const PathGrid before = grid;
+  AdjacencyPenaltyCalculator calc(db, 0.5f);
+  OptimizationConfig cfg;
+  cfg.max_iterations = 100, cfg.report_interval = 25;
+  const OptimizationResult r = MosaicOptimizer(calc, cfg).optimize(grid);
+  CHECK(r.iterations == 100 && r.final_cost >= 0.0f && r.initial_cost >= 0.0f);
+  CHECK(same_multiset(grid, before));
+  CHECK(r.best_cost <= r.initial_cost);
+  CHECK(r.improved_count <= r.accepted_count && r.accepted_count <= 100);
+}
+
+static void test_optimization_identical_tiles() {  // optimizer.rs:589-618
+  SimilarityDatabase db;
+  for (int i = 1; i <= 4; ++i) db.add_tile("identical" + std::to_string(i) + ".png", Lab{50.0f, 0.0f, 0.0f});
+  db.build_similarities();
+  PathGrid grid(2, std::vector<std::optional<std::string>>(2));
+  grid[0][0] = "identical1.png", grid[0][1] = "identical2.png", grid[1][0] = "identical3.png", grid[1][1] = "identical4.png";
+  AdjacencyPenaltyCalculator calc(db, 1.0f);
+  OptimizationConfig cfg;
+  cfg.max_iterations = 50;
+  const OptimizationResult r = MosaicOptimizer(calc, cfg).optimize(grid);
+  CHECK(r.initial_cost > 0.0f && r.iterations == 50);
+  CHECK(r.initial_cost == 4.0f);  // four pairs at similarity 0
+}
+
+static void test_optimization_numerical_stability() {  // optimizer.rs:631-662
+  SimilarityDatabase db;
+  db.add_tile("extreme1.png", Lab{0.0f, -100.0f, -100.0f});
+  db.add_tile("extreme2.png", Lab{100.0f, 100.0f, 100.0f});
+  db.add_tile("extreme3.png", Lab{50.0f, 0.0f, 0.0f});
+  db.add_tile("extreme4.png", Lab{25.0f, -50.0f, 50.0f});
+  db.build_similarities();
+  PathGrid grid(2, std::vector<std::optional<std::string>>(2));
+  grid[0][0] = "extreme1.png", grid[0][1] = "extreme2.png", grid[1][0] = "extreme3.png", grid[1][1] = "extreme4.png";
+  AdjacencyPenaltyCalculator calc(db, 2.0f);
+  OptimizationConfig cfg;
+  cfg.max_iterations = 30, cfg.initial_temperature = 1000.0f;
+  const OptimizationResult r = MosaicOptimizer(calc, cfg).optimize(grid);
+  CHECK(std::isfinite(r.initial_cost) && std::isfinite(r.final_cost) && std::isfinite(r.best_cost) && r.iterations == 30);
+}
+
+static void test_lab_color_calculation() {  // lib.rs:133-158: solid red and gray, ±1.0
+  RgbImage red(10, 10), gray(10, 10);
+  for (size_t i = 0; i < red.data.size(); i += 3) red.data[i] = 255;
+  std::fill(gray.data.begin(), gray.data.end(), (uint8_t)128);
+  const Lab r = MosaicGeneratorImpl::calculate_average_lab(red);
+  CHECK(std::fabs(r.l - 53.24f) < 1.0f && std::fabs(r.a - 80.09f) < 1.0f && std::fabs(r.b - 67.20f) < 1.0f);
+  const Lab g = MosaicGeneratorImpl::calculate_average_lab(gray);
+  CHECK(std::fabs(g.l - 53.59f) < 1.0f && std::fabs(g.a) < 1.0f && std::fabs(g.b) < 1.0f);
+}
+
+// ---------------------------------------------------------------- end to end (driven by the Python parity test)
+static std::vector<uint8_t> read_all(const std::string& f) {
+  std::ifstream in(f, std::ios::binary);
+  return std::vector<uint8_t>((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
+}
+
+static int generate(const std::string& dir) {
+  int n, mw, mh, tw, th, gw, gh, max_usage, optimize, rebuild;
+  unsigned long long iters, seed;
+  float weight, strength;
+  std::string db_path;
+  {
+    std::ifstream meta(dir + "/meta.txt");
+    meta >> n >> mw >> mh >> tw >> th >> gw >> gh >> max_usage >> weight >> strength >> optimize >> iters >> seed >> rebuild >> db_path;
+    if (!meta) {
+      std::printf("bad meta.txt\n");
+      return 2;
+    }
+  }
+  if (db_path == "-") db_path.clear();
+  const std::vector<uint8_t> mats = read_all(dir + "/materials.bin");
+  RgbImage target(tw, th);
+  target.data = read_all(dir + "/target.bin");
+  if (mats.size() != (size_t)n * mw * mh * 3 || target.data.size() != (size_t)tw * th * 3) {
+    std::printf("input sizes do not match meta.txt\n");
+    return 2;
+  }
+  std::vector<std::string> paths;
+  for (int i = 0; i < n; ++i) paths.push_back("materials/m" + std::to_string(i) + ".png");
+  MosaicGenerator gen(paths, mats.data(), mw, mh, (size_t)max_usage, db_path, rebuild != 0, weight, strength);
+  PathGrid placed;
+  mosaic_report rep{};
+  const RgbImage out = gen.generate_mosaic(target, gw, gh, optimize != 0, iters, seed, &placed, &rep);
+  std::vector<int32_t> ids;
+  std::map<std::string, int32_t> index;
+  for (int i = 0; i < n; ++i) index[paths[i]] = i;
+  for (const auto& row : placed)
+    for (const auto& c : row) ids.push_back(c ? index[*c] : -1);
+  std::ofstream(dir + "/placed.bin", std::ios::binary).write((const char*)ids.data(), (std::streamsize)(ids.size() * 4));
+  std::ofstream(dir + "/image.bin", std::ios::binary).write((const char*)out.data.data(), (std::streamsize)out.data.size());
+  std::ofstream rpt(dir + "/report.txt");
+  rpt << out.width << " " << out.height << " " << rep.n_fallbacks << " " << rep.annealed << " " << rep.opt.accepted_count << " "
+      << rep.opt.improved_count << " " << gen.similarity_db().len() << "\n";
+  return 0;
+}
+
+int main(int argc, char** argv) {
+  const bool cpu_only = argc > 1 && std::string(argv[1]) == "--cpu";
+  if (argc > 2 && std::string(argv[1]) == "--generate") {
+    try {
+      return generate(argv[2]);
+    } catch (const std::exception& e) {
+      std::printf("EXCEPTION %s\n", e.what());
+      return 1;
+    }
+  }
+  RUN(test_similarity_database_get_lab_color);
+  RUN(test_similarity_database_empty);
+  RUN(test_similarity_database_load_or_new);
+  RUN(test_similarity_database_load_from_invalid_file);
+  RUN(test_grid_position_adjacent);
+  RUN(test_optimization_result_improvement);
+  RUN(test_optimization_config_defaults);
+  RUN(test_optimization_empty_grid);
+  if (cpu_only) {
+    RUN(test_no_gpu_is_loud);
+  } else {
+    RUN(test_similarity_database_basic);
+    RUN(test_similarity_database_multiple_tiles);
+    RUN(test_similarity_database_single_tile);
+    RUN(test_similarity_database_save_load);
+    RUN(test_adjacency_penalty_calculation);
+    RUN(test_total_cost_calculation);
+    RUN(test_optimization_basic);
+    RUN(test_optimization_single_tile_grid);
+    RUN(test_optimization_grid_with_empty_cells);
+    RUN(test_optimization_extreme_temperature_values);
+    RUN(test_optimization_decay_edge_cases);
+    RUN(test_optimization_zero_and_single_iteration);
+    RUN(test_optimization_large_grid);
+    RUN(test_optimization_identical_tiles);
+    RUN(test_optimization_numerical_stability);
+    RUN(test_lab_color_calculation);
+  }
+  std::printf("%d tests, %d failed checks\n", g_run, g_failed);
+  return g_failed ? 1 : 0;
+}

@@ -127,6 +127,36 @@ def test_place_bit_exact(ctx, n, gw, gh, max_usage, weight):
     assert (placed == rplaced).all()
 
 
+@pytest.mark.parametrize("n,gw,gh", [(300, 24, 16), (300, 48, 20), (100, 40, 12)])
+def test_loaded_database_colours_drive_the_similarities(ctx, n, gw, gh):
+    """main.rs:120-143: with a database loaded from a file, matching uses the tiles' Lab means but every similarity
+    (matrix, adjacency penalty, annealing energy) comes from the colours stored in the file."""
+    mat_lab = synth.lab_points(n, seed=n)
+    db_lab = (mat_lab + np.random.default_rng(5).normal(0, 6.0, mat_lab.shape)).astype(np.float32)  # a stale file
+    yy, xx = np.mgrid[0:gh, 0:gw]
+    cell_lab = np.stack([50 + 30 * np.sin(xx / 5.0), 40 * np.cos(yy / 4.0), 30 * np.sin((xx + yy) / 6.0)], -1)
+    cell_lab = cell_lab.reshape(-1, 3).astype(np.float32)
+    ctx.set_material_lab(mat_lab)
+    ctx.set_cell_lab(cell_lab, gw, gh)
+    ctx.set_similarity_lab(db_lab)
+    idx, d2 = ctx.candidates()
+    ridx, rd2 = orc.topk(mat_lab, cell_lab, 100)                      # candidates: the tiles' colours
+    assert (idx == ridx).all() and (d2.view(np.uint32) == rd2.view(np.uint32)).all()
+    placed, nfb = ctx.place(3, 0.3)
+    rplaced, rnfb, rfb, _ = orc.place(idx, d2, db_lab, gw, gh, 3, 0.3)  # penalties: the database's colours
+    assert nfb == rnfb and (placed == rplaced).all()
+    plain, _, _, _ = orc.place(idx, d2, mat_lab, gw, gh, 3, 0.3)
+    assert (plain != rplaced).any(), "the fixture must make the two colour sets disagree"
+    assert (ctx.similarity_tri().view(np.uint32) == orc.similarity_tri(db_lab).view(np.uint32)).all()
+    out, res = ctx.anneal(1500, 11)
+    rgrid, rres = orc.anneal(db_lab, rplaced.reshape(gh, gw), 1500, 11)
+    assert (out.reshape(gh, gw) == rgrid).all()
+    assert np.float32(res.final_cost).view(np.uint32) == np.float32(rres.final_cost).view(np.uint32)
+    ctx.set_similarity_lab(None)                                        # back to the tiles' own colours
+    placed2, _ = ctx.place(3, 0.3)
+    assert (placed2 == plain).all()
+
+
 def test_place_randomized_against_the_replay(ctx):
     """Random shapes, caps, weights and colour fields through the chain kernel (hot blocks, contended cells, the
     multi-chunk path, usage resets, narrow-grid kernel) against the oracle's replay of main.rs:335-475."""

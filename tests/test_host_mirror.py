@@ -1,0 +1,207 @@
+"""The C++ host mirror of the reference's interface (include/mosaic_b200.hpp) — the reference is a Rust crate and this
+image has no rustc, so the host side above the C ABI is C++ with the reference's names.  tests/cpp/test_host_mirror.cpp
+restates the reference's own unit tests (similarity.rs, adjacency.rs, optimizer.rs, lib.rs) against it; this file
+builds that binary, runs it, and checks MosaicGenerator end to end against the ctypes path (which the stage-wise parity
+tests pin to the oracle), including the saved / reloaded / stale similarity-database cases of main.rs:120-143."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "mosaic-art-rust_b200")
+SRC = os.path.join(ROOT, "tests", "cpp", "test_host_mirror.cpp")
+BIN = os.path.join(ROOT, "tests", "cpp", "_build", "test_host_mirror")
+
+
+@pytest.fixture(scope="module")
+def binary(lib_built):
+    deps = [SRC, os.path.join(ROOT, "include", "mosaic_b200.hpp"), os.path.join(ROOT, "include", "mosaic_b200.h"),
+            os.path.join(PKG, "libmosaic_b200.so")]
+    if not os.path.exists(BIN) or any(os.path.getmtime(d) > os.path.getmtime(BIN) for d in deps):
+        os.makedirs(os.path.dirname(BIN), exist_ok=True)
+        subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+                               SRC, "-L", PKG, "-lmosaic_b200", "-Wl,-rpath," + PKG, "-o", BIN])
+    return BIN
+
+
+def _run(args, **kw):
+    r = subprocess.run(args, capture_output=True, text=True, timeout=600, **kw)
+    assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-2000:]
+    return r.stdout
+
+
+def test_mirror_builds_and_host_only_tests_pass(binary, tmp_path):
+    """Compiles with -Wall -Wextra -Werror against the shipped header, links every entry point the mirror uses, and runs
+    the reference tests that need no device (bookkeeping, file format, loud failure without a GPU)."""
+    out = _run([binary, "--cpu"], env=dict(os.environ, TMPDIR=str(tmp_path)))
+    assert "0 failed checks" in out
+
+
+@pytest.mark.gpu
+def test_reference_unit_tests_through_the_mirror(binary, tmp_path):
+    out = _run([binary], env=dict(os.environ, TMPDIR=str(tmp_path)))
+    assert "0 failed checks" in out and "test_optimization_numerical_stability" in out
+
+
+def _write_case(d, mats, tgt, gw, gh, max_usage, weight, strength, optimize, iters, seed, rebuild, db_path):
+    mats.tofile(os.path.join(d, "materials.bin"))
+    tgt.tofile(os.path.join(d, "target.bin"))
+    n, mh, mw, _ = mats.shape
+    with open(os.path.join(d, "meta.txt"), "w") as f:
+        f.write(f"{n} {mw} {mh} {tgt.shape[1]} {tgt.shape[0]} {gw} {gh} {max_usage} {weight!r} {strength!r} "
+                f"{int(optimize)} {iters} {seed} {int(rebuild)} {db_path or '-'}\n")
+
+
+def _read_result(d, gw, gh):
+    w, h, nfb, annealed, acc, imp, dblen = (int(v) for v in open(os.path.join(d, "report.txt")).read().split())
+    placed = np.fromfile(os.path.join(d, "placed.bin"), np.int32)
+    img = np.fromfile(os.path.join(d, "image.bin"), np.uint8).reshape(h, w, 3)
+    assert placed.size == gw * gh
+    return placed, img, dict(n_fallbacks=nfb, annealed=annealed, accepted=acc, improved=imp, db_len=dblen)
+
+
+@pytest.mark.gpu
+def test_mosaic_generator_matches_the_c_abi_path(binary, ctx, tmp_path):
+    import mosaic_b200
+    from mosaic_b200 import synth
+
+    n, gw, gh = 300, 40, 24
+    mats = synth.materials(n)
+    tgt = synth.target(640, 384)
+    args = dict(max_usage=3, weight=0.3, strength=0.3, optimize=True, iters=800, seed=42)
+
+    def through_ctypes(sim_lab=None):
+        ctx.set_materials(mats)
+        ctx.set_target(tgt, gw, gh)
+        ctx.material_lab()
+        ctx.set_similarity_lab(sim_lab)
+        placed = np.zeros(gw * gh, np.int32)
+        img = np.zeros(ctx.output_shape(), np.uint8)
+        rep = ctx.generate(max_usage=3, adjacency_weight=0.3, color_strength=0.3, enable_optimization=True,
+                           optimization_iterations=800, seed=42, build_similarity=False, placed_out=placed, image_out=img)
+        return placed, img, rep
+
+    ref_placed, ref_img, ref_rep = through_ctypes()
+
+    # 1. no database file
+    d = str(tmp_path)
+    _write_case(d, mats, tgt, gw, gh, rebuild=False, db_path=None, **args)
+    _run([binary, "--generate", d])
+    placed, img, rep = _read_result(d, gw, gh)
+    assert (placed == ref_placed).all() and (img == ref_img).all()
+    assert rep["n_fallbacks"] == ref_rep.n_fallbacks and rep["annealed"] == 1 and rep["accepted"] == ref_rep.opt.accepted_count
+
+    # 2. the file does not exist: built, saved (main.rs:120-134); second run loads it (135-137): same mosaic both times
+    db = os.path.join(d, "similarity_db.json")
+    _write_case(d, mats, tgt, gw, gh, rebuild=False, db_path=db, **args)
+    _run([binary, "--generate", d])
+    assert os.path.exists(db)
+    p1, i1, _ = _read_result(d, gw, gh)
+    _run([binary, "--generate", d])
+    p2, i2, r2 = _read_result(d, gw, gh)
+    assert (p1 == ref_placed).all() and (p2 == ref_placed).all() and (i1 == ref_img).all() and (i2 == ref_img).all()
+    assert r2["db_len"] == n
+
+    # 3. a stale file: other colours for the known paths, two paths missing (topped up), one foreign path —
+    #    similarities follow the FILE's colours, matching the tiles' (main.rs:135-143)
+    sdb = mosaic_b200.SimilarityDb.load(db)
+    lab, sim = sdb.arrays()
+    paths = [sdb.path(i) for i in range(n)]
+    sdb.close()
+    stale = (lab + np.random.default_rng(3).normal(0, 8.0, lab.shape)).astype(np.float32)
+    keep = [i for i in range(n) if i not in (7, 123)]
+    file_paths = [paths[i] for i in keep] + ["elsewhere/foreign.png"]
+    file_lab = np.concatenate([stale[keep], np.array([[10.0, 20.0, -30.0]], np.float32)])
+    m = len(file_paths)
+    mosaic_b200.SimilarityDb.save(db, file_paths, file_lab, np.zeros(m * (m - 1) // 2, np.float32))
+    _run([binary, "--generate", d])
+    p3, i3, r3 = _read_result(d, gw, gh)
+    assert r3["db_len"] == n + 1
+    expect_lab = stale.copy()
+    tile_lab = ctx.material_lab()
+    expect_lab[[7, 123]] = tile_lab[[7, 123]]
+    e_placed, e_img, _ = through_ctypes(expect_lab)
+    assert (p3 == e_placed).all() and (i3 == e_img).all()
+    assert (e_placed != ref_placed).any(), "the stale colours must change the mosaic for this test to mean anything"
+
+    # 4. --rebuild-similarity-db ignores the stale file and overwrites it
+    _write_case(d, mats, tgt, gw, gh, rebuild=True, db_path=db, **args)
+    _run([binary, "--generate", d])
+    p4, i4, r4 = _read_result(d, gw, gh)
+    assert (p4 == ref_placed).all() and (i4 == ref_img).all() and r4["db_len"] == n
+
+
+# ---------------------------------------------------------------- the C++ host CLI (reference flag names)
+CLI = os.path.join(PKG, "host", "mosaic-b200")
+
+
+@pytest.fixture(scope="module")
+def cli(lib_built):
+    subprocess.check_call(["make", "-C", PKG, "host/mosaic-b200"], stdout=subprocess.DEVNULL)
+    return CLI
+
+
+def _write_ppm(path, img):
+    with open(path, "wb") as f:
+        f.write(b"P6\n%d %d\n255\n" % (img.shape[1], img.shape[0]))
+        f.write(np.ascontiguousarray(img, np.uint8).tobytes())
+
+
+def _read_ppm(path):
+    with open(path, "rb") as f:
+        assert f.readline() == b"P6\n"
+        w, h = (int(v) for v in f.readline().split())
+        assert f.readline() == b"255\n"
+        return np.frombuffer(f.read(), np.uint8).reshape(h, w, 3)
+
+
+def test_cli_flags_and_errors(cli, tmp_path):
+    r = subprocess.run([cli], capture_output=True, text=True)
+    assert r.returncode == 2 and "--target" in r.stderr
+    r = subprocess.run([cli, "-t", "a", "-m", "b", "-o", "c", "--no-such-flag", "1"], capture_output=True, text=True)
+    assert r.returncode == 2 and "unexpected argument" in r.stderr
+    r = subprocess.run([cli, "-t", str(tmp_path / "none.ppm"), "-m", str(tmp_path), "-o", str(tmp_path / "o.ppm")],
+                       capture_output=True, text=True)
+    assert r.returncode == 1 and "cannot read target" in r.stderr
+
+
+@pytest.mark.gpu
+def test_cli_end_to_end(cli, ctx, tmp_path):
+    from mosaic_b200 import synth
+
+    n, gw, gh = 60, 20, 12
+    mats = synth.materials(n + 5)
+    tgt = synth.target(320, 192)
+    mdir = tmp_path / "materials"
+    mdir.mkdir()
+    for i in range(n + 5):
+        _write_ppm(mdir / f"m{i:04d}.ppm", mats[i])
+    (mdir / "notes.txt").write_text("not an image")
+    _write_ppm(tmp_path / "target.ppm", tgt)
+    out = tmp_path / "out.ppm"
+    db = tmp_path / "similarity_db.json"
+    # square materials against a 5:3 target: the aspect filter matches nothing -> fallback takes min(len, 2*max) files,
+    # then truncate to --max-materials (main.rs:211-257)
+    stdout = _run([cli, "--target", str(tmp_path / "target.ppm"), "--material-src", str(mdir), "--output", str(out),
+                   "--grid-w", str(gw), "--grid-h", str(gh), "--max-materials", str(n), "--max-usage-per-image", "4",
+                   "--adjacency-penalty-weight", "0.25", "--color-adjustment-strength", "0.4",
+                   "--optimization-iterations", "300", "--similarity-db", str(db), "--seed", "7"])
+    assert "No tiles matched target aspect ratio" in stdout and f"Loaded {n} tiles" in stdout
+    assert db.exists()
+    ctx.set_materials(mats[:n])
+    ctx.set_target(tgt, gw, gh)
+    img = np.zeros(ctx.output_shape(), np.uint8)
+    ctx.generate(max_usage=4, adjacency_weight=0.25, color_strength=0.4, enable_optimization=True,
+                 optimization_iterations=300, seed=7, build_similarity=False, image_out=img)
+    assert (_read_ppm(out) == img).all()
+    # --enable-optimization false, database reloaded from the file
+    stdout = _run([cli, "-t", str(tmp_path / "target.ppm"), "-m", str(mdir), "-o", str(out), "--grid-w", str(gw),
+                   "--grid-h", str(gh), "--max-materials", str(n), "--max-usage-per-image", "4",
+                   "--adjacency-penalty-weight", "0.25", "--color-adjustment-strength", "0.4",
+                   "--enable-optimization", "false", "--similarity-db", str(db)])
+    assert "Optimization complete" not in stdout
+    ctx.generate(max_usage=4, adjacency_weight=0.25, color_strength=0.4, enable_optimization=False,
+                 optimization_iterations=0, seed=0, build_similarity=False, image_out=img)
+    assert (_read_ppm(out) == img).all()
