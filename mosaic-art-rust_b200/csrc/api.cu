@@ -417,7 +417,7 @@ void mosaic_ctx_destroy(mosaic_ctx* c) {
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   dist_destroy(c);
-  void* bufs[] = {c->d_sim_lab4_own, c->d_materials_owned, c->d_mat_lab, c->d_mat_lab4, c->d_mat_soa, c->d_target_owned, c->d_cell_lab,
+  void* bufs[] = {c->d_sim_lab4_own, c->d_sim_soa_own, c->d_materials_owned, c->d_mat_lab, c->d_mat_lab4, c->d_mat_soa, c->d_target_owned, c->d_cell_lab,
                   c->d_cell_rgbsum,     c->d_cand_idx, c->d_cand_d2, c->d_placed,  c->d_usage,        c->d_place_info, c->d_place_rec,
                   c->d_sim,             c->d_sim_counter, c->d_opt_res,  c->d_rng_ring, c->d_terms, c->d_deltas, c->d_thumbs, c->d_thumb_sums, c->d_thumb_state, c->d_out,    c->axis_h.start,   c->axis_h.size,
                   c->axis_h.w,          c->axis_v.start, c->axis_v.size, c->axis_v.w};
@@ -559,10 +559,17 @@ int mosaic_set_similarity_lab(mosaic_ctx* c, const float* lab, int n) {
     return MOSAIC_OK;
   }
   if (n <= 0 || n != c->n) return fail(c, MOSAIC_ERR_INVALID, "similarity Lab count differs from the material count");
-  MOSAIC_TRY(ensure(c, &c->d_sim_lab4_own, &c->sim_lab_cap, (size_t)n));
-  std::vector<float4> packed((size_t)n);
-  for (int i = 0; i < n; ++i) packed[(size_t)i] = make_float4(lab[3 * (size_t)i], lab[3 * (size_t)i + 1], lab[3 * (size_t)i + 2], 0.0f);
-  MOSAIC_CUDA(c, cudaMemcpyAsync(c->d_sim_lab4_own, packed.data(), sizeof(float4) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+  const size_t n_pad = (size_t)((n + 3) & ~3);  // == ctx->n_pad of the material tables
+  MOSAIC_TRY(ensure(c, &c->d_sim_lab4_own, &c->sim_lab_cap, n_pad));
+  MOSAIC_TRY(ensure(c, &c->d_sim_soa_own, &c->sim_soa_cap, 3 * n_pad));
+  std::vector<float4> packed(n_pad);
+  std::vector<float> soa(3 * n_pad, __builtin_inff());
+  for (int i = 0; i < n; ++i) {
+    packed[(size_t)i] = make_float4(lab[3 * (size_t)i], lab[3 * (size_t)i + 1], lab[3 * (size_t)i + 2], 0.0f);
+    soa[(size_t)i] = lab[3 * (size_t)i], soa[n_pad + i] = lab[3 * (size_t)i + 1], soa[2 * n_pad + i] = lab[3 * (size_t)i + 2];
+  }
+  MOSAIC_CUDA(c, cudaMemcpyAsync(c->d_sim_lab4_own, packed.data(), sizeof(float4) * n_pad, cudaMemcpyHostToDevice, c->stream));
+  MOSAIC_CUDA(c, cudaMemcpyAsync(c->d_sim_soa_own, soa.data(), sizeof(float) * 3 * n_pad, cudaMemcpyHostToDevice, c->stream));
   MOSAIC_TRY(sync(c));
   c->sim_lab_override = true;
   c->have_sim = c->have_placed = false;

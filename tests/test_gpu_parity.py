@@ -131,6 +131,7 @@ def test_place_bit_exact(ctx, n, gw, gh, max_usage, weight):
 def test_loaded_database_colours_drive_the_similarities(ctx, n, gw, gh):
     """main.rs:120-143: with a database loaded from a file, matching uses the tiles' Lab means but every similarity
     (matrix, adjacency penalty, annealing energy) comes from the colours stored in the file."""
+    W = 200.0  # a weight at which the penalty decides between candidates, so that the two colour sets give different mosaics
     mat_lab = synth.lab_points(n, seed=n)
     db_lab = (mat_lab + np.random.default_rng(5).normal(0, 6.0, mat_lab.shape)).astype(np.float32)  # a stale file
     yy, xx = np.mgrid[0:gh, 0:gw]
@@ -142,10 +143,10 @@ def test_loaded_database_colours_drive_the_similarities(ctx, n, gw, gh):
     idx, d2 = ctx.candidates()
     ridx, rd2 = orc.topk(mat_lab, cell_lab, 100)                      # candidates: the tiles' colours
     assert (idx == ridx).all() and (d2.view(np.uint32) == rd2.view(np.uint32)).all()
-    placed, nfb = ctx.place(3, 0.3)
-    rplaced, rnfb, rfb, _ = orc.place(idx, d2, db_lab, gw, gh, 3, 0.3)  # penalties: the database's colours
+    placed, nfb = ctx.place(3, W)
+    rplaced, rnfb, rfb, _ = orc.place(idx, d2, db_lab, gw, gh, 3, W)  # penalties: the database's colours
     assert nfb == rnfb and (placed == rplaced).all()
-    plain, _, _, _ = orc.place(idx, d2, mat_lab, gw, gh, 3, 0.3)
+    plain, _, _, _ = orc.place(idx, d2, mat_lab, gw, gh, 3, W)
     assert (plain != rplaced).any(), "the fixture must make the two colour sets disagree"
     assert (ctx.similarity_tri().view(np.uint32) == orc.similarity_tri(db_lab).view(np.uint32)).all()
     out, res = ctx.anneal(1500, 11)
@@ -153,7 +154,7 @@ def test_loaded_database_colours_drive_the_similarities(ctx, n, gw, gh):
     assert (out.reshape(gh, gw) == rgrid).all()
     assert np.float32(res.final_cost).view(np.uint32) == np.float32(rres.final_cost).view(np.uint32)
     ctx.set_similarity_lab(None)                                        # back to the tiles' own colours
-    placed2, _ = ctx.place(3, 0.3)
+    placed2, _ = ctx.place(3, W)
     assert (placed2 == plain).all()
 
 

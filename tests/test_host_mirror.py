@@ -70,7 +70,8 @@ def test_mosaic_generator_matches_the_c_abi_path(binary, ctx, tmp_path):
     n, gw, gh = 300, 40, 24
     mats = synth.materials(n)
     tgt = synth.target(640, 384)
-    args = dict(max_usage=3, weight=0.3, strength=0.3, optimize=True, iters=800, seed=42)
+    W = 200.0  # a weight at which the penalty decides between candidates (so that stale database colours change the mosaic)
+    args = dict(max_usage=3, weight=W, strength=0.3, optimize=True, iters=800, seed=42)
 
     def through_ctypes(sim_lab=None):
         ctx.set_materials(mats)
@@ -79,7 +80,7 @@ def test_mosaic_generator_matches_the_c_abi_path(binary, ctx, tmp_path):
         ctx.set_similarity_lab(sim_lab)
         placed = np.zeros(gw * gh, np.int32)
         img = np.zeros(ctx.output_shape(), np.uint8)
-        rep = ctx.generate(max_usage=3, adjacency_weight=0.3, color_strength=0.3, enable_optimization=True,
+        rep = ctx.generate(max_usage=3, adjacency_weight=W, color_strength=0.3, enable_optimization=True,
                            optimization_iterations=800, seed=42, build_similarity=False, placed_out=placed, image_out=img)
         return placed, img, rep
 
