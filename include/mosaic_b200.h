@@ -81,6 +81,13 @@ uint64_t mosaic_kernel_launches(const mosaic_ctx* ctx);
 /* n uniform-size RGB8 materials, n*h*w*3 bytes, host memory (replaces the decoded `image::open`
  * results of process_tile, main.rs:263-301).  Copies H2D. */
 int mosaic_set_materials_rgb8(mosaic_ctx* ctx, const uint8_t* rgb, int n, int w, int h);
+/* n materials of INDIVIDUAL sizes — what the reference handles: it opens files of any size (process_tile,
+ * main.rs:263-301: Lab mean of the image as it is) and resizes each to the tile (resize_image, main.rs:710-738).
+ * Material i is widths[i] x heights[i] x 3 bytes (row-major RGB8) at rgb + offsets[i]; sizes 1..32768 per axis.
+ * Copies H2D.  The Lab means, the resampling coefficients (one table per distinct width / height) and the render
+ * follow each material's own size; everything else is unchanged. */
+int mosaic_set_materials_ragged_rgb8(mosaic_ctx* ctx, const uint8_t* rgb, const uint64_t* offsets,
+                                     const int32_t* widths, const int32_t* heights, int n);
 /* Same, but `dev_rgb` is device memory on ctx's GPU that stays valid until replaced (no copy). */
 int mosaic_set_materials_device(mosaic_ctx* ctx, const void* dev_rgb, int n, int w, int h);
 /* Target image w*h*3 RGB8 and the grid (main.rs:492-496: tile = img / grid, u32 floor). */

@@ -355,8 +355,37 @@ class MosaicGenerator {
         max_usage_(max_usage_per_image),
         weight_(adjacency_penalty_weight),
         strength_(std::min(std::max(color_adjustment_strength, 0.0f), 1.0f)) {  // main.rs:162
+    ctx_.check(mosaic_set_materials_rgb8(ctx_.get(), rgb, (int)paths.size(), mat_w, mat_h));
+    init(paths, similarity_db_path, rebuild_similarity);
+  }
+
+  // Same, with materials of individual sizes — what the reference's directory of image files is (process_tile,
+  // main.rs:263-301): each image keeps its own size for the Lab mean and is resized to the tile at render time.
+  MosaicGenerator(const std::vector<std::string>& paths, const std::vector<RgbImage>& images, size_t max_usage_per_image,
+                  const std::string& similarity_db_path, bool rebuild_similarity, float adjacency_penalty_weight,
+                  float color_adjustment_strength, int device = 0)
+      : ctx_(device),
+        max_usage_(max_usage_per_image),
+        weight_(adjacency_penalty_weight),
+        strength_(std::min(std::max(color_adjustment_strength, 0.0f), 1.0f)) {
+    std::vector<uint8_t> blob;
+    std::vector<uint64_t> offsets;
+    std::vector<int32_t> widths, heights;
+    for (const RgbImage& im : images) {
+      offsets.push_back(blob.size());
+      widths.push_back(im.width);
+      heights.push_back(im.height);
+      blob.insert(blob.end(), im.data.begin(), im.data.end());
+    }
+    if (paths.size() != images.size()) throw Error(MOSAIC_ERR_INVALID, "MosaicGenerator: one path per image");
+    ctx_.check(mosaic_set_materials_ragged_rgb8(ctx_.get(), blob.data(), offsets.data(), widths.data(), heights.data(),
+                                                (int)images.size()));
+    init(paths, similarity_db_path, rebuild_similarity);
+  }
+
+ private:
+  void init(const std::vector<std::string>& paths, const std::string& similarity_db_path, bool rebuild_similarity) {
     const int n = (int)paths.size();
-    ctx_.check(mosaic_set_materials_rgb8(ctx_.get(), rgb, n, mat_w, mat_h));
     std::vector<float> lab((size_t)n * 3);
     ctx_.check(mosaic_material_lab(ctx_.get(), lab.data()));
     for (int i = 0; i < n; ++i) tiles_.push_back(Tile{paths[i], Lab{lab[3 * i], lab[3 * i + 1], lab[3 * i + 2]}});
@@ -395,6 +424,8 @@ class MosaicGenerator {
     }
     if (differs) ctx_.check(mosaic_set_similarity_lab(ctx_.get(), db_lab.data(), n));
   }
+
+ public:
 
   // generate_mosaic (main.rs:477-685) minus file I/O: returns the mosaic image; `placed` (optional) receives the grid
   RgbImage generate_mosaic(const RgbImage& target, int grid_w, int grid_h, bool enable_optimization,

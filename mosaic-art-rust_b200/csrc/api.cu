@@ -148,7 +148,18 @@ int sync(mosaic_ctx* c) {
 int run_material_lab(mosaic_ctx* c) {
   MOSAIC_TRY(require(c, c->have_materials, "materials (mosaic_set_materials_rgb8)"));
   MOSAIC_TRY(ensure_mat_lab_buffers(c, c->n));
-  if (c->world == 1) {
+  if (c->ragged) {
+    // every rank holds all the materials (mosaic_set_materials_ragged_rgb8 uploads everything); index-sharded means
+    int b = 0, e = c->n;
+    if (c->world > 1) shard_mats(c, c->rank, &b, &e);
+    if (e > b) MOSAIC_TRY(launch_material_lab_ragged(c, b, e));
+    MOSAIC_TRY(allgather_slices(c, c->d_mat_lab, 3 * sizeof(float), [&](int r, uint64_t* sb, uint64_t* se) {
+      int ib, ie;
+      shard_mats(c, r, &ib, &ie);
+      *sb = (uint64_t)ib;
+      *se = (uint64_t)ie;
+    }));
+  } else if (c->world == 1) {
     MOSAIC_TRY(launch_material_lab(c));
   } else {
     // index-sharded: this rank's slice, then allgather of 12 B x N
@@ -309,7 +320,7 @@ int run_render(mosaic_ctx* c, float strength, uint8_t* out_rgb) {
   for (int b = 0; b < std::max(bands, 1); ++b) {
     const int b0 = rb + (int)((long long)rows * b / std::max(bands, 1)), b1 = rb + (int)((long long)rows * (b + 1) / std::max(bands, 1));
     if (b1 <= b0) continue;
-    MOSAIC_TRY(launch_render(c, strength, b0, b1));
+    MOSAIC_TRY(c->ragged ? launch_render_ragged(c, strength, b0, b1) : launch_render(c, strength, b0, b1));
     if (out_rgb) {
       MOSAIC_CUDA(c, cudaEventRecord(c->ev_band[b], c->stream));
       MOSAIC_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_band[b], 0));
@@ -417,7 +428,8 @@ void mosaic_ctx_destroy(mosaic_ctx* c) {
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   dist_destroy(c);
-  void* bufs[] = {c->d_sim_lab4_own, c->d_sim_soa_own, c->d_materials_owned, c->d_mat_lab, c->d_mat_lab4, c->d_mat_soa, c->d_target_owned, c->d_cell_lab,
+  void* bufs[] = {c->d_mat_off, c->d_mat_w, c->d_mat_h, c->d_rag_bounds, c->d_rag_weights, c->d_rag_desc, c->d_rag_midx, c->d_rag_scratch,
+                  c->d_sim_lab4_own, c->d_sim_soa_own, c->d_materials_owned, c->d_mat_lab, c->d_mat_lab4, c->d_mat_soa, c->d_target_owned, c->d_cell_lab,
                   c->d_cell_rgbsum,     c->d_cand_idx, c->d_cand_d2, c->d_placed,  c->d_usage,        c->d_place_info, c->d_place_rec,
                   c->d_sim,             c->d_sim_counter, c->d_opt_res,  c->d_rng_ring, c->d_terms, c->d_deltas, c->d_thumbs, c->d_thumb_sums, c->d_thumb_state, c->d_out,    c->axis_h.start,   c->axis_h.size,
                   c->axis_h.w,          c->axis_v.start, c->axis_v.size, c->axis_v.w};
@@ -463,19 +475,22 @@ uint64_t mosaic_kernel_launches(const mosaic_ctx* c) { return c ? c->launches : 
 
 // ---- inputs ----------------------------------------------------------------------------------
 static int set_materials_common(mosaic_ctx* c, int n, int w, int h) {
-  if (n <= 0 || w <= 0 || h <= 0) return fail(c, MOSAIC_ERR_INVALID, "materials: n, w, h must be positive");
+  if (n <= 0 || w < 0 || h < 0 || ((w == 0) != (h == 0))) return fail(c, MOSAIC_ERR_INVALID, "materials: n, w, h must be positive");
   c->n = n;
   c->mw = w;
   c->mh = h;
   c->have_materials = true;
   c->have_mat_lab = c->have_cand = c->have_placed = c->have_sim = c->have_out = false;
   c->sim_lab_override = false;  // a new material set: the database colours of the old one do not apply
+  c->ragged = false;
+  c->materials_version++;
   return MOSAIC_OK;
 }
 
 int mosaic_set_materials_rgb8(mosaic_ctx* c, const uint8_t* rgb, int n, int w, int h) {
   if (!c) return MOSAIC_ERR_INVALID;
   if (!rgb) return fail(c, MOSAIC_ERR_INVALID, "materials pointer is NULL");
+  if (w <= 0 || h <= 0) return fail(c, MOSAIC_ERR_INVALID, "materials: n, w, h must be positive");
   MOSAIC_CUDA(c, cudaSetDevice(c->device));
   MOSAIC_TRY(set_materials_common(c, n, w, h));
   c->have_materials = false;
@@ -497,9 +512,41 @@ int mosaic_set_materials_rgb8(mosaic_ctx* c, const uint8_t* rgb, int n, int w, i
   return MOSAIC_OK;
 }
 
+int mosaic_set_materials_ragged_rgb8(mosaic_ctx* c, const uint8_t* rgb, const uint64_t* offsets, const int32_t* widths,
+                                     const int32_t* heights, int n) {
+  if (!c) return MOSAIC_ERR_INVALID;
+  if (!rgb || !offsets || !widths || !heights || n <= 0) return fail(c, MOSAIC_ERR_INVALID, "ragged materials: bad arguments");
+  MOSAIC_CUDA(c, cudaSetDevice(c->device));
+  size_t total = 0;
+  for (int i = 0; i < n; ++i) {
+    if (widths[i] <= 0 || heights[i] <= 0 || widths[i] > 32768 || heights[i] > 32768)
+      return fail(c, MOSAIC_ERR_INVALID, "ragged materials: material " + std::to_string(i) + " has a size outside 1..32768");
+    total = std::max(total, (size_t)offsets[i] + (size_t)widths[i] * (size_t)heights[i] * 3);
+  }
+  MOSAIC_TRY(set_materials_common(c, n, 0, 0));
+  c->have_materials = false;
+  c->ragged = true;
+  MOSAIC_TRY(ensure(c, &c->d_materials_owned, &c->materials_cap, total));
+  MOSAIC_TRY(ensure(c, &c->d_mat_off, &c->mat_off_cap, (size_t)n));
+  MOSAIC_TRY(ensure(c, &c->d_mat_w, &c->mat_w_cap, (size_t)n));
+  MOSAIC_TRY(ensure(c, &c->d_mat_h, &c->mat_h_cap, (size_t)n));
+  c->d_materials = c->d_materials_owned;
+  c->h_mat_off.assign(offsets, offsets + n);
+  c->h_mat_w.assign(widths, widths + n);
+  c->h_mat_h.assign(heights, heights + n);
+  // (sharded contexts: every rank uploads everything — the per-rank PCIe split of the uniform path needs equal sizes)
+  MOSAIC_CUDA(c, cudaMemcpyAsync(c->d_materials_owned, rgb, total, cudaMemcpyHostToDevice, c->stream));
+  MOSAIC_CUDA(c, cudaMemcpyAsync(c->d_mat_off, c->h_mat_off.data(), sizeof(unsigned long long) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+  MOSAIC_CUDA(c, cudaMemcpyAsync(c->d_mat_w, c->h_mat_w.data(), sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+  MOSAIC_CUDA(c, cudaMemcpyAsync(c->d_mat_h, c->h_mat_h.data(), sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+  c->have_materials = true;
+  return MOSAIC_OK;
+}
+
 int mosaic_set_materials_device(mosaic_ctx* c, const void* dev_rgb, int n, int w, int h) {
   if (!c) return MOSAIC_ERR_INVALID;
   if (!dev_rgb) return fail(c, MOSAIC_ERR_INVALID, "materials pointer is NULL");
+  if (w <= 0 || h <= 0) return fail(c, MOSAIC_ERR_INVALID, "materials: n, w, h must be positive");
   MOSAIC_CUDA(c, cudaSetDevice(c->device));
   MOSAIC_TRY(set_materials_common(c, n, w, h));
   c->d_materials = (const uint8_t*)dev_rgb;

@@ -116,6 +116,38 @@ __global__ void __launch_bounds__(256) lab_mean_images_kernel(const uint8_t* __r
   }
 }
 
+// Materials of individual sizes (the reference opens files of any size, main.rs:263-301): one warp per image, pixels
+// lane-strided in row-major order.  Sums are kept in two levels (64 pixels per lane, then folded) so that a
+// multi-megapixel image does not lose the small a/b terms in a long single-precision accumulation.
+__global__ void __launch_bounds__(256) lab_mean_images_ragged_kernel(const uint8_t* __restrict__ imgs,
+                                                                     const unsigned long long* __restrict__ offs,
+                                                                     const int32_t* __restrict__ widths,
+                                                                     const int32_t* __restrict__ heights, int mat_begin,
+                                                                     int mat_end, float* __restrict__ lab_out) {
+  __shared__ float lut_s[256 * kLutRep];
+  load_lut(lut_s);
+  const int lane = threadIdx.x & 31;
+  const float* lut = lut_s + (lane & (kLutRep - 1));
+  const int warps_per_grid = (gridDim.x * blockDim.x) >> 5;
+  for (int img = mat_begin + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5); img < mat_end; img += warps_per_grid) {
+    const uint8_t* base = imgs + offs[img];
+    const int pixels = widths[img] * heights[img];
+    LabAcc total;
+    for (int p0 = 0; p0 < pixels; p0 += 32 * 64) {
+      LabAcc acc;
+      const int p1 = min(pixels, p0 + 32 * 64);
+      for (int px = p0 + lane; px < p1; px += 32) {
+        const uint8_t* q = base + 3 * (size_t)px;
+        accumulate_pixel(lut, q[0], q[1], q[2], acc);
+      }
+      total.fy += acc.fy;
+      total.dxy += acc.dxy;
+      total.dyz += acc.dyz;
+    }
+    finish(total, (float)pixels, lab_out + 3 * (size_t)img);
+  }
+}
+
 // One warp per grid cell: the tile_w x tile_h crop at (x*tile_w, y*tile_h) of the target
 // (main.rs:536-541).  Pixels are visited in the crop's row-major order, lane-strided.  Also emits
 // the integer channel sums of the crop (target_avg_rgb of main.rs:554, used by the render kernel).
@@ -303,6 +335,22 @@ int launch_material_lab(mosaic_ctx* ctx) {
   {
     StageTimer t(ctx, MOSAIC_STAGE_MATERIAL_LAB);
     lab_mean_images_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->d_materials, ctx->n, pixels, vec_ok, ctx->d_mat_lab);
+    ctx->launches++;
+  }
+  MOSAIC_CUDA(ctx, cudaGetLastError());
+  return MOSAIC_OK;
+}
+
+int launch_material_lab_ragged(mosaic_ctx* ctx, int mat_begin, int mat_end) {
+  MOSAIC_TRY(upload_lut(ctx));
+  int blocks = (mat_end - mat_begin + 7) / 8;
+  const int max_blocks = ctx->sm_count * 8;
+  if (blocks > max_blocks) blocks = max_blocks;
+  if (blocks < 1) blocks = 1;
+  {
+    StageTimer t(ctx, MOSAIC_STAGE_MATERIAL_LAB);
+    lab_mean_images_ragged_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->d_materials, ctx->d_mat_off, ctx->d_mat_w, ctx->d_mat_h,
+                                                                   mat_begin, mat_end, ctx->d_mat_lab);
     ctx->launches++;
   }
   MOSAIC_CUDA(ctx, cudaGetLastError());

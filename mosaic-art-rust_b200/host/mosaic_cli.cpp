@@ -2,8 +2,8 @@
 // main()'s sequence (main.rs:741-779): target aspect -> MosaicGenerator::new -> generate_mosaic -> save.
 //
 // Out of scope here (the reference's control plane): image codecs.  Images are binary PPM
-// (P6, maxval 255); --material-src is a directory of *.ppm of ONE size (the reference decodes png/jpg/webp of any size;
-// the variable-size material path is not built).  The material selection follows load_tiles (main.rs:166-261): aspect
+// (P6, maxval 255); --material-src is a directory of *.ppm of any sizes (the reference decodes png/jpg/webp of any size).
+// The material selection follows load_tiles (main.rs:166-261): aspect
 // filter (lib.rs:121-123), no-match fallback to the first min(len, 2*max) files, truncate to --max-materials; files are
 // taken in sorted order (read_dir order is unspecified in the reference).
 //
@@ -166,8 +166,7 @@ int main(int argc, char** argv) {
     }
     if (chosen.size() > args.max_materials) chosen.resize(args.max_materials);  // main.rs:255-257
     if (chosen.empty()) throw std::runtime_error("no material images found in " + args.material_src);
-    std::vector<uint8_t> rgb;
-    int mw = 0, mh = 0;
+    std::vector<RgbImage> images;
     std::vector<std::string> paths;
     for (const std::string& p : chosen) {
       RgbImage m;
@@ -175,17 +174,13 @@ int main(int argc, char** argv) {
         std::fprintf(stderr, "Error processing \"%s\": truncated PPM\n", p.c_str());
         continue;
       }
-      if (paths.empty()) mw = m.width, mh = m.height;
-      if (m.width != mw || m.height != mh)
-        throw std::runtime_error("materials of different sizes are not supported (" + p + " is " + std::to_string(m.width) + "x" +
-                                 std::to_string(m.height) + ", expected " + std::to_string(mw) + "x" + std::to_string(mh) + ")");
-      rgb.insert(rgb.end(), m.data.begin(), m.data.end());
+      images.push_back(std::move(m));
       paths.push_back(p);
     }
     std::printf("Loaded %zu tiles (aspect ratio matched)\n", paths.size());
     const auto t1 = std::chrono::steady_clock::now();
 
-    MosaicGenerator generator(paths, rgb.data(), mw, mh, args.max_usage_per_image, args.similarity_db, args.rebuild_similarity_db,
+    MosaicGenerator generator(paths, images, args.max_usage_per_image, args.similarity_db, args.rebuild_similarity_db,
                               args.adjacency_penalty_weight, args.color_adjustment_strength);
     if (!generator.save_warning().empty()) std::fprintf(stderr, "%s\n", generator.save_warning().c_str());
     const auto t2 = std::chrono::steady_clock::now();

@@ -71,6 +71,7 @@ def load_library():
         "mosaic_stage_ms": ([vp, C.c_int, f32p], C.c_int),
         "mosaic_kernel_launches": ([vp], C.c_uint64),
         "mosaic_set_materials_rgb8": ([vp, vp, C.c_int, C.c_int, C.c_int], C.c_int),
+        "mosaic_set_materials_ragged_rgb8": ([vp, u8p, C.POINTER(C.c_uint64), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int], C.c_int),
         "mosaic_set_materials_device": ([vp, vp, C.c_int, C.c_int, C.c_int], C.c_int),
         "mosaic_set_target_rgb8": ([vp, vp, C.c_int, C.c_int, C.c_int, C.c_int], C.c_int),
         "mosaic_set_target_device": ([vp, vp, C.c_int, C.c_int, C.c_int, C.c_int], C.c_int),
@@ -116,7 +117,7 @@ def load_library():
 EXPORTED_SYMBOLS = (
     "mosaic_ctx_create", "mosaic_ctx_create_sharded", "mosaic_nccl_unique_id", "mosaic_ctx_destroy",
     "mosaic_last_error", "mosaic_ctx_set_stream", "mosaic_ctx_sync", "mosaic_stage_ms", "mosaic_kernel_launches",
-    "mosaic_set_materials_rgb8", "mosaic_set_materials_device", "mosaic_set_target_rgb8",
+    "mosaic_set_materials_rgb8", "mosaic_set_materials_ragged_rgb8", "mosaic_set_materials_device", "mosaic_set_target_rgb8",
     "mosaic_set_target_device", "mosaic_set_material_lab", "mosaic_set_similarity_lab", "mosaic_set_cell_lab", "mosaic_material_lab",
     "mosaic_cell_lab", "mosaic_similarity_tri", "mosaic_candidates", "mosaic_place", "mosaic_fallback_cells",
     "mosaic_set_placement", "mosaic_anneal", "mosaic_render", "mosaic_generate", "mosaic_selftest", "mosaic_dims",
@@ -308,6 +309,20 @@ class Context:
         n, h, w, c = mats.shape
         assert c == 3
         self._check(self._L.mosaic_set_materials_rgb8(self._h, _ptr(mats), n, w, h))
+
+    def set_materials_ragged(self, images):
+        """Materials of individual sizes: a list of (h_i, w_i, 3) uint8 arrays (the reference opens files of any size)."""
+        imgs = [np.ascontiguousarray(im, np.uint8) for im in images]
+        assert all(im.ndim == 3 and im.shape[2] == 3 for im in imgs)
+        sizes = np.array([im.size for im in imgs], np.uint64)
+        offs = np.zeros(len(imgs), np.uint64)
+        offs[1:] = np.cumsum(sizes)[:-1]
+        blob = np.concatenate([im.ravel() for im in imgs])
+        w = np.array([im.shape[1] for im in imgs], np.int32)
+        h = np.array([im.shape[0] for im in imgs], np.int32)
+        self._check(self._L.mosaic_set_materials_ragged_rgb8(
+            self._h, blob.ctypes.data_as(C.POINTER(C.c_uint8)), offs.ctypes.data_as(C.POINTER(C.c_uint64)),
+            w.ctypes.data_as(C.POINTER(C.c_int32)), h.ctypes.data_as(C.POINTER(C.c_int32)), len(imgs)))
 
     def set_materials_device(self, dev_tensor):
         n, h, w, c = dev_tensor.shape

@@ -191,7 +191,7 @@ def test_cli_end_to_end(cli, ctx, tmp_path):
                    "--optimization-iterations", "300", "--similarity-db", str(db), "--seed", "7"])
     assert "No tiles matched target aspect ratio" in stdout and f"Loaded {n} tiles" in stdout
     assert db.exists()
-    ctx.set_materials(mats[:n])
+    ctx.set_materials_ragged(list(mats[:n]))  # the CLI hands the files over as materials of individual sizes
     ctx.set_target(tgt, gw, gh)
     img = np.zeros(ctx.output_shape(), np.uint8)
     ctx.generate(max_usage=4, adjacency_weight=0.25, color_strength=0.4, enable_optimization=True,
@@ -205,4 +205,24 @@ def test_cli_end_to_end(cli, ctx, tmp_path):
     assert "Optimization complete" not in stdout
     ctx.generate(max_usage=4, adjacency_weight=0.25, color_strength=0.4, enable_optimization=False,
                  optimization_iterations=0, seed=0, build_similarity=False, image_out=img)
+    assert (_read_ppm(out) == img).all()
+
+    # a directory of mixed sizes: the aspect filter keeps the 5:3 files (80x48, 50x30, 200x120), drops the squares
+    mixed = tmp_path / "mixed"
+    mixed.mkdir()
+    kept = []
+    for i in range(90):
+        w, h = [(64, 64), (80, 48), (50, 30), (200, 120), (30, 70)][i % 5]
+        m = synth.materials(1, w=w, h=h, start=i)[0]
+        _write_ppm(mixed / f"p{i:04d}.ppm", m)
+        if abs(w / h - 320 / 192) <= 0.1:
+            kept.append(m)
+    stdout = _run([cli, "-t", str(tmp_path / "target.ppm"), "-m", str(mixed), "-o", str(out), "--grid-w", str(gw),
+                   "--grid-h", str(gh), "--max-materials", "50", "--optimization-iterations", "200",
+                   "--similarity-db", str(tmp_path / "db2.json"), "--seed", "3"])
+    assert "No tiles matched" not in stdout and "Loaded 50 tiles" in stdout
+    ctx.set_materials_ragged(kept[:50])
+    ctx.set_target(tgt, gw, gh)
+    ctx.generate(max_usage=3, adjacency_weight=0.3, color_strength=0.3, enable_optimization=True,
+                 optimization_iterations=200, seed=3, build_similarity=False, image_out=img)
     assert (_read_ppm(out) == img).all()
