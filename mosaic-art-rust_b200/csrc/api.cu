@@ -526,7 +526,7 @@ int mosaic_set_materials_ragged_rgb8(mosaic_ctx* c, const uint8_t* rgb, const ui
   MOSAIC_TRY(set_materials_common(c, n, 0, 0));
   c->have_materials = false;
   c->ragged = true;
-  MOSAIC_TRY(ensure(c, &c->d_materials_owned, &c->materials_cap, total));
+  MOSAIC_TRY(ensure(c, &c->d_materials_owned, &c->materials_cap, total + 16));  // slack: the Lab kernel reads whole aligned words
   MOSAIC_TRY(ensure(c, &c->d_mat_off, &c->mat_off_cap, (size_t)n));
   MOSAIC_TRY(ensure(c, &c->d_mat_w, &c->mat_w_cap, (size_t)n));
   MOSAIC_TRY(ensure(c, &c->d_mat_h, &c->mat_h_cap, (size_t)n));

@@ -116,35 +116,70 @@ __global__ void __launch_bounds__(256) lab_mean_images_kernel(const uint8_t* __r
   }
 }
 
-// Materials of individual sizes (the reference opens files of any size, main.rs:263-301): one warp per image, pixels
-// lane-strided in row-major order.  Sums are kept in two levels (64 pixels per lane, then folded) so that a
-// multi-megapixel image does not lose the small a/b terms in a long single-precision accumulation.
+// Materials of individual sizes (the reference opens files of any size, main.rs:263-301): one CTA per image — sizes
+// differ by orders of magnitude, so a warp per image would leave the GPU waiting for the largest ones.  Threads take
+// groups of 4 pixels (12 bytes) strided by the CTA; sums are kept in two levels (64 pixels per thread, then folded)
+// so that a multi-megapixel image does not lose the small a/b terms in a long single-precision accumulation, and the
+// per-warp totals are combined in warp order: run-to-run deterministic.
 __global__ void __launch_bounds__(256) lab_mean_images_ragged_kernel(const uint8_t* __restrict__ imgs,
                                                                      const unsigned long long* __restrict__ offs,
                                                                      const int32_t* __restrict__ widths,
                                                                      const int32_t* __restrict__ heights, int mat_begin,
                                                                      int mat_end, float* __restrict__ lab_out) {
   __shared__ float lut_s[256 * kLutRep];
+  __shared__ float s_part[8][3];
   load_lut(lut_s);
-  const int lane = threadIdx.x & 31;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float* lut = lut_s + (lane & (kLutRep - 1));
-  const int warps_per_grid = (gridDim.x * blockDim.x) >> 5;
-  for (int img = mat_begin + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5); img < mat_end; img += warps_per_grid) {
+  for (int img = mat_begin + blockIdx.x; img < mat_end; img += gridDim.x) {
     const uint8_t* base = imgs + offs[img];
     const int pixels = widths[img] * heights[img];
     LabAcc total;
-    for (int p0 = 0; p0 < pixels; p0 += 32 * 64) {
+    // the image starts at an arbitrary byte: a thread reads the four ALIGNED words that cover its 12 bytes and
+    // funnel-shifts them by the image's byte phase (the buffer is allocated with slack for the last word)
+    const unsigned phase = (unsigned)((uintptr_t)base & 3u) * 8u;
+    const uint32_t* words = reinterpret_cast<const uint32_t*>(base - ((uintptr_t)base & 3u));
+    const int groups = pixels / 4;
+    for (int g0 = 0; g0 < groups; g0 += 256 * 16) {
       LabAcc acc;
-      const int p1 = min(pixels, p0 + 32 * 64);
-      for (int px = p0 + lane; px < p1; px += 32) {
-        const uint8_t* q = base + 3 * (size_t)px;
-        accumulate_pixel(lut, q[0], q[1], q[2], acc);
+      const int g1 = min(groups, g0 + 256 * 16);
+      for (int g = g0 + tid; g < g1; g += 256) {
+        const uint32_t* w = words + 3 * (size_t)g;
+        const uint32_t w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2), w3 = __ldg(w + 3);
+        const unsigned a = __funnelshift_r(w0, w1, phase), b = __funnelshift_r(w1, w2, phase), c = __funnelshift_r(w2, w3, phase);
+        accumulate_pixel(lut, a & 255u, (a >> 8) & 255u, (a >> 16) & 255u, acc);
+        accumulate_pixel(lut, a >> 24, b & 255u, (b >> 8) & 255u, acc);
+        accumulate_pixel(lut, (b >> 16) & 255u, b >> 24, c & 255u, acc);
+        accumulate_pixel(lut, (c >> 8) & 255u, (c >> 16) & 255u, c >> 24, acc);
       }
       total.fy += acc.fy;
       total.dxy += acc.dxy;
       total.dyz += acc.dyz;
     }
-    finish(total, (float)pixels, lab_out + 3 * (size_t)img);
+    for (int px = groups * 4 + tid; px < pixels; px += 256) {
+      const uint8_t* q = base + 3 * (size_t)px;
+      accumulate_pixel(lut, q[0], q[1], q[2], total);
+    }
+    const float sfy = warp_sum(total.fy), sxy = warp_sum(total.dxy), syz = warp_sum(total.dyz);
+    if (lane == 0) {
+      s_part[warp][0] = sfy;
+      s_part[warp][1] = sxy;
+      s_part[warp][2] = syz;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      float fy = 0.f, xy = 0.f, yz = 0.f;
+      for (int w = 0; w < 8; ++w) {
+        fy += s_part[w][0];
+        xy += s_part[w][1];
+        yz += s_part[w][2];
+      }
+      const float cnt = (float)pixels;
+      lab_out[3 * (size_t)img] = fmaf(116.0f, fy / cnt, -16.0f);
+      lab_out[3 * (size_t)img + 1] = 500.0f * (xy / cnt);
+      lab_out[3 * (size_t)img + 2] = 200.0f * (yz / cnt);
+    }
+    __syncthreads();  // s_part is reused by the CTA's next image
   }
 }
 
@@ -343,7 +378,7 @@ int launch_material_lab(mosaic_ctx* ctx) {
 
 int launch_material_lab_ragged(mosaic_ctx* ctx, int mat_begin, int mat_end) {
   MOSAIC_TRY(upload_lut(ctx));
-  int blocks = (mat_end - mat_begin + 7) / 8;
+  int blocks = mat_end - mat_begin;
   const int max_blocks = ctx->sm_count * 8;
   if (blocks > max_blocks) blocks = max_blocks;
   if (blocks < 1) blocks = 1;
