@@ -140,7 +140,26 @@ int d2h(mosaic_ctx* c, void* dst, const void* src, size_t bytes) {
 }
 
 int sync(mosaic_ctx* c) {
+  if (c->upload_stream) MOSAIC_CUDA(c, cudaStreamSynchronize(c->upload_stream));  // (no-op unless an upload is in flight)
   MOSAIC_CUDA(c, cudaStreamSynchronize(c->stream));
+  return MOSAIC_OK;
+}
+
+// uploads run on their own stream, after whatever the context's stream is still doing with the old buffers
+int begin_upload(mosaic_ctx* c) {
+  MOSAIC_CUDA(c, cudaEventRecord(c->ev_main_idle, c->stream));
+  MOSAIC_CUDA(c, cudaStreamWaitEvent(c->upload_stream, c->ev_main_idle, 0));
+  return MOSAIC_OK;
+}
+// the context's stream must not touch the materials / the target before their upload has landed
+int wait_materials(mosaic_ctx* c) {
+  if (c->mat_upload_pending) MOSAIC_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_mat_up, 0));
+  c->mat_upload_pending = false;
+  return MOSAIC_OK;
+}
+int wait_target(mosaic_ctx* c) {
+  if (c->tgt_upload_pending && c->tgt_bands > 0) MOSAIC_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_tgt_band[c->tgt_bands - 1], 0));
+  c->tgt_upload_pending = false;
   return MOSAIC_OK;
 }
 
@@ -148,6 +167,7 @@ int sync(mosaic_ctx* c) {
 int run_material_lab(mosaic_ctx* c) {
   MOSAIC_TRY(require(c, c->have_materials, "materials (mosaic_set_materials_rgb8)"));
   MOSAIC_TRY(ensure_mat_lab_buffers(c, c->n));
+  MOSAIC_TRY(wait_materials(c));
   if (c->ragged) {
     // every rank holds all the materials (mosaic_set_materials_ragged_rgb8 uploads everything); index-sharded means
     int b = 0, e = c->n;
@@ -193,6 +213,7 @@ int run_material_lab(mosaic_ctx* c) {
 int run_cell_lab(mosaic_ctx* c) {
   MOSAIC_TRY(require(c, c->have_target, "target (mosaic_set_target_rgb8)"));
   MOSAIC_TRY(ensure_cell_buffers(c));
+  MOSAIC_TRY(wait_target(c));
   int rb, re;
   shard_rows(c, c->rank, &rb, &re);
   MOSAIC_TRY(launch_cell_lab_range(c, rb * c->gw, re * c->gw));
@@ -211,7 +232,9 @@ int run_cell_lab(mosaic_ctx* c) {
 
 int run_candidates(mosaic_ctx* c, int k) {
   if (!c->have_mat_lab) MOSAIC_TRY(run_material_lab(c));
-  if (!c->have_cell_lab) MOSAIC_TRY(run_cell_lab(c));
+  // a target still on its way up (single GPU): every band's cell Lab means and top-K start when that band has landed
+  const bool banded = !c->have_cell_lab && c->tgt_upload_pending && c->world == 1 && c->tgt_bands > 1;
+  if (!c->have_cell_lab && !banded) MOSAIC_TRY(run_cell_lab(c));
   if (k <= 0 || k > kMaxK) k = kMaxK;
   if (k > c->n) k = c->n;  // main.rs:348 min(len, 100)
   if (k <= 0) return fail(c, MOSAIC_ERR_STATE, "no materials");
@@ -227,6 +250,21 @@ int run_candidates(mosaic_ctx* c, int k) {
     c->cand_cap = cells * (size_t)kMaxK;
   }
   c->k = k;
+  if (banded) {
+    MOSAIC_TRY(require(c, c->have_target, "target (mosaic_set_target_rgb8)"));
+    MOSAIC_TRY(ensure_cell_buffers(c));
+    for (int b = 0; b < c->tgt_bands; ++b) {
+      const int r0 = c->tgt_band_rows[b], r1 = c->tgt_band_rows[b + 1];
+      if (r1 <= r0) continue;
+      MOSAIC_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_tgt_band[b], 0));
+      MOSAIC_TRY(launch_cell_lab_range(c, r0 * c->gw, r1 * c->gw));
+      MOSAIC_TRY(launch_topk_range(c, k, r0 * c->gw, r1 * c->gw));
+    }
+    c->tgt_upload_pending = false;
+    c->have_cell_lab = c->have_cell_rgbsum = true;
+    c->have_cand = true;
+    return MOSAIC_OK;
+  }
   int rb, re;
   shard_rows(c, c->rank, &rb, &re);
   MOSAIC_TRY(launch_topk_range(c, k, rb * c->gw, re * c->gw));
@@ -305,6 +343,7 @@ int run_render(mosaic_ctx* c, float strength, uint8_t* out_rgb) {
   MOSAIC_TRY(require(c, c->have_materials, "materials"));
   MOSAIC_TRY(require(c, c->have_target, "target"));
   MOSAIC_TRY(require(c, c->have_placed, "placement"));
+  MOSAIC_TRY(wait_materials(c));
   if (strength > 0.0f && !c->have_cell_rgbsum) MOSAIC_TRY(run_cell_lab(c));
   if (!c->d_cell_rgbsum) MOSAIC_TRY(ensure_cell_buffers(c));
   const size_t out_bytes = (size_t)c->gw * c->tile_w * (size_t)c->gh * c->tile_h * 3;
@@ -382,6 +421,10 @@ static int ctx_create_common(mosaic_ctx** out, int device) {
   }
   c->stream = c->own_stream;
   cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
+  cudaStreamCreateWithFlags(&c->upload_stream, cudaStreamNonBlocking);
+  cudaEventCreateWithFlags(&c->ev_main_idle, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&c->ev_mat_up, cudaEventDisableTiming);
+  for (int i = 0; i < mosaic_ctx::kBands; ++i) cudaEventCreateWithFlags(&c->ev_tgt_band[i], cudaEventDisableTiming);
   for (int i = 0; i < mosaic_ctx::kBands; ++i) cudaEventCreateWithFlags(&c->ev_band[i], cudaEventDisableTiming);
   cudaEventCreateWithFlags(&c->ev_copy_done, cudaEventDisableTiming);
   for (int i = 0; i < MOSAIC_STAGE_COUNT; ++i) {
@@ -440,6 +483,14 @@ void mosaic_ctx_destroy(mosaic_ctx* c) {
     if (c->ev_begin[i]) cudaEventDestroy(c->ev_begin[i]);
     if (c->ev_end[i]) cudaEventDestroy(c->ev_end[i]);
   }
+  if (c->upload_stream) {
+    cudaStreamSynchronize(c->upload_stream);
+    cudaStreamDestroy(c->upload_stream);
+  }
+  if (c->ev_main_idle) cudaEventDestroy(c->ev_main_idle);
+  if (c->ev_mat_up) cudaEventDestroy(c->ev_mat_up);
+  for (int i = 0; i < mosaic_ctx::kBands; ++i)
+    if (c->ev_tgt_band[i]) cudaEventDestroy(c->ev_tgt_band[i]);
   if (c->copy_stream) {
     cudaStreamSynchronize(c->copy_stream);
     cudaStreamDestroy(c->copy_stream);
@@ -484,6 +535,7 @@ static int set_materials_common(mosaic_ctx* c, int n, int w, int h) {
   c->sim_lab_override = false;  // a new material set: the database colours of the old one do not apply
   c->ragged = false;
   c->materials_version++;
+  c->mat_upload_pending = false;  // (an upload of the previous set still in flight is ordered before the next one)
   return MOSAIC_OK;
 }
 
@@ -497,8 +549,16 @@ int mosaic_set_materials_rgb8(mosaic_ctx* c, const uint8_t* rgb, int n, int w, i
   const size_t per = (size_t)w * h * 3;
   MOSAIC_TRY(ensure(c, &c->d_materials_owned, &c->materials_cap, per * (size_t)n));
   c->d_materials = c->d_materials_owned;
+  if (c->world == 1) {  // own stream: the target that usually follows queues behind it, compute waits for the event
+    MOSAIC_TRY(begin_upload(c));
+    MOSAIC_CUDA(c, cudaMemcpyAsync(c->d_materials_owned, rgb, per * (size_t)n, cudaMemcpyHostToDevice, c->upload_stream));
+    MOSAIC_CUDA(c, cudaEventRecord(c->ev_mat_up, c->upload_stream));
+    c->mat_upload_pending = true;
+    c->have_materials = true;
+    return MOSAIC_OK;
+  }
   int b = 0, e = n;
-  if (c->world > 1) shard_mats(c, c->rank, &b, &e);
+  shard_mats(c, c->rank, &b, &e);
   // each rank uploads its slice over its own PCIe link; slices are exchanged over NVLink
   MOSAIC_CUDA(c, cudaMemcpyAsync(c->d_materials_owned + (size_t)b * per, rgb + (size_t)b * per, (size_t)(e - b) * per,
                                  cudaMemcpyHostToDevice, c->stream));
@@ -535,10 +595,13 @@ int mosaic_set_materials_ragged_rgb8(mosaic_ctx* c, const uint8_t* rgb, const ui
   c->h_mat_w.assign(widths, widths + n);
   c->h_mat_h.assign(heights, heights + n);
   // (sharded contexts: every rank uploads everything — the per-rank PCIe split of the uniform path needs equal sizes)
-  MOSAIC_CUDA(c, cudaMemcpyAsync(c->d_materials_owned, rgb, total, cudaMemcpyHostToDevice, c->stream));
-  MOSAIC_CUDA(c, cudaMemcpyAsync(c->d_mat_off, c->h_mat_off.data(), sizeof(unsigned long long) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
-  MOSAIC_CUDA(c, cudaMemcpyAsync(c->d_mat_w, c->h_mat_w.data(), sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
-  MOSAIC_CUDA(c, cudaMemcpyAsync(c->d_mat_h, c->h_mat_h.data(), sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+  MOSAIC_TRY(begin_upload(c));
+  MOSAIC_CUDA(c, cudaMemcpyAsync(c->d_materials_owned, rgb, total, cudaMemcpyHostToDevice, c->upload_stream));
+  MOSAIC_CUDA(c, cudaMemcpyAsync(c->d_mat_off, c->h_mat_off.data(), sizeof(unsigned long long) * (size_t)n, cudaMemcpyHostToDevice, c->upload_stream));
+  MOSAIC_CUDA(c, cudaMemcpyAsync(c->d_mat_w, c->h_mat_w.data(), sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, c->upload_stream));
+  MOSAIC_CUDA(c, cudaMemcpyAsync(c->d_mat_h, c->h_mat_h.data(), sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, c->upload_stream));
+  MOSAIC_CUDA(c, cudaEventRecord(c->ev_mat_up, c->upload_stream));
+  c->mat_upload_pending = true;
   c->have_materials = true;
   return MOSAIC_OK;
 }
@@ -561,9 +624,28 @@ int mosaic_set_target_rgb8(mosaic_ctx* c, const uint8_t* rgb, int w, int h, int 
   c->have_target = false;
   MOSAIC_TRY(ensure(c, &c->d_target_owned, &c->target_cap, (size_t)w * h * 3));
   c->d_target = c->d_target_owned;
-  int rb = 0, re = grid_h;
-  if (c->world > 1) shard_rows(c, c->rank, &rb, &re);  // only this rank's band of pixel rows is uploaded
   const size_t row_bytes = (size_t)w * 3;
+  if (c->world == 1) {
+    // bands of cell rows on the upload stream, one event each (the last band carries the remainder pixel rows)
+    MOSAIC_TRY(begin_upload(c));
+    const int bands = ((size_t)w * h * 3 >= ((size_t)8 << 20)) ? std::min(mosaic_ctx::kBands, grid_h) : 1;
+    for (int b = 0; b < bands; ++b) {
+      const int r0 = (int)((long long)grid_h * b / bands), r1 = (int)((long long)grid_h * (b + 1) / bands);
+      const size_t p0 = (size_t)r0 * c->tile_h, p1 = (b + 1 == bands) ? (size_t)h : (size_t)r1 * c->tile_h;
+      c->tgt_band_rows[b] = r0;
+      c->tgt_band_rows[b + 1] = r1;
+      if (p1 > p0)
+        MOSAIC_CUDA(c, cudaMemcpyAsync(c->d_target_owned + p0 * row_bytes, rgb + p0 * row_bytes, (p1 - p0) * row_bytes,
+                                       cudaMemcpyHostToDevice, c->upload_stream));
+      MOSAIC_CUDA(c, cudaEventRecord(c->ev_tgt_band[b], c->upload_stream));
+    }
+    c->tgt_bands = bands;
+    c->tgt_upload_pending = true;
+    c->have_target = true;
+    return MOSAIC_OK;
+  }
+  int rb = 0, re = grid_h;
+  shard_rows(c, c->rank, &rb, &re);  // only this rank's band of pixel rows is uploaded
   const size_t y0 = (size_t)rb * c->tile_h, y1 = (c->world > 1) ? (size_t)re * c->tile_h : (size_t)h;
   if (y1 > y0)
     MOSAIC_CUDA(c, cudaMemcpyAsync(c->d_target_owned + y0 * row_bytes, rgb + y0 * row_bytes, (y1 - y0) * row_bytes,
@@ -577,6 +659,7 @@ int mosaic_set_target_device(mosaic_ctx* c, const void* dev_rgb, int w, int h, i
   if (!dev_rgb) return fail(c, MOSAIC_ERR_INVALID, "target pointer is NULL");
   MOSAIC_CUDA(c, cudaSetDevice(c->device));
   MOSAIC_TRY(set_grid(c, w, h, grid_w, grid_h));
+  c->tgt_upload_pending = false;
   c->d_target = (const uint8_t*)dev_rgb;
   c->have_target = true;
   return MOSAIC_OK;
@@ -740,7 +823,7 @@ int mosaic_generate(mosaic_ctx* c, const mosaic_params* p, int32_t* placed_out, 
   MOSAIC_TRY(run_material_lab(c));
   if (p->build_similarity) MOSAIC_TRY(run_similarity(c, /*gather=*/false));
   // ... main.rs:477-685 (generate_mosaic)
-  MOSAIC_TRY(run_cell_lab(c));
+  if (!(c->tgt_upload_pending && c->world == 1)) MOSAIC_TRY(run_cell_lab(c));  // (else: band by band inside run_candidates)
   MOSAIC_TRY(run_candidates(c, kMaxK));
   MOSAIC_TRY(run_place(c, p->max_usage, p->adjacency_weight));
   const bool anneal = p->enable_optimization && p->adjacency_weight > 0.0f;  // main.rs:608
