@@ -597,6 +597,7 @@ int mosaic_set_materials_ragged_rgb8(mosaic_ctx* c, const uint8_t* rgb, const ui
   // (sharded contexts: every rank uploads everything — the per-rank PCIe split of the uniform path needs equal sizes)
   MOSAIC_TRY(begin_upload(c));
   MOSAIC_CUDA(c, cudaMemcpyAsync(c->d_materials_owned, rgb, total, cudaMemcpyHostToDevice, c->upload_stream));
+  MOSAIC_CUDA(c, cudaMemsetAsync(c->d_materials_owned + total, 0, 16, c->upload_stream));  // the slack the Lab kernel's last aligned word may touch
   MOSAIC_CUDA(c, cudaMemcpyAsync(c->d_mat_off, c->h_mat_off.data(), sizeof(unsigned long long) * (size_t)n, cudaMemcpyHostToDevice, c->upload_stream));
   MOSAIC_CUDA(c, cudaMemcpyAsync(c->d_mat_w, c->h_mat_w.data(), sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, c->upload_stream));
   MOSAIC_CUDA(c, cudaMemcpyAsync(c->d_mat_h, c->h_mat_h.data(), sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, c->upload_stream));
