@@ -27,6 +27,8 @@ with mosaic_b200.Context(0) as ctx:
                 ctx.set_materials_ragged(mats)
             else:
                 ctx.set_materials(synth.materials(n)) if it == 0 else None
+            ctx.cell_lab(fetch=False)  # consume the pending uploads: the stage times below are device times of whole stages
+            ctx.sync()
             t0 = time.perf_counter()
             rep = ctx.generate(max_usage=3, adjacency_weight=0.3, color_strength=0.3, enable_optimization=True,
                                optimization_iterations=1000, seed=42, build_similarity=True)
