@@ -282,6 +282,56 @@ int run_candidates(mosaic_ctx* c, int k) {
 
 int ensure_placed(mosaic_ctx* c) { return ensure(c, &c->d_placed, &c->placed_cap, cells_of(c)); }
 
+__global__ void set_u32_kernel(unsigned* p, unsigned v) { *p = v; }
+
+// A target still on its way up (single GPU, chain-kernel configuration): every band's cell Lab means, top-K and
+// placement records are computed when the band has landed, and the placement chain — one CTA, serial — starts after the
+// first band on its own stream and consumes the records as they appear (a device counter of prepared cells), so that
+// most of its 2.6 ms at the 24,000-tile config run under the upload of the remaining bands.
+int run_match_place_banded(mosaic_ctx* c, int k, int max_usage, float weight) {
+  if (k <= 0 || k > kMaxK) k = kMaxK;
+  if (k > c->n) k = c->n;
+  const size_t cells = cells_of(c);
+  if (c->cand_cap < cells * (size_t)kMaxK || !c->d_cand_idx) {
+    if (c->d_cand_idx) cudaFree(c->d_cand_idx);
+    if (c->d_cand_d2) cudaFree(c->d_cand_d2);
+    c->d_cand_idx = nullptr;
+    c->d_cand_d2 = nullptr;
+    c->cand_cap = 0;
+    MOSAIC_CUDA(c, cudaMalloc((void**)&c->d_cand_idx, sizeof(uint32_t) * cells * kMaxK));
+    MOSAIC_CUDA(c, cudaMalloc((void**)&c->d_cand_d2, sizeof(float) * cells * kMaxK));
+    c->cand_cap = cells * (size_t)kMaxK;
+  }
+  c->k = k;
+  MOSAIC_TRY(ensure_cell_buffers(c));
+  MOSAIC_TRY(ensure_placed(c));
+  MOSAIC_TRY(ensure(c, &c->d_ready_cells, &c->ready_cells_cap, (size_t)1));
+  MOSAIC_CUDA(c, cudaMemsetAsync(c->d_ready_cells, 0, sizeof(unsigned), c->stream));
+  for (int b = 0; b < c->tgt_bands; ++b) {
+    const int r0 = c->tgt_band_rows[b], r1 = c->tgt_band_rows[b + 1];
+    if (r1 > r0) {
+      MOSAIC_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_tgt_band[b], 0));
+      MOSAIC_TRY(launch_cell_lab_range(c, r0 * c->gw, r1 * c->gw));
+      MOSAIC_TRY(launch_topk_range(c, k, r0 * c->gw, r1 * c->gw));
+      MOSAIC_TRY(launch_place_prep_range(c, weight, r0 * c->gw, r1 * c->gw));
+      set_u32_kernel<<<1, 1, 0, c->stream>>>(c->d_ready_cells, (unsigned)(r1 * c->gw));
+      c->launches++;
+    }
+    if (b == 0) {  // (the counter was reset and the first band counted before the chain starts polling it)
+      MOSAIC_CUDA(c, cudaEventRecord(c->ev_chain_go, c->stream));
+      MOSAIC_CUDA(c, cudaStreamWaitEvent(c->chain_stream, c->ev_chain_go, 0));
+      MOSAIC_TRY(launch_place_chain_async(c, max_usage, weight, c->chain_stream, c->d_ready_cells));
+      MOSAIC_CUDA(c, cudaEventRecord(c->ev_chain_done, c->chain_stream));
+    }
+  }
+  MOSAIC_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_chain_done, 0));
+  c->tgt_upload_pending = false;
+  c->have_cell_lab = c->have_cell_rgbsum = true;
+  c->have_cand = true;
+  c->have_placed = true;
+  return MOSAIC_OK;
+}
+
 int run_place(mosaic_ctx* c, int max_usage, float weight) {
   if (!c->have_cand) MOSAIC_TRY(run_candidates(c, kMaxK));
   MOSAIC_TRY(ensure_placed(c));
@@ -422,6 +472,9 @@ static int ctx_create_common(mosaic_ctx** out, int device) {
   c->stream = c->own_stream;
   cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
   cudaStreamCreateWithFlags(&c->upload_stream, cudaStreamNonBlocking);
+  cudaStreamCreateWithFlags(&c->chain_stream, cudaStreamNonBlocking);
+  cudaEventCreateWithFlags(&c->ev_chain_go, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&c->ev_chain_done, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&c->ev_main_idle, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&c->ev_mat_up, cudaEventDisableTiming);
   for (int i = 0; i < mosaic_ctx::kBands; ++i) cudaEventCreateWithFlags(&c->ev_tgt_band[i], cudaEventDisableTiming);
@@ -471,7 +524,7 @@ void mosaic_ctx_destroy(mosaic_ctx* c) {
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   dist_destroy(c);
-  void* bufs[] = {c->d_mat_off, c->d_mat_w, c->d_mat_h, c->d_rag_bounds, c->d_rag_weights, c->d_rag_desc, c->d_rag_midx, c->d_rag_scratch,
+  void* bufs[] = {c->d_ready_cells, c->d_mat_off, c->d_mat_w, c->d_mat_h, c->d_rag_bounds, c->d_rag_weights, c->d_rag_desc, c->d_rag_midx, c->d_rag_scratch,
                   c->d_sim_lab4_own, c->d_sim_soa_own, c->d_materials_owned, c->d_mat_lab, c->d_mat_lab4, c->d_mat_soa, c->d_target_owned, c->d_cell_lab,
                   c->d_cell_rgbsum,     c->d_cand_idx, c->d_cand_d2, c->d_placed,  c->d_usage,        c->d_place_info, c->d_place_rec,
                   c->d_sim,             c->d_sim_counter, c->d_opt_res,  c->d_rng_ring, c->d_terms, c->d_deltas, c->d_thumbs, c->d_thumb_sums, c->d_thumb_state, c->d_out,    c->axis_h.start,   c->axis_h.size,
@@ -487,6 +540,12 @@ void mosaic_ctx_destroy(mosaic_ctx* c) {
     cudaStreamSynchronize(c->upload_stream);
     cudaStreamDestroy(c->upload_stream);
   }
+  if (c->chain_stream) {
+    cudaStreamSynchronize(c->chain_stream);
+    cudaStreamDestroy(c->chain_stream);
+  }
+  if (c->ev_chain_go) cudaEventDestroy(c->ev_chain_go);
+  if (c->ev_chain_done) cudaEventDestroy(c->ev_chain_done);
   if (c->ev_main_idle) cudaEventDestroy(c->ev_main_idle);
   if (c->ev_mat_up) cudaEventDestroy(c->ev_mat_up);
   for (int i = 0; i < mosaic_ctx::kBands; ++i)
@@ -824,9 +883,13 @@ int mosaic_generate(mosaic_ctx* c, const mosaic_params* p, int32_t* placed_out, 
   MOSAIC_TRY(run_material_lab(c));
   if (p->build_similarity) MOSAIC_TRY(run_similarity(c, /*gather=*/false));
   // ... main.rs:477-685 (generate_mosaic)
-  if (!(c->tgt_upload_pending && c->world == 1)) MOSAIC_TRY(run_cell_lab(c));  // (else: band by band inside run_candidates)
-  MOSAIC_TRY(run_candidates(c, kMaxK));
-  MOSAIC_TRY(run_place(c, p->max_usage, p->adjacency_weight));
+  if (c->tgt_upload_pending && c->world == 1 && c->tgt_bands > 1 && place_chain_eligible(c, p->max_usage)) {
+    MOSAIC_TRY(run_match_place_banded(c, kMaxK, p->max_usage, p->adjacency_weight));  // matching + placement under the upload
+  } else {
+    if (!(c->tgt_upload_pending && c->world == 1)) MOSAIC_TRY(run_cell_lab(c));  // (else: band by band inside run_candidates)
+    MOSAIC_TRY(run_candidates(c, kMaxK));
+    MOSAIC_TRY(run_place(c, p->max_usage, p->adjacency_weight));
+  }
   const bool anneal = p->enable_optimization && p->adjacency_weight > 0.0f;  // main.rs:608
   if (anneal) MOSAIC_TRY(run_anneal(c, p->optimization_iterations, 100.0f, 0.99995f, p->seed));  // optimizer.rs:18-27
   MOSAIC_TRY(d2h(c, placed_out, c->d_placed, sizeof(int32_t) * cells_of(c)));

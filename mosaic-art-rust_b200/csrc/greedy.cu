@@ -226,8 +226,9 @@ static_assert(sizeof(HRec) == 256 && sizeof(XRec) == 528, "record layout");
 
 __global__ void __launch_bounds__(256) place_prep_kernel(const uint32_t* __restrict__ cand_idx,
                                                          const float* __restrict__ cand_d2, int k,
-                                                         const float4* __restrict__ lab4, int n, int cells, int gw,
-                                                         float weight, HRec* __restrict__ hrec, XRec* __restrict__ xrec,
+                                                         const float4* __restrict__ lab4, int n, int cell_begin,
+                                                         int cells /* end of the range */, int gw, float weight,
+                                                         HRec* __restrict__ hrec, XRec* __restrict__ xrec,
                                                          float* __restrict__ glab /* cells x 3 x 128 */) {
   __shared__ float4 nb_s[8][2][kMaxK];  // per warp: (Lab, id) of every candidate of the cell above / to the left
   const int lane = threadIdx.x & 31;
@@ -235,7 +236,7 @@ __global__ void __launch_bounds__(256) place_prep_kernel(const uint32_t* __restr
   const bool use_penalty = weight > 0.0f;
   const float inf = __int_as_float(0x7f800000);
   float4(*nb)[kMaxK] = nb_s[threadIdx.x >> 5];
-  for (int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; c < cells; c += warps) {
+  for (int c = cell_begin + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5); c < cells; c += warps) {
     uint32_t id = (uint32_t)n;
     float d2 = inf;
     float4 lab = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -320,13 +321,14 @@ __global__ void __launch_bounds__(256) place_prep_kernel(const uint32_t* __restr
 // [8] cycles waiting for a TMA batch, [9] cycles waiting for the committer (row above), [10] total cycles
 __device__ unsigned long long g_chain_prof[16];
 
-template <typename UsageT, bool PROF>
+template <typename UsageT, bool PROF, bool GATED>
 __global__ void __launch_bounds__(64, 1)
     greedy_chain_kernel(const HRec* __restrict__ hrec, const XRec* __restrict__ xrec, const float* __restrict__ glab,
                         const uint32_t* __restrict__ cand_idx, const float* __restrict__ cand_d2, int k,
                         const float4* __restrict__ lab4, int n, int gw, int gh,
                         unsigned max_usage, float weight, int32_t* __restrict__ placed, uint32_t* __restrict__ info,
-                        uint32_t fallback_cap) {
+                        uint32_t fallback_cap,
+                        const volatile unsigned* ready /* cells whose records exist so far; NULL = all of them */) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   HRec* hring = reinterpret_cast<HRec*>(smem_raw);
   XRec* xring = reinterpret_cast<XRec*>(smem_raw + sizeof(HRec) * (CH_DEPTH + CH_SHADOW));
@@ -368,9 +370,34 @@ __global__ void __launch_bounds__(64, 1)
     // ---------------- committer ----------------
     const volatile XRec* vx = xring;
     int next_batch = 0;
-    if (lane == 0)
-      for (; next_batch < min(CH_NBATCH, nbatches); ++next_batch) issue_batch(next_batch);
     int base = 0;
+    // GATED: the records may still be in production (the target image arrives in bands, api.cu): `ready` counts the
+    // cells whose records a finished preparation kernel has written; a batch is fetched only when all its cells are
+    // there.  (A template flag: the ungated instantiation is the tuned kernel, instruction for instruction.)
+    unsigned ready_seen = 0u;
+    auto batch_ready = [&](int batch) {
+      const unsigned need = (unsigned)min(cells, (batch + 1) * CH_BATCH);
+      if (need > ready_seen) {
+        ready_seen = *ready;
+        __threadfence();  // the records were written before the counter moved
+      }
+      return need <= ready_seen;
+    };
+    // ring position free (the first CH_NBATCH batches; later: all 8 cells older than the guard window) and records there
+    auto try_issue = [&]() {
+      while (next_batch < nbatches &&
+             (next_batch < CH_NBATCH || (next_batch - CH_NBATCH + 1) * CH_BATCH + CH_GUARD <= base) &&
+             batch_ready(next_batch)) {
+        issue_batch(next_batch);
+        ++next_batch;
+      }
+    };
+    if (GATED) {
+      if (lane == 0) try_issue();
+    } else {
+      if (lane == 0)
+        for (; next_batch < min(CH_NBATCH, nbatches); ++next_batch) issue_batch(next_batch);
+    }
     while (base < cells) {
       const int cell = base + lane;
       const int s = cell % CH_DEPTH;
@@ -379,6 +406,7 @@ __global__ void __launch_bounds__(64, 1)
       const unsigned ready_mask = __ballot_sync(0xffffffffu, have);
       const int cnt = ready_mask == 0xFFFFFFFFu ? 32 : __ffs(~ready_mask) - 1;  // consecutive from lane 0
       if (cnt == 0) {
+        if (GATED && lane == 0) try_issue();  // (a batch that was not there when its ring position became free)
         __nanosleep(20);
         continue;
       }
@@ -399,9 +427,13 @@ __global__ void __launch_bounds__(64, 1)
       if (lane == 0) {
         decided[0] = (uint32_t)base;
         // ring batches whose 8 cells are all older than the guard window are free: fetch their successors
-        while (next_batch < nbatches && (next_batch - CH_NBATCH + 1) * CH_BATCH + CH_GUARD <= base) {
-          issue_batch(next_batch);
-          ++next_batch;
+        if (GATED) {
+          try_issue();
+        } else {
+          while (next_batch < nbatches && (next_batch - CH_NBATCH + 1) * CH_BATCH + CH_GUARD <= base) {
+            issue_batch(next_batch);
+            ++next_batch;
+          }
         }
       }
     }
@@ -803,32 +835,74 @@ __global__ void __launch_bounds__(64, 1)
 
 }  // namespace
 
-template <typename UsageT, bool PROF>
-static int launch_chain_impl(mosaic_ctx* ctx, unsigned cap, float weight, size_t smem) {
+template <typename UsageT, bool PROF, bool GATED = false>
+static int launch_chain_impl(mosaic_ctx* ctx, unsigned cap, float weight, size_t smem, cudaStream_t stream, const unsigned* ready) {
   const size_t cells = (size_t)ctx->gw * ctx->gh;
-  MOSAIC_CUDA(ctx, cudaFuncSetAttribute(greedy_chain_kernel<UsageT, PROF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  MOSAIC_CUDA(ctx, cudaFuncSetAttribute(greedy_chain_kernel<UsageT, PROF, GATED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)smem));
-  greedy_chain_kernel<UsageT, PROF><<<1, 64, smem, ctx->stream>>>(
+  greedy_chain_kernel<UsageT, PROF, GATED><<<1, 64, smem, stream>>>(
       reinterpret_cast<const HRec*>(ctx->d_place_rec), reinterpret_cast<const XRec*>(ctx->d_place_rec + cells * sizeof(HRec)),
       reinterpret_cast<const float*>(ctx->d_place_rec + cells * (sizeof(HRec) + sizeof(XRec))), ctx->d_cand_idx, ctx->d_cand_d2, ctx->k, ctx->sim_lab4(), ctx->n, ctx->gw, ctx->gh, cap, weight, ctx->d_placed,
-      ctx->d_place_info, mosaic_ctx::kFallbackCap);
+      ctx->d_place_info, mosaic_ctx::kFallbackCap, ready);
   return MOSAIC_OK;
 }
-template <typename UsageT>
-static int launch_chain(mosaic_ctx* ctx, unsigned cap, float weight, size_t smem) {
+
+static int ensure_place_records(mosaic_ctx* ctx) {
   const int cells = ctx->gw * ctx->gh;
-  MOSAIC_TRY(ensure(ctx, &ctx->d_place_rec, &ctx->place_rec_cap,
-                    (size_t)cells * (sizeof(HRec) + sizeof(XRec) + 3 * kKPad * sizeof(float))));
-  int blocks = (cells + 7) / 8;
+  return ensure(ctx, &ctx->d_place_rec, &ctx->place_rec_cap, (size_t)cells * (sizeof(HRec) + sizeof(XRec) + 3 * kKPad * sizeof(float)));
+}
+
+// candidate records of cells [cell_begin, cell_end) (needs the candidate lists of those cells and of the row above)
+int launch_place_prep_range(mosaic_ctx* ctx, float weight, int cell_begin, int cell_end) {
+  if (cell_end <= cell_begin) return MOSAIC_OK;
+  const int cells = ctx->gw * ctx->gh;
+  MOSAIC_TRY(ensure_place_records(ctx));
+  int blocks = (cell_end - cell_begin + 7) / 8;
   if (blocks > ctx->sm_count * 8) blocks = ctx->sm_count * 8;
-  place_prep_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->d_cand_idx, ctx->d_cand_d2, ctx->k, ctx->sim_lab4(), ctx->n, cells,
-                                                     ctx->gw, weight, reinterpret_cast<HRec*>(ctx->d_place_rec),
+  place_prep_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->d_cand_idx, ctx->d_cand_d2, ctx->k, ctx->sim_lab4(), ctx->n, cell_begin,
+                                                     cell_end, ctx->gw, weight, reinterpret_cast<HRec*>(ctx->d_place_rec),
                                                      reinterpret_cast<XRec*>(ctx->d_place_rec + (size_t)cells * sizeof(HRec)),
                                                      reinterpret_cast<float*>(ctx->d_place_rec + (size_t)cells * (sizeof(HRec) + sizeof(XRec))));
   ctx->launches++;
   MOSAIC_CUDA(ctx, cudaGetLastError());
-  return ctx->profile_chain ? launch_chain_impl<UsageT, true>(ctx, cap, weight, smem)
-                            : launch_chain_impl<UsageT, false>(ctx, cap, weight, smem);
+  return MOSAIC_OK;
+}
+
+// shared-memory footprint of the chain kernel, or 0 when the grid / cap / material count need the generic kernel
+static size_t chain_smem(const mosaic_ctx* ctx, unsigned cap) {
+  const size_t smem_limit = 220 * 1024;
+  const int n = ctx->n, gw = ctx->gw;
+  const size_t ring_fixed = sizeof(HRec) * (CH_DEPTH + CH_SHADOW) + sizeof(XRec) * CH_DEPTH + 8 * CH_NBATCH + 8 * CH_DEPTH + 16 +
+                            sizeof(float4) * (size_t)gw + sizeof(int32_t) * (size_t)((gw + 3) & ~3);
+  const size_t usage_bytes = cap <= 255u ? (size_t)n + 1 : (cap <= 65535u ? ((size_t)n + 1) * 2 : (size_t)-1);
+  if (gw >= CH_MIN_GW && n < (1 << 26) && usage_bytes != (size_t)-1 && ring_fixed + usage_bytes + 16 <= smem_limit)
+    return ring_fixed + usage_bytes + 16;
+  return 0;
+}
+bool place_chain_eligible(const mosaic_ctx* ctx, int max_usage) {
+  return chain_smem(ctx, max_usage < 0 ? 0u : (unsigned)max_usage) != 0 && !ctx->profile_chain;
+}
+
+// the chain kernel alone, on `stream`, consuming records as `ready` (a device counter of prepared cells) advances
+int launch_place_chain_async(mosaic_ctx* ctx, int max_usage, float weight, cudaStream_t stream, const unsigned* ready) {
+  const unsigned cap = max_usage < 0 ? 0u : (unsigned)max_usage;
+  const size_t smem = chain_smem(ctx, cap);
+  if (!smem) return fail(ctx, MOSAIC_ERR_STATE, "placement: the chain kernel does not cover this configuration");
+  MOSAIC_TRY(ensure_place_records(ctx));
+  if (cap <= 255u)
+    MOSAIC_TRY((launch_chain_impl<uint8_t, false, true>(ctx, cap, weight, smem, stream, ready)));
+  else
+    MOSAIC_TRY((launch_chain_impl<uint16_t, false, true>(ctx, cap, weight, smem, stream, ready)));
+  ctx->launches++;
+  MOSAIC_CUDA(ctx, cudaGetLastError());
+  return MOSAIC_OK;
+}
+
+template <typename UsageT>
+static int launch_chain(mosaic_ctx* ctx, unsigned cap, float weight, size_t smem) {
+  MOSAIC_TRY(launch_place_prep_range(ctx, weight, 0, ctx->gw * ctx->gh));
+  return ctx->profile_chain ? launch_chain_impl<UsageT, true>(ctx, cap, weight, smem, ctx->stream, nullptr)
+                            : launch_chain_impl<UsageT, false>(ctx, cap, weight, smem, ctx->stream, nullptr);
 }
 
 int read_chain_profile(mosaic_ctx* ctx, unsigned long long* out16) {
@@ -842,15 +916,13 @@ int launch_place(mosaic_ctx* ctx, int max_usage, float weight) {
   const unsigned cap = max_usage < 0 ? 0u : (unsigned)max_usage;
   const size_t smem_limit = 220 * 1024;
   // fast path: record ring + row state + usage counters in shared memory
-  const size_t ring_fixed = sizeof(HRec) * (CH_DEPTH + CH_SHADOW) + sizeof(XRec) * CH_DEPTH + 8 * CH_NBATCH + 8 * CH_DEPTH + 16 +
-                            sizeof(float4) * (size_t)gw + sizeof(int32_t) * (size_t)((gw + 3) & ~3);
-  const size_t usage_bytes = cap <= 255u ? (size_t)n + 1 : (cap <= 65535u ? ((size_t)n + 1) * 2 : (size_t)-1);
+  const size_t fast_smem = chain_smem(ctx, cap);
   StageTimer t(ctx, MOSAIC_STAGE_PLACE);
-  if (gw >= CH_MIN_GW && ctx->n < (1 << 26) && usage_bytes != (size_t)-1 && ring_fixed + usage_bytes + 16 <= smem_limit) {
+  if (fast_smem) {
     if (cap <= 255u)
-      MOSAIC_TRY(launch_chain<uint8_t>(ctx, cap, weight, ring_fixed + usage_bytes + 16));
+      MOSAIC_TRY(launch_chain<uint8_t>(ctx, cap, weight, fast_smem));
     else
-      MOSAIC_TRY(launch_chain<uint16_t>(ctx, cap, weight, ring_fixed + usage_bytes + 16));
+      MOSAIC_TRY(launch_chain<uint16_t>(ctx, cap, weight, fast_smem));
   } else {
     // generic path: single warp, usage counters in shared memory when they fit, else in HBM
     const size_t row_bytes = ((size_t)gw * 4 + 15) & ~(size_t)15;

@@ -425,6 +425,50 @@ def test_generate_matches_stagewise(ctx):
     assert np.abs(img.astype(np.int16) - ref.astype(np.int16)).max() <= 1
 
 
+@pytest.mark.parametrize("max_usage,weight,iters,pinned", [(3, 0.3, 600, True), (1, 1.0, 0, True), (300, 0.3, 200, False),
+                                                           (3, 0.3, 0, False)])
+def test_generate_with_banded_upload_matches_stagewise(ctx, max_usage, weight, iters, pinned):
+    """A host target of >= 8 MB goes up in bands; mosaic_generate then matches band by band and runs the placement
+    chain on its own stream while the later bands are still being uploaded and matched (api.cu,
+    run_match_place_banded).  Same results as the stage-by-stage oracle replay, and as the unbanded stage calls."""
+    n, gw, gh = 1500, 96, 60                       # tile 24 x 24; capacity 4500 < 5760 cells at cap 3: resets fire
+    mats = synth.materials(n)
+    tgt = synth.target(2304 + 5, 1440 + 3, seed=77)  # 10 MB; remainder pixels right / below the grid
+    assert tgt.nbytes >= 8 << 20
+    if pinned:  # page-locked host buffers: the copies really are asynchronous and the chain really waits for its records
+        import torch
+        keep = [torch.empty(mats.shape, dtype=torch.uint8, pin_memory=True), torch.empty(tgt.shape, dtype=torch.uint8, pin_memory=True)]
+        keep[0].numpy()[...] = mats
+        keep[1].numpy()[...] = tgt
+        mats, tgt = keep[0].numpy(), keep[1].numpy()
+    ctx.set_materials(mats)
+    ctx.set_target(tgt, gw, gh)
+    placed = np.zeros(gw * gh, np.int32)
+    img = np.zeros(ctx.output_shape(), np.uint8)
+    rep = ctx.generate(max_usage, weight, 0.3, iters > 0, iters, 5, build_similarity=False, placed_out=placed, image_out=img)
+    mlab, clab = ctx.material_lab(), ctx.cell_lab()
+    assert_lab_close(clab, orc.cell_lab(tgt, gw, gh, threads=8))
+    idx, d2 = ctx.candidates()                      # the lists the banded run left behind
+    ridx, rd2 = orc.topk(mlab, clab, 100, threads=8)
+    assert (idx == ridx).all() and (d2.view(np.uint32) == rd2.view(np.uint32)).all()
+    rplaced, rnfb, rfb, _ = orc.place(ridx, rd2, mlab, gw, gh, max_usage, weight)
+    assert rep.n_fallbacks == rnfb
+    assert (ctx.fallback_cells() == rfb).all()
+    if iters > 0 and weight > 0:
+        rgrid, rres = orc.anneal(mlab, rplaced.reshape(gh, gw), iters, 5)
+        assert rep.annealed == 1 and rep.opt.accepted_count == rres.accepted_count
+        assert (placed == rgrid.ravel()).all()
+    else:
+        assert (placed == rplaced).all()
+    ref = orc.render(tgt, gw, gh, mats, placed, 0.3, threads=8)
+    assert np.abs(img.astype(np.int16) - ref.astype(np.int16)).max() <= 1
+    # the unbanded stage calls on the same inputs
+    ctx.set_target(tgt, gw, gh)
+    ctx.cell_lab(fetch=False)
+    p2, nfb2 = ctx.place(max_usage, weight)
+    assert nfb2 == rnfb and (p2 == rplaced).all()
+
+
 def test_fast_ieee_helpers_exhaustive(ctx):
     # sqrt/rcp sequences of the serial chains == correctly rounded builtins on all 2^32 bit patterns
     assert ctx.selftest() == (0, 0)
