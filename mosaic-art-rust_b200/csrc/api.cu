@@ -317,13 +317,15 @@ int run_match_place_banded(mosaic_ctx* c, int k, int max_usage, float weight) {
       set_u32_kernel<<<1, 1, 0, c->stream>>>(c->d_ready_cells, (unsigned)(r1 * c->gw));
       c->launches++;
     }
-    if (b == 0) {  // (the counter was reset and the first band counted before the chain starts polling it)
-      MOSAIC_CUDA(c, cudaEventRecord(c->ev_chain_go, c->stream));
-      MOSAIC_CUDA(c, cudaStreamWaitEvent(c->chain_stream, c->ev_chain_go, 0));
-      MOSAIC_TRY(launch_place_chain_async(c, max_usage, weight, c->chain_stream, c->d_ready_cells));
-      MOSAIC_CUDA(c, cudaEventRecord(c->ev_chain_done, c->chain_stream));
-    }
+    if (b == 0) MOSAIC_CUDA(c, cudaEventRecord(c->ev_chain_go, c->stream));  // the counter is reset and covers the first band
   }
+  // The chain is ENQUEUED after every band's kernels (the host gets here long before the first band has landed) but
+  // only waits for the first band's event: on the device it starts as soon as that band is prepared.  In this order a
+  // tool that serialises kernel execution (ncu) runs the bands first and the chain last instead of dead-locking on a
+  // chain that polls for records of kernels not launched yet.
+  MOSAIC_CUDA(c, cudaStreamWaitEvent(c->chain_stream, c->ev_chain_go, 0));
+  MOSAIC_TRY(launch_place_chain_async(c, max_usage, weight, c->chain_stream, c->d_ready_cells));
+  MOSAIC_CUDA(c, cudaEventRecord(c->ev_chain_done, c->chain_stream));
   MOSAIC_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_chain_done, 0));
   c->tgt_upload_pending = false;
   c->have_cell_lab = c->have_cell_rgbsum = true;
