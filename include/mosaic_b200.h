@@ -78,6 +78,10 @@ int mosaic_stage_ms(mosaic_ctx* ctx, int stage, float* ms_out);
 uint64_t mosaic_kernel_launches(const mosaic_ctx* ctx);
 
 /* ---- inputs -------------------------------------------------------------------------------- */
+/* Host pointers belong to the caller.  Pageable buffers are staged before the call returns.  With PAGE-LOCKED buffers
+ * the uploads are asynchronous (single-GPU contexts run them on their own stream — materials first, then the target in
+ * bands of cell rows — and mosaic_generate matches and places each band while the following ones are still on the PCIe
+ * link): keep such a buffer unchanged until the next call that returns results, or mosaic_ctx_sync. */
 /* n uniform-size RGB8 materials, n*h*w*3 bytes, host memory (replaces the decoded `image::open`
  * results of process_tile, main.rs:263-301).  Copies H2D. */
 int mosaic_set_materials_rgb8(mosaic_ctx* ctx, const uint8_t* rgb, int n, int w, int h);
