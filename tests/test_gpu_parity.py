@@ -469,6 +469,23 @@ def test_generate_with_banded_upload_matches_stagewise(ctx, max_usage, weight, i
     assert nfb2 == rnfb and (p2 == rplaced).all()
 
 
+def test_generate_with_banded_upload_narrow_grid(ctx):
+    """A >= 8 MB host target on a grid the chain kernel does not cover (grid_w < 33): the bands still feed the cell Lab
+    means and the top-K as they land, the generic placement kernel runs afterwards."""
+    n, gw, gh = 400, 24, 40
+    mats = synth.materials(n)
+    tgt = synth.target(1920, 1480, seed=31)  # 8.5 MB, tile 80 x 37
+    assert tgt.nbytes >= 8 << 20
+    ctx.set_materials(mats)
+    ctx.set_target(tgt, gw, gh)
+    placed = np.zeros(gw * gh, np.int32)
+    rep = ctx.generate(2, 0.4, 0.0, False, 0, 0, build_similarity=False, placed_out=placed)
+    mlab, clab = ctx.material_lab(), ctx.cell_lab()
+    ridx, rd2 = orc.topk(mlab, clab, 100, threads=8)
+    rplaced, rnfb, _, _ = orc.place(ridx, rd2, mlab, gw, gh, 2, 0.4)
+    assert rep.n_fallbacks == rnfb and (placed == rplaced).all()
+
+
 def test_fast_ieee_helpers_exhaustive(ctx):
     # sqrt/rcp sequences of the serial chains == correctly rounded builtins on all 2^32 bit patterns
     assert ctx.selftest() == (0, 0)
