@@ -59,6 +59,9 @@ def config_block(cfg, world):
             "color_strength": cfg["color_strength"], "sa_iterations": cfg["sa_iterations"],
             "seed": cfg["seed"], "similarity_matrix_built": True,
             "l2": "inputs (222 MB of RGB8 at C3) are larger than the 126 MB L2; no explicit flush",
+            "e2e_schedule": ("host buffers: uploads on their own stream (materials, then the target in 8 bands); at 1 GPU "
+                             "every band is matched and its placement records prepared as it lands, and the placement "
+                             "chain consumes them under the remaining upload; output rows return in 8 bands"),
             "parallelism": ("1 GPU" if world == 1 else
                             f"grid rows / material indices / similarity ranges sharded over {world} GPUs, "
                             "NCCL allgather of Lab means + candidate lists, greedy + annealing on rank 0")}
