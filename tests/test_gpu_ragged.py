@@ -122,6 +122,29 @@ def test_ragged_generate_matches_stagewise(ctx):
         assert (i1[cy * th:(cy + 1) * th, cx * tw:(cx + 1) * tw] == i2[cy * th:(cy + 1) * th, cx * tw:(cx + 1) * tw]).all()
 
 
+def test_ragged_generate_with_banded_upload(ctx):
+    """Materials of individual sizes together with a >= 8 MB host target: the upload stream carries the ragged block
+    and the size tables first, then the target in bands that are matched and placed as they land (api.cu)."""
+    mats = ragged_materials(700)
+    tgt = synth.target(2304, 1440, seed=13)
+    gw, gh = 96, 60
+    assert tgt.nbytes >= 8 << 20
+    ctx.set_materials_ragged(mats)
+    ctx.set_target(tgt, gw, gh)
+    placed = np.zeros(gw * gh, np.int32)
+    img = np.zeros(ctx.output_shape(), np.uint8)
+    rep = ctx.generate(max_usage=9, adjacency_weight=0.3, color_strength=0.3, enable_optimization=True,
+                       optimization_iterations=400, seed=2, build_similarity=False, placed_out=placed, image_out=img)
+    mlab, clab = ctx.material_lab(), ctx.cell_lab()
+    idx, d2 = orc.topk(mlab, clab, 100, threads=8)
+    rplaced, rnfb, _, _ = orc.place(idx, d2, mlab, gw, gh, 9, 0.3)
+    assert rep.n_fallbacks == rnfb
+    rgrid, rres = orc.anneal(mlab, rplaced.reshape(gh, gw), 400, 2)
+    assert (placed.reshape(gh, gw) == rgrid).all() and rep.opt.accepted_count == rres.accepted_count
+    ref = oracle_render_ragged(tgt, gw, gh, mats, placed, 0.3)
+    assert np.abs(img.astype(np.int16) - ref.astype(np.int16)).max() <= 1
+
+
 def test_ragged_errors_are_loud(ctx):
     import mosaic_b200
     with pytest.raises(mosaic_b200.MosaicError):
