@@ -393,6 +393,119 @@ void orc_topk(const float* mat_lab, int n, const float* cell_lab, int c, int k,
   });
 }
 
+// ---- the same k nearest by a bucketed k-d tree (what the reference's CPU path costs: kiddo, main.rs:90, 145-151, 348-352) --
+// Same results as orc_topk — the k smallest (d2, index) pairs, d2 by the same unfused arithmetic — found in O(log n + k)
+// per query instead of O(n): leaves of <= 32 points, median split on the axis of largest spread, near child first, far
+// child only if the split plane is not farther than the current k-th distance.  The plane test is an exact bound:
+// rounding is monotone, so fl(fl(|q - split|)^2) <= fl(dl^2) <= d2 for every point behind the plane; on equality the
+// child is visited (it may hold an equal distance with a smaller index).
+namespace {
+struct KdNode {
+  int axis;     // -1: leaf
+  float split;
+  int left, right;
+  int begin, end;  // leaf: range in `order`
+};
+struct KdTree {
+  std::vector<KdNode> nodes;
+  std::vector<int> order;
+  const float* pts;
+  int build(int b, int e) {
+    KdNode nd{-1, 0.f, -1, -1, b, e};
+    const int id = (int)nodes.size();
+    nodes.push_back(nd);
+    if (e - b <= 32) return id;
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (int i = b; i < e; ++i)
+      for (int a = 0; a < 3; ++a) {
+        const float v = pts[3 * (size_t)order[i] + a];
+        lo[a] = std::min(lo[a], v);
+        hi[a] = std::max(hi[a], v);
+      }
+    int axis = 0;
+    for (int a = 1; a < 3; ++a)
+      if (hi[a] - lo[a] > hi[axis] - lo[axis]) axis = a;
+    if (!(hi[axis] > lo[axis])) return id;  // all points equal: one (large) leaf
+    const int mid = (b + e) / 2;
+    std::nth_element(order.begin() + b, order.begin() + mid, order.begin() + e,
+                     [&](int x, int y) { return pts[3 * (size_t)x + axis] < pts[3 * (size_t)y + axis]; });
+    const float split = pts[3 * (size_t)order[mid] + axis];  // left: values <= split, right: values >= split
+    const int l = build(b, mid), r = build(mid, e);
+    nodes[id].axis = axis;
+    nodes[id].split = split;
+    nodes[id].left = l;
+    nodes[id].right = r;
+    return id;
+  }
+};
+}  // namespace
+
+void orc_topk_kdtree(const float* mat_lab, int n, const float* cell_lab, int c, int k, uint32_t* out_idx, float* out_d2,
+                     int threads) {
+  if (k > n) k = n;
+  if (k <= 0) return;
+  KdTree tree;
+  tree.pts = mat_lab;
+  tree.order.resize(n);
+  for (int i = 0; i < n; ++i) tree.order[i] = i;
+  tree.nodes.reserve((size_t)n / 8 + 16);
+  tree.build(0, n);
+  const KdTree* T = &tree;
+  parallel_for(c, threads, [=](int64_t b, int64_t e) {
+    std::vector<uint64_t> heap;  // max-heap of (d2 bits << 32 | index): the top is the current k-th
+    heap.reserve(k + 1);
+    struct Entry {
+      int node;
+      uint32_t bound;  // bit pattern of a lower bound of every d2 in the subtree (0: none known)
+    };
+    std::vector<Entry> stack;
+    for (int64_t q = b; q < e; ++q) {
+      const float* ql = cell_lab + 3 * q;
+      heap.clear();
+      stack.clear();
+      stack.push_back(Entry{0, 0u});
+      while (!stack.empty()) {
+        const Entry en = stack.back();
+        stack.pop_back();
+        // the heap may have tightened since the entry was pushed; equality still visits (equal d2, smaller index)
+        if ((int)heap.size() == k && en.bound > (uint32_t)(heap.front() >> 32)) continue;
+        const KdNode& nd = T->nodes[en.node];
+        if (nd.axis < 0) {
+          for (int i = nd.begin; i < nd.end; ++i) {
+            const int id = T->order[i];
+            const float d2 = sq_dist(ql, mat_lab + 3 * (size_t)id);
+            uint32_t bits;
+            std::memcpy(&bits, &d2, 4);
+            const uint64_t key = ((uint64_t)bits << 32) | (uint32_t)id;
+            if ((int)heap.size() < k) {
+              heap.push_back(key);
+              std::push_heap(heap.begin(), heap.end());
+            } else if (key < heap.front()) {
+              std::pop_heap(heap.begin(), heap.end());
+              heap.back() = key;
+              std::push_heap(heap.begin(), heap.end());
+            }
+          }
+          continue;
+        }
+        const float diff = ql[nd.axis] - nd.split;
+        const float plane = diff * diff;  // every point p on the far side has |q - p| >= |q - split| on this axis
+        uint32_t pbits;
+        std::memcpy(&pbits, &plane, 4);
+        const bool left_near = diff <= 0.f;
+        stack.push_back(Entry{left_near ? nd.right : nd.left, std::max(pbits, en.bound)});  // far: popped after ...
+        stack.push_back(Entry{left_near ? nd.left : nd.right, en.bound});                   // ... the near child
+      }
+      std::sort_heap(heap.begin(), heap.end());
+      for (int j = 0; j < k; ++j) {
+        const uint32_t bits = (uint32_t)(heap[j] >> 32);
+        out_idx[(size_t)q * k + j] = (uint32_t)heap[j];
+        std::memcpy(&out_d2[(size_t)q * k + j], &bits, 4);
+      }
+    }
+  });
+}
+
 float orc_lab_distance(const float a[3], const float b[3]) { return lab_distance(a, b); }
 
 uint64_t orc_tri_index(uint64_t i, uint64_t j, uint64_t n) { return i * n - i * (i + 1) / 2 + j - i - 1; }

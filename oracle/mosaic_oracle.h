@@ -43,6 +43,11 @@ void orc_average_rgb_region(const uint8_t* rgb, int img_w, int x0, int y0, int r
 void orc_topk(const float* mat_lab, int n, const float* cell_lab, int c, int k,
               uint32_t* out_idx, float* out_d2, int threads);
 
+/* Same result through a bucketed k-d tree (the cost structure of the reference's kiddo search): used by the CPU arm
+ * of bench.py; tests pin it to orc_topk. */
+void orc_topk_kdtree(const float* mat_lab, int n, const float* cell_lab, int c, int k,
+                     uint32_t* out_idx, float* out_d2, int threads);
+
 /* ---- similarity (similarity.rs:69-82, 141-146) ---- */
 float orc_lab_distance(const float a[3], const float b[3]);
 void orc_similarity_tri(const float* lab, int n, float* out, int threads);

@@ -47,6 +47,8 @@ def lib():
         L.orc_cell_lab.argtypes = [u8p, C.c_int, C.c_int, C.c_int, C.c_int, f32p, C.c_int]
         L.orc_average_rgb_region.argtypes = [u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, u8p]
         L.orc_topk.argtypes = [f32p, C.c_int, f32p, C.c_int, C.c_int, u32p, f32p, C.c_int]
+        L.orc_topk_kdtree.argtypes = [f32p, C.c_int, f32p, C.c_int, C.c_int, u32p, f32p, C.c_int]
+        L.orc_topk_kdtree.restype = None
         L.orc_lab_distance.argtypes = [f32p, f32p]
         L.orc_lab_distance.restype = C.c_float
         L.orc_similarity_tri.argtypes = [f32p, C.c_int, f32p, C.c_int]
@@ -151,6 +153,19 @@ def topk(mat_lab, cell_lab_, k=100, threads=1):
     d2 = np.zeros((c, k), np.float32)
     lib().orc_topk(_p(mat_lab, C.c_float), n, _p(cell_lab_, C.c_float), c, k, _p(idx, C.c_uint32),
                    _p(d2, C.c_float), threads)
+    return idx, d2
+
+
+def topk_kdtree(mat_lab, cell_lab_, k=100, threads=1):
+    """orc_topk's result through a bucketed k-d tree (O(log n + k) per query, like the reference's kiddo search)."""
+    mat_lab = _c(mat_lab, np.float32)
+    cell_lab_ = _c(cell_lab_, np.float32)
+    n, c = mat_lab.shape[0], cell_lab_.shape[0]
+    k = min(k, n)
+    idx = np.zeros((c, k), np.uint32)
+    d2 = np.zeros((c, k), np.float32)
+    lib().orc_topk_kdtree(_p(mat_lab, C.c_float), n, _p(cell_lab_, C.c_float), c, k, _p(idx, C.c_uint32),
+                          _p(d2, C.c_float), threads)
     return idx, d2
 
 

@@ -362,3 +362,20 @@ def test_render_composes_tiles():  # main.rs:1380-1424: 100x100 target, 4x4 grid
     assert (out[25:50, 50:75] == orc.resize_rgb8(mats[placed[6]], 25, 25)).all()
     out2 = orc.render(tgt, 4, 4, mats, placed, 0.3, threads=4)
     assert out2.shape == out.shape and (out2 != out).any()
+
+
+def test_kdtree_topk_equals_brute_force():
+    """The CPU arm of bench.py searches a bucketed k-d tree (the cost structure of the reference's kiddo search): same
+    (d2 bits, index) lists as the brute force the GPU parity tests use, including exact ties and duplicates."""
+    from mosaic_b200 import synth
+    rng = np.random.default_rng(3)
+    for n, c, k in [(5000, 800, 100), (500, 200, 100), (37, 50, 100), (1, 4, 100), (3000, 300, 7)]:
+        m, q = synth.lab_points(n, seed=n), synth.lab_points(c, seed=c + 1)
+        a, b = orc.topk(m, q, k, threads=4), orc.topk_kdtree(m, q, k, threads=4)
+        assert (a[0] == b[0]).all() and (a[1].view(np.uint32) == b[1].view(np.uint32)).all()
+    m = (rng.integers(0, 6, (4000, 3)) * 10).astype(np.float32)   # quantised colours: ties everywhere
+    q = (rng.integers(0, 6, (300, 3)) * 10).astype(np.float32)
+    a, b = orc.topk(m, q, 100, threads=4), orc.topk_kdtree(m, q, 100, threads=4)
+    assert (a[0] == b[0]).all() and (a[1].view(np.uint32) == b[1].view(np.uint32)).all()
+    m, q = np.zeros((500, 3), np.float32), np.ones((5, 3), np.float32)  # every material the same colour: one big leaf
+    assert (orc.topk(m, q, 100)[0] == orc.topk_kdtree(m, q, 100)[0]).all()
