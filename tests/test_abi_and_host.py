@@ -194,3 +194,16 @@ def test_reference_arm_of_the_bench_runs_on_cpu(tmp_path):
     assert line["cpu_baseline"]["value"] == line["value"]
     assert line["e2e"] == {"value": line["value"], "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert line["config"]["workload"].startswith("C1:")
+
+
+def test_header_is_plain_c(tmp_path):
+    """The boundary is a C ABI: include/mosaic_b200.h must compile as C99 (what cgo, bindgen or a C host would feed it to),
+    with no C++ or torch types in the signatures."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "use_header.c"
+    src.write_text('#include "mosaic_b200.h"\n'
+                   "int main(void) { mosaic_params p; mosaic_report r; (void)p; (void)r; return MOSAIC_OK; }\n")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(root, "include"),
+                           "-fsyntax-only", str(src)])
+    text = open(os.path.join(root, "include", "mosaic_b200.h")).read()
+    assert "torch" not in text.lower() and "std::" not in text and "at::" not in text
