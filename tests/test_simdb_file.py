@@ -164,3 +164,45 @@ def test_context_writes_the_database_file(tmp_path):
     lab, sim = db.arrays()
     assert (lab.view(np.uint32) == mlab.view(np.uint32)).all()
     assert (sim.view(np.uint32) == orc.similarity_tri(mlab).view(np.uint32)).all()
+
+
+# ---------------------------------------------------------------- fuzz (hypothesis): any paths, any finite floats
+def test_fuzz_round_trip_and_json_validity(tmp_path):
+    """Random databases — paths with quotes, backslashes, control characters, non-ASCII; floats over the whole finite
+    f32 range incl. denormals and negative zero: the file must be valid JSON that Python's parser reads to the same
+    values, and the library's own reader must return every bit."""
+    hyp = pytest.importorskip("hypothesis")
+    st = pytest.importorskip("hypothesis.strategies")
+    f32 = st.floats(width=32, allow_nan=False, allow_infinity=False)
+    path = st.text(st.characters(blacklist_categories=("Cs",), blacklist_characters="\x00"), min_size=1, max_size=24)
+
+    @hyp.settings(max_examples=60, deadline=None, suppress_health_check=list(hyp.HealthCheck))
+    @hyp.given(st.lists(path, min_size=0, max_size=7, unique=True), st.data())
+    def run(paths, data):
+        n = len(paths)
+        lab = np.array(data.draw(st.lists(f32, min_size=3 * n, max_size=3 * n)), np.float32).reshape(n, 3)
+        m = n * (n - 1) // 2
+        sim = np.array(data.draw(st.lists(f32, min_size=m, max_size=m)), np.float32)
+        file = str(tmp_path / "fuzz.json")
+        mosaic_b200.SimilarityDb.save(file, paths, lab, sim)
+        doc = json.load(open(file, encoding="utf-8"))           # valid JSON, UTF-8
+        assert doc["path_to_index"] == {p: i for i, p in enumerate(paths)}
+        assert doc["index_to_path"] == {str(i): p for i, p in enumerate(paths)}
+        got_lab = np.array([[c["l"], c["a"], c["b"]] for c in doc["lab_colors"]], np.float64).reshape(n, 3)
+        assert (got_lab.astype(np.float32).view(np.uint32) == lab.view(np.uint32)).all()   # shortest text round-trips
+        assert (np.array(doc["similarities"], np.float64).astype(np.float32).view(np.uint32) == sim.view(np.uint32)).all()
+        db = mosaic_b200.SimilarityDb.load(file)
+        try:
+            info = db.info()
+            assert info["rows"] == n and info["similarities"] == m and info["paths"] == n
+            l2, s2 = db.arrays()
+            assert (l2.view(np.uint32) == lab.view(np.uint32)).all() and (s2.view(np.uint32) == sim.view(np.uint32)).all()
+            for i, p in enumerate(paths):
+                assert db.path(i) == p and db.index_of(p) == i
+            if n >= 2:
+                assert np.float32(db.get_similarity(paths[0], paths[1])).view(np.uint32) == sim[:1].view(np.uint32)[0]
+                assert db.get_similarity(paths[0], paths[0]) == 0.0
+        finally:
+            db.close()
+
+    run()
