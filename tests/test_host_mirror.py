@@ -226,3 +226,50 @@ def test_cli_end_to_end(cli, ctx, tmp_path):
     ctx.generate(max_usage=3, adjacency_weight=0.3, color_strength=0.3, enable_optimization=True,
                  optimization_iterations=200, seed=3, build_similarity=False, image_out=img)
     assert (_read_ppm(out) == img).all()
+
+
+def test_cli_material_selection_follows_load_tiles(cli, tmp_path):
+    """The selection logic of load_tiles (main.rs:166-261) runs before any device work, so it is checked on CPU: PPM
+    headers with comments, the aspect filter (lib.rs:121-123), the no-match fallback to min(len, 2 * max) files, the
+    truncation to --max-materials, files that are not images.  Without a GPU the run then stops with the library's loud
+    error (no CPU fallback); with one it completes."""
+    rng = np.random.default_rng(0)
+    tgt = rng.integers(0, 256, (60, 100, 3), dtype=np.uint8)                   # aspect 1.667
+    with open(tmp_path / "target.ppm", "wb") as f:
+        f.write(b"P6\n# a comment line\n100 60\n# another\n255\n" + tgt.tobytes())
+    mdir = tmp_path / "m"
+    mdir.mkdir()
+    sizes = [(50, 30), (64, 64), (25, 15), (30, 70), (100, 60), (10, 6), (48, 48)]  # 4 of 7 match 5:3 within 0.1
+    for i in range(21):
+        w, h = sizes[i % 7]
+        _write_ppm(mdir / f"f{i:02d}.ppm", rng.integers(0, 256, (h, w, 3), dtype=np.uint8))
+    (mdir / "readme.txt").write_text("x")
+    (mdir / "broken.ppm").write_bytes(b"P5\n2 2\n255\n0000")                    # wrong magic: reported, skipped
+
+    def run(material_dir, *extra):
+        r = subprocess.run([cli, "-t", str(tmp_path / "target.ppm"), "-m", str(material_dir), "-o", str(tmp_path / "o.ppm"),
+                            "--grid-w", "5", "--grid-h", "3", "--similarity-db", str(tmp_path / "db.json"), *extra],
+                           capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0 or "no usable CUDA device" in r.stderr, r.stderr[-1500:]
+        return r
+
+    r = run(mdir)
+    assert "Target aspect ratio: 1.667" in r.stdout
+    assert "Loaded 12 tiles" in r.stdout and "No tiles matched" not in r.stdout   # 3 rounds x 4 matching sizes
+    assert "broken.ppm" in r.stderr and "not a binary PPM" in r.stderr
+    r = run(mdir, "--max-materials", "5")
+    assert "Loaded 5 tiles" in r.stdout                                            # truncate (main.rs:255-257)
+    r = run(mdir, "--aspect-tolerance", "0.001", "--max-materials", "4")
+    assert "Loaded 4 tiles" in r.stdout   # only exact 5:3 files pass the filter (50x30, 25x15, 100x60, 10x6 -> 12), truncated
+    sq = tmp_path / "squares"
+    sq.mkdir()
+    for i in range(9):
+        _write_ppm(sq / f"s{i}.ppm", rng.integers(0, 256, (16, 16, 3), dtype=np.uint8))
+    r = run(sq, "--max-materials", "3")
+    assert "No tiles matched target aspect ratio 1.667" in r.stdout               # fallback: min(9, 2 * 3) = 6 files ...
+    assert "Loaded 3 tiles" in r.stdout                                            # ... truncated to 3
+    empty = tmp_path / "empty"
+    empty.mkdir()
+    r = subprocess.run([cli, "-t", str(tmp_path / "target.ppm"), "-m", str(empty), "-o", str(tmp_path / "o.ppm")],
+                       capture_output=True, text=True)
+    assert r.returncode == 1 and "no material images found" in r.stderr
