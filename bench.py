@@ -2,19 +2,25 @@
 """bench.py — headline benchmark of the B200-native mosaic matching path.
 
 Metric (BASELINE.json): cells placed / second (+ end-to-end ms per mosaic = ms_per_step).
-Workload at every N: the 24,000-tile mosaic (BASELINE.json configs[2], the one the north-star target
-"<50 ms on 1 B200" is quoted on): synthetic 7680x4320 target, 10,000 synthetic 64x64 materials,
-grid 200x120, max-usage 3, adjacency 0.3, colour 0.3, 1000 annealing iterations, similarity matrix
-built every run (main.rs:143).  A step = one whole mosaic: material Lab means, similarity matrix,
-cell Lab means, top-100 candidates, greedy placement, annealing, resize+adjust+composite.
+Default workload at every N: the 24,000-tile mosaic (BASELINE.json configs[2], the one the north-star target
+"<50 ms on 1 B200" is quoted on): synthetic 7680x4320 target, 10,000 synthetic 64x64 materials, grid 200x120,
+max-usage 3, adjacency 0.3, colour 0.3, 1000 annealing iterations, similarity matrix built every run (main.rs:143).
+A step = one whole mosaic: material Lab means, similarity matrix, cell Lab means, top-100 candidates, greedy
+placement, annealing, resize+adjust+composite.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config C3]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config C1|C2|C3|C4|C5]
 
-`value`  : inputs already resident in HBM, results left in HBM (CUDA events, max over ranks).
-`e2e`    : same metric through the C ABI with pinned HOST buffers: H2D of materials + target and D2H of
-           the placement + output image are inside the timed region, every step.
-`--impl reference`: the CPU path (oracle/ = C++ restatement of the reference; the Rust reference cannot
-           be built in this image) on the box's host cores, same metric/config.
+`value`    : inputs already resident in HBM, results left in HBM (CUDA events on the launch stream, max over ranks).
+`e2e`      : same metric through the C ABI with pinned HOST buffers: H2D of materials + target and D2H of the
+             placement + output image are inside the timed region, every step.
+`verified` : AFTER the timed regions, on every N, the last step's results are checked against the CPU oracle fed with
+             the GPU's own Lab means (the stage-wise parity protocol of tests/test_gpu_parity.py): Lab means <= 1e-4
+             relative, candidate lists / placements / fallback count / annealed grid / counters / cost bits identical,
+             a band of output rows of EVERY rank <= 1 LSB.  The oracle is the checker here, never the thing measured.
+`--impl reference`: the CPU path (oracle/ = C++ restatement of the reference; the Rust reference cannot be built in
+             this image) on the box's host cores, same metric/config, compiled -O3 -march=native on the box.
+`--config C4`: the similarity-database build (BASELINE.json configs[3]: 50,000 materials, 1.25 G packed entries,
+             ranges sharded over the ranks), metric similarity_entries_per_sec; C5: the giant mosaic (configs[4]).
 """
 from __future__ import annotations
 
@@ -35,6 +41,7 @@ import numpy as np  # noqa: E402
 
 METRIC = "cells_placed_per_sec"
 UNIT = "cells/s"
+FP32_LANES_PER_SM = 128  # non-tensor FP32 lanes of one sm_100 SM
 
 
 def load_peaks():
@@ -47,6 +54,8 @@ def load_peaks():
 
 def workload_config(name):
     from mosaic_b200 import synth
+    if name == "C4":
+        return dict(name="C4", n_materials=50000)
     cfg = dict(synth.CONFIGS[name])
     cfg["name"] = name
     return cfg
@@ -54,17 +63,25 @@ def workload_config(name):
 
 def config_block(cfg, world):
     """The `config` object of the JSON line — identical for both arms (the driver compares them)."""
+    if cfg["name"] == "C4":
+        n = cfg["n_materials"]
+        return {"workload": f"C4: similarity-database build, {n} materials -> {n * (n - 1) // 2} packed f32 entries",
+                "materials": n, "l2": "the 5 GB matrix is larger than the 126 MB L2; no explicit flush",
+                "parallelism": ("1 GPU" if world == 1 else f"packed ranges of equal entry count over {world} GPUs")}
+    in_mb = (cfg["n_materials"] * 64 * 64 * 3 + cfg["target_w"] * cfg["target_h"] * 3) / 1e6
     return {"workload": describe(cfg), "grid": [cfg["grid_w"], cfg["grid_h"]], "materials": cfg["n_materials"],
             "max_usage": cfg["max_usage"], "adjacency_weight": cfg["adjacency_weight"],
             "color_strength": cfg["color_strength"], "sa_iterations": cfg["sa_iterations"],
             "seed": cfg["seed"], "similarity_matrix_built": True,
-            "l2": "inputs (222 MB of RGB8 at C3) are larger than the 126 MB L2; no explicit flush",
-            "e2e_schedule": ("host buffers: uploads on their own stream (materials, then the target in 8 bands); at 1 GPU "
-                             "every band is matched and its placement records prepared as it lands, and the placement "
-                             "chain consumes them under the remaining upload; output rows return in 8 bands"),
+            "l2": f"inputs ({in_mb:.0f} MB of RGB8) " + ("are larger than" if in_mb > 126 else "fit in") +
+                  " the 126 MB L2; no explicit flush",
+            "e2e_schedule": ("host buffers: uploads on their own stream (materials, then the target in bands); every band is "
+                             "matched and its placement records prepared as it lands, the placement chain consumes them "
+                             "under the remaining upload; output rows return in bands"),
             "parallelism": ("1 GPU" if world == 1 else
-                            f"grid rows / material indices / similarity ranges sharded over {world} GPUs, "
-                            "NCCL allgather of Lab means + candidate lists, greedy + annealing on rank 0")}
+                            f"grid rows / material indices / similarity ranges sharded over {world} GPUs; "
+                            "Lab means all-gathered, candidate lists sent to rank 0 only, greedy + annealing on rank 0, "
+                            "placement broadcast, every rank renders and returns its own rows")}
 
 
 def describe(cfg):
@@ -76,7 +93,8 @@ def describe(cfg):
 def cpu_pipeline(orc, mats, tgt, cfg, threads):
     """One whole mosaic on the CPU with the reference's structure: parallel over materials where the reference
     uses Rayon (main.rs:193-208) and — as a courtesy the reference does not have — over cells / rows for the
-    other data-parallel stages; greedy placement and annealing are serial (as in the reference)."""
+    other data-parallel stages; greedy placement and annealing are serial (as in the reference).
+    threads = 1 is the reference's own structure everywhere except main.rs:193-208."""
     t = {}
     gw, gh = cfg["grid_w"], cfg["grid_h"]
     t0 = time.perf_counter()
@@ -117,20 +135,51 @@ def scaled_config(cfg, scale):
                f"(scale {scale:.3f})")
 
 
-def run_cpu(cfg, steps, warmup, budget_s):
+def run_cpu_c4(cfg, steps, warmup, budget_s):
     from mosaic_b200 import synth
     from oracle import oracle as orc
-    orc.lib()
+    flags = orc.select("fast")
+    threads = os.cpu_count() or 1
+    n = cfg["n_materials"]
+    lab = synth.lab_points(n)
+    t0 = time.perf_counter()
+    orc.similarity_tri(lab, threads=threads)
+    probe = time.perf_counter() - t0
+    sample = "whole workload"
+    runs = steps + max(warmup - 1, 0)
+    if probe * runs > budget_s:
+        n = max(2000, int(n * (budget_s / (probe * runs)) ** 0.5))
+        lab, sample = lab[:n], f"first {n} of {cfg['n_materials']} materials ({n * (n - 1) // 2} entries)"
+    times = []
+    for i in range(runs):
+        t0 = time.perf_counter()
+        orc.similarity_tri(lab, threads=threads)
+        if i >= runs - steps:
+            times.append(time.perf_counter() - t0)
+    sec = sum(times) / len(times)
+    return dict(value=n * (n - 1) / 2 / sec, ms_per_step=sec * 1e3, cores=threads, sample=sample, flags=flags,
+                stage_ms={"similarity": sec * 1e3})
+
+
+def run_cpu(cfg, steps, warmup, budget_s, one_thread_budget_s=0.0):
+    if cfg["name"] == "C4":
+        return run_cpu_c4(cfg, steps, warmup, budget_s)
+    from mosaic_b200 import synth
+    from oracle import oracle as orc
+    flags = orc.select("fast")  # -O3 -march=native -ffp-contract=off, built on this host
     threads = os.cpu_count() or 1
     sample_cfg, sample = dict(cfg), "whole workload"
+    if cfg["grid_w"] * cfg["grid_h"] > 100000:  # C5: start from a 10 % sample, the probe alone would take minutes
+        sample_cfg, sample = scaled_config(cfg, 0.1)
     mats = synth.materials(sample_cfg["n_materials"])
-    tgt = synth.target(sample_cfg["target_w"], sample_cfg["target_h"])
+    tgt = synth.target(cfg["target_w"], cfg["target_h"])[:sample_cfg["target_h"]]
+    tgt = np.ascontiguousarray(tgt)
     t0 = time.perf_counter()
     cpu_pipeline(orc, mats, tgt, sample_cfg, threads)  # probe (doubles as the first warm-up)
     probe = time.perf_counter() - t0
     total_runs = steps + max(warmup - 1, 0)
     if probe * total_runs > budget_s:  # shrink the sample so that the run ends within the budget
-        scale = max(0.02, budget_s / (probe * total_runs))
+        scale = max(0.02, budget_s / (probe * total_runs)) * (sample_cfg["grid_h"] / cfg["grid_h"])
         sample_cfg, sample = scaled_config(cfg, scale)
         mats = mats[:sample_cfg["n_materials"]]
         tgt = np.ascontiguousarray(tgt[:sample_cfg["target_h"]])
@@ -145,8 +194,23 @@ def run_cpu(cfg, steps, warmup, budget_s):
             stage_acc[k] = stage_acc.get(k, 0.0) + v
     cells = sample_cfg["grid_w"] * sample_cfg["grid_h"]
     sec = sum(times) / len(times)
-    return dict(value=cells / sec, ms_per_step=sec * 1e3, cores=threads, sample=sample, cells=cells,
-                stage_ms={k: v / steps * 1e3 for k, v in stage_acc.items()})
+    out = dict(value=cells / sec, ms_per_step=sec * 1e3, cores=threads, sample=sample, cells=cells, flags=flags,
+               stage_ms={k: v / steps * 1e3 for k, v in stage_acc.items()})
+    if one_thread_budget_s > 0:
+        # the reference's own structure: one thread everywhere (its Rayon loop over material files, main.rs:193-208,
+        # is the only parallel stage it has; the aspect-fallback branch synthetic materials take is serial too)
+        est = sec * threads * 0.6 + sec  # data-parallel stages scale with the threads, the serial ones do not
+        c1, s1 = scaled_config(sample_cfg, min(1.0, one_thread_budget_s / max(est, 1e-9)))
+        m1, t1 = mats[:c1["n_materials"]], np.ascontiguousarray(tgt[:c1["target_h"]])
+        t0 = time.perf_counter()
+        st1 = cpu_pipeline(orc, m1, t1, c1, 1)
+        sec1 = time.perf_counter() - t0
+        out["one_thread"] = dict(value=c1["grid_w"] * c1["grid_h"] / sec1, ms_per_step=sec1 * 1e3, cores=1,
+                                 sample=s1 if c1 != sample_cfg else sample,
+                                 stage_ms={k: v * 1e3 for k, v in st1.items()},
+                                 note="reference structure: every stage on one thread")
+    orc.select("strict")
+    return out
 
 
 # --------------------------------------------------------------------------- clocks
@@ -223,44 +287,162 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
 
 
+# --------------------------------------------------------------------------- distributed plumbing
+class Dist:
+    """torch.distributed as plumbing only: rendezvous, the NCCL id hand-off, barriers and the max over ranks."""
+
+    def __init__(self, gpus):
+        import torch
+        self.torch = torch
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if self.world != gpus and self.world > 1:
+            raise SystemExit(f"--gpus {gpus} but WORLD_SIZE={self.world}")
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback (use --impl reference "
+                             "for the CPU baseline)")
+        torch.cuda.set_device(self.local_rank)
+        self.nccl_id = None
+        if self.world > 1:
+            import torch.distributed as dist
+            import mosaic_b200
+            self.dist = dist
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
+            ids = [mosaic_b200.Context.nccl_unique_id() if self.rank == 0 else None]
+            dist.broadcast_object_list(ids, src=0)
+            self.nccl_id = ids[0]
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max(self, x):
+        if self.world == 1:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def all_true(self, flag):
+        if self.world == 1:
+            return bool(flag)
+        t = self.torch.tensor([1 if flag else 0], dtype=self.torch.int32, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN)
+        return bool(t.item())
+
+    def gather_objects(self, obj):
+        if self.world == 1:
+            return [obj]
+        out = [None] * self.world
+        self.dist.all_gather_object(out, obj)
+        return out
+
+    def close(self):
+        if self.world > 1:
+            self.dist.barrier()
+            self.dist.destroy_process_group()
+
+
 # --------------------------------------------------------------------------- GPU arm
-def hbm_kernels(cfg, world):
-    """Algorithmic HBM bytes per launch of the throughput kernels (SURVEY.md §8(d) per-unit figures x units of
-    one launch on ONE rank)."""
+def throughput_kernels(cfg, world):
+    """Algorithmic work per launch of the throughput kernels on ONE rank (SURVEY.md §8(d) per-unit figures x the units
+    one launch processes): bytes for the HBM-bound ones, flops for the brute-force matching."""
     n, cells = cfg["n_materials"], cfg["grid_w"] * cfg["grid_h"]
     tw, th = cfg["target_w"] // cfg["grid_w"], cfg["target_h"] // cfg["grid_h"]
     mat_px = 64 * 64
     return {
-        "material_lab": (n / world) * mat_px * 3 + (n / world) * 12,           # 3 B per pixel read + 12 B per image
-        "cell_lab": (cells / world) * tw * th * 3 + (cells / world) * (12 + 24),  # 3 B per pixel + Lab + rgb sums
-        "similarity": (n * (n - 1) / 2 / world) * 4,                             # 4 B written per pair
-        "render": (cells / world) * (mat_px * 3 + tw * th * 3),                  # material read + tile written
+        "material_lab": ("hbm", (n / world) * mat_px * 3 + (n / world) * 12),            # 3 B per pixel read + 12 B per image
+        "cell_lab": ("hbm", (cells / world) * tw * th * 3 + (cells / world) * (12 + 24)),  # 3 B per pixel + Lab + rgb sums
+        "topk": ("fp32", 8.0 * (cells / world) * n),                                       # 8 flop per (cell, material) pair
+        "similarity": ("hbm", (n * (n - 1) / 2 / world) * 4),                              # 4 B written per pair
+        "render": ("hbm", (cells / world) * (mat_px * 3 + tw * th * 3)),                   # material read + tile written
     }
+
+
+def load_traffic(cfg, world):
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(tpath):
+        return {}, None
+    with open(tpath) as f:
+        t = json.load(f)
+    return ({k.split(":")[1]: v for k, v in t.items() if k.startswith(f"{cfg['name']}:") and k.endswith(f":{world}")},
+            t.get("_source", "ncu --set full capture of an earlier build (profiles/traffic.json), not of this run"))
+
+
+def verify_mosaic(D, ctx, cfg, mats, tgt, placed_h, img_h, rep):
+    """The timed run's results against the CPU oracle fed with the GPU's Lab means (checker only; runs after timing)."""
+    from oracle import oracle as orc
+    orc.select("strict")
+    gw, gh, n = cfg["grid_w"], cfg["grid_h"], cfg["n_materials"]
+    cells = gw * gh
+    threads = os.cpu_count() or 1
+    big = cells > 100000
+    tol = lambda ref: np.maximum(1e-4 * np.abs(ref), 1e-4)
+    res = {}
+    shard = ctx.shard()
+    rb, re_ = shard["rows"]
+    th = cfg["target_h"] // gh
+    placed = placed_h.numpy().copy()
+    img = img_h.numpy()
+    # every rank: the output rows it delivered (a band of at most 3 cell rows in the middle of its shard)
+    b0 = rb + max(0, (re_ - rb) // 2 - 1)
+    b1 = min(re_, b0 + (1 if big else 3))
+    ref_band = orc.render(np.ascontiguousarray(tgt[b0 * th:b1 * th]), gw, b1 - b0, mats, placed[b0 * gw:b1 * gw],
+                          cfg["color_strength"], threads=threads)
+    band_ok = bool(np.abs(img[b0 * th:b1 * th].astype(np.int16) - ref_band.astype(np.int16)).max() <= 1)
+    # every rank: the Lab means of its own cells (all ranks hold all material Lab means)
+    clab = ctx.cell_lab()
+    mlab = ctx.material_lab()
+    rows = slice(rb * gw, re_ * gw)
+    ref_clab = orc.cell_lab(np.ascontiguousarray(tgt[rb * th:re_ * th]), gw, re_ - rb, threads=threads)
+    clab_ok = bool((np.abs(clab[rows] - ref_clab) <= tol(ref_clab)).all())
+    res["image_band"] = D.all_true(band_ok)
+    res["cell_lab"] = D.all_true(clab_ok)
+    idx, d2 = ctx.candidates()  # (stage call: every rank takes part in its exchange)
+    if D.rank == 0:
+        msel = slice(0, n) if not big else slice(0, 2000)
+        ref_mlab = orc.material_lab(mats[msel], threads=threads)
+        res["material_lab"] = bool((np.abs(mlab[msel] - ref_mlab) <= tol(ref_mlab)).all())
+        if big:  # sampled cells against the brute force over all materials; the whole greedy replay from the GPU's lists
+            rng = np.random.default_rng(5)
+            sample = np.sort(rng.choice(cells, 256, replace=False))
+            ridx, rd2 = orc.topk(mlab, clab[sample], 100, threads=threads)
+            res["candidates"] = bool((ridx == idx[sample]).all() and
+                                     (rd2.view(np.uint32) == d2[sample].view(np.uint32)).all())
+            ridx, rd2 = idx, d2
+        else:
+            ridx, rd2 = orc.topk_kdtree(mlab, clab, 100, threads=threads)
+            res["candidates"] = bool((ridx == idx).all() and (rd2.view(np.uint32) == d2.view(np.uint32)).all())
+        rplaced, rnfb, _, _ = orc.place(ridx, rd2, mlab, gw, gh, cfg["max_usage"], cfg["adjacency_weight"])
+        res["n_fallbacks"] = bool(int(rep.n_fallbacks) == int(rnfb))
+        if rep.annealed:
+            rgrid, rres = orc.anneal(mlab, rplaced.reshape(gh, gw), cfg["sa_iterations"], cfg["seed"])
+            rplaced = rgrid.ravel()
+            res["anneal_counters"] = bool(rep.opt.accepted_count == rres.accepted_count and
+                                          rep.opt.improved_count == rres.improved_count)
+            f32 = lambda v: np.float32(v).view(np.uint32)
+            res["anneal_cost_bits"] = bool(f32(rep.opt.initial_cost) == f32(rres.initial_cost) and
+                                           f32(rep.opt.final_cost) == f32(rres.final_cost) and
+                                           f32(rep.opt.best_cost) == f32(rres.best_cost))
+        res["placements"] = bool((placed == rplaced).all())
+        res["ranks_checked"] = D.world
+        res["how"] = ("CPU oracle (strict build) fed with the GPU's Lab means, after the timed regions: Lab <= 1e-4 rel; "
+                      "candidates (idx, d2 bits), fallback count, final grid, annealing counters and cost bits identical; "
+                      "a band of output rows of every rank <= 1 LSB")
+        res["all"] = all(v for k, v in res.items() if isinstance(v, bool))
+    return res
 
 
 def run_gpu(args, cfg):
     import torch
-    import torch.distributed as dist
 
     import mosaic_b200
     from mosaic_b200 import synth
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus and world > 1:
-        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback (use --impl reference "
-                         "for the CPU baseline)")
-    torch.cuda.set_device(local_rank)
-    nccl_id = None
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-        ids = [mosaic_b200.Context.nccl_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(ids, src=0)
-        nccl_id = ids[0]
-
+    D = Dist(args.gpus)
+    rank, world, local_rank = D.rank, D.world, D.local_rank
     gw, gh, n = cfg["grid_w"], cfg["grid_h"], cfg["n_materials"]
     cells = gw * gh
     # synthetic inputs in pinned host memory
@@ -269,24 +451,12 @@ def run_gpu(args, cfg):
     tgt_h = torch.empty((cfg["target_h"], cfg["target_w"], 3), dtype=torch.uint8, pin_memory=True)
     tgt_h.numpy()[...] = synth.target(cfg["target_w"], cfg["target_h"])
 
-    ctx = mosaic_b200.Context(local_rank, rank, world, nccl_id)
+    ctx = mosaic_b200.Context(local_rank, rank, world, D.nccl_id)
     stream = torch.cuda.current_stream()
     ctx.set_stream(stream.cuda_stream)
     gen_kw = dict(max_usage=cfg["max_usage"], adjacency_weight=cfg["adjacency_weight"],
                   color_strength=cfg["color_strength"], enable_optimization=cfg["sa_iterations"] > 0,
                   optimization_iterations=cfg["sa_iterations"], seed=cfg["seed"], build_similarity=True)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
 
     # ---------------- value: inputs resident in HBM, outputs left in HBM
     ctx.set_materials(mats_h)            # (sharded: own slice over PCIe + NVLink allgather)
@@ -294,8 +464,9 @@ def run_gpu(args, cfg):
     for _ in range(args.warmup):
         rep = ctx.generate(**gen_kw)
     stage_acc = {s: 0.0 for s in mosaic_b200.STAGES}
+    coll_acc = 0.0
     clocks = ClockSampler(local_rank)
-    barrier()
+    D.barrier()
     launches0 = ctx.kernel_launches()
     if rank == 0:
         clocks.start()
@@ -308,12 +479,14 @@ def run_gpu(args, cfg):
                 stage_acc[s] += ctx.stage_ms(s)
             except mosaic_b200.MosaicError:
                 pass
+        coll_acc += ctx.collective_ms()
     e1.record(stream)
-    barrier()
+    D.barrier()
     clk = clocks.stop() if rank == 0 else None
     launches = ctx.kernel_launches() - launches0
-    ms_value = max_over_ranks(e0.elapsed_time(e1) / args.steps)
-    stage_ms = {s: max_over_ranks(v / args.steps) for s, v in stage_acc.items()}
+    ms_value = D.max(e0.elapsed_time(e1) / args.steps)
+    stage_ms = {s: D.max(v / args.steps) for s, v in stage_acc.items()}
+    coll_ms = D.max(coll_acc / args.steps)
 
     # ---------------- e2e: host buffers in, host buffers out, every step
     placed_h = torch.empty(cells, dtype=torch.int32, pin_memory=True)
@@ -333,65 +506,169 @@ def run_gpu(args, cfg):
 
     for _ in range(max(1, min(args.warmup, 3))):
         e2e_step()
-    barrier()
+    D.barrier()
     w0 = time.perf_counter()
     e0.record(stream)
+    coll_e2e = 0.0
     for _ in range(args.steps):
         rep = e2e_step()
+        coll_e2e += ctx.collective_ms()
     e1.record(stream)
-    barrier()
+    D.barrier()
     wall_ms = (time.perf_counter() - w0) * 1e3 / args.steps
-    ms_e2e = max_over_ranks(e0.elapsed_time(e1) / args.steps)
-    h2d_total = max_over_ranks(float(h2d))
-    d2h_total = max_over_ranks(float(d2h))
+    ms_e2e = D.max(e0.elapsed_time(e1) / args.steps)
+    h2d_total = D.max(float(h2d))
+    d2h_total = D.max(float(d2h))
+    coll_e2e = D.max(coll_e2e / args.steps)
+
+    # ---------------- verification of what the timed e2e run returned (oracle = checker, outside every timed region)
+    verified = None
+    if not args.no_verify:
+        verified = verify_mosaic(D, ctx, cfg, mats_h.numpy(), tgt_h.numpy(), placed_h, img_h, rep)
 
     result = None
     if rank == 0:
         peak, peak_src = load_peaks()
-        algo = hbm_kernels(cfg, world)
-        dominant = max(algo, key=lambda s: stage_ms.get(s, 0.0))
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tpath):
-            with open(tpath) as f:
-                traffic = json.load(f).get(f"{cfg['name']}:{dominant}:{world}")
-        achieved = algo[dominant] / (stage_ms[dominant] * 1e-3) / 1e9
-        kernels = []
+        algo = throughput_kernels(cfg, world)
+        traffic, traffic_src = load_traffic(cfg, world)
+        sm_max = (clk or {}).get("sm_max_mhz") or 1965.0
+        fp32_peak = ctx.sm_count() * FP32_LANES_PER_SM * 2 * sm_max * 1e6 / 1e12  # TFLOP/s, non-tensor FP32 at max clock
+        kernels, rooflines = [], []
         for s in mosaic_b200.STAGES:
             ent = {"kernel": s, "ms": round(stage_ms[s], 4), "share_of_step": round(stage_ms[s] / ms_value, 4)}
-            if s in algo:
-                ent.update(bound="hbm", algorithmic_bytes=int(algo[s]),
-                           achieved_gbs=round(algo[s] / (stage_ms[s] * 1e-3) / 1e9, 1) if stage_ms[s] > 0 else None)
-            elif s == "topk":
-                pairs = cells / world * n
-                ent.update(bound="fp32", pairs=int(pairs),
-                           achieved_tflops=round(8 * pairs / (stage_ms[s] * 1e-3) / 1e12, 3) if stage_ms[s] > 0 else None)
+            if s in algo and stage_ms[s] > 0:
+                bound, work = algo[s]
+                if bound == "hbm":
+                    ach = work / (stage_ms[s] * 1e-3) / 1e9
+                    ent.update(bound="hbm", algorithmic_bytes=int(work), achieved_gbs=round(ach, 1))
+                    rooflines.append({"kernel": s, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
+                                      "frac": ach / peak, "traffic": traffic.get(s)})
+                else:
+                    ach = work / (stage_ms[s] * 1e-3) / 1e12
+                    ent.update(bound="fp32", pairs=int(work / 8), achieved_tflops=round(ach, 3))
+                    rooflines.append({"kernel": s, "bound": "fp32", "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s",
+                                      "frac": ach / fp32_peak, "traffic": None})
             elif s == "place":
                 ent.update(bound="latency", ns_per_cell=round(stage_ms[s] * 1e6 / cells, 1))
             elif s == "anneal":
                 ent.update(bound="latency", ns_per_iteration=round(stage_ms[s] * 1e6 / max(cfg["sa_iterations"], 1), 1))
             kernels.append(ent)
+        worst = min(rooflines, key=lambda r: r["frac"])
+        headline = dict(worst)
+        headline.update(peak_source=peak_src if worst["bound"] == "hbm" else
+                        f"{ctx.sm_count()} SMs x {FP32_LANES_PER_SM} lanes x 2 flop x {sm_max:.0f} MHz (no measured FP32 peak in MEASURED_PEAKS.json)",
+                        traffic_source=traffic_src,
+                        note="the WORST throughput kernel of the step (rooflines[] lists all five); the greedy placement "
+                             "and annealing kernels are serial latency-bound chains (kernels[]: ns per cell / iteration)")
         result = {
             "metric": METRIC, "value": cells / (ms_value * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_value, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": config_block(cfg, world),
             "e2e": {"value": cells / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e, "wall_ms_per_step": wall_ms,
-                    "h2d_bytes_per_step": int(h2d_total), "d2h_bytes_per_step": int(d2h_total)},
+                    "h2d_bytes_per_step": int(h2d_total), "d2h_bytes_per_step": int(d2h_total),
+                    "collective_ms": round(coll_e2e, 4)},
             "gpu_launches": int(launches),
+            "collective_ms": round(coll_ms, 4),
+            "exchange_path": ctx.exchange_path(),
             "clocks": clk,
-            "roofline": {"kernel": dominant, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "note": "dominant HBM-roofline kernel of the step; the greedy placement and annealing "
-                                 "kernels are serial latency-bound chains (see kernels[])"},
+            "roofline": headline,
+            "rooflines": rooflines,
             "kernels": kernels,
             "report": {"n_fallbacks": int(rep.n_fallbacks), "annealed": int(rep.annealed),
                        "accepted": int(rep.opt.accepted_count)},
+            "verified": verified,
         }
     ctx.close()
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    D.close()
+    return result, rank, world
+
+
+def run_gpu_c4(args, cfg):
+    """BASELINE.json configs[3]: the 50,000-material similarity database, packed ranges sharded over the ranks."""
+    import torch
+
+    import mosaic_b200
+    from mosaic_b200 import synth
+
+    D = Dist(args.gpus)
+    rank, world, local_rank = D.rank, D.world, D.local_rank
+    n = cfg["n_materials"]
+    total = n * (n - 1) // 2
+    lab = synth.lab_points(n)
+    ctx = mosaic_b200.Context(local_rank, rank, world, D.nccl_id)
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+    ctx.set_material_lab(lab)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def timed(fn):
+        for _ in range(args.warmup):
+            fn()
+        clocks = ClockSampler(local_rank)
+        D.barrier()
+        if rank == 0:
+            clocks.start()
+        e0.record(stream)
+        acc, coll = 0.0, 0.0
+        for _ in range(args.steps):
+            fn()
+            acc += ctx.stage_ms("similarity")
+            coll += ctx.collective_ms()
+        e1.record(stream)
+        D.barrier()
+        clk = clocks.stop() if rank == 0 else None
+        return D.max(e0.elapsed_time(e1) / args.steps), D.max(acc / args.steps), D.max(coll / args.steps), clk
+
+    launches0 = ctx.kernel_launches()
+    ms_local, k_local, _, clk = timed(lambda: ctx.similarity_local())          # every rank's own range, left in HBM
+    launches = ctx.kernel_launches() - launches0
+    ms_gather, k_gather, coll_gather, _ = timed(lambda: ctx.similarity_tri(fetch=False))  # + all-gather of the ranges
+    # e2e: Lab means from the host, this rank's range of the matrix back to pinned host memory
+    tb, te = ctx.shard()["tri"]
+    sim_h = torch.empty(te - tb, dtype=torch.float32, pin_memory=True)
+
+    def e2e_step():
+        ctx.set_material_lab(lab)
+        ctx.similarity_local(out=sim_h)
+
+    ms_e2e, _, _, _ = timed(e2e_step)
+    verified = None
+    if not args.no_verify:
+        from oracle import oracle as orc
+        orc.select("strict")
+        ref = orc.similarity_tri(lab, threads=os.cpu_count() or 1)
+        ok = bool((sim_h.numpy().view(np.uint32) == ref[tb:te].view(np.uint32)).all())
+        verified = {"similarity_bits": D.all_true(ok), "ranks_checked": world,
+                    "how": "every rank's range of the packed matrix (as returned to the host by the timed e2e step) "
+                           "bit-equal to the CPU oracle"}
+        verified["all"] = verified["similarity_bits"]
+    result = None
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        per_rank = total / world * 4
+        ach = per_rank / (k_local * 1e-3) / 1e9
+        nvlink = None
+        if world > 1 and coll_gather > 0:  # bytes every rank receives over NVLink / time of the all-gather
+            nvlink = total * 4 * (world - 1) / world / (coll_gather * 1e-3) / 1e9
+        result = {
+            "metric": "similarity_entries_per_sec", "value": total / (ms_local * 1e-3), "unit": "entries/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_local, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_block(cfg, world),
+            "with_allgather": {"ms_per_step": ms_gather, "collective_ms": round(coll_gather, 4),
+                               "nvlink_rx_gbs_per_rank": None if nvlink is None else round(nvlink, 1),
+                               "note": "mosaic_similarity_tri: every rank ends up with the whole 5 GB matrix"},
+            "e2e": {"value": total / (ms_e2e * 1e-3), "unit": "entries/s", "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": n * 12, "d2h_bytes_per_step": int((te - tb) * 4)},
+            "gpu_launches": int(launches), "clocks": clk,
+            "roofline": {"kernel": "similarity", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
+                         "frac": ach / peak, "traffic": None, "peak_source": peak_src},
+            "kernels": [{"kernel": "similarity", "ms": round(k_local, 4), "bound": "hbm", "algorithmic_bytes": int(per_rank),
+                         "achieved_gbs": round(ach, 1)}],
+            "verified": verified,
+        }
+    ctx.close()
+    D.close()
     return result, rank, world
 
 
@@ -401,38 +678,43 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default="C3")
+    ap.add_argument("--config", default="C3", choices=["C1", "C2", "C3", "C4", "C5"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-verify", action="store_true")
     ap.add_argument("--cpu-budget-s", type=float, default=150.0)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     cfg = workload_config(args.config)
     rank = int(os.environ.get("RANK", "0"))
+    c4 = cfg["name"] == "C4"
+    metric, unit = ("similarity_entries_per_sec", "entries/s") if c4 else (METRIC, UNIT)
 
     if args.impl == "reference":
         if rank != 0:
             return 0  # the CPU arm runs once, on rank 0
         r = run_cpu(cfg, args.steps, args.warmup, args.cpu_budget_s)
-        line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+        line = {"impl": "reference", "metric": metric, "value": r["value"], "unit": unit, "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic", "config": config_block(cfg, max(args.gpus, 1)),
-                "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
-                                 "sample": r["sample"], "stage_ms": r["stage_ms"],
+                "cpu_baseline": {"value": r["value"], "unit": unit, "cores": r["cores"], "kind": "port",
+                                 "sample": r["sample"], "stage_ms": r["stage_ms"], "compiler_flags": "g++ " + r["flags"],
                                  "note": "C++ restatement of the reference CPU path (Rust toolchain unavailable); "
                                          "k-NN through a bucketed k-d tree like kiddo's (same results as the brute force); threads over materials as "
                                          "Rayon does, plus over cells/rows as a courtesy; greedy + annealing serial"},
-                "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+                "e2e": {"value": r["value"], "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line), flush=True)
         return 0
 
-    result, rank, world = run_gpu(args, cfg)
+    result, rank, world = run_gpu_c4(args, cfg) if c4 else run_gpu(args, cfg)
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
-            r = run_cpu(cfg, 1, 1, 30.0)
-            result["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+            r = run_cpu(cfg, 1, 1, 30.0, one_thread_budget_s=0.0 if c4 else 12.0)
+            result["cpu_baseline"] = {"value": r["value"], "unit": unit, "cores": r["cores"], "kind": "port",
                                       "sample": r["sample"], "ms_per_step": r["ms_per_step"],
-                                      "stage_ms": r["stage_ms"]}
+                                      "stage_ms": r["stage_ms"], "compiler_flags": "g++ " + r["flags"]}
+            if "one_thread" in r:
+                result["cpu_baseline"]["one_thread"] = r["one_thread"]
         print(json.dumps(result), flush=True)
     return 0
 

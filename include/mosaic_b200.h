@@ -76,6 +76,15 @@ int mosaic_ctx_sync(mosaic_ctx* ctx);
 int mosaic_stage_ms(mosaic_ctx* ctx, int stage, float* ms_out);
 /* number of kernels this library has launched on ctx since creation */
 uint64_t mosaic_kernel_launches(const mosaic_ctx* ctx);
+/* device time (ms, CUDA events on the context's stream) this rank spent in exchange steps — NCCL collectives and the
+ * waits for peer-memory hand-offs — since the previous call of this function.  0 on single-GPU contexts. */
+int mosaic_collective_ms(mosaic_ctx* ctx, float* ms_out);
+/* How mosaic_generate exchanges data between the ranks of a sharded context: "single" (one GPU), "peer" (every rank's
+ * buffers mapped into every other rank over NVLink, kernels store into the consumer's memory, flag hand-offs) or
+ * "nccl: <why the peer windows could not be mapped>" (grouped NCCL broadcasts).  Valid after the first mosaic_generate. */
+const char* mosaic_exchange_path(const mosaic_ctx* ctx);
+/* number of SMs of the context's device (grid sizing, FP32 roofline of the matching kernel) */
+int mosaic_sm_count(const mosaic_ctx* ctx);
 
 /* ---- inputs -------------------------------------------------------------------------------- */
 /* Host pointers belong to the caller.  Pageable buffers are staged before the call returns.  With PAGE-LOCKED buffers
@@ -119,6 +128,10 @@ int mosaic_cell_lab(mosaic_ctx* ctx, float* lab_out);
 /* packed upper triangle, n(n-1)/2 floats, entry (i<j) at i*n - i(i+1)/2 + j - i - 1
  * (similarity.rs:100).  sim_out may be NULL (matrix stays on the device). */
 int mosaic_similarity_tri(mosaic_ctx* ctx, float* sim_out);
+/* Sharded build without the exchange: this rank's range [tri_begin, tri_end) of the packed matrix (mosaic_shard) is
+ * computed and, if range_out is not NULL, copied to the host (tri_end - tri_begin floats).  On a single-GPU context
+ * the range is the whole matrix.  Row blocks of a 50,000-material database (5 GB) stay on the GPU that built them. */
+int mosaic_similarity_local(mosaic_ctx* ctx, float* range_out);
 
 /* ---- B4: matching + greedy placement -------------------------------------------------------- */
 /* K nearest materials per cell (kdtree.nearest_n::<SquaredEuclidean>, main.rs:348-352), ascending

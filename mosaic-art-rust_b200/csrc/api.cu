@@ -38,14 +38,8 @@ inline size_t cells_of(const mosaic_ctx* c) { return (size_t)c->gw * (size_t)c->
 
 // contiguous split of [0, total) over `world` ranks, boundaries rounded down to `align`
 inline void split_range(uint64_t total, int world, int rank, uint64_t align, uint64_t* b, uint64_t* e) {
-  auto bound = [&](int r) -> uint64_t {
-    if (r <= 0) return 0;
-    if (r >= world) return total;
-    uint64_t v = (total / (uint64_t)world) * (uint64_t)r + std::min<uint64_t>((uint64_t)r, total % (uint64_t)world);
-    return align > 1 ? (v / align) * align : v;
-  };
-  *b = bound(rank);
-  *e = bound(rank + 1);
+  *b = split_bound(total, world, rank, align);
+  *e = split_bound(total, world, rank + 1, align);
 }
 
 void shard_rows(const mosaic_ctx* c, int rank, int* b, int* e) {
@@ -210,13 +204,7 @@ int run_material_lab(mosaic_ctx* c) {
   return MOSAIC_OK;
 }
 
-int run_cell_lab(mosaic_ctx* c) {
-  MOSAIC_TRY(require(c, c->have_target, "target (mosaic_set_target_rgb8)"));
-  MOSAIC_TRY(ensure_cell_buffers(c));
-  MOSAIC_TRY(wait_target(c));
-  int rb, re;
-  shard_rows(c, c->rank, &rb, &re);
-  MOSAIC_TRY(launch_cell_lab_range(c, rb * c->gw, re * c->gw));
+int gather_cell_lab(mosaic_ctx* c) {
   MOSAIC_TRY(allgather_slices(c, c->d_cell_lab, 3 * sizeof(float) * (size_t)c->gw,
                               [&](int r, uint64_t* sb, uint64_t* se) {
                                 int ib, ie;
@@ -224,20 +212,24 @@ int run_cell_lab(mosaic_ctx* c) {
                                 *sb = (uint64_t)ib;
                                 *se = (uint64_t)ie;
                               }));
-  c->have_cell_lab = true;
-  c->have_cell_rgbsum = true;  // valid for this rank's rows (all the render kernel needs)
-  c->have_cand = false;
+  c->cell_lab_gathered = true;
   return MOSAIC_OK;
 }
 
-int run_candidates(mosaic_ctx* c, int k) {
-  if (!c->have_mat_lab) MOSAIC_TRY(run_material_lab(c));
-  // a target still on its way up (single GPU): every band's cell Lab means and top-K start when that band has landed
-  const bool banded = !c->have_cell_lab && c->tgt_upload_pending && c->world == 1 && c->tgt_bands > 1;
-  if (!c->have_cell_lab && !banded) MOSAIC_TRY(run_cell_lab(c));
-  if (k <= 0 || k > kMaxK) k = kMaxK;
-  if (k > c->n) k = c->n;  // main.rs:348 min(len, 100)
-  if (k <= 0) return fail(c, MOSAIC_ERR_STATE, "no materials");
+int gather_candidates(mosaic_ctx* c) {
+  auto rows = [&](int r, uint64_t* sb, uint64_t* se) {
+    int ib, ie;
+    shard_rows(c, r, &ib, &ie);
+    *sb = (uint64_t)ib;
+    *se = (uint64_t)ie;
+  };
+  MOSAIC_TRY(allgather_slices(c, c->d_cand_idx, sizeof(uint32_t) * (size_t)c->gw * c->k, rows));
+  MOSAIC_TRY(allgather_slices(c, c->d_cand_d2, sizeof(float) * (size_t)c->gw * c->k, rows));
+  c->cand_gathered = true;
+  return MOSAIC_OK;
+}
+
+int ensure_cand_buffers(mosaic_ctx* c) {
   const size_t cells = cells_of(c);
   if (c->cand_cap < cells * (size_t)kMaxK || !c->d_cand_idx) {
     if (c->d_cand_idx) cudaFree(c->d_cand_idx);
@@ -249,6 +241,48 @@ int run_candidates(mosaic_ctx* c, int k) {
     MOSAIC_CUDA(c, cudaMalloc((void**)&c->d_cand_d2, sizeof(float) * cells * kMaxK));
     c->cand_cap = cells * (size_t)kMaxK;
   }
+  return MOSAIC_OK;
+}
+
+// sharded contexts upload only their own slice of the material pixels; whoever needs all of them on this rank (the
+// NCCL fallback of the render) gathers them here
+int gather_material_pixels(mosaic_ctx* c) {
+  if (!c->mats_sliced) return MOSAIC_OK;
+  const size_t per = (size_t)c->mw * c->mh * 3;
+  MOSAIC_TRY(allgather_slices(c, c->d_materials_owned, per, [&](int r, uint64_t* sb, uint64_t* se) {
+    int ib, ie;
+    shard_mats(c, r, &ib, &ie);
+    *sb = (uint64_t)ib;
+    *se = (uint64_t)ie;
+  }));
+  c->mats_sliced = false;
+  return MOSAIC_OK;
+}
+
+int run_cell_lab(mosaic_ctx* c) {
+  MOSAIC_TRY(require(c, c->have_target, "target (mosaic_set_target_rgb8)"));
+  MOSAIC_TRY(ensure_cell_buffers(c));
+  MOSAIC_TRY(wait_target(c));
+  int rb, re;
+  shard_rows(c, c->rank, &rb, &re);
+  MOSAIC_TRY(launch_cell_lab_range(c, rb * c->gw, re * c->gw));
+  MOSAIC_TRY(gather_cell_lab(c));
+  c->have_cell_lab = true;
+  c->have_cell_rgbsum = true;  // valid for this rank's rows (all the render kernel needs)
+  c->have_cand = false;
+  return MOSAIC_OK;
+}
+
+int run_candidates(mosaic_ctx* c, int k) {
+  if (!c->have_mat_lab) MOSAIC_TRY(run_material_lab(c));
+  if (c->have_cell_lab && !c->cell_lab_gathered) MOSAIC_TRY(gather_cell_lab(c));
+  // a target still on its way up (single GPU): every band's cell Lab means and top-K start when that band has landed
+  const bool banded = !c->have_cell_lab && c->tgt_upload_pending && c->world == 1 && c->tgt_bands > 1;
+  if (!c->have_cell_lab && !banded) MOSAIC_TRY(run_cell_lab(c));
+  if (k <= 0 || k > kMaxK) k = kMaxK;
+  if (k > c->n) k = c->n;  // main.rs:348 min(len, 100)
+  if (k <= 0) return fail(c, MOSAIC_ERR_STATE, "no materials");
+  MOSAIC_TRY(ensure_cand_buffers(c));
   c->k = k;
   if (banded) {
     MOSAIC_TRY(require(c, c->have_target, "target (mosaic_set_target_rgb8)"));
@@ -268,19 +302,38 @@ int run_candidates(mosaic_ctx* c, int k) {
   int rb, re;
   shard_rows(c, c->rank, &rb, &re);
   MOSAIC_TRY(launch_topk_range(c, k, rb * c->gw, re * c->gw));
-  auto rows = [&](int r, uint64_t* sb, uint64_t* se) {
-    int ib, ie;
-    shard_rows(c, r, &ib, &ie);
-    *sb = (uint64_t)ib;
-    *se = (uint64_t)ie;
-  };
-  MOSAIC_TRY(allgather_slices(c, c->d_cand_idx, sizeof(uint32_t) * (size_t)c->gw * k, rows));
-  MOSAIC_TRY(allgather_slices(c, c->d_cand_d2, sizeof(float) * (size_t)c->gw * k, rows));
+  MOSAIC_TRY(gather_candidates(c));
   c->have_cand = true;
   return MOSAIC_OK;
 }
 
-int ensure_placed(mosaic_ctx* c) { return ensure(c, &c->d_placed, &c->placed_cap, cells_of(c)); }
+// the result arena: [opt result | fallback info | placements] — one contiguous hand-off from rank 0 to the other ranks
+int ensure_result(mosaic_ctx* c, size_t cells) {
+  if (c->d_result && c->placed_cap >= cells) return MOSAIC_OK;
+  const size_t head = mosaic_ctx::kResultHead;
+  static_assert(mosaic_ctx::kResultHead % 16 == 0, "arena head keeps the placements 16-byte aligned");
+  unsigned char* fresh = nullptr;
+  const size_t cap = std::max<size_t>(cells, 1);
+  cudaError_t e = cudaMalloc((void**)&fresh, head + cap * sizeof(int32_t));
+  if (e != cudaSuccess)
+    return e == cudaErrorMemoryAllocation ? fail(c, MOSAIC_ERR_NOMEM, "cudaMalloc: out of device memory") : cuda_fail(c, e, "cudaMalloc");
+  MOSAIC_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (c->d_result) {
+    MOSAIC_CUDA(c, cudaMemcpy(fresh, c->d_result, head, cudaMemcpyDeviceToDevice));
+    cudaFree(c->d_result);
+  } else {
+    MOSAIC_CUDA(c, cudaMemset(fresh, 0, head));
+  }
+  c->d_result = fresh;
+  c->result_cap = head + cap * sizeof(int32_t);
+  c->d_opt_res = fresh;
+  c->d_place_info = reinterpret_cast<uint32_t*>(fresh + 256);
+  c->d_placed = reinterpret_cast<int32_t*>(fresh + head);
+  c->placed_cap = cap;
+  c->have_placed = false;
+  return MOSAIC_OK;
+}
+int ensure_placed(mosaic_ctx* c) { return ensure_result(c, cells_of(c)); }
 
 __global__ void set_u32_kernel(unsigned* p, unsigned v) { *p = v; }
 
@@ -291,17 +344,7 @@ __global__ void set_u32_kernel(unsigned* p, unsigned v) { *p = v; }
 int run_match_place_banded(mosaic_ctx* c, int k, int max_usage, float weight) {
   if (k <= 0 || k > kMaxK) k = kMaxK;
   if (k > c->n) k = c->n;
-  const size_t cells = cells_of(c);
-  if (c->cand_cap < cells * (size_t)kMaxK || !c->d_cand_idx) {
-    if (c->d_cand_idx) cudaFree(c->d_cand_idx);
-    if (c->d_cand_d2) cudaFree(c->d_cand_d2);
-    c->d_cand_idx = nullptr;
-    c->d_cand_d2 = nullptr;
-    c->cand_cap = 0;
-    MOSAIC_CUDA(c, cudaMalloc((void**)&c->d_cand_idx, sizeof(uint32_t) * cells * kMaxK));
-    MOSAIC_CUDA(c, cudaMalloc((void**)&c->d_cand_d2, sizeof(float) * cells * kMaxK));
-    c->cand_cap = cells * (size_t)kMaxK;
-  }
+  MOSAIC_TRY(ensure_cand_buffers(c));
   c->k = k;
   MOSAIC_TRY(ensure_cell_buffers(c));
   MOSAIC_TRY(ensure_placed(c));
@@ -357,6 +400,120 @@ int run_anneal(mosaic_ctx* c, uint64_t iterations, float t0, float decay, uint64
   return MOSAIC_OK;
 }
 
+int run_similarity(mosaic_ctx* c, bool gather);
+
+// ---- sharded mosaic_generate over peer windows (no collective on the data path) -----------------------------------------
+//   every rank : Lab means of its material slice -> stored into every rank's table; similarity range; Lab means and
+//                top-K of its grid rows, the candidate lists stored straight into RANK 0's buffers over NVLink
+//   rank 0     : placement records band by band as the other ranks' lists land, the serial chain behind them (gated
+//                instantiation), annealing; the result arena (placements, fallback info, optimisation result) is
+//                stored into every rank's arena
+//   every rank : renders its rows, reading the placed materials from their owners' memory; one barrier at the end
+//                (nobody overwrites a window a peer may still be reading)
+int run_generate_peer(mosaic_ctx* c, const mosaic_params* p, bool anneal) {
+  const int world = c->world, rank = c->rank;
+  int mb, me, rb, re;
+  shard_mats(c, rank, &mb, &me);
+  shard_rows(c, rank, &rb, &re);
+  int k = std::min(kMaxK, c->n);
+  c->k = k;
+  if (c->mat_signal_pending) {  // this rank's material slice has landed (the upload is ordered on this stream)
+    MOSAIC_TRY(dist_peer_signal(c, FLAG_MAT + rank, c->ep_mat, -1, c->stream));
+    c->mat_signal_pending = false;
+  }
+  // --- material Lab means: own slice, then into every rank's table
+  MOSAIC_TRY(wait_materials(c));
+  if (c->ragged) {
+    if (me > mb) MOSAIC_TRY(launch_material_lab_ragged(c, mb, me));
+  } else {
+    const uint8_t* all = c->d_materials;
+    float* lab_all = c->d_mat_lab;
+    const int n_all = c->n;
+    c->d_materials = all + (size_t)mb * c->mw * c->mh * 3;
+    c->d_mat_lab = lab_all + 3 * (size_t)mb;
+    c->n = me - mb;
+    int rc = c->n > 0 ? launch_material_lab(c) : MOSAIC_OK;
+    c->d_materials = all;
+    c->d_mat_lab = lab_all;
+    c->n = n_all;
+    MOSAIC_TRY(rc);
+  }
+  const unsigned e_lab = ++c->ep_lab;
+  {
+    CollTimer t(c, c->stream);
+    MOSAIC_TRY(dist_peer_push(c, mosaic_ctx::PW_MAT_LAB, (size_t)mb * 12, (size_t)(me - mb) * 12, -1, c->stream));
+    MOSAIC_TRY(dist_peer_signal(c, FLAG_LAB + rank, e_lab, -1, c->stream));
+    MOSAIC_TRY(dist_peer_wait(c, FLAG_LAB, world, e_lab, c->stream));
+  }
+  MOSAIC_TRY(launch_pack_lab(c));
+  c->have_mat_lab = true;
+  c->have_sim = false;
+  if (p->build_similarity) MOSAIC_TRY(run_similarity(c, /*gather=*/false));
+  // --- own rows: cell Lab means + top-K, stored into rank 0's candidate buffers
+  MOSAIC_TRY(wait_target(c));
+  MOSAIC_TRY(launch_cell_lab_range(c, rb * c->gw, re * c->gw));
+  c->have_cell_lab = c->have_cell_rgbsum = true;
+  c->cell_lab_gathered = false;
+  c->cand_dst_idx = reinterpret_cast<uint32_t*>(c->pw_peer[mosaic_ctx::PW_CAND_IDX][0]);
+  c->cand_dst_d2 = reinterpret_cast<float*>(c->pw_peer[mosaic_ctx::PW_CAND_D2][0]);
+  int rc = launch_topk_range(c, k, rb * c->gw, re * c->gw);
+  c->cand_dst_idx = nullptr;
+  c->cand_dst_d2 = nullptr;
+  MOSAIC_TRY(rc);
+  const unsigned e_cand = ++c->ep_cand, e_res = ++c->ep_res;
+  c->have_cand = true;
+  c->cand_gathered = false;
+  if (rank != 0) {
+    CollTimer t(c, c->stream);
+    MOSAIC_TRY(dist_peer_signal(c, FLAG_CAND + rank, e_cand, 0, c->stream));
+    MOSAIC_TRY(dist_peer_wait(c, FLAG_RES, 1, e_res, c->stream));  // placements + report from rank 0
+  } else {
+    const bool chain = place_chain_eligible(c, p->max_usage);
+    MOSAIC_CUDA(c, cudaEventRecord(c->ev_begin[MOSAIC_STAGE_PLACE], c->stream));
+    if (chain) {
+      MOSAIC_TRY(ensure(c, &c->d_ready_cells, &c->ready_cells_cap, (size_t)1));
+      MOSAIC_CUDA(c, cudaMemsetAsync(c->d_ready_cells, 0, sizeof(unsigned), c->stream));
+    }
+    for (int r = 0; r < world; ++r) {
+      int b0, b1;
+      shard_rows(c, r, &b0, &b1);
+      if (r > 0) {
+        CollTimer t(c, c->stream);
+        MOSAIC_TRY(dist_peer_wait(c, FLAG_CAND + r, 1, e_cand, c->stream));
+      }
+      if (chain && b1 > b0) {
+        MOSAIC_TRY(launch_place_prep_range(c, p->adjacency_weight, b0 * c->gw, b1 * c->gw));
+        set_u32_kernel<<<1, 1, 0, c->stream>>>(c->d_ready_cells, (unsigned)(b1 * c->gw));
+        c->launches++;
+      }
+      if (chain && r == 0) MOSAIC_CUDA(c, cudaEventRecord(c->ev_chain_go, c->stream));
+    }
+    if (chain) {  // (enqueued behind every band's kernels, waits only for the first band: see run_match_place_banded)
+      MOSAIC_CUDA(c, cudaStreamWaitEvent(c->chain_stream, c->ev_chain_go, 0));
+      MOSAIC_TRY(launch_place_chain_async(c, p->max_usage, p->adjacency_weight, c->chain_stream, c->d_ready_cells));
+      MOSAIC_CUDA(c, cudaEventRecord(c->ev_chain_done, c->chain_stream));
+      MOSAIC_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_chain_done, 0));
+      MOSAIC_CUDA(c, cudaEventRecord(c->ev_end[MOSAIC_STAGE_PLACE], c->stream));
+      c->ev_valid[MOSAIC_STAGE_PLACE] = true;
+    } else {
+      MOSAIC_TRY(launch_place(c, p->max_usage, p->adjacency_weight));
+    }
+    c->have_placed = true;
+    if (anneal) MOSAIC_TRY(launch_anneal(c, p->optimization_iterations, 100.0f, 0.99995f, p->seed));
+    CollTimer t(c, c->stream);
+    MOSAIC_TRY(dist_peer_push(c, mosaic_ctx::PW_RESULT, 0, mosaic_ctx::kResultHead + cells_of(c) * sizeof(int32_t), -1, c->stream));
+    MOSAIC_TRY(dist_peer_signal(c, FLAG_RES, e_res, -1, c->stream));
+  }
+  c->have_placed = true;
+  // the render reads the placed materials from their owners: every owner's slice must have landed
+  if (c->mats_sliced) {
+    CollTimer t(c, c->stream);
+    MOSAIC_TRY(dist_peer_wait(c, FLAG_MAT, world, c->ep_mat, c->stream));
+  }
+  c->peer_render_ready = true;
+  return MOSAIC_OK;
+}
+
 int gather_similarity(mosaic_ctx* c) {
   if (c->world == 1 || c->sim_gathered) return MOSAIC_OK;
   MOSAIC_TRY(allgather_slices(c, c->d_sim, sizeof(float), [&](int r, uint64_t* sb, uint64_t* se) { shard_tri(c, r, sb, se); }));
@@ -366,7 +523,7 @@ int gather_similarity(mosaic_ctx* c) {
 
 // gather = false (the fused path): a sharded context computes its own range and leaves the all-gather to the first
 // caller that wants the whole matrix — no kernel reads it (they recompute entries from the Lab means)
-int run_similarity(mosaic_ctx* c, bool gather = true) {
+int run_similarity(mosaic_ctx* c, bool gather) {
   if (!c->have_mat_lab) MOSAIC_TRY(run_material_lab(c));
   const uint64_t n = (uint64_t)c->n;
   const uint64_t total = n > 1 ? n * (n - 1) / 2 : 0;  // similarity.rs:71 (n == 0 underflows in the reference)
@@ -396,6 +553,7 @@ int run_render(mosaic_ctx* c, float strength, uint8_t* out_rgb) {
   MOSAIC_TRY(require(c, c->have_target, "target"));
   MOSAIC_TRY(require(c, c->have_placed, "placement"));
   MOSAIC_TRY(wait_materials(c));
+  if (c->mats_sliced && !(c->peer_ok && c->peer_render_ready)) MOSAIC_TRY(gather_material_pixels(c));
   if (strength > 0.0f && !c->have_cell_rgbsum) MOSAIC_TRY(run_cell_lab(c));
   if (!c->d_cell_rgbsum) MOSAIC_TRY(ensure_cell_buffers(c));
   const size_t out_bytes = (size_t)c->gw * c->tile_w * (size_t)c->gh * c->tile_h * 3;
@@ -486,11 +644,9 @@ static int ctx_create_common(mosaic_ctx** out, int device) {
     cudaEventCreate(&c->ev_begin[i]);
     cudaEventCreate(&c->ev_end[i]);
   }
-  bool ok = cudaMalloc((void**)&c->d_place_info, (1 + mosaic_ctx::kFallbackCap) * sizeof(uint32_t)) == cudaSuccess &&
-            cudaMalloc(&c->d_opt_res, sizeof(mosaic_opt_result)) == cudaSuccess &&
-            cudaMemset(c->d_place_info, 0, (1 + mosaic_ctx::kFallbackCap) * sizeof(uint32_t)) == cudaSuccess &&
-            cudaMemset(c->d_opt_res, 0, sizeof(mosaic_opt_result)) == cudaSuccess;
-  if (!ok) {
+  static_assert(sizeof(mosaic_opt_result) <= 256, "arena layout");
+  if (ensure_result(c, 1) != MOSAIC_OK) {
+    set_global_error(c->err);
     mosaic_ctx_destroy(c);
     return fail(nullptr, MOSAIC_ERR_CUDA, "context allocation failed");
   }
@@ -528,8 +684,8 @@ void mosaic_ctx_destroy(mosaic_ctx* c) {
   dist_destroy(c);
   void* bufs[] = {c->d_ready_cells, c->d_mat_off, c->d_mat_w, c->d_mat_h, c->d_rag_bounds, c->d_rag_weights, c->d_rag_desc, c->d_rag_midx, c->d_rag_scratch,
                   c->d_sim_lab4_own, c->d_sim_soa_own, c->d_materials_owned, c->d_mat_lab, c->d_mat_lab4, c->d_mat_soa, c->d_target_owned, c->d_cell_lab,
-                  c->d_cell_rgbsum,     c->d_cand_idx, c->d_cand_d2, c->d_placed,  c->d_usage,        c->d_place_info, c->d_place_rec,
-                  c->d_sim,             c->d_sim_counter, c->d_opt_res,  c->d_rng_ring, c->d_terms, c->d_deltas, c->d_thumbs, c->d_thumb_sums, c->d_thumb_state, c->d_out,    c->axis_h.start,   c->axis_h.size,
+                  c->d_cell_rgbsum,     c->d_cand_idx, c->d_cand_d2, c->d_result,  c->d_usage,        c->d_flags, c->d_peer_err, c->d_place_rec,
+                  c->d_sim,             c->d_sim_counter, c->d_rng_ring, c->d_terms, c->d_deltas, c->d_thumbs, c->d_thumb_sums, c->d_thumb_state, c->d_out,    c->axis_h.start,   c->axis_h.size,
                   c->axis_h.w,          c->axis_v.start, c->axis_v.size, c->axis_v.w};
   for (void* p : bufs)
     if (p) cudaFree(p);
@@ -560,6 +716,9 @@ void mosaic_ctx_destroy(mosaic_ctx* c) {
     if (c->ev_band[i]) cudaEventDestroy(c->ev_band[i]);
   if (c->ev_copy_done) cudaEventDestroy(c->ev_copy_done);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  for (int i = 0; i < mosaic_ctx::kCollEvents; ++i)
+    for (int j = 0; j < 2; ++j)
+      if (c->coll_ev[i][j]) cudaEventDestroy(c->coll_ev[i][j]);
   delete c;
 }
 
@@ -585,6 +744,31 @@ int mosaic_stage_ms(mosaic_ctx* c, int stage, float* ms_out) {
 
 uint64_t mosaic_kernel_launches(const mosaic_ctx* c) { return c ? c->launches : 0; }
 
+int mosaic_collective_ms(mosaic_ctx* c, float* ms_out) {
+  if (!c || !ms_out) return MOSAIC_ERR_INVALID;
+  float total = 0.0f;
+  for (int i = 0; i < c->coll_n; ++i) {
+    float ms = 0.0f;
+    MOSAIC_CUDA(c, cudaEventSynchronize(c->coll_ev[i][1]));
+    MOSAIC_CUDA(c, cudaEventElapsedTime(&ms, c->coll_ev[i][0], c->coll_ev[i][1]));
+    total += ms;
+  }
+  c->coll_n = 0;
+  *ms_out = total;
+  return MOSAIC_OK;
+}
+
+int mosaic_sm_count(const mosaic_ctx* c) { return c ? c->sm_count : 0; }
+
+const char* mosaic_exchange_path(const mosaic_ctx* c) {
+  if (!c || c->world == 1) return "single";
+  if (c->peer_ok) return "peer";
+  static thread_local std::string note;
+  note = "nccl: " + (c->peer_failed ? (c->peer_note.empty() ? std::string("peer windows unavailable") : c->peer_note)
+                                    : std::string("peer windows not set up yet"));
+  return note.c_str();
+}
+
 // ---- inputs ----------------------------------------------------------------------------------
 static int set_materials_common(mosaic_ctx* c, int n, int w, int h) {
   if (n <= 0 || w < 0 || h < 0 || ((w == 0) != (h == 0))) return fail(c, MOSAIC_ERR_INVALID, "materials: n, w, h must be positive");
@@ -595,6 +779,7 @@ static int set_materials_common(mosaic_ctx* c, int n, int w, int h) {
   c->have_mat_lab = c->have_cand = c->have_placed = c->have_sim = c->have_out = false;
   c->sim_lab_override = false;  // a new material set: the database colours of the old one do not apply
   c->ragged = false;
+  c->mats_sliced = false;
   c->materials_version++;
   c->mat_upload_pending = false;  // (an upload of the previous set still in flight is ordered before the next one)
   return MOSAIC_OK;
@@ -620,15 +805,14 @@ int mosaic_set_materials_rgb8(mosaic_ctx* c, const uint8_t* rgb, int n, int w, i
   }
   int b = 0, e = n;
   shard_mats(c, c->rank, &b, &e);
-  // each rank uploads its slice over its own PCIe link; slices are exchanged over NVLink
+  // Each rank uploads ITS slice over its own PCIe link and keeps only that: the Lab means need nothing else, and the
+  // render reads the materials placed in this rank's rows from their owners' memory over NVLink (peer windows) — or,
+  // without peer access, gathers the slices with NCCL when it first needs them (gather_material_pixels).
   MOSAIC_CUDA(c, cudaMemcpyAsync(c->d_materials_owned + (size_t)b * per, rgb + (size_t)b * per, (size_t)(e - b) * per,
                                  cudaMemcpyHostToDevice, c->stream));
-  MOSAIC_TRY(allgather_slices(c, c->d_materials_owned, per, [&](int r, uint64_t* sb, uint64_t* se) {
-    int ib, ie;
-    shard_mats(c, r, &ib, &ie);
-    *sb = (uint64_t)ib;
-    *se = (uint64_t)ie;
-  }));
+  c->mats_sliced = true;
+  c->ep_mat++;  // (every rank calls this function the same number of times)
+  c->mat_signal_pending = true;
   c->have_materials = true;
   return MOSAIC_OK;
 }
@@ -806,9 +990,19 @@ int mosaic_cell_lab(mosaic_ctx* c, float* lab_out) {
 int mosaic_similarity_tri(mosaic_ctx* c, float* sim_out) {
   if (!c) return MOSAIC_ERR_INVALID;
   MOSAIC_CUDA(c, cudaSetDevice(c->device));
-  MOSAIC_TRY(run_similarity(c));
+  MOSAIC_TRY(run_similarity(c, /*gather=*/true));
   const uint64_t n = (uint64_t)c->n;
   MOSAIC_TRY(d2h(c, sim_out, c->d_sim, sizeof(float) * (size_t)(n > 1 ? n * (n - 1) / 2 : 0)));
+  return sync(c);
+}
+
+int mosaic_similarity_local(mosaic_ctx* c, float* range_out) {
+  if (!c) return MOSAIC_ERR_INVALID;
+  MOSAIC_CUDA(c, cudaSetDevice(c->device));
+  MOSAIC_TRY(run_similarity(c, /*gather=*/false));
+  uint64_t b, e;
+  shard_tri(c, c->rank, &b, &e);
+  MOSAIC_TRY(d2h(c, range_out, c->d_sim + b, sizeof(float) * (size_t)(e - b)));
   return sync(c);
 }
 
@@ -881,6 +1075,20 @@ int mosaic_generate(mosaic_ctx* c, const mosaic_params* p, int32_t* placed_out, 
   MOSAIC_CUDA(c, cudaSetDevice(c->device));
   MOSAIC_TRY(require(c, c->have_materials, "materials"));
   MOSAIC_TRY(require(c, c->have_target, "target"));
+  const bool anneal = p->enable_optimization && p->adjacency_weight > 0.0f;  // main.rs:608
+  bool peer = false;
+  if (c->world > 1) {  // sharded: buffers every rank exchanges through are allocated (whole-problem sizes) and mapped
+    MOSAIC_TRY(ensure_mat_lab_buffers(c, c->n));
+    MOSAIC_TRY(ensure_cell_buffers(c));
+    MOSAIC_TRY(ensure_cand_buffers(c));
+    MOSAIC_TRY(ensure_placed(c));
+    MOSAIC_TRY(dist_peer_setup(c));
+    peer = c->peer_ok;
+  }
+  c->peer_render_ready = false;
+  if (peer) {
+    MOSAIC_TRY(run_generate_peer(c, p, anneal));
+  } else {
   // main.rs:105-164 (MosaicGenerator::new) ...
   MOSAIC_TRY(run_material_lab(c));
   if (p->build_similarity) MOSAIC_TRY(run_similarity(c, /*gather=*/false));
@@ -892,17 +1100,23 @@ int mosaic_generate(mosaic_ctx* c, const mosaic_params* p, int32_t* placed_out, 
     MOSAIC_TRY(run_candidates(c, kMaxK));
     MOSAIC_TRY(run_place(c, p->max_usage, p->adjacency_weight));
   }
-  const bool anneal = p->enable_optimization && p->adjacency_weight > 0.0f;  // main.rs:608
   if (anneal) MOSAIC_TRY(run_anneal(c, p->optimization_iterations, 100.0f, 0.99995f, p->seed));  // optimizer.rs:18-27
+  }
   MOSAIC_TRY(d2h(c, placed_out, c->d_placed, sizeof(int32_t) * cells_of(c)));
   MOSAIC_TRY(run_render(c, p->color_strength, out_rgb));
+  if (peer) {
+    CollTimer t(c, c->stream);
+    MOSAIC_TRY(dist_peer_barrier(c, c->stream));
+    c->peer_render_ready = false;  // (a later stand-alone mosaic_render has no hand-off protecting the peers' slices)
+  }
   if (report) {
     std::memset(report, 0, sizeof *report);
     MOSAIC_TRY(d2h(c, &report->n_fallbacks, c->d_place_info, sizeof(uint32_t)));
     if (anneal) MOSAIC_TRY(d2h(c, &report->opt, c->d_opt_res, sizeof(mosaic_opt_result)));
     report->annealed = anneal ? 1 : 0;
   }
-  return sync(c);
+  MOSAIC_TRY(sync(c));
+  return dist_peer_check(c);
 }
 
 int mosaic_selftest(mosaic_ctx* c, uint64_t mismatches[2]) {

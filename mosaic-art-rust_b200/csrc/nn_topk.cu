@@ -261,7 +261,8 @@ int launch_topk_range(mosaic_ctx* ctx, int k, int cell_begin, int cell_end) {
     StageTimer t(ctx, MOSAIC_STAGE_TOPK);
     nn_topk_kernel<<<blocks, TK_WARPS * 32, kTopkSmem, ctx->stream>>>(ctx->d_mat_soa, ctx->d_mat_lab4, ctx->n, ctx->n_pad,
                                                                       ctx->d_cell_lab, cell_begin, cell_end, k, rounds,
-                                                                      ctx->d_cand_idx, ctx->d_cand_d2);
+                                                                      ctx->cand_dst_idx ? ctx->cand_dst_idx : ctx->d_cand_idx,
+                                                                      ctx->cand_dst_d2 ? ctx->cand_dst_d2 : ctx->d_cand_d2);
     ctx->launches++;
   }
   MOSAIC_CUDA(ctx, cudaGetLastError());

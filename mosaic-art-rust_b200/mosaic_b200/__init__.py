@@ -70,6 +70,10 @@ def load_library():
         "mosaic_ctx_sync": ([vp], C.c_int),
         "mosaic_stage_ms": ([vp, C.c_int, f32p], C.c_int),
         "mosaic_kernel_launches": ([vp], C.c_uint64),
+        "mosaic_collective_ms": ([vp, f32p], C.c_int),
+        "mosaic_sm_count": ([vp], C.c_int),
+        "mosaic_exchange_path": ([vp], C.c_char_p),
+        "mosaic_similarity_local": ([vp, vp], C.c_int),
         "mosaic_set_materials_rgb8": ([vp, vp, C.c_int, C.c_int, C.c_int], C.c_int),
         "mosaic_set_materials_ragged_rgb8": ([vp, u8p, C.POINTER(C.c_uint64), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int], C.c_int),
         "mosaic_set_materials_device": ([vp, vp, C.c_int, C.c_int, C.c_int], C.c_int),
@@ -117,6 +121,7 @@ def load_library():
 EXPORTED_SYMBOLS = (
     "mosaic_ctx_create", "mosaic_ctx_create_sharded", "mosaic_nccl_unique_id", "mosaic_ctx_destroy",
     "mosaic_last_error", "mosaic_ctx_set_stream", "mosaic_ctx_sync", "mosaic_stage_ms", "mosaic_kernel_launches",
+    "mosaic_collective_ms", "mosaic_sm_count", "mosaic_similarity_local", "mosaic_exchange_path",
     "mosaic_set_materials_rgb8", "mosaic_set_materials_ragged_rgb8", "mosaic_set_materials_device", "mosaic_set_target_rgb8",
     "mosaic_set_target_device", "mosaic_set_material_lab", "mosaic_set_similarity_lab", "mosaic_set_cell_lab", "mosaic_material_lab",
     "mosaic_cell_lab", "mosaic_similarity_tri", "mosaic_candidates", "mosaic_place", "mosaic_fallback_cells",
@@ -292,6 +297,19 @@ class Context:
     def kernel_launches(self) -> int:
         return int(self._L.mosaic_kernel_launches(self._h))
 
+    def collective_ms(self) -> float:
+        """Device time spent in exchange steps (collectives, peer hand-off waits) since the previous call."""
+        ms = C.c_float()
+        self._check(self._L.mosaic_collective_ms(self._h, C.byref(ms)))
+        return ms.value
+
+    def sm_count(self) -> int:
+        return int(self._L.mosaic_sm_count(self._h))
+
+    def exchange_path(self) -> str:
+        """"single", "peer" (NVLink peer windows) or "nccl: <reason>" — how a sharded mosaic_generate exchanges data."""
+        return (self._L.mosaic_exchange_path(self._h) or b"").decode()
+
     def dims(self):
         v = [C.c_int() for _ in range(5)]
         self._check(self._L.mosaic_dims(self._h, *[C.byref(x) for x in v]))
@@ -376,6 +394,11 @@ class Context:
         n = self.dims()["n"]
         out = np.empty(n * (n - 1) // 2 if n > 1 else 0, np.float32) if fetch else None
         self._check(self._L.mosaic_similarity_tri(self._h, _ptr(out)))
+        return out
+
+    def similarity_local(self, out=None):
+        """This rank's range of the packed matrix, without the all-gather; `out` (host, tri_end - tri_begin floats) or None."""
+        self._check(self._L.mosaic_similarity_local(self._h, _ptr(out)))
         return out
 
     def candidates(self, k=MAX_K, fetch=True):

@@ -14,16 +14,52 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "liboracle.so")
+# Flags of the two builds (oracle/Makefile).  "strict" is the parity checker; "fast" is the same source compiled the way
+# BASELINE.md section 3 promises for the timed CPU arm (-O3 -march=native, still no FMA contraction / fast-math, so the
+# results are identical — tests/test_oracle_golden.py checks that).  -march=native binds the binary to the host it was
+# built on, so the fast library is built on the machine that runs it and carries a tag of that host's CPU in its name.
+FLAGS = {"strict": "-O2 -std=c++17 -ffp-contract=off -fno-fast-math -fPIC -Wall -Wextra -pthread",
+         "fast": "-O3 -march=native -std=c++17 -ffp-contract=off -fno-fast-math -fPIC -Wall -Wextra -pthread"}
+
+
+def _host_tag() -> str:
+    import hashlib
+    sig = ""
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith(("model name", "flags")):
+                    sig += line
+                if line.strip() == "" and sig:
+                    break
+    except OSError:
+        pass
+    return hashlib.sha1(sig.encode()).hexdigest()[:10]
+
+
+def fast_lib_path() -> str:
+    return os.path.join(_HERE, f"liboracle_fast_{_host_tag()}.so")
+
+
+def _stale(target) -> bool:
+    src = os.path.join(_HERE, "mosaic_oracle.cpp")
+    hdr = os.path.join(_HERE, "mosaic_oracle.h")
+    return (not os.path.exists(target)) or any(os.path.getmtime(p) > os.path.getmtime(target) for p in (src, hdr))
 
 
 def build(force: bool = False) -> str:
-    src = os.path.join(_HERE, "mosaic_oracle.cpp")
-    hdr = os.path.join(_HERE, "mosaic_oracle.h")
-    stale = (not os.path.exists(_LIB_PATH)) or any(
-        os.path.getmtime(p) > os.path.getmtime(_LIB_PATH) for p in (src, hdr))
-    if force or stale:
+    if force or _stale(_LIB_PATH):
         subprocess.check_call(["make", "-C", _HERE, "-B", "liboracle.so"], stdout=subprocess.DEVNULL)
     return _LIB_PATH
+
+
+def build_fast(force: bool = False) -> str:
+    """The timed CPU arm's build: -O3 -march=native on THIS host (bench.py only)."""
+    target = fast_lib_path()
+    if force or _stale(target):
+        subprocess.check_call(["make", "-C", _HERE, "-B", "fast", f"FAST_LIB={os.path.basename(target)}"],
+                              stdout=subprocess.DEVNULL)
+    return target
 
 
 class OptResult(C.Structure):
@@ -32,13 +68,25 @@ class OptResult(C.Structure):
 
 
 _lib = None
+_libs = {}
+_variant = "strict"
+
+
+def select(variant: str) -> str:
+    """Switch every wrapper of this module to the "strict" (parity, default) or the "fast" (timed CPU arm) build.
+    Returns the compiler flags of the selected build."""
+    global _lib, _variant
+    assert variant in FLAGS
+    _variant = variant
+    _lib = _libs.get(variant)
+    lib()
+    return FLAGS[variant]
 
 
 def lib():
     global _lib
     if _lib is None:
-        build()
-        L = C.CDLL(_LIB_PATH)
+        L = C.CDLL(build_fast() if _variant == "fast" else build())
         u8p, f32p, i32p, u32p, i16p = (C.POINTER(C.c_uint8), C.POINTER(C.c_float), C.POINTER(C.c_int32),
                                        C.POINTER(C.c_uint32), C.POINTER(C.c_int16))
         L.orc_rgb8_to_lab.argtypes = [C.c_uint8, C.c_uint8, C.c_uint8, f32p]
@@ -92,6 +140,7 @@ def lib():
         L.orc_render.argtypes = [u8p, C.c_int, C.c_int, C.c_int, C.c_int, u8p, C.c_int, C.c_int, C.c_int,
                                  i32p, C.c_float, u8p, C.c_int]
         _lib = L
+        _libs[_variant] = L
     return _lib
 
 
