@@ -215,18 +215,20 @@ def run_cpu(cfg, steps, warmup, budget_s, one_thread_budget_s=0.0):
 
 # --------------------------------------------------------------------------- clocks
 class ClockSampler:
-    """SM clock + throttle reasons DURING the timed region.  NVML polled from a thread of this process every few
-    milliseconds (the timed region of a 24,000-tile mosaic is tens of milliseconds: an `nvidia-smi -lms` child does not
-    even start that fast); `nvidia-smi` is the fallback when the NVML binding is missing."""
-    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown"}
+    """SM clock + throttle reasons DURING the timed regions: the profiling recipe's `nvidia-smi --query-gpu=... -lms`
+    child process (started before the warm-up, killed after the last timed region), its time-stamped samples filtered
+    to the windows the timed regions covered.  A child process, not a thread of this one: polling NVML from a thread
+    of the process that launches the kernels measurably slowed the step (4.27 -> 4.54 ms at 2 GPUs)."""
+    QUERY = ("timestamp,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
-    def __init__(self, gpu_index):
+    def __init__(self, gpu_index, interval_ms=20):
         self.gpu_index = gpu_index
-        self.samples, self.reason_bits = [], 0
-        self.smax = None
-        self._stop = False
-        self._thread = None
-        self._nvml = None
+        self.interval_ms = interval_ms
+        self.proc = None
+        self.windows = []
+        self._open = None
 
     def _physical_index(self):
         vis = os.environ.get("CUDA_VISIBLE_DEVICES")
@@ -238,53 +240,50 @@ class ClockSampler:
 
     def start(self):
         try:
-            import pynvml
-            pynvml.nvmlInit()
-            self._nvml = pynvml
-            self._h = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index())
-            self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-i",
+                                          str(self._physical_index()), "-lms", str(self.interval_ms)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
-            self._nvml = None
-            return
-        import threading
+            self.proc = None
 
-        def loop():
-            nv = self._nvml
-            while not self._stop:
-                try:
-                    self.samples.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
-                    self.reason_bits |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h))
-                except Exception:
-                    pass
-                time.sleep(0.003)
+    def begin_window(self):
+        self._open = time.time()
 
-        self._thread = threading.Thread(target=loop, daemon=True)
-        self._thread.start()
+    def end_window(self):
+        if self._open is not None:
+            self.windows.append((self._open, time.time()))
+            self._open = None
 
     def stop(self):
-        if self._nvml is None:
-            return self._smi_once()
-        self._stop = True
-        self._thread.join(timeout=2)
-        if not self.samples:
-            return self._smi_once()
-        reasons = sorted(name for bit, name in self.REASONS.items() if self.reason_bits & bit)
-        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.smax, "reasons": reasons,
-                "samples": len(self.samples), "source": "nvml, polled during the timed region"}
-
-    def _smi_once(self):
-        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-        try:
-            out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i",
-                                  str(self._physical_index())], capture_output=True, text=True, timeout=20).stdout
-            parts = [x.strip() for x in out.strip().splitlines()[0].split(",")]
-            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-            reasons = sorted(n for n, v in zip(names, parts[2:6]) if v.lower().startswith("active"))
-            return {"sm_mhz": float(parts[0]), "sm_max_mhz": float(parts[1]), "reasons": reasons, "samples": 1,
-                    "source": "nvidia-smi, one sample right after the timed region"}
-        except Exception:
+        if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
+        time.sleep(2.5 * self.interval_ms / 1000.0)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=10)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        import datetime
+        rows = []
+        for line in out.strip().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                ts = datetime.datetime.strptime(parts[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(parts[1]), float(parts[2]), [v.lower().startswith("active") for v in parts[3:7]]))
+            except ValueError:
+                continue
+        pad = self.interval_ms / 1000.0
+        inside = [r for r in rows if any(w0 - pad <= r[0] <= w1 + pad for w0, w1 in self.windows)]
+        used, where = (inside, "inside the timed regions") if inside else (rows, "around the timed regions (none fell inside)")
+        if not used:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no nvidia-smi samples"], "samples": 0}
+        reasons = sorted({n for r in used for n, act in zip(self.NAMES, r[3]) if act})
+        return {"sm_mhz": statistics.median(r[1] for r in used), "sm_max_mhz": used[0][2], "reasons": reasons,
+                "samples": len(used), "samples_total": len(rows),
+                "source": f"nvidia-smi -lms {self.interval_ms} child process, samples {where}"}
 
 
 # --------------------------------------------------------------------------- distributed plumbing
@@ -461,15 +460,16 @@ def run_gpu(args, cfg):
     # ---------------- value: inputs resident in HBM, outputs left in HBM
     ctx.set_materials(mats_h)            # (sharded: own slice over PCIe + NVLink allgather)
     ctx.set_target(tgt_h, gw, gh)
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
     for _ in range(args.warmup):
         rep = ctx.generate(**gen_kw)
     stage_acc = {s: 0.0 for s in mosaic_b200.STAGES}
     coll_acc = 0.0
-    clocks = ClockSampler(local_rank)
     D.barrier()
     launches0 = ctx.kernel_launches()
-    if rank == 0:
-        clocks.start()
+    clocks.begin_window()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for _ in range(args.steps):
@@ -482,11 +482,11 @@ def run_gpu(args, cfg):
         coll_acc += ctx.collective_ms()
     e1.record(stream)
     D.barrier()
-    clk = clocks.stop() if rank == 0 else None
+    clocks.end_window()
     launches = ctx.kernel_launches() - launches0
     ms_value = D.max(e0.elapsed_time(e1) / args.steps)
     stage_ms = {s: D.max(v / args.steps) for s, v in stage_acc.items()}
-    coll_ms = D.max(coll_acc / args.steps)
+    coll_by_rank = D.gather_objects(round(coll_acc / args.steps, 4))  # rank 0 = the critical path (it runs the serial chains)
 
     # ---------------- e2e: host buffers in, host buffers out, every step
     placed_h = torch.empty(cells, dtype=torch.int32, pin_memory=True)
@@ -507,6 +507,7 @@ def run_gpu(args, cfg):
     for _ in range(max(1, min(args.warmup, 3))):
         e2e_step()
     D.barrier()
+    clocks.begin_window()
     w0 = time.perf_counter()
     e0.record(stream)
     coll_e2e = 0.0
@@ -516,10 +517,12 @@ def run_gpu(args, cfg):
     e1.record(stream)
     D.barrier()
     wall_ms = (time.perf_counter() - w0) * 1e3 / args.steps
+    clocks.end_window()
+    clk = clocks.stop() if rank == 0 else None
     ms_e2e = D.max(e0.elapsed_time(e1) / args.steps)
     h2d_total = D.max(float(h2d))
     d2h_total = D.max(float(d2h))
-    coll_e2e = D.max(coll_e2e / args.steps)
+    coll_e2e_by_rank = D.gather_objects(round(coll_e2e / args.steps, 4))
 
     # ---------------- verification of what the timed e2e run returned (oracle = checker, outside every timed region)
     verified = None
@@ -567,9 +570,13 @@ def run_gpu(args, cfg):
             "config": config_block(cfg, world),
             "e2e": {"value": cells / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e, "wall_ms_per_step": wall_ms,
                     "h2d_bytes_per_step": int(h2d_total), "d2h_bytes_per_step": int(d2h_total),
-                    "collective_ms": round(coll_e2e, 4)},
+                    "collective_ms": coll_e2e_by_rank[0], "collective_ms_by_rank": coll_e2e_by_rank},
             "gpu_launches": int(launches),
-            "collective_ms": round(coll_ms, 4),
+            "collective_ms": coll_by_rank[0],
+            "collective_ms_by_rank": coll_by_rank,
+            "collective_note": "device time inside exchange steps (stores into peer windows, flag hand-offs and their waits); "
+                               "rank 0 runs the serial placement + annealing, so its figure is the exchange cost on the critical "
+                               "path; the other ranks' figures are mostly their wait for rank 0's result",
             "exchange_path": ctx.exchange_path(),
             "clocks": clk,
             "roofline": headline,
@@ -603,12 +610,13 @@ def run_gpu_c4(args, cfg):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
     def timed(fn):
-        for _ in range(args.warmup):
-            fn()
         clocks = ClockSampler(local_rank)
-        D.barrier()
         if rank == 0:
             clocks.start()
+        for _ in range(args.warmup):
+            fn()
+        D.barrier()
+        clocks.begin_window()
         e0.record(stream)
         acc, coll = 0.0, 0.0
         for _ in range(args.steps):
@@ -617,6 +625,7 @@ def run_gpu_c4(args, cfg):
             coll += ctx.collective_ms()
         e1.record(stream)
         D.barrier()
+        clocks.end_window()
         clk = clocks.stop() if rank == 0 else None
         return D.max(e0.elapsed_time(e1) / args.steps), D.max(acc / args.steps), D.max(coll / args.steps), clk
 

@@ -2,6 +2,7 @@
 // the fused whole-path call.  Host code only; every compute step is one of the sm_100a kernels in
 // lab_mean.cu / nn_topk.cu / greedy.cu / similarity.cu / anneal.cu / render.cu.  There is no CPU
 // fallback: without a usable CUDA device every entry point fails with MOSAIC_ERR_CUDA.
+#include <chrono>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
@@ -446,9 +447,11 @@ int run_generate_peer(mosaic_ctx* c, const mosaic_params* p, bool anneal) {
     MOSAIC_TRY(dist_peer_wait(c, FLAG_LAB, world, e_lab, c->stream));
   }
   MOSAIC_TRY(launch_pack_lab(c));
+  trace_point(c, "lab_exchanged");
   c->have_mat_lab = true;
   c->have_sim = false;
   if (p->build_similarity) MOSAIC_TRY(run_similarity(c, /*gather=*/false));
+  trace_point(c, "sim");
   // --- own rows: cell Lab means + top-K, stored into rank 0's candidate buffers
   MOSAIC_TRY(wait_target(c));
   MOSAIC_TRY(launch_cell_lab_range(c, rb * c->gw, re * c->gw));
@@ -460,6 +463,7 @@ int run_generate_peer(mosaic_ctx* c, const mosaic_params* p, bool anneal) {
   c->cand_dst_idx = nullptr;
   c->cand_dst_d2 = nullptr;
   MOSAIC_TRY(rc);
+  trace_point(c, "topk");
   const unsigned e_cand = ++c->ep_cand, e_res = ++c->ep_res;
   c->have_cand = true;
   c->cand_gathered = false;
@@ -487,6 +491,7 @@ int run_generate_peer(mosaic_ctx* c, const mosaic_params* p, bool anneal) {
         c->launches++;
       }
       if (chain && r == 0) MOSAIC_CUDA(c, cudaEventRecord(c->ev_chain_go, c->stream));
+      trace_point(c, "band_prepared");
     }
     if (chain) {  // (enqueued behind every band's kernels, waits only for the first band: see run_match_place_banded)
       MOSAIC_CUDA(c, cudaStreamWaitEvent(c->chain_stream, c->ev_chain_go, 0));
@@ -499,7 +504,9 @@ int run_generate_peer(mosaic_ctx* c, const mosaic_params* p, bool anneal) {
       MOSAIC_TRY(launch_place(c, p->max_usage, p->adjacency_weight));
     }
     c->have_placed = true;
+    trace_point(c, "chain_done");
     if (anneal) MOSAIC_TRY(launch_anneal(c, p->optimization_iterations, 100.0f, 0.99995f, p->seed));
+    trace_point(c, "annealed");
     CollTimer t(c, c->stream);
     MOSAIC_TRY(dist_peer_push(c, mosaic_ctx::PW_RESULT, 0, mosaic_ctx::kResultHead + cells_of(c) * sizeof(int32_t), -1, c->stream));
     MOSAIC_TRY(dist_peer_signal(c, FLAG_RES, e_res, -1, c->stream));
@@ -1076,6 +1083,8 @@ int mosaic_generate(mosaic_ctx* c, const mosaic_params* p, int32_t* placed_out, 
   MOSAIC_TRY(require(c, c->have_materials, "materials"));
   MOSAIC_TRY(require(c, c->have_target, "target"));
   const bool anneal = p->enable_optimization && p->adjacency_weight > 0.0f;  // main.rs:608
+  trace_point(c, "begin");
+  const auto host_t0 = std::chrono::steady_clock::now();
   bool peer = false;
   if (c->world > 1) {  // sharded: buffers every rank exchanges through are allocated (whole-problem sizes) and mapped
     MOSAIC_TRY(ensure_mat_lab_buffers(c, c->n));
@@ -1102,8 +1111,10 @@ int mosaic_generate(mosaic_ctx* c, const mosaic_params* p, int32_t* placed_out, 
   }
   if (anneal) MOSAIC_TRY(run_anneal(c, p->optimization_iterations, 100.0f, 0.99995f, p->seed));  // optimizer.rs:18-27
   }
+  trace_point(c, "placed");
   MOSAIC_TRY(d2h(c, placed_out, c->d_placed, sizeof(int32_t) * cells_of(c)));
   MOSAIC_TRY(run_render(c, p->color_strength, out_rgb));
+  trace_point(c, "rendered");
   if (peer) {
     CollTimer t(c, c->stream);
     MOSAIC_TRY(dist_peer_barrier(c, c->stream));
@@ -1115,7 +1126,29 @@ int mosaic_generate(mosaic_ctx* c, const mosaic_params* p, int32_t* placed_out, 
     if (anneal) MOSAIC_TRY(d2h(c, &report->opt, c->d_opt_res, sizeof(mosaic_opt_result)));
     report->annealed = anneal ? 1 : 0;
   }
+  trace_point(c, "end");
+  const auto host_t1 = std::chrono::steady_clock::now();
   MOSAIC_TRY(sync(c));
+  if (!c->trace.empty()) {
+    static thread_local std::chrono::steady_clock::time_point last_exit;
+    const auto host_t2 = std::chrono::steady_clock::now();
+    auto ms = [](std::chrono::steady_clock::duration d) { return std::chrono::duration<double, std::milli>(d).count(); };
+    char hb[160];
+    snprintf(hb, sizeof hb, " | host: since_last_exit=%.3f enqueue=%.3f sync=%.3f", ms(host_t0 - last_exit), ms(host_t1 - host_t0), ms(host_t2 - host_t1));
+    last_exit = host_t2;
+    std::string line = "[mosaic trace rank " + std::to_string(c->rank) + "]" + hb;
+    for (size_t i = 0; i < c->trace.size(); ++i) {
+      float ms = 0.0f;
+      cudaEventSynchronize(c->trace[i].second);
+      cudaEventElapsedTime(&ms, c->trace[0].second, c->trace[i].second);
+      char buf[96];
+      snprintf(buf, sizeof buf, " %s=%.3f", c->trace[i].first, ms);
+      line += buf;
+    }
+    fprintf(stderr, "%s\n", line.c_str());
+    for (auto& t : c->trace) cudaEventDestroy(t.second);
+    c->trace.clear();
+  }
   return dist_peer_check(c);
 }
 
