@@ -192,6 +192,10 @@ int mosaic_generate(mosaic_ctx* ctx, const mosaic_params* params, int32_t* place
 typedef struct mosaic_simdb mosaic_simdb;
 /* paths[i] = path of material i (UTF-8), lab = n*3, sim = n(n-1)/2 (NULL allowed when n < 2). */
 int mosaic_simdb_save_json(const char* file, const char* const* paths, int n, const float* lab, const float* sim);
+/* Same with an explicit number of similarity entries: the reference serialises whatever `similarities` holds, also a
+ * list that is out of date because tiles were added after the last build_similarities (similarity.rs:112-116). */
+int mosaic_simdb_save_json_n(const char* file, const char* const* paths, int n, const float* lab, const float* sim,
+                             uint64_t n_similarities);
 /* Lab means + freshly computed packed matrix of a context -> file (main.rs:122-131). */
 int mosaic_simdb_save_ctx(mosaic_ctx* ctx, const char* file, const char* const* paths);
 int mosaic_simdb_load_json(const char* file, mosaic_simdb** out); /* SimilarityDatabase::load_from_file */
@@ -216,6 +220,11 @@ int mosaic_selftest(mosaic_ctx* ctx, uint64_t mismatches[2]);
  * resolved by the bound-only / exact-first-chunk / generic / generic+reset path, [4..7] the cell counts
  * per path, [8] cycles waiting for producers, [9] cycles waiting for the committer, [10] total cycles. */
 int mosaic_debug_chain_profile(mosaic_ctx* ctx, int enable, uint64_t counters[16]);
+
+/* Which placement chain later calls use: 0 = the default, 1 = the 32-candidates-per-cell chain (greedy.cu), 2 = the
+ * windowed chain (greedy_window.cu: one lane per cell scans, shortlists, two warps alternate windows).  Both replay
+ * main.rs:335-475 bit for bit; the first is the faster one on every measured configuration. */
+int mosaic_debug_set_chain(mosaic_ctx* ctx, int version);
 
 /* ---- introspection -------------------------------------------------------------------------- */
 int mosaic_dims(const mosaic_ctx* ctx, int* n_materials, int* grid_w, int* grid_h, int* tile_w, int* tile_h);

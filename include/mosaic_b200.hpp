@@ -26,6 +26,7 @@
 #ifndef MOSAIC_B200_HPP
 #define MOSAIC_B200_HPP
 #include <algorithm>
+#include <cmath>
 #include <cstdint>
 #include <cstdlib>
 #include <fstream>
@@ -71,12 +72,17 @@ class Context {
 };
 
 namespace detail {
-inline Context& scratch_context() {  // created on first use; throws Error when there is no sm_100a GPU
-  static std::unique_ptr<Context> ctx;
-  if (!ctx) {
+// one lazily created scratch Context per device; device < 0: MOSAIC_B200_DEVICE, default 0.  Throws Error when there is
+// no sm_100a GPU.  Every helper that uses it injects ALL the state it needs (Lab means, grid, placement), so the
+// helpers can be called in any order (mosaic_set_material_lab replaces the material set when the count changes).
+inline Context& scratch_context(int device = -1) {
+  static std::map<int, std::unique_ptr<Context>> ctxs;
+  if (device < 0) {
     const char* dev = std::getenv("MOSAIC_B200_DEVICE");
-    ctx = std::make_unique<Context>(dev ? std::atoi(dev) : 0);
+    device = dev ? std::atoi(dev) : 0;
   }
+  auto& ctx = ctxs[device];
+  if (!ctx) ctx = std::make_unique<Context>(device);
   return *ctx;
 }
 }  // namespace detail
@@ -121,13 +127,12 @@ class SimilarityDatabase {
   }
 
   void save_to_file(const std::string& file) const {  // similarity.rs:112-116
-    const size_t n = lab_.size() / 3;
-    // the C entry point writes the whole packed matrix: a database whose matrix is out of date (tiles added after the
-    // last build — the reference would write the stale, shorter list) must be rebuilt first
-    if (sim_.size() != (n > 1 ? n * (n - 1) / 2 : 0)) throw Error(MOSAIC_ERR_STATE, "save_to_file: call build_similarities() first");
+    // like the reference, whatever `similarities` holds is written — also a list that is out of date because tiles were
+    // added after the last build_similarities()
     std::vector<const char*> paths;
     for (const auto& p : index_to_path_) paths.push_back(p.c_str());
-    const int rc = mosaic_simdb_save_json(file.c_str(), paths.data(), (int)paths.size(), lab_.data(), sim_.data());
+    const int rc = mosaic_simdb_save_json_n(file.c_str(), paths.data(), (int)paths.size(), lab_.data(), sim_.data(),
+                                            (uint64_t)sim_.size());
     if (rc != MOSAIC_OK) throw Error(rc, mosaic_last_error(nullptr));
   }
 
@@ -174,16 +179,41 @@ class SimilarityDatabase {
 };
 
 namespace detail {
-// grid of paths -> material indices of `db` (-1 = empty cell or unknown path: get_similarity would return None and
-// the reference skips the pair, adjacency.rs:104-124)
-inline std::vector<int32_t> grid_ids(const SimilarityDatabase& db, const PathGrid& grid, int* gw, int* gh) {
+// grid of paths -> material indices of `db`; -1 = empty cell.  A path the database does not know is an OCCUPIED cell
+// for the reference (the optimiser swaps it, draws random numbers for it and cools down, optimizer.rs:71-102; only its
+// similarity terms are skipped because get_similarity returns None — also against itself, adjacency.rs:104-124,
+// similarity.rs:85-90): `unknown` collects those cells' paths, and every such CELL gets its own pseudo index
+// >= db.len(); the callers extend the Lab table with colours so far apart that every squared distance overflows to
+// +inf (unknown_lab): 1/(sqrt(inf) + 1) = 0, the term the reference skips contributes +0.0, and x + 0.0 == x.
+inline std::vector<int32_t> grid_ids(const SimilarityDatabase& db, const PathGrid& grid, int* gw, int* gh,
+                                     std::vector<std::string>* unknown = nullptr) {
   *gh = (int)grid.size();
   *gw = *gh ? (int)grid[0].size() : 0;
   std::vector<int32_t> ids;
   ids.reserve((size_t)*gw * *gh);
   for (const auto& row : grid)
-    for (const auto& cell : row) ids.push_back(cell ? (int32_t)db.index_of(*cell) : -1);
+    for (const auto& cell : row) {
+      if (!cell) {
+        ids.push_back(-1);
+        continue;
+      }
+      const int64_t i = db.index_of(*cell);
+      if (i >= 0) {
+        ids.push_back((int32_t)i);
+      } else if (unknown) {
+        ids.push_back((int32_t)(db.len() + unknown->size()));
+        unknown->push_back(*cell);
+      } else {
+        ids.push_back(-1);
+      }
+    }
   return ids;
+}
+// Lab colour of pseudo material i (see grid_ids): differences of at least 3e19 in L, whose squares exceed FLT_MAX
+inline void unknown_lab(size_t i, float out[3]) {
+  out[0] = 3.0e19f * (float)(i + 1);
+  out[1] = 0.0f;
+  out[2] = 0.0f;
 }
 }  // namespace detail
 
@@ -230,9 +260,10 @@ class AdjacencyPenaltyCalculator {
   }
   float calculate_total_cost(Context& ctx, const PathGrid& grid) const {
     int gw, gh;
-    const std::vector<int32_t> ids = detail::grid_ids(db_, grid, &gw, &gh);
+    std::vector<std::string> unknown;
+    const std::vector<int32_t> ids = detail::grid_ids(db_, grid, &gw, &gh, &unknown);
     if (gw == 0 || gh == 0) return 0.0f;
-    load(ctx, ids, gw, gh);
+    load(ctx, ids, gw, gh, unknown.size());
     mosaic_opt_result res{};
     ctx.check(mosaic_anneal(ctx.get(), 0, 100.0f, 0.99995f, 0, nullptr, &res));  // 0 iterations: the cost only
     return res.initial_cost;
@@ -241,8 +272,16 @@ class AdjacencyPenaltyCalculator {
   const SimilarityDatabase& database() const { return db_; }
   float penalty_weight() const { return weight_; }
 
-  void load(Context& ctx, const std::vector<int32_t>& ids, int gw, int gh) const {
-    ctx.check(mosaic_set_material_lab(ctx.get(), db_.lab_colors().data(), (int)db_.len()));
+  // `n_unknown` pseudo materials (cells whose path the database does not know) follow the database's colours
+  void load(Context& ctx, const std::vector<int32_t>& ids, int gw, int gh, size_t n_unknown = 0) const {
+    std::vector<float> lab = db_.lab_colors();
+    for (size_t i = 0; i < n_unknown; ++i) {
+      float c[3];
+      detail::unknown_lab(i, c);
+      lab.insert(lab.end(), c, c + 3);
+    }
+    if (lab.empty()) lab.assign(3, 0.0f);  // (a grid of empty cells over an empty database: nothing is ever read)
+    ctx.check(mosaic_set_material_lab(ctx.get(), lab.data(), (int)(lab.size() / 3)));
     const std::vector<float> zeros((size_t)gw * gh * 3, 0.0f);  // cell colours play no role in the energy
     ctx.check(mosaic_set_cell_lab(ctx.get(), zeros.data(), gw, gh));
     ctx.check(mosaic_set_placement(ctx.get(), ids.data()));
@@ -281,19 +320,21 @@ class MosaicOptimizer {
   }
   OptimizationResult optimize(Context& ctx, PathGrid& grid) const {  // optimizer.rs:41-129
     int gw, gh;
-    const std::vector<int32_t> ids = detail::grid_ids(calc_.database(), grid, &gw, &gh);
+    std::vector<std::string> unknown;
+    const std::vector<int32_t> ids = detail::grid_ids(calc_.database(), grid, &gw, &gh, &unknown);
     if (gh == 0 || gw == 0) return OptimizationResult();  // optimizer.rs:43-45
-    calc_.load(ctx, ids, gw, gh);
+    calc_.load(ctx, ids, gw, gh, unknown.size());
     std::vector<int32_t> out(ids.size());
     mosaic_opt_result r{};
     ctx.check(mosaic_anneal(ctx.get(), config_.max_iterations, config_.initial_temperature, config_.temperature_decay,
                             config_.seed, out.data(), &r));
-    // the kernel swaps material indices; cells whose path is unknown to the database carry -1 and never move
-    // (they are "empty" for the optimiser exactly as for get_similarity)
-    std::vector<std::string> path_of(calc_.database().len());
+    // the kernel swaps material indices; cells whose path the database does not know carry pseudo indices behind the
+    // database's (occupied cells without similarity terms, as in the reference)
+    std::vector<std::string> path_of(calc_.database().len() + unknown.size());
     for (const auto& row : grid)
       for (const auto& c : row)
         if (c && calc_.database().index_of(*c) >= 0) path_of[(size_t)calc_.database().index_of(*c)] = *c;
+    for (size_t i = 0; i < unknown.size(); ++i) path_of[calc_.database().len() + i] = unknown[i];
     for (int y = 0; y < gh; ++y)
       for (int x = 0; x < gw; ++x) {
         const int32_t id = out[(size_t)y * gw + x];
@@ -322,9 +363,31 @@ struct RgbImage {  // image::RgbImage: interleaved RGB8, row-major
   RgbImage(int w, int h) : width(w), height(h), data((size_t)w * h * 3, 0) {}
 };
 
-struct MosaicGeneratorImpl {
+// UsageTracker (lib.rs:57-89): per-path use counts with a cap.  The placement kernel keeps its own counters in shared
+// memory (u8 / u16 per material, greedy_window.cu) with exactly these semantics; this class is the public type of
+// lib.rs for host code that tracks usage itself.
+class UsageTracker {
+ public:
+  explicit UsageTracker(size_t max_usage_per_image) : max_usage_per_image_(max_usage_per_image) {}  // lib.rs:63-68
+  bool can_use_image(const std::string& path) const { return get_usage_count(path) < max_usage_per_image_; }  // lib.rs:70-73
+  void use_image(const std::string& path) { usage_counts_[path] = get_usage_count(path) + 1; }                // lib.rs:75-78
+  size_t get_usage_count(const std::string& path) const {                                                       // lib.rs:80-83
+    const auto it = usage_counts_.find(path);
+    return it == usage_counts_.end() ? 0 : it->second;
+  }
+  void reset() { usage_counts_.clear(); }  // lib.rs:85-87
+
+ private:
+  std::map<std::string, size_t> usage_counts_;
+  size_t max_usage_per_image_;
+};
+
+struct MosaicGeneratorImpl {  // impl MosaicGenerator for MosaicGeneratorImpl (trait at lib.rs:52-55)
+  // MosaicGenerator::is_aspect_ratio_match (lib.rs:121-123)
+  static bool is_aspect_ratio_match(float img_aspect, float target_aspect, float tolerance) {
+    return std::fabs(img_aspect - target_aspect) <= tolerance;
+  }
   // MosaicGenerator::calculate_average_lab (lib.rs:94-119)
-  // is_aspect_ratio_match (lib.rs:121-123) is the directory scan's filter: control plane, not mirrored
   static Lab calculate_average_lab(const RgbImage& img) { return calculate_average_lab(detail::scratch_context(), img); }
   static Lab calculate_average_lab(Context& ctx, const RgbImage& img) {
     float lab[3];
@@ -334,9 +397,10 @@ struct MosaicGeneratorImpl {
   }
 };
 
-struct Tile {  // lib.rs:45-49
+struct Tile {  // lib.rs:44-50
   std::string path;
   Lab lab_color;
+  float aspect_ratio = 1.0f;
 };
 
 // ---- src/main.rs: struct MosaicGenerator (private to the CLI binary) ------------------------------------------
@@ -352,11 +416,13 @@ class MosaicGenerator {
                   size_t max_usage_per_image, const std::string& similarity_db_path, bool rebuild_similarity,
                   float adjacency_penalty_weight, float color_adjustment_strength, int device = 0)
       : ctx_(device),
+        device_(device),
         max_usage_(max_usage_per_image),
         weight_(adjacency_penalty_weight),
         strength_(std::min(std::max(color_adjustment_strength, 0.0f), 1.0f)) {  // main.rs:162
     ctx_.check(mosaic_set_materials_rgb8(ctx_.get(), rgb, (int)paths.size(), mat_w, mat_h));
     init(paths, similarity_db_path, rebuild_similarity);
+    for (Tile& t : tiles_) t.aspect_ratio = (float)mat_w / (float)mat_h;  // main.rs:277 / 291
   }
 
   // Same, with materials of individual sizes — what the reference's directory of image files is (process_tile,
@@ -365,6 +431,7 @@ class MosaicGenerator {
                   const std::string& similarity_db_path, bool rebuild_similarity, float adjacency_penalty_weight,
                   float color_adjustment_strength, int device = 0)
       : ctx_(device),
+        device_(device),
         max_usage_(max_usage_per_image),
         weight_(adjacency_penalty_weight),
         strength_(std::min(std::max(color_adjustment_strength, 0.0f), 1.0f)) {
@@ -381,6 +448,7 @@ class MosaicGenerator {
     ctx_.check(mosaic_set_materials_ragged_rgb8(ctx_.get(), blob.data(), offsets.data(), widths.data(), heights.data(),
                                                 (int)images.size()));
     init(paths, similarity_db_path, rebuild_similarity);
+    for (size_t i = 0; i < tiles_.size(); ++i) tiles_[i].aspect_ratio = (float)widths[i] / (float)heights[i];
   }
 
  private:
@@ -388,7 +456,7 @@ class MosaicGenerator {
     const int n = (int)paths.size();
     std::vector<float> lab((size_t)n * 3);
     ctx_.check(mosaic_material_lab(ctx_.get(), lab.data()));
-    for (int i = 0; i < n; ++i) tiles_.push_back(Tile{paths[i], Lab{lab[3 * i], lab[3 * i + 1], lab[3 * i + 2]}});
+    for (int i = 0; i < n; ++i) tiles_.push_back(Tile{paths[i], Lab{lab[3 * i], lab[3 * i + 1], lab[3 * i + 2]}, 1.0f});
 
     const bool exists = !similarity_db_path.empty() && std::ifstream(similarity_db_path).good();
     if (rebuild_similarity || !exists) {  // main.rs:120-134
@@ -411,9 +479,9 @@ class MosaicGenerator {
         topped_up = true;
       }
     if (topped_up || !(rebuild_similarity || !exists)) {
-      // the database may now hold other paths too: its matrix is built on the scratch context, the generator's context
-      // keeps the tiles
-      similarity_db_.build_similarities();
+      // the database may now hold other paths too: its matrix is built on the scratch context of the generator's device,
+      // the generator's own context keeps the tiles
+      similarity_db_.build_similarities(detail::scratch_context(device_));
     }
     std::vector<float> db_lab((size_t)n * 3);
     bool differs = false;
@@ -433,7 +501,7 @@ class MosaicGenerator {
                            mosaic_report* report = nullptr) {
     ctx_.check(mosaic_set_target_rgb8(ctx_.get(), target.data.data(), target.width, target.height, grid_w, grid_h));
     mosaic_params p{};
-    p.max_usage = (int)max_usage_;
+    p.max_usage = (int)std::min<size_t>(max_usage_, (size_t)0x7fffffff);  // usize -> int: a huge cap stays "no cap"
     p.adjacency_weight = weight_;
     p.color_strength = strength_;
     p.enable_optimization = enable_optimization ? 1 : 0;
@@ -463,6 +531,7 @@ class MosaicGenerator {
 
  private:
   Context ctx_;
+  int device_ = 0;
   std::string save_warning_;
   std::vector<Tile> tiles_;
   SimilarityDatabase similarity_db_;

@@ -922,7 +922,15 @@ int mosaic_set_material_lab(mosaic_ctx* c, const float* lab, int n) {
   if (!c) return MOSAIC_ERR_INVALID;
   if (!lab || n <= 0) return fail(c, MOSAIC_ERR_INVALID, "material Lab: bad arguments");
   MOSAIC_CUDA(c, cudaSetDevice(c->device));
-  if (c->have_materials && n != c->n) return fail(c, MOSAIC_ERR_INVALID, "material Lab count differs from the material count");
+  // Injected Lab means stand on their own (similarity-database-only use, stage-wise tests, the C++ mirror's static
+  // helpers on a shared scratch context): a different count replaces the material set — pixels of the old one no
+  // longer apply, and neither do database colours, placements or images made from it.
+  if (n != c->n) {
+    c->have_materials = false;
+    c->mats_sliced = false;
+    c->sim_lab_override = false;
+    c->have_placed = c->have_out = false;
+  }
   c->n = n;
   MOSAIC_TRY(ensure_mat_lab_buffers(c, n));
   MOSAIC_CUDA(c, cudaMemcpyAsync(c->d_mat_lab, lab, sizeof(float) * 3 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
@@ -1052,6 +1060,10 @@ int mosaic_set_placement(mosaic_ctx* c, const int32_t* placed) {
   if (!placed) return fail(c, MOSAIC_ERR_INVALID, "placement pointer is NULL");
   MOSAIC_CUDA(c, cudaSetDevice(c->device));
   if (c->gw <= 0 || c->gh <= 0) return fail(c, MOSAIC_ERR_STATE, "grid is not set");
+  for (size_t i = 0, cells = cells_of(c); i < cells; ++i)  // -1 = empty cell (main.rs:628); anything else indexes the materials
+    if (placed[i] < -1 || placed[i] >= c->n)
+      return fail(c, MOSAIC_ERR_INVALID, "placement: cell " + std::to_string(i) + " holds material index " + std::to_string(placed[i]) +
+                                             " outside [-1, " + std::to_string(c->n) + ")");
   MOSAIC_TRY(ensure_placed(c));
   MOSAIC_CUDA(c, cudaMemcpyAsync(c->d_placed, placed, sizeof(int32_t) * cells_of(c), cudaMemcpyHostToDevice, c->stream));
   MOSAIC_TRY(sync(c));
@@ -1171,6 +1183,13 @@ int mosaic_debug_chain_profile(mosaic_ctx* c, int enable, uint64_t counters[16])
     for (int i = 0; i < 16; ++i) counters[i] = v[i];
   }
   c->profile_chain = enable != 0;
+  return MOSAIC_OK;
+}
+
+int mosaic_debug_set_chain(mosaic_ctx* c, int version) {
+  if (!c || version < 0 || version > 2) return MOSAIC_ERR_INVALID;
+  c->chain_version = version;
+  c->have_placed = false;
   return MOSAIC_OK;
 }
 

@@ -852,8 +852,28 @@ static int ensure_place_records(mosaic_ctx* ctx) {
   return ensure(ctx, &ctx->d_place_rec, &ctx->place_rec_cap, (size_t)cells * (sizeof(HRec) + sizeof(XRec) + 3 * kKPad * sizeof(float)));
 }
 
+// ---- which chain: the windowed one (greedy_window.cu) unless MOSAIC_CHAIN=v1 asks for the first generation (A/B runs)
+bool window_chain_eligible(const mosaic_ctx* ctx, int max_usage);
+int launch_window_prep_range(mosaic_ctx* ctx, float weight, int cell_begin, int cell_end);
+int launch_window_chain(mosaic_ctx* ctx, int max_usage, float weight, cudaStream_t stream, const unsigned* ready, bool prof);
+int read_window_profile(mosaic_ctx* ctx, unsigned long long* out16);
+// The first-generation chain (this file) is the default: on the 24,000-tile mosaic it places a cell in 108 ns, the
+// windowed one in 200 ns (profiles/r02_chain_window_experiment.json; DESIGN.md has the anatomy).  MOSAIC_CHAIN=window
+// in the environment or mosaic_debug_set_chain(ctx, 2) selects the windowed chain (parity-tested like the default).
+static bool env_window_chain() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MOSAIC_CHAIN");
+    v = (e && e[0] == 'w') ? 1 : 0;
+  }
+  return v == 1;
+}
+static bool use_v1_chain(const mosaic_ctx* ctx) { return !(ctx->chain_version == 2 || (ctx->chain_version == 0 && env_window_chain())); }
+static bool use_window(const mosaic_ctx* ctx, int max_usage) { return !use_v1_chain(ctx) && window_chain_eligible(ctx, max_usage); }
+
 // candidate records of cells [cell_begin, cell_end) (needs the candidate lists of those cells and of the row above)
 int launch_place_prep_range(mosaic_ctx* ctx, float weight, int cell_begin, int cell_end) {
+  if (!use_v1_chain(ctx)) return launch_window_prep_range(ctx, weight, cell_begin, cell_end);
   if (cell_end <= cell_begin) return MOSAIC_OK;
   const int cells = ctx->gw * ctx->gh;
   MOSAIC_TRY(ensure_place_records(ctx));
@@ -880,11 +900,13 @@ static size_t chain_smem(const mosaic_ctx* ctx, unsigned cap) {
   return 0;
 }
 bool place_chain_eligible(const mosaic_ctx* ctx, int max_usage) {
+  if (!use_v1_chain(ctx)) return window_chain_eligible(ctx, max_usage) && !ctx->profile_chain;
   return chain_smem(ctx, max_usage < 0 ? 0u : (unsigned)max_usage) != 0 && !ctx->profile_chain;
 }
 
 // the chain kernel alone, on `stream`, consuming records as `ready` (a device counter of prepared cells) advances
 int launch_place_chain_async(mosaic_ctx* ctx, int max_usage, float weight, cudaStream_t stream, const unsigned* ready) {
+  if (!use_v1_chain(ctx)) return launch_window_chain(ctx, max_usage, weight, stream, ready, false);
   const unsigned cap = max_usage < 0 ? 0u : (unsigned)max_usage;
   const size_t smem = chain_smem(ctx, cap);
   if (!smem) return fail(ctx, MOSAIC_ERR_STATE, "placement: the chain kernel does not cover this configuration");
@@ -906,6 +928,7 @@ static int launch_chain(mosaic_ctx* ctx, unsigned cap, float weight, size_t smem
 }
 
 int read_chain_profile(mosaic_ctx* ctx, unsigned long long* out16) {
+  if (!use_v1_chain(ctx)) return read_window_profile(ctx, out16);
   MOSAIC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   MOSAIC_CUDA(ctx, cudaMemcpyFromSymbol(out16, g_chain_prof, sizeof(unsigned long long) * 16));
   return MOSAIC_OK;
@@ -918,7 +941,11 @@ int launch_place(mosaic_ctx* ctx, int max_usage, float weight) {
   // fast path: record ring + row state + usage counters in shared memory
   const size_t fast_smem = chain_smem(ctx, cap);
   StageTimer t(ctx, MOSAIC_STAGE_PLACE);
-  if (fast_smem) {
+  if (use_window(ctx, max_usage)) {
+    MOSAIC_TRY(launch_window_prep_range(ctx, weight, 0, gw * gh));
+    return launch_window_chain(ctx, max_usage, weight, ctx->stream, nullptr, ctx->profile_chain);
+  }
+  if (use_v1_chain(ctx) && fast_smem) {
     if (cap <= 255u)
       MOSAIC_TRY(launch_chain<uint8_t>(ctx, cap, weight, fast_smem));
     else

@@ -314,8 +314,12 @@ using namespace mosaic;
 extern "C" {
 
 int mosaic_simdb_save_json(const char* file, const char* const* paths, int n, const float* lab, const float* sim) {
-  if (!file || n < 0 || (n > 0 && (!paths || !lab))) return fail(nullptr, MOSAIC_ERR_INVALID, "simdb_save: bad arguments");
   const uint64_t nsim = n > 1 ? (uint64_t)n * (uint64_t)(n - 1) / 2 : 0;
+  return mosaic_simdb_save_json_n(file, paths, n, lab, sim, nsim);
+}
+
+int mosaic_simdb_save_json_n(const char* file, const char* const* paths, int n, const float* lab, const float* sim, uint64_t nsim) {
+  if (!file || n < 0 || (n > 0 && (!paths || !lab))) return fail(nullptr, MOSAIC_ERR_INVALID, "simdb_save: bad arguments");
   if (nsim && !sim) return fail(nullptr, MOSAIC_ERR_INVALID, "simdb_save: similarity matrix is NULL");
   FILE* f = std::fopen(file, "wb");
   if (!f) return fail(nullptr, MOSAIC_ERR_INVALID, std::string("simdb_save: cannot open ") + file + ": " + std::strerror(errno));
@@ -439,8 +443,17 @@ int mosaic_simdb_save_ctx(mosaic_ctx* c, const char* file, const char* const* pa
   const size_t n = (size_t)c->n, nsim = n > 1 ? n * (n - 1) / 2 : 0;
   std::vector<float> lab(3 * n), sim(nsim);
   MOSAIC_CUDA(c, cudaSetDevice(c->device));
-  MOSAIC_CUDA(c, cudaMemcpyAsync(lab.data(), c->d_mat_lab, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, c->stream));
-  MOSAIC_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (c->sim_lab_override) {
+    // the matrix is computed from the DATABASE's colours (mosaic_set_similarity_lab): those are the lab_colors the file
+    // must hold next to it (similarity.rs:31-42 — a database stores the colours its similarities were computed from)
+    std::vector<float4> packed(n);
+    MOSAIC_CUDA(c, cudaMemcpyAsync(packed.data(), c->d_sim_lab4_own, sizeof(float4) * n, cudaMemcpyDeviceToHost, c->stream));
+    MOSAIC_CUDA(c, cudaStreamSynchronize(c->stream));
+    for (size_t i = 0; i < n; ++i) lab[3 * i] = packed[i].x, lab[3 * i + 1] = packed[i].y, lab[3 * i + 2] = packed[i].z;
+  } else {
+    MOSAIC_CUDA(c, cudaMemcpyAsync(lab.data(), c->d_mat_lab, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, c->stream));
+    MOSAIC_CUDA(c, cudaStreamSynchronize(c->stream));
+  }
   int rc = mosaic_similarity_tri(c, sim.data());
   if (rc != MOSAIC_OK) return rc;
   rc = mosaic_simdb_save_json(file, paths, (int)n, lab.data(), sim.data());

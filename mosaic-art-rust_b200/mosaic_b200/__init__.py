@@ -94,6 +94,7 @@ def load_library():
         "mosaic_generate": ([vp, C.POINTER(Params), vp, vp, C.POINTER(Report)], C.c_int),
         "mosaic_selftest": ([vp, u64p], C.c_int),
         "mosaic_debug_chain_profile": ([vp, C.c_int, u64p], C.c_int),
+        "mosaic_debug_set_chain": ([vp, C.c_int], C.c_int),
         "mosaic_dims": ([vp] + [C.POINTER(C.c_int)] * 5, C.c_int),
         "mosaic_device_output": ([vp], vp),
         "mosaic_device_placement": ([vp], vp),
@@ -101,6 +102,7 @@ def load_library():
         "mosaic_shard": ([vp] + [C.POINTER(C.c_int)] * 4 + [u64p, u64p], C.c_int),
         "mosaic_shard_plan": ([C.c_int] * 4 + [C.POINTER(C.c_int)] * 4 + [u64p, u64p], C.c_int),
         "mosaic_simdb_save_json": ([C.c_char_p, C.POINTER(C.c_char_p), C.c_int, f32p, f32p], C.c_int),
+        "mosaic_simdb_save_json_n": ([C.c_char_p, C.POINTER(C.c_char_p), C.c_int, f32p, f32p, C.c_uint64], C.c_int),
         "mosaic_simdb_save_ctx": ([vp, C.c_char_p, C.POINTER(C.c_char_p)], C.c_int),
         "mosaic_simdb_load_json": ([C.c_char_p, C.POINTER(vp)], C.c_int),
         "mosaic_simdb_free": ([vp], None),
@@ -126,10 +128,10 @@ EXPORTED_SYMBOLS = (
     "mosaic_set_target_device", "mosaic_set_material_lab", "mosaic_set_similarity_lab", "mosaic_set_cell_lab", "mosaic_material_lab",
     "mosaic_cell_lab", "mosaic_similarity_tri", "mosaic_candidates", "mosaic_place", "mosaic_fallback_cells",
     "mosaic_set_placement", "mosaic_anneal", "mosaic_render", "mosaic_generate", "mosaic_selftest", "mosaic_dims",
-    "mosaic_debug_chain_profile",
+    "mosaic_debug_chain_profile", "mosaic_debug_set_chain",
     "mosaic_device_output", "mosaic_device_placement", "mosaic_device_similarity", "mosaic_shard",
     "mosaic_shard_plan",
-    "mosaic_simdb_save_json", "mosaic_simdb_save_ctx", "mosaic_simdb_load_json", "mosaic_simdb_free",
+    "mosaic_simdb_save_json", "mosaic_simdb_save_json_n", "mosaic_simdb_save_ctx", "mosaic_simdb_load_json", "mosaic_simdb_free",
     "mosaic_simdb_info", "mosaic_simdb_path", "mosaic_simdb_index_of", "mosaic_simdb_copy",
     "mosaic_simdb_get_similarity",
 )
@@ -458,12 +460,23 @@ class Context:
         self._check(self._L.mosaic_selftest(self._h, m))
         return int(m[0]), int(m[1])
 
+    def set_chain(self, version):
+        """0 = default placement chain, 1 = greedy.cu, 2 = the windowed chain of greedy_window.cu."""
+        self._check(self._L.mosaic_debug_set_chain(self._h, int(version)))
+        self._chain = int(version)
+
     def chain_profile(self, enable=True):
         """Enable/disable the instrumented placement kernel and return the counters of its last launch."""
         m = (C.c_uint64 * 16)()
         self._check(self._L.mosaic_debug_chain_profile(self._h, 1 if enable else 0, m))
-        keys = ("cyc_fast", "cyc_exact", "cyc_generic", "cyc_fallback", "n_fast", "n_exact", "n_generic",
-                "n_fallback", "cyc_wait_producer", "cyc_wait_committer", "cyc_total")
+        window = getattr(self, "_chain", 0) == 2 or (getattr(self, "_chain", 0) == 0 and
+                                                      os.environ.get("MOSAIC_CHAIN", "").startswith("w"))
+        if not window:  # first-generation chain kernel
+            keys = ("cyc_fast", "cyc_exact", "cyc_generic", "cyc_fallback", "n_fast", "n_exact", "n_generic",
+                    "n_fallback", "cyc_wait_producer", "cyc_wait_committer", "cyc_total")
+        else:  # windowed chain: cycle counters are summed over its two warps
+            keys = ("cyc_sets", "n_sets", "cyc_slow", "cyc_reset", "cyc_scan", "cyc_listen", "cyc_ring_wait", "n_fast",
+                    "n_slow", "n_reset", "n_rescans", "cyc_total_both_warps")
         return dict(zip(keys, (int(x) for x in m)))
 
     def output_shape(self):

@@ -23,7 +23,7 @@ for name in (sys.argv[1:] or ["C1", "C2", "C3"]):
         assert (placed == placed2).all()
         cells = cfg["grid_w"] * cfg["grid_h"]
         out = dict(config=name, cells=cells, ms=ms, ms_profiled=ms_prof, ns_per_cell=ms * 1e6 / cells, fallbacks=nfb, **prof)
-        for k in ("fast", "exact", "generic", "fallback"):
-            if prof["n_" + k]:
+        for k in ("fast", "exact", "generic", "fallback", "slow", "reset"):
+            if prof.get("n_" + k) and ("cyc_" + k) in prof:
                 out["cyc_per_" + k] = prof["cyc_" + k] / prof["n_" + k]
         print(json.dumps(out), flush=True)

@@ -119,6 +119,66 @@ static void test_optimization_empty_grid() {  // optimizer.rs:295-307 — return
   CHECK(r.initial_cost == 0.0f && r.final_cost == 0.0f && r.improved_count == 0);
 }
 
+static void test_aspect_ratio_match() {  // lib.rs:160-210
+  CHECK(MosaicGeneratorImpl::is_aspect_ratio_match(16.0f / 9.0f, 16.0f / 9.0f, 0.1f));
+  CHECK(MosaicGeneratorImpl::is_aspect_ratio_match(1.8f, 16.0f / 9.0f, 0.1f));
+  CHECK(!MosaicGeneratorImpl::is_aspect_ratio_match(4.0f / 3.0f, 16.0f / 9.0f, 0.1f));
+  CHECK(!MosaicGeneratorImpl::is_aspect_ratio_match(16.0f / 9.0f, 9.0f / 16.0f, 0.1f));
+}
+
+static void test_tile_creation() {  // lib.rs:229-240
+  const Tile tile{"test.png", Lab{50.0f, 0.0f, 0.0f}, 16.0f / 9.0f};
+  CHECK(tile.path == "test.png");
+  CHECK(tile.aspect_ratio == 16.0f / 9.0f);
+  CHECK(tile.lab_color.l == 50.0f);
+}
+
+static void test_usage_tracker() {  // lib.rs:242-307
+  {
+    UsageTracker tracker(3);  // test_usage_tracker_creation
+    CHECK(tracker.can_use_image("test.png"));
+    CHECK(tracker.get_usage_count("test.png") == 0);
+  }
+  {
+    UsageTracker tracker(2);  // test_usage_tracker_use_image
+    CHECK(tracker.can_use_image("test.png"));
+    tracker.use_image("test.png");
+    CHECK(tracker.get_usage_count("test.png") == 1 && tracker.can_use_image("test.png"));
+    tracker.use_image("test.png");
+    CHECK(tracker.get_usage_count("test.png") == 2 && !tracker.can_use_image("test.png"));
+  }
+  {
+    UsageTracker tracker(1);  // test_usage_tracker_multiple_images
+    tracker.use_image("image1.png");
+    CHECK(!tracker.can_use_image("image1.png") && tracker.can_use_image("image2.png"));
+    tracker.use_image("image2.png");
+    CHECK(!tracker.can_use_image("image2.png"));
+  }
+  {
+    UsageTracker tracker(1);  // test_usage_tracker_reset
+    tracker.use_image("test.png");
+    CHECK(!tracker.can_use_image("test.png"));
+    tracker.reset();
+    CHECK(tracker.can_use_image("test.png") && tracker.get_usage_count("test.png") == 0);
+  }
+  {
+    UsageTracker tracker(0);  // test_usage_tracker_max_usage_zero
+    CHECK(!tracker.can_use_image("test.png"));
+  }
+}
+
+static void test_save_to_file_writes_a_stale_matrix() {  // similarity.rs:112-116: whatever `similarities` holds is written
+  SimilarityDatabase db;
+  db.add_tile("a.png", Lab{50.0f, 0.0f, 0.0f});
+  db.add_tile("b.png", Lab{60.0f, 10.0f, 10.0f});
+  const std::string f = tmp_path("stale_db.json");
+  db.save_to_file(f);  // two tiles, no build_similarities yet: an empty list, as the reference writes it
+  const SimilarityDatabase back = SimilarityDatabase::load_from_file(f);
+  CHECK(back.len() == 2);
+  CHECK(!back.get_similarity("a.png", "b.png").has_value());  // similarity.rs:100-102: index beyond the list -> None
+  std::remove(f.c_str());
+}
+
 static void test_no_gpu_is_loud() {  // there is no CPU fallback behind the mirror: without a device the call throws
   SimilarityDatabase db;
   db.add_tile("a.png", Lab{50.0f, 0.0f, 0.0f});
@@ -380,6 +440,56 @@ static void test_optimization_numerical_stability() {  // optimizer.rs:631-662
   CHECK(std::isfinite(r.initial_cost) && std::isfinite(r.final_cost) && std::isfinite(r.best_cost) && r.iterations == 30);
 }
 
+// the mirror's static helpers share one scratch context: any order of calls must work (each injects all it needs)
+static void test_helpers_in_any_order() {
+  RgbImage img(10, 10);
+  for (size_t i = 0; i < img.data.size(); i += 3) img.data[i] = 255;
+  const Lab red = MosaicGeneratorImpl::calculate_average_lab(img);  // leaves ONE material on the scratch context
+  CHECK(std::fabs(red.l - 53.24f) < 1.0f);
+  SimilarityDatabase db;  // ... then a three-tile database is built on it
+  db.add_tile("tile1.png", Lab{50.0f, 0.0f, 0.0f});
+  db.add_tile("tile2.png", Lab{60.0f, 10.0f, 10.0f});
+  db.add_tile("tile3.png", Lab{70.0f, 20.0f, 20.0f});
+  db.build_similarities();
+  CHECK(db.get_similarity("tile1.png", "tile2.png").has_value());
+  CHECK(std::fabs(*db.get_similarity("tile1.png", "tile2.png") - std::sqrt(300.0f)) < 1e-4f);
+  AdjacencyPenaltyCalculator calc(db, 1.0f);
+  PathGrid grid = {{std::string("tile1.png"), std::string("tile2.png")}};
+  const float cost = calc.calculate_total_cost(grid);
+  CHECK(std::fabs(cost - 1.0f / (std::sqrt(300.0f) + 1.0f)) < 1e-6f);
+  const Lab again = MosaicGeneratorImpl::calculate_average_lab(img);
+  CHECK(again.l == red.l && again.a == red.a && again.b == red.b);
+}
+
+// A path the database does not know is an occupied cell without similarity terms (adjacency.rs:104-124,
+// optimizer.rs:71-102): it contributes nothing to the cost — also next to itself — and the optimiser moves it.
+static void test_unknown_paths_are_occupied_cells() {
+  SimilarityDatabase db;
+  db.add_tile("tile1.png", Lab{50.0f, 0.0f, 0.0f});
+  db.add_tile("tile2.png", Lab{60.0f, 10.0f, 10.0f});
+  db.build_similarities();
+  AdjacencyPenaltyCalculator calc(db, 1.0f);
+  const float pair = 1.0f / (std::sqrt(300.0f) + 1.0f);
+  PathGrid grid = {{std::string("tile1.png"), std::string("tile2.png")}, {std::string("ghost.png"), std::string("ghost.png")}};
+  CHECK(calc.calculate_total_cost(grid) == pair);  // only tile1-tile2; ghost-ghost, tile-ghost pairs are skipped
+  PathGrid all_ghosts = {{std::string("g1.png"), std::string("g2.png")}, {std::string("g1.png"), std::string("g3.png")}};
+  CHECK(calc.calculate_total_cost(all_ghosts) == 0.0f);
+  OptimizationConfig cfg;
+  cfg.max_iterations = 200;
+  cfg.seed = 3;
+  MosaicOptimizer opt(calc, cfg);
+  const OptimizationResult r = opt.optimize(all_ghosts);  // every delta is 0: every valid swap is accepted
+  CHECK(r.initial_cost == 0.0f && r.final_cost == 0.0f);
+  CHECK(r.accepted_count > 0);
+  size_t n1 = 0, n2 = 0, n3 = 0;
+  for (const auto& row : all_ghosts)
+    for (const auto& c : row) {
+      CHECK(c.has_value());
+      n1 += *c == "g1.png", n2 += *c == "g2.png", n3 += *c == "g3.png";
+    }
+  CHECK(n1 == 2 && n2 == 1 && n3 == 1);  // the same multiset of paths, only moved
+}
+
 static void test_lab_color_calculation() {  // lib.rs:133-158: solid red and gray, ±1.0
   RgbImage red(10, 10), gray(10, 10);
   for (size_t i = 0; i < red.data.size(); i += 3) red.data[i] = 255;
@@ -454,6 +564,10 @@ int main(int argc, char** argv) {
   RUN(test_optimization_result_improvement);
   RUN(test_optimization_config_defaults);
   RUN(test_optimization_empty_grid);
+  RUN(test_aspect_ratio_match);
+  RUN(test_tile_creation);
+  RUN(test_usage_tracker);
+  RUN(test_save_to_file_writes_a_stale_matrix);
   if (cpu_only) {
     RUN(test_no_gpu_is_loud);
   } else {
@@ -473,6 +587,8 @@ int main(int argc, char** argv) {
     RUN(test_optimization_identical_tiles);
     RUN(test_optimization_numerical_stability);
     RUN(test_lab_color_calculation);
+    RUN(test_helpers_in_any_order);  // (after the Lab test on purpose: the scratch context holds one material then)
+    RUN(test_unknown_paths_are_occupied_cells);
   }
   std::printf("%d tests, %d failed checks\n", g_run, g_failed);
   return g_failed ? 1 : 0;
