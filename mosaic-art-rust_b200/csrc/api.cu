@@ -342,7 +342,7 @@ __global__ void set_u32_kernel(unsigned* p, unsigned v) { *p = v; }
 // placement records are computed when the band has landed, and the placement chain — one CTA, serial — starts after the
 // first band on its own stream and consumes the records as they appear (a device counter of prepared cells), so that
 // most of its 2.6 ms at the 24,000-tile config run under the upload of the remaining bands.
-int run_match_place_banded(mosaic_ctx* c, int k, int max_usage, float weight) {
+int run_match_place_banded(mosaic_ctx* c, int k, int max_usage, float weight, bool with_progress) {
   if (k <= 0 || k > kMaxK) k = kMaxK;
   if (k > c->n) k = c->n;
   MOSAIC_TRY(ensure_cand_buffers(c));
@@ -351,6 +351,10 @@ int run_match_place_banded(mosaic_ctx* c, int k, int max_usage, float weight) {
   MOSAIC_TRY(ensure_placed(c));
   MOSAIC_TRY(ensure(c, &c->d_ready_cells, &c->ready_cells_cap, (size_t)1));
   MOSAIC_CUDA(c, cudaMemsetAsync(c->d_ready_cells, 0, sizeof(unsigned), c->stream));
+  if (with_progress) {
+    MOSAIC_TRY(ensure(c, &c->d_progress, &c->progress_cap, (size_t)1));
+    MOSAIC_CUDA(c, cudaMemsetAsync(c->d_progress, 0, sizeof(unsigned), c->stream));
+  }
   for (int b = 0; b < c->tgt_bands; ++b) {
     const int r0 = c->tgt_band_rows[b], r1 = c->tgt_band_rows[b + 1];
     if (r1 > r0) {
@@ -368,7 +372,7 @@ int run_match_place_banded(mosaic_ctx* c, int k, int max_usage, float weight) {
   // tool that serialises kernel execution (ncu) runs the bands first and the chain last instead of dead-locking on a
   // chain that polls for records of kernels not launched yet.
   MOSAIC_CUDA(c, cudaStreamWaitEvent(c->chain_stream, c->ev_chain_go, 0));
-  MOSAIC_TRY(launch_place_chain_async(c, max_usage, weight, c->chain_stream, c->d_ready_cells));
+  MOSAIC_TRY(launch_place_chain_async(c, max_usage, weight, c->chain_stream, c->d_ready_cells, with_progress ? c->d_progress : nullptr));
   MOSAIC_CUDA(c, cudaEventRecord(c->ev_chain_done, c->chain_stream));
   MOSAIC_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_chain_done, 0));
   c->tgt_upload_pending = false;
@@ -592,6 +596,58 @@ int run_render(mosaic_ctx* c, float strength, uint8_t* out_rgb) {
   return MOSAIC_OK;
 }
 
+__global__ void wait_progress_kernel(const volatile unsigned* progress, unsigned need) {
+  if (threadIdx.x == 0) {
+    const long long t0 = clock64();
+    while (*progress < need) {
+      __nanosleep(200);
+      if (clock64() - t0 > 20000000000ll) __trap();  // the chain died: do not hang the GPU
+    }
+    __threadfence();
+  }
+}
+
+// The image of the GREEDY placement, rendered and sent to the host band by band WHILE the placement chain is still
+// walking the rows below: a band is rendered as soon as the chain's progress counter has passed it.  Kernels on
+// render_stream, copies on copy_stream; the caller's stream is not involved (it waits for ev_copy_done at the end).
+// The reference renders the greedy placement first as well (main.rs:533-593) and again after annealing (625-664).
+int run_render_under_chain(mosaic_ctx* c, float strength, uint8_t* out_rgb) {
+  MOSAIC_TRY(wait_materials(c));
+  const size_t out_bytes = (size_t)c->gw * c->tile_w * (size_t)c->gh * c->tile_h * 3;
+  MOSAIC_TRY(ensure(c, &c->d_out, &c->out_cap, out_bytes));
+  const size_t row_bytes = (size_t)c->gw * c->tile_w * 3 * (size_t)c->tile_h;
+  // What the render stream needs from the other streams: the materials (upload event), the reset of the progress
+  // counter (enqueued before the first band's records, i.e. before ev_chain_go) — everything else is covered by the
+  // progress counter itself (a band's cell sums and records exist before the chain can pass it).  NOT an event recorded
+  // on the caller's stream now: that stream already waits for the end of the chain.
+  MOSAIC_CUDA(c, cudaStreamWaitEvent(c->render_stream, c->ev_mat_up, 0));
+  MOSAIC_CUDA(c, cudaStreamWaitEvent(c->render_stream, c->ev_chain_go, 0));
+  cudaStream_t caller = c->stream;
+  c->stream = c->render_stream;
+  int rc = render_reset_cache(c);
+  for (int b = 0; b < c->tgt_bands && rc == MOSAIC_OK; ++b) {
+    const int b0 = c->tgt_band_rows[b], b1 = c->tgt_band_rows[b + 1];
+    if (b1 <= b0) continue;
+    wait_progress_kernel<<<1, 32, 0, c->render_stream>>>(c->d_progress, (unsigned)(b1 * c->gw));
+    c->launches++;
+    rc = c->ragged ? launch_render_ragged(c, strength, b0, b1) : launch_render(c, strength, b0, b1);
+    if (rc != MOSAIC_OK) break;
+    cudaEventRecord(c->ev_band[b], c->render_stream);
+    if (b == 0 || b + 1 == c->tgt_bands) trace_point(c, b == 0 ? "band0_rendered" : "last_band_rendered", c->render_stream);
+    cudaStreamWaitEvent(c->copy_stream, c->ev_band[b], 0);
+    cudaMemcpyAsync(out_rgb + (size_t)b0 * row_bytes, c->d_out + (size_t)b0 * row_bytes, (size_t)(b1 - b0) * row_bytes,
+                    cudaMemcpyDeviceToHost, c->copy_stream);
+    if (b == 0 || b + 1 == c->tgt_bands) trace_point(c, b == 0 ? "band0_copied" : "last_band_copied", c->copy_stream);
+  }
+  c->stream = caller;
+  MOSAIC_TRY(rc);
+  MOSAIC_CUDA(c, cudaEventRecord(c->ev_render_done, c->render_stream));
+  MOSAIC_CUDA(c, cudaEventRecord(c->ev_copy_done, c->copy_stream));
+  MOSAIC_CUDA(c, cudaGetLastError());
+  c->have_out = true;
+  return MOSAIC_OK;
+}
+
 }  // namespace
 }  // namespace mosaic
 
@@ -640,6 +696,8 @@ static int ctx_create_common(mosaic_ctx** out, int device) {
   cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
   cudaStreamCreateWithFlags(&c->upload_stream, cudaStreamNonBlocking);
   cudaStreamCreateWithFlags(&c->chain_stream, cudaStreamNonBlocking);
+  cudaStreamCreateWithFlags(&c->render_stream, cudaStreamNonBlocking);
+  cudaEventCreateWithFlags(&c->ev_render_done, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&c->ev_chain_go, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&c->ev_chain_done, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&c->ev_main_idle, cudaEventDisableTiming);
@@ -692,6 +750,7 @@ void mosaic_ctx_destroy(mosaic_ctx* c) {
   void* bufs[] = {c->d_ready_cells, c->d_mat_off, c->d_mat_w, c->d_mat_h, c->d_rag_bounds, c->d_rag_weights, c->d_rag_desc, c->d_rag_midx, c->d_rag_scratch,
                   c->d_sim_lab4_own, c->d_sim_soa_own, c->d_materials_owned, c->d_mat_lab, c->d_mat_lab4, c->d_mat_soa, c->d_target_owned, c->d_cell_lab,
                   c->d_cell_rgbsum,     c->d_cand_idx, c->d_cand_d2, c->d_result,  c->d_usage,        c->d_flags, c->d_peer_err, c->d_place_rec,
+                  c->d_patch_list, c->d_patch_count, c->d_placed_greedy, c->d_progress,
                   c->d_sim,             c->d_sim_counter, c->d_rng_ring, c->d_terms, c->d_deltas, c->d_thumbs, c->d_thumb_sums, c->d_thumb_state, c->d_out,    c->axis_h.start,   c->axis_h.size,
                   c->axis_h.w,          c->axis_v.start, c->axis_v.size, c->axis_v.w};
   for (void* p : bufs)
@@ -709,6 +768,11 @@ void mosaic_ctx_destroy(mosaic_ctx* c) {
     cudaStreamSynchronize(c->chain_stream);
     cudaStreamDestroy(c->chain_stream);
   }
+  if (c->render_stream) {
+    cudaStreamSynchronize(c->render_stream);
+    cudaStreamDestroy(c->render_stream);
+  }
+  if (c->ev_render_done) cudaEventDestroy(c->ev_render_done);
   if (c->ev_chain_go) cudaEventDestroy(c->ev_chain_go);
   if (c->ev_chain_done) cudaEventDestroy(c->ev_chain_done);
   if (c->ev_main_idle) cudaEventDestroy(c->ev_main_idle);
@@ -1097,7 +1161,7 @@ int mosaic_generate(mosaic_ctx* c, const mosaic_params* p, int32_t* placed_out, 
   const bool anneal = p->enable_optimization && p->adjacency_weight > 0.0f;  // main.rs:608
   trace_point(c, "begin");
   const auto host_t0 = std::chrono::steady_clock::now();
-  bool peer = false;
+  bool peer = false, under_chain = false;
   if (c->world > 1) {  // sharded: buffers every rank exchanges through are allocated (whole-problem sizes) and mapped
     MOSAIC_TRY(ensure_mat_lab_buffers(c, c->n));
     MOSAIC_TRY(ensure_cell_buffers(c));
@@ -1115,18 +1179,56 @@ int mosaic_generate(mosaic_ctx* c, const mosaic_params* p, int32_t* placed_out, 
   if (p->build_similarity) MOSAIC_TRY(run_similarity(c, /*gather=*/false));
   // ... main.rs:477-685 (generate_mosaic)
   if (c->tgt_upload_pending && c->world == 1 && c->tgt_bands > 1 && place_chain_eligible(c, p->max_usage)) {
-    MOSAIC_TRY(run_match_place_banded(c, kMaxK, p->max_usage, p->adjacency_weight));  // matching + placement under the upload
+    // matching + placement under the upload; with a host destination the finished rows are rendered and sent down
+    // under the chain too
+    under_chain = out_rgb != nullptr && place_chain_has_progress(c);
+    MOSAIC_TRY(run_match_place_banded(c, kMaxK, p->max_usage, p->adjacency_weight, under_chain));
+    if (under_chain) MOSAIC_TRY(run_render_under_chain(c, p->color_strength, out_rgb));
   } else {
     if (!(c->tgt_upload_pending && c->world == 1)) MOSAIC_TRY(run_cell_lab(c));  // (else: band by band inside run_candidates)
     MOSAIC_TRY(run_candidates(c, kMaxK));
     MOSAIC_TRY(run_place(c, p->max_usage, p->adjacency_weight));
   }
+  if (under_chain) {
+    // The greedy image is on its way.  Annealing permutes materials between cells: the cells it changes (at most two
+    // per accepted swap) are composed again from the thumbnail cache, straight into the device image and — when the
+    // caller's buffer is page-locked, hence visible to the device — into the caller's image, after the bulk copies.
+    trace_point(c, "chain_done");
+    if (anneal) {
+      MOSAIC_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_render_done, 0));  // the early render reads the greedy grid
+      uint8_t* host_dev = nullptr;
+      cudaPointerAttributes attr;
+      if (cudaPointerGetAttributes(&attr, out_rgb) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer)
+        host_dev = reinterpret_cast<uint8_t*>(attr.devicePointer);
+      (void)cudaGetLastError();
+      const bool patch = host_dev != nullptr && render_patch_possible(c);
+      if (patch) {
+        MOSAIC_TRY(ensure(c, &c->d_placed_greedy, &c->placed_greedy_cap, cells_of(c)));
+        MOSAIC_CUDA(c, cudaMemcpyAsync(c->d_placed_greedy, c->d_placed, sizeof(int32_t) * cells_of(c), cudaMemcpyDeviceToDevice, c->stream));
+      }
+      trace_point(c, "anneal_starts");
+      MOSAIC_TRY(run_anneal(c, p->optimization_iterations, 100.0f, 0.99995f, p->seed));  // optimizer.rs:18-27
+      trace_point(c, "annealed");
+      MOSAIC_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_copy_done, 0));  // nothing may overwrite a patched tile afterwards
+      if (patch)
+        MOSAIC_TRY(launch_render_patch(c, c->d_placed_greedy, host_dev));
+      else
+        MOSAIC_TRY(run_render(c, p->color_strength, out_rgb));  // pageable destination / per-cell render path: once more, whole
+    } else {
+      MOSAIC_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_copy_done, 0));
+    }
+    MOSAIC_TRY(d2h(c, placed_out, c->d_placed, sizeof(int32_t) * cells_of(c)));
+    trace_point(c, "rendered");
+  } else {
   if (anneal) MOSAIC_TRY(run_anneal(c, p->optimization_iterations, 100.0f, 0.99995f, p->seed));  // optimizer.rs:18-27
   }
+  }
+  if (!under_chain) {
   trace_point(c, "placed");
   MOSAIC_TRY(d2h(c, placed_out, c->d_placed, sizeof(int32_t) * cells_of(c)));
   MOSAIC_TRY(run_render(c, p->color_strength, out_rgb));
   trace_point(c, "rendered");
+  }
   if (peer) {
     CollTimer t(c, c->stream);
     MOSAIC_TRY(dist_peer_barrier(c, c->stream));

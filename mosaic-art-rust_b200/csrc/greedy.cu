@@ -328,7 +328,8 @@ __global__ void __launch_bounds__(64, 1)
                         const float4* __restrict__ lab4, int n, int gw, int gh,
                         unsigned max_usage, float weight, int32_t* __restrict__ placed, uint32_t* __restrict__ info,
                         uint32_t fallback_cap,
-                        const volatile unsigned* ready /* cells whose records exist so far; NULL = all of them */) {
+                        const volatile unsigned* ready /* cells whose records exist so far; NULL = all of them */,
+                        volatile unsigned* progress /* GATED: cells committed so far, for whoever renders rows under the chain */) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   HRec* hring = reinterpret_cast<HRec*>(smem_raw);
   XRec* xring = reinterpret_cast<XRec*>(smem_raw + sizeof(HRec) * (CH_DEPTH + CH_SHADOW));
@@ -426,6 +427,10 @@ __global__ void __launch_bounds__(64, 1)
       base += cnt;
       if (lane == 0) {
         decided[0] = (uint32_t)base;
+        if (GATED && progress) {  // the placements of the cells before `base` are in HBM
+          __threadfence();
+          *progress = (unsigned)base;
+        }
         // ring batches whose 8 cells are all older than the guard window are free: fetch their successors
         if (GATED) {
           try_issue();
@@ -836,14 +841,18 @@ __global__ void __launch_bounds__(64, 1)
 }  // namespace
 
 template <typename UsageT, bool PROF, bool GATED = false>
-static int launch_chain_impl(mosaic_ctx* ctx, unsigned cap, float weight, size_t smem, cudaStream_t stream, const unsigned* ready) {
+static int launch_chain_impl(mosaic_ctx* ctx, unsigned cap, float weight, size_t smem, cudaStream_t stream, const unsigned* ready,
+                             unsigned* progress = nullptr) {
   const size_t cells = (size_t)ctx->gw * ctx->gh;
+  // under the chain other kernels run (matching of later bands, the render of finished rows): claiming all of the SM's
+  // shared memory keeps their CTAs off the SM of the one warp everything waits for
+  if (GATED) smem = std::max(smem, (size_t)226 * 1024);
   MOSAIC_CUDA(ctx, cudaFuncSetAttribute(greedy_chain_kernel<UsageT, PROF, GATED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)smem));
   greedy_chain_kernel<UsageT, PROF, GATED><<<1, 64, smem, stream>>>(
       reinterpret_cast<const HRec*>(ctx->d_place_rec), reinterpret_cast<const XRec*>(ctx->d_place_rec + cells * sizeof(HRec)),
       reinterpret_cast<const float*>(ctx->d_place_rec + cells * (sizeof(HRec) + sizeof(XRec))), ctx->d_cand_idx, ctx->d_cand_d2, ctx->k, ctx->sim_lab4(), ctx->n, ctx->gw, ctx->gh, cap, weight, ctx->d_placed,
-      ctx->d_place_info, mosaic_ctx::kFallbackCap, ready);
+      ctx->d_place_info, mosaic_ctx::kFallbackCap, ready, progress);
   return MOSAIC_OK;
 }
 
@@ -899,22 +908,27 @@ static size_t chain_smem(const mosaic_ctx* ctx, unsigned cap) {
     return ring_fixed + usage_bytes + 16;
   return 0;
 }
+bool place_chain_has_progress(const mosaic_ctx* ctx) { return use_v1_chain(ctx); }
+
 bool place_chain_eligible(const mosaic_ctx* ctx, int max_usage) {
   if (!use_v1_chain(ctx)) return window_chain_eligible(ctx, max_usage) && !ctx->profile_chain;
   return chain_smem(ctx, max_usage < 0 ? 0u : (unsigned)max_usage) != 0 && !ctx->profile_chain;
 }
 
 // the chain kernel alone, on `stream`, consuming records as `ready` (a device counter of prepared cells) advances
-int launch_place_chain_async(mosaic_ctx* ctx, int max_usage, float weight, cudaStream_t stream, const unsigned* ready) {
-  if (!use_v1_chain(ctx)) return launch_window_chain(ctx, max_usage, weight, stream, ready, false);
+int launch_place_chain_async(mosaic_ctx* ctx, int max_usage, float weight, cudaStream_t stream, const unsigned* ready, unsigned* progress) {
+  if (!use_v1_chain(ctx)) {
+    if (progress) return fail(ctx, MOSAIC_ERR_STATE, "the windowed chain publishes no progress counter");
+    return launch_window_chain(ctx, max_usage, weight, stream, ready, false);
+  }
   const unsigned cap = max_usage < 0 ? 0u : (unsigned)max_usage;
   const size_t smem = chain_smem(ctx, cap);
   if (!smem) return fail(ctx, MOSAIC_ERR_STATE, "placement: the chain kernel does not cover this configuration");
   MOSAIC_TRY(ensure_place_records(ctx));
   if (cap <= 255u)
-    MOSAIC_TRY((launch_chain_impl<uint8_t, false, true>(ctx, cap, weight, smem, stream, ready)));
+    MOSAIC_TRY((launch_chain_impl<uint8_t, false, true>(ctx, cap, weight, smem, stream, ready, progress)));
   else
-    MOSAIC_TRY((launch_chain_impl<uint16_t, false, true>(ctx, cap, weight, smem, stream, ready)));
+    MOSAIC_TRY((launch_chain_impl<uint16_t, false, true>(ctx, cap, weight, smem, stream, ready, progress)));
   ctx->launches++;
   MOSAIC_CUDA(ctx, cudaGetLastError());
   return MOSAIC_OK;

@@ -1,0 +1,9 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -8 gpurun_out/pytest_gpu.log
+MOSAIC_TRACE=1 python bench.py --steps 4 --warmup 3 --no-cpu-baseline --no-verify 2>&1 >/dev/null | grep "mosaic trace" | tail -3
+python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"; python - <<'PY'
+import json
+d = json.loads(open('gpurun_out/bench.json').read().strip().splitlines()[-1])
+print({k: d[k] for k in ('value', 'ms_per_step')}, 'e2e', d['e2e']['ms_per_step'], 'verified', d['verified'])
+PY
