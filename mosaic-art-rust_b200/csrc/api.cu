@@ -366,12 +366,14 @@ int run_match_place_banded(mosaic_ctx* c, int k, int max_usage, float weight, bo
       c->launches++;
     }
     if (b == 0) MOSAIC_CUDA(c, cudaEventRecord(c->ev_chain_go, c->stream));  // the counter is reset and covers the first band
+    if (b == 0 || b + 1 == c->tgt_bands) trace_point(c, b == 0 ? "band0_prepared" : "last_band_prepared");
   }
   // The chain is ENQUEUED after every band's kernels (the host gets here long before the first band has landed) but
   // only waits for the first band's event: on the device it starts as soon as that band is prepared.  In this order a
   // tool that serialises kernel execution (ncu) runs the bands first and the chain last instead of dead-locking on a
   // chain that polls for records of kernels not launched yet.
   MOSAIC_CUDA(c, cudaStreamWaitEvent(c->chain_stream, c->ev_chain_go, 0));
+  trace_point(c, "chain_starts", c->chain_stream);
   MOSAIC_TRY(launch_place_chain_async(c, max_usage, weight, c->chain_stream, c->d_ready_cells, with_progress ? c->d_progress : nullptr));
   MOSAIC_CUDA(c, cudaEventRecord(c->ev_chain_done, c->chain_stream));
   MOSAIC_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_chain_done, 0));
