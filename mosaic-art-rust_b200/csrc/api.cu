@@ -75,6 +75,11 @@ int allgather_slices(mosaic_ctx* c, void* buf, size_t elem_bytes, F slice_of_ran
   return dist_allgatherv_inplace(c, buf, offs.data(), sizes.data());
 }
 
+// every compute entry point starts a fresh set of stage intervals (mosaic_stage_ms reports the most recent call)
+void begin_call(mosaic_ctx* c) {
+  for (int s = 0; s < MOSAIC_STAGE_COUNT; ++s) c->ev_count[s] = 0;
+}
+
 int require(mosaic_ctx* c, bool cond, const char* what) {
   if (!cond) return fail(c, MOSAIC_ERR_STATE, std::string("missing input: ") + what);
   return MOSAIC_OK;
@@ -343,6 +348,12 @@ __global__ void set_u32_kernel(unsigned* p, unsigned v) { *p = v; }
 // first band on its own stream and consumes the records as they appear (a device counter of prepared cells), so that
 // most of its 2.6 ms at the 24,000-tile config run under the upload of the remaining bands.
 int run_match_place_banded(mosaic_ctx* c, int k, int max_usage, float weight, bool with_progress) {
+  const bool uploading = c->tgt_upload_pending;  // bands of an upload in flight (each with its event) — else: bands of rows
+  if (!uploading) {
+    const int bands = (int)std::max<size_t>(1, std::min<size_t>((size_t)mosaic_ctx::kBands, std::min<size_t>((size_t)c->gh, cells_of(c) / 3000)));
+    for (int b = 0; b <= bands; ++b) c->tgt_band_rows[b] = (int)((long long)c->gh * b / bands);
+    c->tgt_bands = bands;
+  }
   if (k <= 0 || k > kMaxK) k = kMaxK;
   if (k > c->n) k = c->n;
   MOSAIC_TRY(ensure_cand_buffers(c));
@@ -358,9 +369,14 @@ int run_match_place_banded(mosaic_ctx* c, int k, int max_usage, float weight, bo
   for (int b = 0; b < c->tgt_bands; ++b) {
     const int r0 = c->tgt_band_rows[b], r1 = c->tgt_band_rows[b + 1];
     if (r1 > r0) {
-      MOSAIC_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_tgt_band[b], 0));
+      if (uploading) MOSAIC_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_tgt_band[b], 0));
       MOSAIC_TRY(launch_cell_lab_range(c, r0 * c->gw, r1 * c->gw));
-      MOSAIC_TRY(launch_topk_range(c, k, r0 * c->gw, r1 * c->gw));
+      // the first band is on the critical path; the others only have to keep ahead of the chain (experiment knob)
+      static const int band_rounds = getenv("MOSAIC_BAND_ROUNDS") ? atoi(getenv("MOSAIC_BAND_ROUNDS")) : 0;
+      c->topk_force_rounds = b == 0 ? 0 : band_rounds;
+      int trc = launch_topk_range(c, k, r0 * c->gw, r1 * c->gw);
+      c->topk_force_rounds = 0;
+      MOSAIC_TRY(trc);
       MOSAIC_TRY(launch_place_prep_range(c, weight, r0 * c->gw, r1 * c->gw));
       set_u32_kernel<<<1, 1, 0, c->stream>>>(c->d_ready_cells, (unsigned)(r1 * c->gw));
       c->launches++;
@@ -374,7 +390,9 @@ int run_match_place_banded(mosaic_ctx* c, int k, int max_usage, float weight, bo
   // chain that polls for records of kernels not launched yet.
   MOSAIC_CUDA(c, cudaStreamWaitEvent(c->chain_stream, c->ev_chain_go, 0));
   trace_point(c, "chain_starts", c->chain_stream);
+  const int place_slot = stage_interval_begin(c, MOSAIC_STAGE_PLACE, c->chain_stream);
   MOSAIC_TRY(launch_place_chain_async(c, max_usage, weight, c->chain_stream, c->d_ready_cells, with_progress ? c->d_progress : nullptr));
+  stage_interval_end(c, MOSAIC_STAGE_PLACE, place_slot, c->chain_stream);
   MOSAIC_CUDA(c, cudaEventRecord(c->ev_chain_done, c->chain_stream));
   MOSAIC_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_chain_done, 0));
   c->tgt_upload_pending = false;
@@ -479,7 +497,7 @@ int run_generate_peer(mosaic_ctx* c, const mosaic_params* p, bool anneal) {
     MOSAIC_TRY(dist_peer_wait(c, FLAG_RES, 1, e_res, c->stream));  // placements + report from rank 0
   } else {
     const bool chain = place_chain_eligible(c, p->max_usage);
-    MOSAIC_CUDA(c, cudaEventRecord(c->ev_begin[MOSAIC_STAGE_PLACE], c->stream));
+    const int place_slot = stage_interval_begin(c, MOSAIC_STAGE_PLACE, c->stream);
     if (chain) {
       MOSAIC_TRY(ensure(c, &c->d_ready_cells, &c->ready_cells_cap, (size_t)1));
       MOSAIC_CUDA(c, cudaMemsetAsync(c->d_ready_cells, 0, sizeof(unsigned), c->stream));
@@ -504,9 +522,9 @@ int run_generate_peer(mosaic_ctx* c, const mosaic_params* p, bool anneal) {
       MOSAIC_TRY(launch_place_chain_async(c, p->max_usage, p->adjacency_weight, c->chain_stream, c->d_ready_cells));
       MOSAIC_CUDA(c, cudaEventRecord(c->ev_chain_done, c->chain_stream));
       MOSAIC_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_chain_done, 0));
-      MOSAIC_CUDA(c, cudaEventRecord(c->ev_end[MOSAIC_STAGE_PLACE], c->stream));
-      c->ev_valid[MOSAIC_STAGE_PLACE] = true;
+      stage_interval_end(c, MOSAIC_STAGE_PLACE, place_slot, c->stream);
     } else {
+      stage_interval_end(c, MOSAIC_STAGE_PLACE, place_slot, c->stream);
       MOSAIC_TRY(launch_place(c, p->max_usage, p->adjacency_weight));
     }
     c->have_placed = true;
@@ -632,14 +650,19 @@ int run_render_under_chain(mosaic_ctx* c, float strength, uint8_t* out_rgb) {
     if (b1 <= b0) continue;
     wait_progress_kernel<<<1, 32, 0, c->render_stream>>>(c->d_progress, (unsigned)(b1 * c->gw));
     c->launches++;
-    rc = c->ragged ? launch_render_ragged(c, strength, b0, b1) : launch_render(c, strength, b0, b1);
+    {
+      StageTimer t(c, MOSAIC_STAGE_RENDER);  // (c->stream is the render stream here)
+      rc = c->ragged ? launch_render_ragged(c, strength, b0, b1) : launch_render(c, strength, b0, b1);
+    }
     if (rc != MOSAIC_OK) break;
     cudaEventRecord(c->ev_band[b], c->render_stream);
     if (b == 0 || b + 1 == c->tgt_bands) trace_point(c, b == 0 ? "band0_rendered" : "last_band_rendered", c->render_stream);
-    cudaStreamWaitEvent(c->copy_stream, c->ev_band[b], 0);
-    cudaMemcpyAsync(out_rgb + (size_t)b0 * row_bytes, c->d_out + (size_t)b0 * row_bytes, (size_t)(b1 - b0) * row_bytes,
-                    cudaMemcpyDeviceToHost, c->copy_stream);
-    if (b == 0 || b + 1 == c->tgt_bands) trace_point(c, b == 0 ? "band0_copied" : "last_band_copied", c->copy_stream);
+    if (out_rgb) {
+      cudaStreamWaitEvent(c->copy_stream, c->ev_band[b], 0);
+      cudaMemcpyAsync(out_rgb + (size_t)b0 * row_bytes, c->d_out + (size_t)b0 * row_bytes, (size_t)(b1 - b0) * row_bytes,
+                      cudaMemcpyDeviceToHost, c->copy_stream);
+      if (b == 0 || b + 1 == c->tgt_bands) trace_point(c, b == 0 ? "band0_copied" : "last_band_copied", c->copy_stream);
+    }
   }
   c->stream = caller;
   MOSAIC_TRY(rc);
@@ -700,6 +723,8 @@ static int ctx_create_common(mosaic_ctx** out, int device) {
   cudaStreamCreateWithFlags(&c->chain_stream, cudaStreamNonBlocking);
   cudaStreamCreateWithFlags(&c->render_stream, cudaStreamNonBlocking);
   cudaEventCreateWithFlags(&c->ev_render_done, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&c->ev_mat_lab, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&c->ev_sim_done, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&c->ev_chain_go, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&c->ev_chain_done, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&c->ev_main_idle, cudaEventDisableTiming);
@@ -707,10 +732,6 @@ static int ctx_create_common(mosaic_ctx** out, int device) {
   for (int i = 0; i < mosaic_ctx::kBands; ++i) cudaEventCreateWithFlags(&c->ev_tgt_band[i], cudaEventDisableTiming);
   for (int i = 0; i < mosaic_ctx::kBands; ++i) cudaEventCreateWithFlags(&c->ev_band[i], cudaEventDisableTiming);
   cudaEventCreateWithFlags(&c->ev_copy_done, cudaEventDisableTiming);
-  for (int i = 0; i < MOSAIC_STAGE_COUNT; ++i) {
-    cudaEventCreate(&c->ev_begin[i]);
-    cudaEventCreate(&c->ev_end[i]);
-  }
   static_assert(sizeof(mosaic_opt_result) <= 256, "arena layout");
   if (ensure_result(c, 1) != MOSAIC_OK) {
     set_global_error(c->err);
@@ -758,10 +779,11 @@ void mosaic_ctx_destroy(mosaic_ctx* c) {
   for (void* p : bufs)
     if (p) cudaFree(p);
   if (c->h_pinned) cudaFreeHost(c->h_pinned);
-  for (int i = 0; i < MOSAIC_STAGE_COUNT; ++i) {
-    if (c->ev_begin[i]) cudaEventDestroy(c->ev_begin[i]);
-    if (c->ev_end[i]) cudaEventDestroy(c->ev_end[i]);
-  }
+  for (int i = 0; i < MOSAIC_STAGE_COUNT; ++i)
+    for (int j = 0; j < mosaic_ctx::kStageIntervals; ++j) {
+      if (c->ev_begin[i][j]) cudaEventDestroy(c->ev_begin[i][j]);
+      if (c->ev_end[i][j]) cudaEventDestroy(c->ev_end[i][j]);
+    }
   if (c->upload_stream) {
     cudaStreamSynchronize(c->upload_stream);
     cudaStreamDestroy(c->upload_stream);
@@ -775,6 +797,8 @@ void mosaic_ctx_destroy(mosaic_ctx* c) {
     cudaStreamDestroy(c->render_stream);
   }
   if (c->ev_render_done) cudaEventDestroy(c->ev_render_done);
+  if (c->ev_mat_lab) cudaEventDestroy(c->ev_mat_lab);
+  if (c->ev_sim_done) cudaEventDestroy(c->ev_sim_done);
   if (c->ev_chain_go) cudaEventDestroy(c->ev_chain_go);
   if (c->ev_chain_done) cudaEventDestroy(c->ev_chain_done);
   if (c->ev_main_idle) cudaEventDestroy(c->ev_main_idle);
@@ -809,9 +833,15 @@ int mosaic_ctx_sync(mosaic_ctx* c) {
 
 int mosaic_stage_ms(mosaic_ctx* c, int stage, float* ms_out) {
   if (!c || !ms_out || stage < 0 || stage >= MOSAIC_STAGE_COUNT) return MOSAIC_ERR_INVALID;
-  if (!c->ev_valid[stage]) return fail(c, MOSAIC_ERR_STATE, "stage has not run");
-  MOSAIC_CUDA(c, cudaEventSynchronize(c->ev_end[stage]));
-  MOSAIC_CUDA(c, cudaEventElapsedTime(ms_out, c->ev_begin[stage], c->ev_end[stage]));
+  if (c->ev_count[stage] == 0) return fail(c, MOSAIC_ERR_STATE, "stage has not run");
+  float total = 0.0f;
+  for (int i = 0; i < c->ev_count[stage]; ++i) {
+    float ms = 0.0f;
+    MOSAIC_CUDA(c, cudaEventSynchronize(c->ev_end[stage][i]));
+    MOSAIC_CUDA(c, cudaEventElapsedTime(&ms, c->ev_begin[stage][i], c->ev_end[stage][i]));
+    total += ms;
+  }
+  *ms_out = total;
   return MOSAIC_OK;
 }
 
@@ -1055,6 +1085,7 @@ int mosaic_set_cell_lab(mosaic_ctx* c, const float* lab, int grid_w, int grid_h)
 int mosaic_material_lab(mosaic_ctx* c, float* lab_out) {
   if (!c) return MOSAIC_ERR_INVALID;
   MOSAIC_CUDA(c, cudaSetDevice(c->device));
+  begin_call(c);
   MOSAIC_TRY(run_material_lab(c));
   MOSAIC_TRY(d2h(c, lab_out, c->d_mat_lab, sizeof(float) * 3 * (size_t)c->n));
   return sync(c);
@@ -1063,6 +1094,7 @@ int mosaic_material_lab(mosaic_ctx* c, float* lab_out) {
 int mosaic_cell_lab(mosaic_ctx* c, float* lab_out) {
   if (!c) return MOSAIC_ERR_INVALID;
   MOSAIC_CUDA(c, cudaSetDevice(c->device));
+  begin_call(c);
   MOSAIC_TRY(run_cell_lab(c));
   MOSAIC_TRY(d2h(c, lab_out, c->d_cell_lab, sizeof(float) * 3 * cells_of(c)));
   return sync(c);
@@ -1071,6 +1103,7 @@ int mosaic_cell_lab(mosaic_ctx* c, float* lab_out) {
 int mosaic_similarity_tri(mosaic_ctx* c, float* sim_out) {
   if (!c) return MOSAIC_ERR_INVALID;
   MOSAIC_CUDA(c, cudaSetDevice(c->device));
+  begin_call(c);
   MOSAIC_TRY(run_similarity(c, /*gather=*/true));
   const uint64_t n = (uint64_t)c->n;
   MOSAIC_TRY(d2h(c, sim_out, c->d_sim, sizeof(float) * (size_t)(n > 1 ? n * (n - 1) / 2 : 0)));
@@ -1080,6 +1113,7 @@ int mosaic_similarity_tri(mosaic_ctx* c, float* sim_out) {
 int mosaic_similarity_local(mosaic_ctx* c, float* range_out) {
   if (!c) return MOSAIC_ERR_INVALID;
   MOSAIC_CUDA(c, cudaSetDevice(c->device));
+  begin_call(c);
   MOSAIC_TRY(run_similarity(c, /*gather=*/false));
   uint64_t b, e;
   shard_tri(c, c->rank, &b, &e);
@@ -1090,6 +1124,7 @@ int mosaic_similarity_local(mosaic_ctx* c, float* range_out) {
 int mosaic_candidates(mosaic_ctx* c, int k, uint32_t* idx_out, float* d2_out) {
   if (!c) return MOSAIC_ERR_INVALID;
   MOSAIC_CUDA(c, cudaSetDevice(c->device));
+  begin_call(c);
   MOSAIC_TRY(run_candidates(c, k));
   MOSAIC_TRY(d2h(c, idx_out, c->d_cand_idx, sizeof(uint32_t) * cells_of(c) * c->k));
   MOSAIC_TRY(d2h(c, d2_out, c->d_cand_d2, sizeof(float) * cells_of(c) * c->k));
@@ -1099,6 +1134,7 @@ int mosaic_candidates(mosaic_ctx* c, int k, uint32_t* idx_out, float* d2_out) {
 int mosaic_place(mosaic_ctx* c, int max_usage, float adjacency_weight, int32_t* placed_out, uint32_t* n_fallbacks) {
   if (!c) return MOSAIC_ERR_INVALID;
   MOSAIC_CUDA(c, cudaSetDevice(c->device));
+  begin_call(c);
   MOSAIC_TRY(run_place(c, max_usage, adjacency_weight));
   MOSAIC_TRY(d2h(c, placed_out, c->d_placed, sizeof(int32_t) * cells_of(c)));
   MOSAIC_TRY(d2h(c, n_fallbacks, c->d_place_info, sizeof(uint32_t)));
@@ -1141,6 +1177,7 @@ int mosaic_anneal(mosaic_ctx* c, uint64_t iterations, float t0, float decay, uin
                   mosaic_opt_result* res) {
   if (!c) return MOSAIC_ERR_INVALID;
   MOSAIC_CUDA(c, cudaSetDevice(c->device));
+  begin_call(c);
   MOSAIC_TRY(run_anneal(c, iterations, t0, decay, seed));
   MOSAIC_TRY(d2h(c, placed_out, c->d_placed, sizeof(int32_t) * cells_of(c)));
   MOSAIC_TRY(d2h(c, res, c->d_opt_res, sizeof(mosaic_opt_result)));
@@ -1150,6 +1187,7 @@ int mosaic_anneal(mosaic_ctx* c, uint64_t iterations, float t0, float decay, uin
 int mosaic_render(mosaic_ctx* c, float color_strength, uint8_t* out_rgb) {
   if (!c) return MOSAIC_ERR_INVALID;
   MOSAIC_CUDA(c, cudaSetDevice(c->device));
+  begin_call(c);
   MOSAIC_TRY(run_render(c, color_strength, out_rgb));
   return sync(c);
 }
@@ -1161,9 +1199,10 @@ int mosaic_generate(mosaic_ctx* c, const mosaic_params* p, int32_t* placed_out, 
   MOSAIC_TRY(require(c, c->have_materials, "materials"));
   MOSAIC_TRY(require(c, c->have_target, "target"));
   const bool anneal = p->enable_optimization && p->adjacency_weight > 0.0f;  // main.rs:608
+  begin_call(c);
   trace_point(c, "begin");
   const auto host_t0 = std::chrono::steady_clock::now();
-  bool peer = false, under_chain = false;
+  bool peer = false, under_chain = false, sim_aside = false;
   if (c->world > 1) {  // sharded: buffers every rank exchanges through are allocated (whole-problem sizes) and mapped
     MOSAIC_TRY(ensure_mat_lab_buffers(c, c->n));
     MOSAIC_TRY(ensure_cell_buffers(c));
@@ -1178,13 +1217,33 @@ int mosaic_generate(mosaic_ctx* c, const mosaic_params* p, int32_t* placed_out, 
   } else {
   // main.rs:105-164 (MosaicGenerator::new) ...
   MOSAIC_TRY(run_material_lab(c));
-  if (p->build_similarity) MOSAIC_TRY(run_similarity(c, /*gather=*/false));
   // ... main.rs:477-685 (generate_mosaic)
-  if (c->tgt_upload_pending && c->world == 1 && c->tgt_bands > 1 && place_chain_eligible(c, p->max_usage)) {
-    // matching + placement under the upload; with a host destination the finished rows are rendered and sent down
-    // under the chain too
-    under_chain = out_rgb != nullptr && place_chain_has_progress(c);
+  static const int sched = getenv("MOSAIC_SCHED") ? atoi(getenv("MOSAIC_SCHED")) : 0;  // experiment knob (bit 0: resident inputs are not banded, bit 1: no render under the chain)
+  const bool banded = c->world == 1 && place_chain_eligible(c, p->max_usage) && (c->tgt_upload_pending ? c->tgt_bands > 1 : !(sched & 1));
+  if (p->build_similarity && !banded) MOSAIC_TRY(run_similarity(c, /*gather=*/false));
+  if (banded) {
+    // The serial placement chain (one CTA) is the longest kernel of the step: everything else runs around it.  Rows
+    // are matched band by band — bands of an upload in flight, or plain bands of rows with resident inputs — the chain
+    // starts behind the first band and consumes the records as they appear; finished rows are rendered (and sent to the
+    // host, if a destination is given) under the chain as well.
+    under_chain = place_chain_has_progress(c) && !(sched & 2);
+    const bool uploading = c->tgt_upload_pending;
+    MOSAIC_CUDA(c, cudaEventRecord(c->ev_mat_lab, c->stream));
     MOSAIC_TRY(run_match_place_banded(c, kMaxK, p->max_usage, p->adjacency_weight, under_chain));
+    if (p->build_similarity) {
+      // Nothing on the placement path reads the matrix (K2b / K5 recompute their entries from the Lab means): it is
+      // built on the render stream, which is idle until the chain has finished the first band of rows — under the
+      // target's upload when there is one, else behind the first band's records (beside them it would only delay
+      // the start of the chain).
+      MOSAIC_CUDA(c, cudaStreamWaitEvent(c->render_stream, uploading ? c->ev_mat_lab : c->ev_chain_go, 0));
+      cudaStream_t caller = c->stream;
+      c->stream = c->render_stream;
+      int rc = run_similarity(c, /*gather=*/false);
+      c->stream = caller;
+      MOSAIC_TRY(rc);
+      MOSAIC_CUDA(c, cudaEventRecord(c->ev_sim_done, c->render_stream));
+      sim_aside = true;
+    }
     if (under_chain) MOSAIC_TRY(run_render_under_chain(c, p->color_strength, out_rgb));
   } else {
     if (!(c->tgt_upload_pending && c->world == 1)) MOSAIC_TRY(run_cell_lab(c));  // (else: band by band inside run_candidates)
@@ -1197,26 +1256,44 @@ int mosaic_generate(mosaic_ctx* c, const mosaic_params* p, int32_t* placed_out, 
     // caller's buffer is page-locked, hence visible to the device — into the caller's image, after the bulk copies.
     trace_point(c, "chain_done");
     if (anneal) {
-      MOSAIC_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_render_done, 0));  // the early render reads the greedy grid
       uint8_t* host_dev = nullptr;
       cudaPointerAttributes attr;
-      if (cudaPointerGetAttributes(&attr, out_rgb) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer)
+      if (out_rgb && cudaPointerGetAttributes(&attr, out_rgb) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer)
         host_dev = reinterpret_cast<uint8_t*>(attr.devicePointer);
       (void)cudaGetLastError();
-      const bool patch = host_dev != nullptr && render_patch_possible(c);
+      const bool patch = (out_rgb == nullptr || host_dev != nullptr) && render_patch_possible(c);
       if (patch) {
+        // The last rows of the greedy image are still being drawn from the placement grid: annealing works on a copy
+        // (the context's grid pointer is redirected for its kernels and for the patch pass), so it starts right behind
+        // the chain; the annealed grid is copied back once the early render has finished.
+        struct GridRedirect {
+          mosaic_ctx* c;
+          int32_t* home;
+          ~GridRedirect() { c->d_placed = home; }
+        } redirect{c, c->d_placed};
         MOSAIC_TRY(ensure(c, &c->d_placed_greedy, &c->placed_greedy_cap, cells_of(c)));
         MOSAIC_CUDA(c, cudaMemcpyAsync(c->d_placed_greedy, c->d_placed, sizeof(int32_t) * cells_of(c), cudaMemcpyDeviceToDevice, c->stream));
-      }
-      trace_point(c, "anneal_starts");
-      MOSAIC_TRY(run_anneal(c, p->optimization_iterations, 100.0f, 0.99995f, p->seed));  // optimizer.rs:18-27
-      trace_point(c, "annealed");
-      MOSAIC_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_copy_done, 0));  // nothing may overwrite a patched tile afterwards
-      if (patch)
-        MOSAIC_TRY(launch_render_patch(c, c->d_placed_greedy, host_dev));
-      else
+        c->d_placed = c->d_placed_greedy;
+        trace_point(c, "anneal_starts");
+        MOSAIC_TRY(run_anneal(c, p->optimization_iterations, 100.0f, 0.99995f, p->seed));  // optimizer.rs:18-27
+        trace_point(c, "annealed");
+        MOSAIC_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_render_done, 0));
+        MOSAIC_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_copy_done, 0));  // nothing may overwrite a patched tile afterwards
+        {
+          StageTimer t(c, MOSAIC_STAGE_RENDER);
+          MOSAIC_TRY(launch_render_patch(c, redirect.home, host_dev));  // cells whose material differs from the greedy grid's
+        }
+        MOSAIC_CUDA(c, cudaMemcpyAsync(redirect.home, c->d_placed_greedy, sizeof(int32_t) * cells_of(c), cudaMemcpyDeviceToDevice, c->stream));
+      } else {
+        MOSAIC_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_render_done, 0));  // the early render reads the greedy grid
+        trace_point(c, "anneal_starts");
+        MOSAIC_TRY(run_anneal(c, p->optimization_iterations, 100.0f, 0.99995f, p->seed));  // optimizer.rs:18-27
+        trace_point(c, "annealed");
+        MOSAIC_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_copy_done, 0));
         MOSAIC_TRY(run_render(c, p->color_strength, out_rgb));  // pageable destination / per-cell render path: once more, whole
+      }
     } else {
+      MOSAIC_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_render_done, 0));
       MOSAIC_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_copy_done, 0));
     }
     MOSAIC_TRY(d2h(c, placed_out, c->d_placed, sizeof(int32_t) * cells_of(c)));
@@ -1236,6 +1313,7 @@ int mosaic_generate(mosaic_ctx* c, const mosaic_params* p, int32_t* placed_out, 
     MOSAIC_TRY(dist_peer_barrier(c, c->stream));
     c->peer_render_ready = false;  // (a later stand-alone mosaic_render has no hand-off protecting the peers' slices)
   }
+  if (sim_aside) MOSAIC_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_sim_done, 0));
   if (report) {
     std::memset(report, 0, sizeof *report);
     MOSAIC_TRY(d2h(c, &report->n_fallbacks, c->d_place_info, sizeof(uint32_t)));

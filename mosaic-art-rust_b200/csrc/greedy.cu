@@ -399,6 +399,7 @@ __global__ void __launch_bounds__(64, 1)
       if (lane == 0)
         for (; next_batch < min(CH_NBATCH, nbatches); ++next_batch) issue_batch(next_batch);
     }
+    int next_pub = gw;
     while (base < cells) {
       const int cell = base + lane;
       const int s = cell % CH_DEPTH;
@@ -427,9 +428,12 @@ __global__ void __launch_bounds__(64, 1)
       base += cnt;
       if (lane == 0) {
         decided[0] = (uint32_t)base;
-        if (GATED && progress) {  // the placements of the cells before `base` are in HBM
+        if (GATED && progress && (base >= next_pub || base >= cells)) {  // the placements of the cells before `base` are in HBM
+          // (once per grid row: the fence is a round trip to L2 in the loop that also refills the ring, and whoever
+          // renders under the chain waits for whole rows anyway)
           __threadfence();
           *progress = (unsigned)base;
+          next_pub = (base / gw + 1) * gw;
         }
         // ring batches whose 8 cells are all older than the guard window are free: fetch their successors
         if (GATED) {

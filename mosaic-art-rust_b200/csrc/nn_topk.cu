@@ -255,6 +255,9 @@ int launch_topk_range(mosaic_ctx* ctx, int k, int cell_begin, int cell_end) {
   // rounds per warp: as many as keep at least two CTAs per SM in flight (a sharded context has fewer cells per GPU)
   int rounds = TK_MAX_ROUNDS;
   while (rounds > 1 && (cells + TK_WARPS * TK_Q * rounds - 1) / (TK_WARPS * TK_Q * rounds) < 2 * ctx->sm_count) rounds >>= 1;
+  // A band that only has to stay ahead of the serial placement chain (api.cu) wants the least WORK, not the least
+  // latency: every group after a warp's first starts from its predecessor's answer (a third of the selection work).
+  if (ctx->topk_force_rounds > 0) rounds = ctx->topk_force_rounds;
   const int per_cta = TK_WARPS * TK_Q * rounds;
   const int blocks = (cells + per_cta - 1) / per_cta;
   {
