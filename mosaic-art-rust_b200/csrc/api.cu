@@ -1369,7 +1369,7 @@ int mosaic_debug_chain_profile(mosaic_ctx* c, int enable, uint64_t counters[16])
 }
 
 int mosaic_debug_set_chain(mosaic_ctx* c, int version) {
-  if (!c || version < 0 || version > 2) return MOSAIC_ERR_INVALID;
+  if (!c || version < 0 || version > 3) return MOSAIC_ERR_INVALID;
   c->chain_version = version;
   c->have_placed = false;
   return MOSAIC_OK;

@@ -17,6 +17,7 @@
 // State-independent data (candidate ids, d2, candidate Lab) of the NEXT cells is prefetched into
 // registers while the current cell is resolved.
 #include "common.cuh"
+#include "place_records.cuh"
 
 namespace mosaic {
 
@@ -210,19 +211,8 @@ constexpr int CH_NBATCH = CH_DEPTH / CH_BATCH;
 constexpr int CH_SHADOW = 4;   // hot slots 64..67 mirror slots 0..3: a hot block reads five consecutive slots
 constexpr int CH_GUARD = 3;    // slots of the last decided cells stay intact (the exact path re-reads them)
 constexpr int CH_MIN_GW = 33;  // the committer handles up to 32 consecutive cells at once: one per column
-constexpr uint32_t CH_IDMASK = 0x03FFFFFFu;
 
-struct __align__(16) HRec {  // what every cell needs
-  uint2 wm[32];  // .x = lane << 26 | material id (the dummy id `n`, usage pinned at the cap, for lanes >= k)
-                 // .y = threat window mask
-};
-struct __align__(16) XRec {  // what only contended cells need
-  float d2[32], l[32], a[32], b[32];
-  float d2_32;          // d2 of candidate 32 (+inf if k <= 32)
-  uint32_t win32;       // window mask of candidate 32 (lane 0 of HRec carries all ones in the first column)
-  uint32_t pad[2];
-};
-static_assert(sizeof(HRec) == 256 && sizeof(XRec) == 528, "record layout");
+
 
 __global__ void __launch_bounds__(256) place_prep_kernel(const uint32_t* __restrict__ cand_idx,
                                                          const float* __restrict__ cand_d2, int k,
@@ -865,24 +855,33 @@ static int ensure_place_records(mosaic_ctx* ctx) {
   return ensure(ctx, &ctx->d_place_rec, &ctx->place_rec_cap, (size_t)cells * (sizeof(HRec) + sizeof(XRec) + 3 * kKPad * sizeof(float)));
 }
 
-// ---- which chain: the windowed one (greedy_window.cu) unless MOSAIC_CHAIN=v1 asks for the first generation (A/B runs)
+// ---- which chain ------------------------------------------------------------------------------------------------------
+//   1  first generation (this file): one consumer warp behind a TMA ring, 108 ns per cell on the 24,000-tile mosaic
+//   2  windowed (greedy_window.cu): lane = cell scans + shortlists, 200 ns per cell — a measured experiment
+//      (profiles/r02_chain_window_experiment.json)
+//   3  wave (greedy_wave.cu): a window of 32 cells iterated to its fixed point, one warp per cell
+// mosaic_debug_set_chain(ctx, v) or MOSAIC_CHAIN=v1|window|wave in the environment select one (all parity-tested);
+// configurations a chain does not cover fall back to the first generation / the generic kernel.
 bool window_chain_eligible(const mosaic_ctx* ctx, int max_usage);
 int launch_window_prep_range(mosaic_ctx* ctx, float weight, int cell_begin, int cell_end);
 int launch_window_chain(mosaic_ctx* ctx, int max_usage, float weight, cudaStream_t stream, const unsigned* ready, bool prof);
 int read_window_profile(mosaic_ctx* ctx, unsigned long long* out16);
-// The first-generation chain (this file) is the default: on the 24,000-tile mosaic it places a cell in 108 ns, the
-// windowed one in 200 ns (profiles/r02_chain_window_experiment.json; DESIGN.md has the anatomy).  MOSAIC_CHAIN=window
-// in the environment or mosaic_debug_set_chain(ctx, 2) selects the windowed chain (parity-tested like the default).
-static bool env_window_chain() {
-  static int v = -1;
-  if (v < 0) {
+bool wave_chain_eligible(const mosaic_ctx* ctx, int max_usage);
+int launch_wave_chain(mosaic_ctx* ctx, int max_usage, float weight, cudaStream_t stream, const unsigned* ready, unsigned* progress,
+                      bool prof);
+int read_wave_profile(mosaic_ctx* ctx, unsigned long long* out16);
+constexpr int kDefaultChain = 1;
+static int chain_choice(const mosaic_ctx* ctx) {
+  static int env = -1;
+  if (env < 0) {
     const char* e = getenv("MOSAIC_CHAIN");
-    v = (e && e[0] == 'w') ? 1 : 0;
+    env = !e ? kDefaultChain : (e[0] == 'w' && e[1] == 'a') ? 3 : (e[0] == 'w') ? 2 : (e[0] == 'v') ? 1 : kDefaultChain;
   }
-  return v == 1;
+  return ctx->chain_version ? ctx->chain_version : env;
 }
-static bool use_v1_chain(const mosaic_ctx* ctx) { return !(ctx->chain_version == 2 || (ctx->chain_version == 0 && env_window_chain())); }
-static bool use_window(const mosaic_ctx* ctx, int max_usage) { return !use_v1_chain(ctx) && window_chain_eligible(ctx, max_usage); }
+static bool use_v1_chain(const mosaic_ctx* ctx) { return chain_choice(ctx) != 2; }  // (the wave chain reads the first generation's records)
+static bool use_window(const mosaic_ctx* ctx, int max_usage) { return chain_choice(ctx) == 2 && window_chain_eligible(ctx, max_usage); }
+static bool use_wave(const mosaic_ctx* ctx, int max_usage) { return chain_choice(ctx) == 3 && wave_chain_eligible(ctx, max_usage); }
 
 // candidate records of cells [cell_begin, cell_end) (needs the candidate lists of those cells and of the row above)
 int launch_place_prep_range(mosaic_ctx* ctx, float weight, int cell_begin, int cell_end) {
@@ -916,6 +915,7 @@ bool place_chain_has_progress(const mosaic_ctx* ctx) { return use_v1_chain(ctx);
 
 bool place_chain_eligible(const mosaic_ctx* ctx, int max_usage) {
   if (!use_v1_chain(ctx)) return window_chain_eligible(ctx, max_usage) && !ctx->profile_chain;
+  if (use_wave(ctx, max_usage)) return !ctx->profile_chain;
   return chain_smem(ctx, max_usage < 0 ? 0u : (unsigned)max_usage) != 0 && !ctx->profile_chain;
 }
 
@@ -926,6 +926,12 @@ int launch_place_chain_async(mosaic_ctx* ctx, int max_usage, float weight, cudaS
     return launch_window_chain(ctx, max_usage, weight, stream, ready, false);
   }
   const unsigned cap = max_usage < 0 ? 0u : (unsigned)max_usage;
+  if (use_wave(ctx, max_usage)) {
+    MOSAIC_TRY(ensure_place_records(ctx));
+    MOSAIC_TRY(launch_wave_chain(ctx, max_usage, weight, stream, ready, progress, false));
+    ctx->launches++;
+    return MOSAIC_OK;
+  }
   const size_t smem = chain_smem(ctx, cap);
   if (!smem) return fail(ctx, MOSAIC_ERR_STATE, "placement: the chain kernel does not cover this configuration");
   MOSAIC_TRY(ensure_place_records(ctx));
@@ -947,6 +953,7 @@ static int launch_chain(mosaic_ctx* ctx, unsigned cap, float weight, size_t smem
 
 int read_chain_profile(mosaic_ctx* ctx, unsigned long long* out16) {
   if (!use_v1_chain(ctx)) return read_window_profile(ctx, out16);
+  if (chain_choice(ctx) == 3) return read_wave_profile(ctx, out16);
   MOSAIC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   MOSAIC_CUDA(ctx, cudaMemcpyFromSymbol(out16, g_chain_prof, sizeof(unsigned long long) * 16));
   return MOSAIC_OK;
@@ -963,7 +970,10 @@ int launch_place(mosaic_ctx* ctx, int max_usage, float weight) {
     MOSAIC_TRY(launch_window_prep_range(ctx, weight, 0, gw * gh));
     return launch_window_chain(ctx, max_usage, weight, ctx->stream, nullptr, ctx->profile_chain);
   }
-  if (use_v1_chain(ctx) && fast_smem) {
+  if (use_wave(ctx, max_usage)) {
+    MOSAIC_TRY(launch_place_prep_range(ctx, weight, 0, gw * gh));
+    MOSAIC_TRY(launch_wave_chain(ctx, max_usage, weight, ctx->stream, nullptr, nullptr, ctx->profile_chain));
+  } else if (use_v1_chain(ctx) && fast_smem) {
     if (cap <= 255u)
       MOSAIC_TRY(launch_chain<uint8_t>(ctx, cap, weight, fast_smem));
     else

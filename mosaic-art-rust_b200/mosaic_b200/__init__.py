@@ -461,7 +461,7 @@ class Context:
         return int(m[0]), int(m[1])
 
     def set_chain(self, version):
-        """0 = default placement chain, 1 = greedy.cu, 2 = the windowed chain of greedy_window.cu."""
+        """0 = default placement chain, 1 = greedy.cu, 2 = the windowed chain of greedy_window.cu, 3 = the wave chain of greedy_wave.cu."""
         self._check(self._L.mosaic_debug_set_chain(self._h, int(version)))
         self._chain = int(version)
 
@@ -469,9 +469,13 @@ class Context:
         """Enable/disable the instrumented placement kernel and return the counters of its last launch."""
         m = (C.c_uint64 * 16)()
         self._check(self._L.mosaic_debug_chain_profile(self._h, 1 if enable else 0, m))
-        window = getattr(self, "_chain", 0) == 2 or (getattr(self, "_chain", 0) == 0 and
-                                                      os.environ.get("MOSAIC_CHAIN", "").startswith("w"))
-        if not window:  # first-generation chain kernel
+        env = os.environ.get("MOSAIC_CHAIN", "")
+        chain = getattr(self, "_chain", 0) or (3 if env.startswith("wa") else 2 if env.startswith("w") else 1)
+        window = chain == 2
+        if chain == 3:  # wave chain: [0..5] from thread 0, [8..11] summed over the other warps
+            keys = ("sweeps", "n_serial_w0", "n_exact_w0", "cyc_phase1_w0", "cyc_barrier_a_w0", "cyc_phase2_w0", "n_eval_w0",
+                    "cyc_barrier_b_w0", "n_eval", "n_exact", "n_serial", "cyc_phase1_others", "cyc_total", "cyc_phase2_others")
+        elif not window:  # first-generation chain kernel
             keys = ("cyc_fast", "cyc_exact", "cyc_generic", "cyc_fallback", "n_fast", "n_exact", "n_generic",
                     "n_fallback", "cyc_wait_producer", "cyc_wait_committer", "cyc_total")
         else:  # windowed chain: cycle counters are summed over its two warps

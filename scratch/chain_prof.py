@@ -12,6 +12,7 @@ for name in (sys.argv[1:] or ["C1", "C2", "C3"]):
     with mosaic_b200.Context(0) as ctx:
         ctx.set_materials(mats); ctx.set_target(tgt, cfg["grid_w"], cfg["grid_h"])
         ctx.candidates(fetch=False)
+        if os.environ.get('CHAIN_V'): ctx.set_chain(int(os.environ['CHAIN_V']))
         ctx.chain_profile(True)
         for _ in range(3):
             placed, nfb = ctx.place(cfg["max_usage"], cfg["adjacency_weight"])
