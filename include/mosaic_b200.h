@@ -157,6 +157,12 @@ int mosaic_set_placement(mosaic_ctx* ctx, const int32_t* placed);
 int mosaic_anneal(mosaic_ctx* ctx, uint64_t iterations, float t0, float decay, uint64_t seed,
                   int32_t* placed_out, mosaic_opt_result* res);
 
+/* MosaicOptimizer::optimize_greedy (optimizer.rs:132-198): the same random swaps, accepted only when the cost drops
+ * (delta < 0.0); no temperature, no acceptance sample — four position draws per iteration.  best_cost = final_cost and
+ * improved_count = accepted_count = the swaps performed, as the reference reports them. */
+int mosaic_optimize_greedy(mosaic_ctx* ctx, uint64_t max_iterations, uint64_t seed, int32_t* placed_out,
+                           mosaic_opt_result* res);
+
 /* ---- B6: render (resize + colour adjustment + composite; main.rs:547-592, 625-664, 687-738;
  *          color_adjustment.rs:40-154) ---------------------------------------------------------- */
 /* out_rgb: (grid_h*tile_h) x (grid_w*tile_w) x 3 bytes, or NULL (image stays on the device). */
@@ -207,6 +213,27 @@ int64_t mosaic_simdb_index_of(const mosaic_simdb* db, const char* path); /* path
 int mosaic_simdb_copy(const mosaic_simdb* db, float* lab_out, float* sim_out); /* either may be NULL */
 /* SimilarityDatabase::get_similarity (similarity.rs:85-103); MOSAIC_ERR_STATE where the reference returns None */
 int mosaic_simdb_get_similarity(const mosaic_simdb* db, const char* path1, const char* path2, float* out);
+
+/* ---- progress surface -------------------------------------------------- */
+/* The GUI's `(f32, String)` progress channel (src/gui/app_full.rs:1597-1616) and the CLI's progress lines
+ * (src/main.rs:521-527, 603-606) are fed from stage events of the DEVICE: while a callback is installed,
+ * mosaic_generate enqueues a host function behind every stage, and it reports as the device passes them —
+ * fractions as in app_full.rs:1716-2193 (0.40 tiles loaded, 0.45 similarity database, 0.50-0.90 grid rows as the
+ * placement chain commits them, 0.92 / 0.98 optimisation, 0.99 image ready; loading and saving are the host's 0.05
+ * and 1.0).  `stage` is the MOSAIC_STAGE_* the event belongs to.  The callback runs on a thread of the CUDA runtime
+ * and must not call into this library or the CUDA API; NULL removes it (no host functions are enqueued then). */
+typedef void (*mosaic_progress_fn)(float fraction, int stage, const char* message, void* user);
+int mosaic_set_progress_callback(mosaic_ctx* ctx, mosaic_progress_fn fn, void* user);
+
+/* ---- host-side codec (no device work) ------------------------------ */
+/* image::open(path)?.to_rgb8() for a PNG file (src/main.rs:263-301, 484, 548, 632): every colour type and bit depth,
+ * Adam7; alpha dropped, grey replicated, 16-bit samples -> (v + 128) / 257.  *rgb_out is malloc'ed
+ * (width * height * 3 bytes): release it with mosaic_host_free. */
+int mosaic_png_decode_rgb8(const char* file, uint8_t** rgb_out, int* width, int* height);
+/* RgbImage::save(path) for a ".png" path (src/main.rs:668-672): 8-bit RGB, lossless (the file bytes are this
+ * writer's own choice of filters and deflate level; the pixels are the contract). */
+int mosaic_png_encode_rgb8(const char* file, const uint8_t* rgb, int width, int height);
+void mosaic_host_free(void* p);
 
 /* ---- self test ------------------------------------------------------------------------------ */
 /* Checks the branch-free IEEE sqrt / reciprocal sequences used on the serial chains against the

@@ -8,7 +8,7 @@
 //                                                           get_lab_color, save_to_file, load_from_file, load_or_new
 //   AdjacencyPenaltyCalculator   src/adjacency.rs:49-130    new(db, weight), calculate_total_cost(grid)
 //   OptimizationConfig/Result,
-//   MosaicOptimizer              src/optimizer.rs:7-129,203-220   new(calculator, config), optimize(grid)
+//   MosaicOptimizer              src/optimizer.rs:7-220           new(calculator, config), optimize(grid), optimize_greedy(grid, n)
 //   MosaicGeneratorImpl          src/lib.rs:91-119          calculate_average_lab(image)
 //   MosaicGenerator              src/main.rs:92-685         new(...), generate_mosaic(...)  (the CLI's private struct,
 //                                                           minus directory scan and codecs: images come in memory)
@@ -319,6 +319,25 @@ class MosaicOptimizer {
     return optimize(detail::scratch_context(), grid);
   }
   OptimizationResult optimize(Context& ctx, PathGrid& grid) const {  // optimizer.rs:41-129
+    return run(ctx, grid, [&](int32_t* out, mosaic_opt_result* r) {
+      return mosaic_anneal(ctx.get(), config_.max_iterations, config_.initial_temperature, config_.temperature_decay, config_.seed,
+                           out, r);
+    });
+  }
+  // optimizer.rs:132-198: only improvements are accepted (the seed is the config's, an extension like optimize's)
+  OptimizationResult optimize_greedy(PathGrid& grid, size_t max_iterations) const {
+    if (grid.empty() || grid[0].empty()) return OptimizationResult();  // optimizer.rs:138-141
+    return optimize_greedy(detail::scratch_context(), grid, max_iterations);
+  }
+  OptimizationResult optimize_greedy(Context& ctx, PathGrid& grid, size_t max_iterations) const {
+    return run(ctx, grid, [&](int32_t* out, mosaic_opt_result* r) {
+      return mosaic_optimize_greedy(ctx.get(), max_iterations, config_.seed, out, r);
+    });
+  }
+
+ private:
+  template <typename Call>
+  OptimizationResult run(Context& ctx, PathGrid& grid, Call call) const {
     int gw, gh;
     std::vector<std::string> unknown;
     const std::vector<int32_t> ids = detail::grid_ids(calc_.database(), grid, &gw, &gh, &unknown);
@@ -326,8 +345,7 @@ class MosaicOptimizer {
     calc_.load(ctx, ids, gw, gh, unknown.size());
     std::vector<int32_t> out(ids.size());
     mosaic_opt_result r{};
-    ctx.check(mosaic_anneal(ctx.get(), config_.max_iterations, config_.initial_temperature, config_.temperature_decay,
-                            config_.seed, out.data(), &r));
+    ctx.check(call(out.data(), &r));
     // the kernel swaps material indices; cells whose path the database does not know carry pseudo indices behind the
     // database's (occupied cells without similarity terms, as in the reference)
     std::vector<std::string> path_of(calc_.database().len() + unknown.size());
@@ -350,7 +368,6 @@ class MosaicOptimizer {
     return res;
   }
 
- private:
   const AdjacencyPenaltyCalculator& calc_;
   OptimizationConfig config_;
 };

@@ -1,4 +1,5 @@
-//! FFI of include/mosaic_b200.h and a safe wrapper: `mod b200;` in the reference's lib.rs / main.rs.
+//! FFI of include/mosaic_b200.h and a safe wrapper: `mod b200;` in the reference's lib.rs / main.rs (and `mod lib_compat;`
+//! beside it for the `lib.rs`-compatible forwarding bodies: Tile / MosaicGenerator / similarity / adjacency / optimizer).
 //! UNVERIFIED SOURCE: there is no rustc/cargo in the image this repository was developed in.  The same sequence of
 //! calls is compiled and tested in C++ (include/mosaic_b200.hpp, tests/cpp/test_host_mirror.cpp).
 //!
@@ -100,6 +101,10 @@ impl Ctx {
             return Err(anyhow!("mosaic_b200 ({rc}): {}", last_error(std::ptr::null())));
         }
         Ok(Ctx(p))
+    }
+    /// the raw handle, for the forwarding bodies of `lib_compat.rs`
+    pub(crate) fn raw(&self) -> *mut mosaic_ctx {
+        self.0
     }
     fn check(&self, rc: c_int) -> Result<()> {
         if rc == 0 {

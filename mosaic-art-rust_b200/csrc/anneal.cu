@@ -239,7 +239,8 @@ template <typename GridT, bool GRID_SMEM, bool LAB_SMEM>
 __global__ void __launch_bounds__(256, 1)
     anneal_kernel(const float4* __restrict__ lab4, int n, int32_t* grid_gmem, const float* __restrict__ terms, int gw,
                   int gh, unsigned long long iterations, float t0, float decay, unsigned long long seed,
-                  mosaic_opt_result* res, float* __restrict__ deltas /* one slot per iteration, or NULL */) {
+                  mosaic_opt_result* res, float* __restrict__ deltas /* one slot per iteration, or NULL */,
+                  bool greedy /* optimize_greedy (optimizer.rs:132-198): only improvements, no acceptance sample */) {
   __shared__ float s_initial;
   __shared__ volatile int s_initial_ready;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -496,8 +497,9 @@ __global__ void __launch_bounds__(256, 1)
     const float u0 = __fmul_rn((float)(ring[(basepos + adv0) & (RNG_RING_WORDS - 1)] >> 8), 1.0f / 16777216.0f);
     bool und0, und1;
     bool accept0 = accept_bounds(delta0, temperature, u0, und0) && !skip0;
-    und0 = und0 && !skip0;
-    const bool nodraw0 = skip0 || delta0 < 0.0f;  // u drawn only when delta >= 0 (optimizer.rs:80-84)
+    und0 = und0 && !skip0 && !greedy;
+    accept0 = greedy ? (delta0 < 0.0f && !skip0) : accept0;   // optimizer.rs:165 (delta < 0.0 only)
+    const bool nodraw0 = greedy || skip0 || delta0 < 0.0f;  // u drawn only when delta >= 0 (optimizer.rs:80-84); never by optimize_greedy
     const float temperature1 = skip0 ? temperature : __fmul_rn(temperature, decay);  // optimizer.rs:102 (not on skips)
     const unsigned cur1 = basepos + adv0 + (nodraw0 ? 0u : 1u);
     // ---- iteration `it + 1`: the slot that sits at cur1 ----
@@ -513,7 +515,8 @@ __global__ void __launch_bounds__(256, 1)
     const bool touch01 = near(bx1, by1, ax1, ay1) || near(bx1, by1, ax2, ay2) || near(bx2, by2, ax1, ay1) || near(bx2, by2, ax2, ay2);
     const float u1 = __fmul_rn((float)(ring[(cur1 + adv1) & (RNG_RING_WORDS - 1)] >> 8), 1.0f / 16777216.0f);
     bool accept1 = accept_bounds(delta1, temperature1, u1, und1) && !skip1;
-    und1 = und1 && !skip1;
+    und1 = und1 && !skip1 && !greedy;
+    accept1 = greedy ? (delta1 < 0.0f && !skip1) : accept1;
     if (__builtin_expect(und0 || (usable1 && und1), 0)) {  // the exact exponential, in order
       if (und0) accept0 = accept_exact(delta0, temperature, u0);
       if (usable1 && !(accept0 && touch01) && und1) accept1 = accept_exact(delta1, temperature1, u1);
@@ -543,7 +546,7 @@ __global__ void __launch_bounds__(256, 1)
     accepted += (accept0 ? 1ull : 0ull) + (accept1 ? 1ull : 0ull);
     const bool decay1 = go1 && !skip1;
     temperature = decay1 ? __fmul_rn(temperature1, decay) : temperature1;
-    const bool nodraw1 = skip1 || delta1 < 0.0f;
+    const bool nodraw1 = greedy || skip1 || delta1 < 0.0f;
     rng.pos = go1 ? cur1 + adv1 + (nodraw1 ? 0u : 1u) : cur1;
     it += go1 ? 2ull : 1ull;
   }
@@ -572,6 +575,10 @@ __global__ void __launch_bounds__(256, 1)
       }
     }
   }
+  if (greedy) {  // optimizer.rs:190-197: best_cost = the final cost, both counters = the swaps performed
+    best = current;
+    improved = accepted;
+  }
   if (lane == 0) {
     res->initial_cost = initial;
     res->final_cost = current;
@@ -595,7 +602,7 @@ static int launch_anneal_variant(mosaic_ctx* ctx, size_t smem, uint64_t iteratio
   }
   anneal_kernel<GridT, GS, LS><<<1, 256, smem, ctx->stream>>>(ctx->sim_lab4(), ctx->n, ctx->d_placed, ctx->d_terms,
                                                               ctx->gw, ctx->gh, iterations, t0, decay, seed,
-                                                              (mosaic_opt_result*)ctx->d_opt_res, deltas);
+                                                              (mosaic_opt_result*)ctx->d_opt_res, deltas, ctx->anneal_greedy);
   return MOSAIC_OK;
 }
 

@@ -78,6 +78,8 @@ int allgather_slices(mosaic_ctx* c, void* buf, size_t elem_bytes, F slice_of_ran
 // every compute entry point starts a fresh set of stage intervals (mosaic_stage_ms reports the most recent call)
 void begin_call(mosaic_ctx* c) {
   for (int s = 0; s < MOSAIC_STAGE_COUNT; ++s) c->ev_count[s] = 0;
+  c->progress_events.clear();  // (every entry point synchronises before it returns: nobody reads the old events)
+  c->progress_reported = 0.0f;
 }
 
 int require(mosaic_ctx* c, bool cond, const char* what) {
@@ -529,6 +531,7 @@ int run_generate_peer(mosaic_ctx* c, const mosaic_params* p, bool anneal) {
     }
     c->have_placed = true;
     trace_point(c, "chain_done");
+    emit_progress(c, c->stream, 0.90f, MOSAIC_STAGE_PLACE, "Grid processing completed");  // app_full.rs:2098
     if (anneal) MOSAIC_TRY(launch_anneal(c, p->optimization_iterations, 100.0f, 0.99995f, p->seed));
     trace_point(c, "annealed");
     CollTimer t(c, c->stream);
@@ -650,6 +653,8 @@ int run_render_under_chain(mosaic_ctx* c, float strength, uint8_t* out_rgb) {
     if (b1 <= b0) continue;
     wait_progress_kernel<<<1, 32, 0, c->render_stream>>>(c->d_progress, (unsigned)(b1 * c->gw));
     c->launches++;
+    emit_progress(c, c->render_stream, 0.5f + 0.4f * (float)b1 / (float)c->gh, MOSAIC_STAGE_PLACE, "Processing grid: %.1f%%",
+                  100.0 * b1 / c->gh);  // app_full.rs:1810-1827
     {
       StageTimer t(c, MOSAIC_STAGE_RENDER);  // (c->stream is the render stream here)
       rc = c->ragged ? launch_render_ragged(c, strength, b0, b1) : launch_render(c, strength, b0, b1);
@@ -1184,6 +1189,19 @@ int mosaic_anneal(mosaic_ctx* c, uint64_t iterations, float t0, float decay, uin
   return sync(c);
 }
 
+int mosaic_optimize_greedy(mosaic_ctx* c, uint64_t max_iterations, uint64_t seed, int32_t* placed_out, mosaic_opt_result* res) {
+  if (!c) return MOSAIC_ERR_INVALID;
+  MOSAIC_CUDA(c, cudaSetDevice(c->device));
+  begin_call(c);
+  c->anneal_greedy = true;
+  const int rc = run_anneal(c, max_iterations, 1.0f, 1.0f, seed);  // (temperature and decay are not used)
+  c->anneal_greedy = false;
+  MOSAIC_TRY(rc);
+  MOSAIC_TRY(d2h(c, placed_out, c->d_placed, sizeof(int32_t) * cells_of(c)));
+  MOSAIC_TRY(d2h(c, res, c->d_opt_res, sizeof(mosaic_opt_result)));
+  return sync(c);
+}
+
 int mosaic_render(mosaic_ctx* c, float color_strength, uint8_t* out_rgb) {
   if (!c) return MOSAIC_ERR_INVALID;
   MOSAIC_CUDA(c, cudaSetDevice(c->device));
@@ -1217,10 +1235,15 @@ int mosaic_generate(mosaic_ctx* c, const mosaic_params* p, int32_t* placed_out, 
   } else {
   // main.rs:105-164 (MosaicGenerator::new) ...
   MOSAIC_TRY(run_material_lab(c));
+  emit_progress(c, c->stream, 0.40f, MOSAIC_STAGE_MATERIAL_LAB, "Loaded %d tiles", c->n);  // app_full.rs:1716
   // ... main.rs:477-685 (generate_mosaic)
   static const int sched = getenv("MOSAIC_SCHED") ? atoi(getenv("MOSAIC_SCHED")) : 0;  // experiment knob (bit 0: resident inputs are not banded, bit 1: no render under the chain)
   const bool banded = c->world == 1 && place_chain_eligible(c, p->max_usage) && (c->tgt_upload_pending ? c->tgt_bands > 1 : !(sched & 1));
-  if (p->build_similarity && !banded) MOSAIC_TRY(run_similarity(c, /*gather=*/false));
+  if (p->build_similarity && !banded) {
+    emit_progress(c, c->stream, 0.45f, MOSAIC_STAGE_SIMILARITY, "Building similarity database...");  // app_full.rs:1738
+    MOSAIC_TRY(run_similarity(c, /*gather=*/false));
+  }
+  emit_progress(c, c->stream, 0.50f, MOSAIC_STAGE_PLACE, "Processing grid cells...");  // app_full.rs:1794
   if (banded) {
     // The serial placement chain (one CTA) is the longest kernel of the step: everything else runs around it.  Rows
     // are matched band by band — bands of an upload in flight, or plain bands of rows with resident inputs — the chain
@@ -1236,6 +1259,7 @@ int mosaic_generate(mosaic_ctx* c, const mosaic_params* p, int32_t* placed_out, 
       // target's upload when there is one, else behind the first band's records (beside them it would only delay
       // the start of the chain).
       MOSAIC_CUDA(c, cudaStreamWaitEvent(c->render_stream, uploading ? c->ev_mat_lab : c->ev_chain_go, 0));
+      emit_progress(c, c->render_stream, 0.45f, MOSAIC_STAGE_SIMILARITY, "Building similarity database...");  // app_full.rs:1738
       cudaStream_t caller = c->stream;
       c->stream = c->render_stream;
       int rc = run_similarity(c, /*gather=*/false);
@@ -1255,6 +1279,7 @@ int mosaic_generate(mosaic_ctx* c, const mosaic_params* p, int32_t* placed_out, 
     // per accepted swap) are composed again from the thumbnail cache, straight into the device image and — when the
     // caller's buffer is page-locked, hence visible to the device — into the caller's image, after the bulk copies.
     trace_point(c, "chain_done");
+    emit_progress(c, c->stream, 0.90f, MOSAIC_STAGE_PLACE, "Grid processing completed");  // app_full.rs:2098
     if (anneal) {
       uint8_t* host_dev = nullptr;
       cudaPointerAttributes attr;
@@ -1275,7 +1300,9 @@ int mosaic_generate(mosaic_ctx* c, const mosaic_params* p, int32_t* placed_out, 
         MOSAIC_CUDA(c, cudaMemcpyAsync(c->d_placed_greedy, c->d_placed, sizeof(int32_t) * cells_of(c), cudaMemcpyDeviceToDevice, c->stream));
         c->d_placed = c->d_placed_greedy;
         trace_point(c, "anneal_starts");
+        emit_progress(c, c->stream, 0.92f, MOSAIC_STAGE_ANNEAL, "Starting optimization phase...");  // app_full.rs:2102
         MOSAIC_TRY(run_anneal(c, p->optimization_iterations, 100.0f, 0.99995f, p->seed));  // optimizer.rs:18-27
+        emit_progress(c, c->stream, 0.98f, MOSAIC_STAGE_ANNEAL, "Optimization phase completed");  // app_full.rs:2193
         trace_point(c, "annealed");
         MOSAIC_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_render_done, 0));
         MOSAIC_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_copy_done, 0));  // nothing may overwrite a patched tile afterwards
@@ -1287,7 +1314,9 @@ int mosaic_generate(mosaic_ctx* c, const mosaic_params* p, int32_t* placed_out, 
       } else {
         MOSAIC_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_render_done, 0));  // the early render reads the greedy grid
         trace_point(c, "anneal_starts");
+        emit_progress(c, c->stream, 0.92f, MOSAIC_STAGE_ANNEAL, "Starting optimization phase...");  // app_full.rs:2102
         MOSAIC_TRY(run_anneal(c, p->optimization_iterations, 100.0f, 0.99995f, p->seed));  // optimizer.rs:18-27
+        emit_progress(c, c->stream, 0.98f, MOSAIC_STAGE_ANNEAL, "Optimization phase completed");  // app_full.rs:2193
         trace_point(c, "annealed");
         MOSAIC_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_copy_done, 0));
         MOSAIC_TRY(run_render(c, p->color_strength, out_rgb));  // pageable destination / per-cell render path: once more, whole
@@ -1299,7 +1328,12 @@ int mosaic_generate(mosaic_ctx* c, const mosaic_params* p, int32_t* placed_out, 
     MOSAIC_TRY(d2h(c, placed_out, c->d_placed, sizeof(int32_t) * cells_of(c)));
     trace_point(c, "rendered");
   } else {
-  if (anneal) MOSAIC_TRY(run_anneal(c, p->optimization_iterations, 100.0f, 0.99995f, p->seed));  // optimizer.rs:18-27
+  emit_progress(c, c->stream, 0.90f, MOSAIC_STAGE_PLACE, "Grid processing completed");  // app_full.rs:2098
+  if (anneal) {
+    emit_progress(c, c->stream, 0.92f, MOSAIC_STAGE_ANNEAL, "Starting optimization phase...");  // app_full.rs:2102
+    MOSAIC_TRY(run_anneal(c, p->optimization_iterations, 100.0f, 0.99995f, p->seed));  // optimizer.rs:18-27
+    emit_progress(c, c->stream, 0.98f, MOSAIC_STAGE_ANNEAL, "Optimization phase completed");  // app_full.rs:2193
+  }
   }
   }
   if (!under_chain) {
@@ -1320,6 +1354,7 @@ int mosaic_generate(mosaic_ctx* c, const mosaic_params* p, int32_t* placed_out, 
     if (anneal) MOSAIC_TRY(d2h(c, &report->opt, c->d_opt_res, sizeof(mosaic_opt_result)));
     report->annealed = anneal ? 1 : 0;
   }
+  emit_progress(c, c->stream, 0.99f, MOSAIC_STAGE_RENDER, "Mosaic image ready");  // (app_full.rs:2201: saving is the host's)
   trace_point(c, "end");
   const auto host_t1 = std::chrono::steady_clock::now();
   MOSAIC_TRY(sync(c));
@@ -1365,6 +1400,15 @@ int mosaic_debug_chain_profile(mosaic_ctx* c, int enable, uint64_t counters[16])
     for (int i = 0; i < 16; ++i) counters[i] = v[i];
   }
   c->profile_chain = enable != 0;
+  return MOSAIC_OK;
+}
+
+int mosaic_set_progress_callback(mosaic_ctx* c, mosaic_progress_fn fn, void* user) {
+  if (!c) return MOSAIC_ERR_INVALID;
+  MOSAIC_CUDA(c, cudaSetDevice(c->device));
+  MOSAIC_TRY(sync(c));
+  c->progress_fn = fn;
+  c->progress_user = user;
   return MOSAIC_OK;
 }
 

@@ -436,6 +436,7 @@ int launch_wave_impl(mosaic_ctx* ctx, unsigned cap, float weight, size_t smem, c
   const size_t cells = (size_t)ctx->gw * ctx->gh;
   if (GATED) smem = std::max(smem, (size_t)226 * 1024);  // other kernels run beside the chain: keep their CTAs off this SM
   auto kern = greedy_wave_kernel<UsageT, WV_WARPS, GATED, PROF>;
+  MOSAIC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<1, WV_WARPS * 32, smem, stream>>>(
       reinterpret_cast<const HRec*>(ctx->d_place_rec), reinterpret_cast<const XRec*>(ctx->d_place_rec + cells * sizeof(HRec)),
       reinterpret_cast<const float*>(ctx->d_place_rec + cells * (sizeof(HRec) + sizeof(XRec))), ctx->d_cand_idx, ctx->d_cand_d2,

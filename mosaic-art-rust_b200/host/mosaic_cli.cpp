@@ -1,8 +1,10 @@
 // mosaic-b200 — a small C++ host over the C ABI with the reference CLI's flag names (struct Args, main.rs:20-88) and
 // main()'s sequence (main.rs:741-779): target aspect -> MosaicGenerator::new -> generate_mosaic -> save.
 //
-// Out of scope here (the reference's control plane): image codecs.  Images are binary PPM
-// (P6, maxval 255); --material-src is a directory of *.ppm of any sizes (the reference decodes png/jpg/webp of any size).
+// Images are PNG (include/mosaic_png.hpp: every colour type / bit depth, as `image::open(path)?.to_rgb8()` reads them) or
+// binary PPM (P6, maxval 255), told apart by the extension, case-insensitively like main.rs:175-184; --material-src is a
+// directory of such files of any sizes; the output format follows the extension of --output (main.rs:668-672).  JPEG and
+// WebP — the other two formats the reference accepts — need codecs this image does not have.
 // The material selection follows load_tiles (main.rs:166-261): aspect
 // filter (lib.rs:121-123), no-match fallback to the first min(len, 2*max) files, truncate to --max-materials; files are
 // taken in sorted order (read_dir order is unspecified in the reference).
@@ -19,6 +21,7 @@
 #include <iostream>
 
 #include "mosaic_b200.hpp"
+#include "mosaic_png.hpp"
 
 using namespace mosaic_b200;
 
@@ -124,13 +127,47 @@ static bool write_ppm(const std::string& file, const RgbImage& img) {
   return (bool)out;
 }
 
+static std::string lower_ext(const std::string& file) {  // main.rs:177-182: extension, lower-cased
+  const size_t dot = file.find_last_of('.'), slash = file.find_last_of('/');
+  if (dot == std::string::npos || (slash != std::string::npos && dot < slash)) return "";
+  std::string e = file.substr(dot + 1);
+  for (char& c : e) c = (char)std::tolower((unsigned char)c);
+  return e;
+}
+
+// image::open(path)?.to_rgb8() (main.rs:268, 484) for the formats this host has
+static bool read_image(const std::string& file, RgbImage* img, bool header_only = false) {
+  if (lower_ext(file) != "png") return read_ppm(file, img, header_only);
+  try {
+    if (header_only) return codec::png_dimensions(file, &img->width, &img->height);
+    codec::Image d = codec::decode_png(file);
+    img->width = d.width, img->height = d.height;
+    img->data = std::move(d.rgb);
+    return true;
+  } catch (const std::exception& e) {
+    std::fprintf(stderr, "%s\n", e.what());
+    return false;
+  }
+}
+
+static bool write_image(const std::string& file, const RgbImage& img) {  // output_img.save(path): by extension
+  if (lower_ext(file) != "png") return write_ppm(file, img);
+  try {
+    codec::encode_png(file, img.data.data(), img.width, img.height);
+    return true;
+  } catch (const std::exception& e) {
+    std::fprintf(stderr, "%s\n", e.what());
+    return false;
+  }
+}
+
 int main(int argc, char** argv) {
   Args args;
   if (!parse(argc, argv, &args)) return 2;
   try {
     const auto t0 = std::chrono::steady_clock::now();
     RgbImage target;
-    if (!read_ppm(args.target, &target)) throw std::runtime_error("cannot read target (binary PPM expected): " + args.target);
+    if (!read_image(args.target, &target)) throw std::runtime_error("cannot read target (PNG or binary PPM expected): " + args.target);
     const float target_aspect = (float)target.width / (float)target.height;  // main.rs:745-747
     std::printf("Target aspect ratio: %.3f\n", target_aspect);
 
@@ -141,7 +178,8 @@ int main(int argc, char** argv) {
       while (dirent* e = readdir(d)) {
         const std::string name = e->d_name, path = args.material_src + "/" + name;
         struct stat st;
-        if (name.size() > 4 && name.substr(name.size() - 4) == ".ppm" && stat(path.c_str(), &st) == 0 && S_ISREG(st.st_mode))
+        const std::string ext = lower_ext(name);
+        if ((ext == "png" || ext == "ppm") && stat(path.c_str(), &st) == 0 && S_ISREG(st.st_mode))
           entries.push_back(path);
       }
       closedir(d);
@@ -152,8 +190,8 @@ int main(int argc, char** argv) {
     std::vector<std::string> chosen;
     std::vector<RgbImage> headers(entries.size());
     for (size_t i = 0; i < entries.size(); ++i) {
-      if (!read_ppm(entries[i], &headers[i], true)) {
-        std::fprintf(stderr, "Error processing \"%s\": not a binary PPM\n", entries[i].c_str());
+      if (!read_image(entries[i], &headers[i], true)) {
+        std::fprintf(stderr, "Error processing \"%s\": not a PNG / binary PPM\n", entries[i].c_str());
         continue;
       }
       const float aspect = (float)headers[i].width / (float)headers[i].height;
@@ -170,8 +208,8 @@ int main(int argc, char** argv) {
     std::vector<std::string> paths;
     for (const std::string& p : chosen) {
       RgbImage m;
-      if (!read_ppm(p, &m)) {
-        std::fprintf(stderr, "Error processing \"%s\": truncated PPM\n", p.c_str());
+      if (!read_image(p, &m)) {
+        std::fprintf(stderr, "Error processing \"%s\": cannot decode\n", p.c_str());
         continue;
       }
       images.push_back(std::move(m));
@@ -196,7 +234,7 @@ int main(int argc, char** argv) {
                   rep.opt.final_cost, (unsigned long long)rep.opt.improved_count, (unsigned long long)rep.opt.accepted_count,
                   (unsigned long long)rep.opt.iterations);
     if (rep.n_fallbacks) std::printf("Fallback selections: %u\n", rep.n_fallbacks);
-    if (!write_ppm(args.output, out)) throw std::runtime_error("cannot write " + args.output);
+    if (!write_image(args.output, out)) throw std::runtime_error("cannot write " + args.output);
     const auto t4 = std::chrono::steady_clock::now();
     if (args.show_time) {
       auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };

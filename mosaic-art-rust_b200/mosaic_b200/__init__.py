@@ -49,6 +49,9 @@ class Report(C.Structure):
 _lib = None
 
 
+PROGRESS_FN = C.CFUNCTYPE(None, C.c_float, C.c_int, C.c_char_p, C.c_void_p)  # mosaic_progress_fn
+
+
 def load_library():
     """Load libmosaic_b200.so; fails loudly when it has not been built (no fallback path exists)."""
     global _lib
@@ -90,6 +93,7 @@ def load_library():
         "mosaic_fallback_cells": ([vp, u32p, C.c_uint32, u32p], C.c_int),
         "mosaic_set_placement": ([vp, i32p], C.c_int),
         "mosaic_anneal": ([vp, C.c_uint64, C.c_float, C.c_float, C.c_uint64, vp, C.POINTER(OptResult)], C.c_int),
+        "mosaic_optimize_greedy": ([vp, C.c_uint64, C.c_uint64, vp, C.POINTER(OptResult)], C.c_int),
         "mosaic_render": ([vp, C.c_float, vp], C.c_int),
         "mosaic_generate": ([vp, C.POINTER(Params), vp, vp, C.POINTER(Report)], C.c_int),
         "mosaic_selftest": ([vp, u64p], C.c_int),
@@ -111,6 +115,10 @@ def load_library():
         "mosaic_simdb_index_of": ([vp, C.c_char_p], C.c_int64),
         "mosaic_simdb_copy": ([vp, f32p, f32p], C.c_int),
         "mosaic_simdb_get_similarity": ([vp, C.c_char_p, C.c_char_p, f32p], C.c_int),
+        "mosaic_set_progress_callback": ([vp, PROGRESS_FN, vp], C.c_int),
+        "mosaic_png_decode_rgb8": ([C.c_char_p, C.POINTER(u8p), C.POINTER(C.c_int), C.POINTER(C.c_int)], C.c_int),
+        "mosaic_png_encode_rgb8": ([C.c_char_p, vp, C.c_int, C.c_int], C.c_int),
+        "mosaic_host_free": ([vp], None),
     }
     for name, (args, res) in sig.items():
         fn = getattr(L, name)  # AttributeError here = the library does not export what the header declares
@@ -127,13 +135,14 @@ EXPORTED_SYMBOLS = (
     "mosaic_set_materials_rgb8", "mosaic_set_materials_ragged_rgb8", "mosaic_set_materials_device", "mosaic_set_target_rgb8",
     "mosaic_set_target_device", "mosaic_set_material_lab", "mosaic_set_similarity_lab", "mosaic_set_cell_lab", "mosaic_material_lab",
     "mosaic_cell_lab", "mosaic_similarity_tri", "mosaic_candidates", "mosaic_place", "mosaic_fallback_cells",
-    "mosaic_set_placement", "mosaic_anneal", "mosaic_render", "mosaic_generate", "mosaic_selftest", "mosaic_dims",
+    "mosaic_set_placement", "mosaic_anneal", "mosaic_optimize_greedy", "mosaic_render", "mosaic_generate", "mosaic_selftest", "mosaic_dims",
     "mosaic_debug_chain_profile", "mosaic_debug_set_chain",
     "mosaic_device_output", "mosaic_device_placement", "mosaic_device_similarity", "mosaic_shard",
     "mosaic_shard_plan",
     "mosaic_simdb_save_json", "mosaic_simdb_save_json_n", "mosaic_simdb_save_ctx", "mosaic_simdb_load_json", "mosaic_simdb_free",
     "mosaic_simdb_info", "mosaic_simdb_path", "mosaic_simdb_index_of", "mosaic_simdb_copy",
     "mosaic_simdb_get_similarity",
+    "mosaic_set_progress_callback", "mosaic_png_decode_rgb8", "mosaic_png_encode_rgb8", "mosaic_host_free",
 )
 
 
@@ -432,6 +441,14 @@ class Context:
         self._check(self._L.mosaic_anneal(self._h, iterations, t0, decay, seed, _ptr(placed), C.byref(res)))
         return placed, res
 
+    def optimize_greedy(self, max_iterations=1000, seed=0, fetch=True):
+        """MosaicOptimizer::optimize_greedy (optimizer.rs:132-198) on the context's placement."""
+        d = self.dims()
+        placed = np.empty(d["grid_w"] * d["grid_h"], np.int32) if fetch else None
+        res = OptResult()
+        self._check(self._L.mosaic_optimize_greedy(self._h, max_iterations, seed, _ptr(placed), C.byref(res)))
+        return placed, res
+
     def render(self, color_strength=0.3, out=None, fetch=True):
         d = self.dims()
         shape = (d["grid_h"] * d["tile_h"], d["grid_w"] * d["tile_w"], 3)
@@ -460,6 +477,21 @@ class Context:
         self._check(self._L.mosaic_selftest(self._h, m))
         return int(m[0]), int(m[1])
 
+    def set_progress_callback(self, fn):
+        """fn(fraction, stage_name, message) is called as the DEVICE passes the stages of generate() (on a thread of the
+        CUDA runtime); None removes it."""
+        if fn is None:
+            self._check(self._L.mosaic_set_progress_callback(self._h, C.cast(None, PROGRESS_FN), None))
+            self._progress_cb = None
+            return
+
+        def tramp(fraction, stage, message, _user):
+            fn(float(fraction), STAGES[stage] if 0 <= stage < len(STAGES) else str(stage), message.decode("utf-8", "replace"))
+
+        cb = PROGRESS_FN(tramp)
+        self._check(self._L.mosaic_set_progress_callback(self._h, cb, None))
+        self._progress_cb = cb  # keep the trampoline alive
+
     def set_chain(self, version):
         """0 = default placement chain, 1 = greedy.cu, 2 = the windowed chain of greedy_window.cu, 3 = the wave chain of greedy_wave.cu."""
         self._check(self._L.mosaic_debug_set_chain(self._h, int(version)))
@@ -486,3 +518,27 @@ class Context:
     def output_shape(self):
         d = self.dims()
         return (d["grid_h"] * d["tile_h"], d["grid_w"] * d["tile_w"], 3)
+
+
+def png_decode(path) -> np.ndarray:
+    """image::open(path)?.to_rgb8() for a PNG file (main.rs:263-301): (h, w, 3) uint8.  Host only."""
+    L = load_library()
+    buf = C.POINTER(C.c_uint8)()
+    w, h = C.c_int(), C.c_int()
+    rc = L.mosaic_png_decode_rgb8(os.fsencode(path), C.byref(buf), C.byref(w), C.byref(h))
+    if rc != 0:
+        raise MosaicError(rc, (L.mosaic_last_error(None) or b"").decode())
+    try:
+        return np.ctypeslib.as_array(buf, shape=(h.value, w.value, 3)).copy()
+    finally:
+        L.mosaic_host_free(buf)
+
+
+def png_encode(path, img) -> None:
+    """RgbImage::save(path) for a ".png" path (main.rs:668-672).  img: (h, w, 3) uint8.  Host only."""
+    L = load_library()
+    img = np.ascontiguousarray(img, np.uint8)
+    assert img.ndim == 3 and img.shape[2] == 3
+    rc = L.mosaic_png_encode_rgb8(os.fsencode(path), img.ctypes.data_as(C.c_void_p), img.shape[1], img.shape[0])
+    if rc != 0:
+        raise MosaicError(rc, (L.mosaic_last_error(None) or b"").decode())

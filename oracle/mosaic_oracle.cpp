@@ -632,6 +632,44 @@ void orc_anneal(const float* mat_lab, int32_t* grid, int gw, int gh, uint64_t it
   if (res) *res = out;
 }
 
+/* MosaicOptimizer::optimize_greedy (optimizer.rs:132-198): only improvements are accepted; no acceptance sample */
+void orc_anneal_greedy(const float* mat_lab, int32_t* grid, int gw, int gh, uint64_t iterations, uint64_t seed,
+                       orc_opt_result* res) {
+  orc_opt_result out;
+  std::memset(&out, 0, sizeof out);
+  if (gh == 0 || gw == 0) { /* optimizer.rs:138-141 */
+    if (res) *res = out;
+    return;
+  }
+  orc_rng* rng = orc_rng_new(seed); /* optimizer.rs:144 thread_rng() -> defined as StdRng::seed_from_u64 */
+  float current = total_cost(mat_lab, grid, gw, gh); /* optimizer.rs:145 */
+  float initial = current;
+  uint64_t improved = 0;
+  for (uint64_t it = 0; it < iterations; ++it) {
+    int x1 = (int)rng->gen_range((uint64_t)gw); /* optimizer.rs:152-155: x before y */
+    int y1 = (int)rng->gen_range((uint64_t)gh);
+    int x2 = (int)rng->gen_range((uint64_t)gw);
+    int y2 = (int)rng->gen_range((uint64_t)gh);
+    if (x1 == x2 && y1 == y2) continue;                              /* optimizer.rs:157-159 */
+    size_t i1 = (size_t)y1 * gw + x1, i2 = (size_t)y2 * gw + x2;
+    if (grid[i1] < 0 || grid[i2] < 0) continue;                      /* optimizer.rs:161-163 */
+    float delta = swap_delta(mat_lab, grid, gw, gh, x1, y1, x2, y2); /* optimizer.rs:165 */
+    if (delta < 0.0f) {                                              /* optimizer.rs:167-175 */
+      std::swap(grid[i1], grid[i2]);
+      current = current + delta;
+      improved += 1;
+    }
+  }
+  orc_rng_free(rng);
+  out.initial_cost = initial; /* optimizer.rs:190-197 */
+  out.final_cost = current;
+  out.best_cost = current;
+  out.improved_count = improved;
+  out.accepted_count = improved;
+  out.iterations = iterations;
+  if (res) *res = out;
+}
+
 /* ------------------------------------------------------------------ resize [3P]
  * fast_image_resize 5.1.4, ResizeOptions::new() = Convolution(Lanczos3), PixelType::U8x3:
  * horizontal pass into an out_w x in_h u8 image, then vertical pass; an axis whose size does not

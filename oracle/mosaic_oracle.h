@@ -89,6 +89,8 @@ typedef struct {
 } orc_opt_result;
 void orc_anneal(const float* mat_lab, int32_t* grid, int gw, int gh, uint64_t iterations,
                 float t0, float decay, uint64_t seed, orc_opt_result* res);
+void orc_anneal_greedy(const float* mat_lab, int32_t* grid, int gw, int gh, uint64_t iterations, uint64_t seed,
+                       orc_opt_result* res);
 
 /* ---- resize (main.rs:710-738; fast_image_resize 5.1.4 Convolution(Lanczos3), U8x3) ---- */
 /* coefficients of one axis: returns window size; bounds_start/size: out_size; coeffs: out_size*window i16 */

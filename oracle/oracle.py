@@ -127,6 +127,7 @@ def lib():
         L.orc_expf.restype = C.c_float
         L.orc_anneal.argtypes = [f32p, i32p, C.c_int, C.c_int, C.c_uint64, C.c_float, C.c_float, C.c_uint64,
                                  C.POINTER(OptResult)]
+        L.orc_anneal_greedy.argtypes = [f32p, i32p, C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.POINTER(OptResult)]
         L.orc_resize_window.argtypes = [C.c_int, C.c_int]
         L.orc_resize_window.restype = C.c_int
         L.orc_resize_coeffs.argtypes = [C.c_int, C.c_int, i32p, i32p, i16p, C.POINTER(C.c_int)]
@@ -315,6 +316,16 @@ def anneal(mat_lab, grid, iterations, seed, t0=100.0, decay=0.99995):
     gh, gw = g.shape if g.ndim == 2 else (0, 0)
     res = OptResult()
     lib().orc_anneal(_p(mat_lab, C.c_float), _p(g, C.c_int32), gw, gh, iterations, t0, decay, seed, C.byref(res))
+    return g, res
+
+
+def anneal_greedy(mat_lab, grid, iterations, seed):
+    """MosaicOptimizer::optimize_greedy (optimizer.rs:132-198). grid: (gh, gw) int32; returns (new grid, OptResult)."""
+    mat_lab = _c(mat_lab, np.float32)
+    g = _c(grid, np.int32).copy()
+    gh, gw = g.shape if g.ndim == 2 else (0, 0)
+    res = OptResult()
+    lib().orc_anneal_greedy(_p(mat_lab, C.c_float), _p(g, C.c_int32), gw, gh, iterations, seed, C.byref(res))
     return g, res
 
 

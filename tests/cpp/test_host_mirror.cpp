@@ -110,6 +110,16 @@ static void test_optimization_config_defaults() {  // optimizer.rs:621-628
   CHECK(c.max_iterations == 1000 && c.initial_temperature == 100.0f && c.temperature_decay == 0.99995f && c.report_interval == 100);
 }
 
+static void test_greedy_optimization_edge_cases() {  // optimizer.rs:520-534 — returns before any device work
+  PathGrid empty_grid;
+  SimilarityDatabase db;
+  AdjacencyPenaltyCalculator calc(db, 1.0f);
+  const OptimizationResult r = MosaicOptimizer(calc, OptimizationConfig()).optimize_greedy(empty_grid, 10);
+  CHECK(r.initial_cost == 0.0f);
+  CHECK(r.final_cost == 0.0f);
+  CHECK(r.improved_count == 0);
+}
+
 static void test_optimization_empty_grid() {  // optimizer.rs:295-307 — returns before any device work
   PathGrid empty;
   SimilarityDatabase db;
@@ -310,6 +320,28 @@ static void test_optimization_basic() {  // optimizer.rs:247-264
   uint32_t bits;
   std::memcpy(&bits, &r.initial_cost, 4);
   CHECK(bits == 0x3E7FBDDAu);
+}
+
+static void test_greedy_optimization() {  // optimizer.rs:266-277
+  const SimilarityDatabase db = four_tiles();
+  PathGrid grid = four_grid();
+  AdjacencyPenaltyCalculator calc(db, 1.0f);
+  const OptimizationResult r = MosaicOptimizer(calc, OptimizationConfig()).optimize_greedy(grid, 10);
+  CHECK(r.final_cost <= r.initial_cost);  // only improvements are accepted
+  CHECK(r.improved_count == r.accepted_count);
+  CHECK(r.iterations == 10 && r.best_cost == r.final_cost);
+  CHECK(same_multiset(grid, four_grid()));
+  CHECK(std::fabs(calc.calculate_total_cost(grid) - r.final_cost) < 1e-4f);
+}
+
+static void test_greedy_optimization_zero_iterations() {  // optimizer.rs:536-547
+  const SimilarityDatabase db = four_tiles();
+  PathGrid grid = four_grid();
+  AdjacencyPenaltyCalculator calc(db, 1.0f);
+  const OptimizationResult r = MosaicOptimizer(calc, OptimizationConfig()).optimize_greedy(grid, 0);
+  CHECK(r.improved_count == 0);
+  CHECK(r.initial_cost == r.final_cost);
+  CHECK(grid == four_grid());
 }
 
 static void test_optimization_single_tile_grid() {  // optimizer.rs:310-331
@@ -564,6 +596,7 @@ int main(int argc, char** argv) {
   RUN(test_optimization_result_improvement);
   RUN(test_optimization_config_defaults);
   RUN(test_optimization_empty_grid);
+  RUN(test_greedy_optimization_edge_cases);
   RUN(test_aspect_ratio_match);
   RUN(test_tile_creation);
   RUN(test_usage_tracker);
@@ -578,6 +611,8 @@ int main(int argc, char** argv) {
     RUN(test_adjacency_penalty_calculation);
     RUN(test_total_cost_calculation);
     RUN(test_optimization_basic);
+    RUN(test_greedy_optimization);
+    RUN(test_greedy_optimization_zero_iterations);
     RUN(test_optimization_single_tile_grid);
     RUN(test_optimization_grid_with_empty_cells);
     RUN(test_optimization_extreme_temperature_values);

@@ -240,6 +240,31 @@ def test_anneal_bit_exact(ctx, n, gw, gh, iters, seed):
     assert res.iterations == iters
 
 
+@pytest.mark.parametrize("n,gw,gh,iters,seed,holes", [(300, 24, 16, 4000, 42, 0.0), (50, 8, 8, 5000, 0, 0.0), (300, 2, 2, 500, 7, 0.0),
+                                                       (300, 1, 1, 100, 1, 0.0), (20, 30, 20, 6000, 9, 0.1), (6, 40, 33, 20000, 5, 0.05)])
+def test_optimize_greedy_bit_exact(ctx, n, gw, gh, iters, seed, holes):
+    """MosaicOptimizer::optimize_greedy (optimizer.rs:132-198): improvements only, four position draws per iteration."""
+    mat_lab = synth.lab_points(n, seed=n + 5)
+    rng = np.random.default_rng(seed)
+    grid = rng.integers(0, n, (gh, gw)).astype(np.int32)
+    grid[rng.random((gh, gw)) < holes] = -1
+    ctx.set_material_lab(mat_lab)
+    ctx.set_cell_lab(np.zeros((gw * gh, 3), np.float32), gw, gh)
+    ctx.set_placement(grid)
+    placed, res = ctx.optimize_greedy(iters, seed)
+    rgrid, rres = orc.anneal_greedy(mat_lab, grid, iters, seed)
+    assert (placed.reshape(gh, gw) == rgrid).all()
+    for f in ("initial_cost", "final_cost", "best_cost"):
+        assert np.float32(getattr(res, f)).view(np.uint32) == np.float32(getattr(rres, f)).view(np.uint32), f
+    assert res.accepted_count == rres.accepted_count == res.improved_count == rres.improved_count
+    assert res.iterations == iters
+    assert res.best_cost == res.final_cost and res.final_cost <= res.initial_cost
+    # a second call continues from the improved grid (the context's placement is the working grid)
+    placed2, res2 = ctx.optimize_greedy(iters, seed + 1)
+    rgrid2, rres2 = orc.anneal_greedy(mat_lab, rgrid, iters, seed + 1)
+    assert (placed2.reshape(gh, gw) == rgrid2).all() and res2.accepted_count == rres2.accepted_count
+
+
 def test_anneal_with_empty_cells_and_duplicates(ctx):
     # empty cells are skipped without cooling (optimizer.rs:71-73); equal materials give delta 0 (adjacency.rs:156-158)
     n, gw, gh = 6, 12, 9

@@ -9,6 +9,8 @@ import subprocess
 import numpy as np
 import pytest
 
+import mosaic_b200
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PKG = os.path.join(ROOT, "mosaic-art-rust_b200")
 SRC = os.path.join(ROOT, "tests", "cpp", "test_host_mirror.cpp")
@@ -214,10 +216,17 @@ def test_cli_end_to_end(cli, ctx, tmp_path):
     for i in range(90):
         w, h = [(64, 64), (80, 48), (50, 30), (200, 120), (30, 70)][i % 5]
         m = synth.materials(1, w=w, h=h, start=i)[0]
-        _write_ppm(mixed / f"p{i:04d}.ppm", m)
+        # PNG and PPM side by side, the extension matched case-insensitively (main.rs:175-184); same sorted order
+        if i % 3 == 0:
+            _write_ppm(mixed / f"p{i:04d}.ppm", m)
+        else:
+            mosaic_b200.png_encode(mixed / f"p{i:04d}.{'PNG' if i % 3 == 1 else 'png'}", m)
         if abs(w / h - 320 / 192) <= 0.1:
             kept.append(m)
-    stdout = _run([cli, "-t", str(tmp_path / "target.ppm"), "-m", str(mixed), "-o", str(out), "--grid-w", str(gw),
+    mosaic_b200.png_encode(tmp_path / "target.png", tgt)
+    out_png = tmp_path / "sub" / "out.png"
+    out_png.parent.mkdir()
+    stdout = _run([cli, "-t", str(tmp_path / "target.png"), "-m", str(mixed), "-o", str(out_png), "--grid-w", str(gw),
                    "--grid-h", str(gh), "--max-materials", "50", "--optimization-iterations", "200",
                    "--similarity-db", str(tmp_path / "db2.json"), "--seed", "3"])
     assert "No tiles matched" not in stdout and "Loaded 50 tiles" in stdout
@@ -225,7 +234,12 @@ def test_cli_end_to_end(cli, ctx, tmp_path):
     ctx.set_target(tgt, gw, gh)
     ctx.generate(max_usage=3, adjacency_weight=0.3, color_strength=0.3, enable_optimization=True,
                  optimization_iterations=200, seed=3, build_similarity=False, image_out=img)
-    assert (_read_ppm(out) == img).all()
+    assert (mosaic_b200.png_decode(out_png) == img).all()   # decode(file) -> device -> encode(file): lossless end to end
+    try:
+        from PIL import Image
+        assert (np.asarray(Image.open(out_png).convert("RGB")) == img).all()   # an independent decoder reads the same pixels
+    except ImportError:
+        pass
 
 
 def test_cli_material_selection_follows_load_tiles(cli, tmp_path):
@@ -245,6 +259,9 @@ def test_cli_material_selection_follows_load_tiles(cli, tmp_path):
         _write_ppm(mdir / f"f{i:02d}.ppm", rng.integers(0, 256, (h, w, 3), dtype=np.uint8))
     (mdir / "readme.txt").write_text("x")
     (mdir / "broken.ppm").write_bytes(b"P5\n2 2\n255\n0000")                    # wrong magic: reported, skipped
+    (mdir / "broken.png").write_bytes(b"\x89PNG but not really")                 # bad signature: reported, skipped
+    for i, (w, h) in enumerate(sizes):                                           # the same sizes once more, as PNG files
+        mosaic_b200.png_encode(mdir / f"g{i:02d}.{'PNG' if i % 2 else 'png'}", rng.integers(0, 256, (h, w, 3), dtype=np.uint8))
 
     def run(material_dir, *extra):
         r = subprocess.run([cli, "-t", str(tmp_path / "target.ppm"), "-m", str(material_dir), "-o", str(tmp_path / "o.ppm"),
@@ -255,8 +272,9 @@ def test_cli_material_selection_follows_load_tiles(cli, tmp_path):
 
     r = run(mdir)
     assert "Target aspect ratio: 1.667" in r.stdout
-    assert "Loaded 12 tiles" in r.stdout and "No tiles matched" not in r.stdout   # 3 rounds x 4 matching sizes
-    assert "broken.ppm" in r.stderr and "not a binary PPM" in r.stderr
+    assert "Loaded 16 tiles" in r.stdout and "No tiles matched" not in r.stdout   # (3 rounds of PPM + 1 of PNG) x 4 matching sizes
+    assert "broken.ppm" in r.stderr and "not a PNG / binary PPM" in r.stderr
+    assert "broken.png" in r.stderr
     r = run(mdir, "--max-materials", "5")
     assert "Loaded 5 tiles" in r.stdout                                            # truncate (main.rs:255-257)
     r = run(mdir, "--aspect-tolerance", "0.001", "--max-materials", "4")
