@@ -655,6 +655,7 @@ def run_gpu_c4(args, cfg):
             clocks.start()
         for _ in range(args.warmup):
             fn()
+        ctx.collective_ms()  # drain: the warm-up's exchange time (NCCL sets its connections up in the first collective)
         D.barrier()
         clocks.begin_window()
         e0.record(stream)
