@@ -453,7 +453,7 @@ __global__ void __launch_bounds__(64, 1)
   constexpr uint32_t NOKEY = 0xFFFFFFFFu;
   const bool l0 = lane == 0;
   uint32_t n_fallbacks = 0;
-  unsigned long long prof[11] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  unsigned long long prof[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};  // [11] cycles from a block's exit to full_step, [12] exits, [13] cycles of full steps of uncontended cells, [14] their count, [15] hot blocks run
 
   struct CellSet {
     uint32_t w, m;  // record words: lane << 26 | id, window mask
@@ -692,6 +692,7 @@ __global__ void __launch_bounds__(64, 1)
     if (PROF) {
       prof[path] += (unsigned long long)(clock64() - t_begin) - (prof[8] + prof[9] - w0);
       prof[4 + path] += 1ull;
+      if (path == 0) prof[13] += (unsigned long long)(clock64() - t_begin), prof[14]++;
     }
   };
 
@@ -807,14 +808,18 @@ __global__ void __launch_bounds__(64, 1)
                        ((unsigned long long)(cell + (uint32_t)lane + 1u) << 32) | myr);
         }
         cell += (uint32_t)done;
+        if (PROF) prof[15]++;
         // one exit test per block: a contended cell, the end of the grid, or records that have not arrived yet
         if (done < 5 || cell + 9u > ucells || !next_ready) break;
         ran_block = true;
       }
+      long long t_exit = 0;
+      if (PROF) t_exit = clock64();
       __syncwarp();
       // the decision of the last cell that went through: lane done-1 of this block, else lane 4 of the one before
       if (done > 0 || ran_block) rprev = __shfl_sync(0xffffffffu, myr, done > 0 ? done - 1 : 4);
       rotate(done % 5);
+      if (PROF) prof[11] += (unsigned long long)(clock64() - t_exit), prof[12]++;
       if (cell >= ucells) break;
       if (done == 5) continue;  // only the next records were missing (or the grid is about to end): wait and go on
     }
@@ -828,7 +833,7 @@ __global__ void __launch_bounds__(64, 1)
     // the hot steps carry no instrumentation: their share is what the other paths and the waits leave
     prof[4] = (unsigned long long)cells - prof[5] - prof[6] - prof[7];
     prof[0] = prof[10] - prof[1] - prof[2] - prof[3] - prof[8] - prof[9];
-    for (int i = 0; i < 11; ++i) g_chain_prof[i] = prof[i];
+    for (int i = 0; i < 16; ++i) g_chain_prof[i] = prof[i];
   }
 }
 

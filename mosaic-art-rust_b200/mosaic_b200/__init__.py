@@ -509,7 +509,8 @@ class Context:
                     "cyc_barrier_b_w0", "n_eval", "n_exact", "n_serial", "cyc_phase1_others", "cyc_total", "cyc_phase2_others")
         elif not window:  # first-generation chain kernel
             keys = ("cyc_fast", "cyc_exact", "cyc_generic", "cyc_fallback", "n_fast", "n_exact", "n_generic",
-                    "n_fallback", "cyc_wait_producer", "cyc_wait_committer", "cyc_total")
+                    "n_fallback", "cyc_wait_producer", "cyc_wait_committer", "cyc_total", "cyc_exit_to_full_step", "n_block_exits",
+                    "cyc_full_step_uncontended", "n_full_step_uncontended", "n_hot_blocks")
         else:  # windowed chain: cycle counters are summed over its two warps
             keys = ("cyc_sets", "n_sets", "cyc_slow", "cyc_reset", "cyc_scan", "cyc_listen", "cyc_ring_wait", "n_fast",
                     "n_slow", "n_reset", "n_rescans", "cyc_total_both_warps")
