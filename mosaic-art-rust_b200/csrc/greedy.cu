@@ -19,6 +19,15 @@
 #include "common.cuh"
 #include "place_records.cuh"
 
+// MOSAIC_CHAIN_PAIRS=1 (measured experiment of round 2, off): take the reductions off the loop-carried chain by finding a
+// cell's first AND second valid candidate one step early (vote + two shuffles) and selecting between them once the
+// winner to its left is known.  Bit-exact, and slower: 3.07 ms instead of 2.59 on the 24,000-tile config — a hot block
+// went from ~600 to ~800 cycles.  The step is not bound by the REDUX latency on its recurrence but by the ~45
+// instructions a lone in-order warp issues per cell; a dozen more cost more than the shorter recurrence saves.
+#ifndef MOSAIC_CHAIN_PAIRS
+#define MOSAIC_CHAIN_PAIRS 0
+#endif
+
 namespace mosaic {
 
 namespace {
@@ -707,15 +716,35 @@ __global__ void __launch_bounds__(64, 1)
   uint32_t myr = 0u;
   bool dead = false;
   int done = 0;
+  // first and second valid candidate of a cell (record words: lane << 26 | id; NOKEY if there is none) and the OR of
+  // the valid candidates' windows — everything the next-but-one step needs from this cell except who wins the cell
+  // in between
+  uint32_t p1 = NOKEY, p2 = NOKEY, TB = 0xFFFFFFFFu;
+  auto find_pair = [&](const CellSet& Cs, uint32_t& q1, uint32_t& q2, uint32_t& tt) {
+    const unsigned v1 = __ballot_sync(0xffffffffu, Cs.k0 != NOKEY);
+    const unsigned v2 = v1 & (v1 - 1u);
+    const uint32_t a = __shfl_sync(0xffffffffu, Cs.w, (__ffs(v1) - 1) & 31), b = __shfl_sync(0xffffffffu, Cs.w, (__ffs(v2) - 1) & 31);
+    q1 = v1 ? a : NOKEY;
+    q2 = v2 ? b : NOKEY;
+    tt = __reduce_or_sync(0xffffffffu, Cs.km);
+  };
   auto hot_step = [&](const int STEP, const uint2* hb, CellSet& A, CellSet& B, CellSet& C, CellSet& D, CellSet& E) {
     const uint32_t rc = r;
     const uint32_t chosen = rc & CH_IDMASK;
     const uint32_t j0 = rc >> 26;
     dead = dead || (__funnelshift_rc(T, 0xFFFFFFFFu, j0) & 1u) != 0u;  // j0 = 63 (no valid candidate) shifts the ones in
     const bool live = !dead;
+#if MOSAIC_CHAIN_PAIRS
+    // The winner of the next cell without a reduction on the loop-carried chain: its first and second valid candidates
+    // (p1, p2: valid by usage and the material above; only the rule of the material to the LEFT — the winner of this
+    // cell — is open) were found a step ago.  If this cell's winner is the first one, the second one wins.
+    r = (p1 & CH_IDMASK) == chosen ? p2 : p1;
+    T = TB;  // (may still count the excluded candidate's window: a superset of the threats, so at worst a cold cell more)
+#else
     const bool same_b = B.id == chosen;
     r = __reduce_min_sync(0xffffffffu, same_b ? NOKEY : B.k0);  // the winner of this cell is presumed
     T = __reduce_or_sync(0xffffffffu, (same_b && !l0) ? 0u : B.km);
+#endif
     // commit: the winner is not the previous winner (that lane's key is NOKEY), so A.u covers every earlier cell
     // (a predicated store, not a branch: the step must stay one basic block.  The warp is converged and its
     // shared-memory accesses execute in program order, so the counter reads below see the store.)
@@ -734,6 +763,9 @@ __global__ void __launch_bounds__(64, 1)
     const bool ok = (int32_t)C.id != C.up && C.u < max_usage;  // main.rs:380 (Up), main.rs:375
     C.k0 = live ? (ok ? C.w : NOKEY) : C.k0;
     C.km = live ? ((ok || l0) ? C.m : 0u) : C.km;
+#if MOSAIC_CHAIN_PAIRS
+    find_pair(C, p1, p2, TB);  // for the step after the next one: two steps of slack for a vote, two shuffles and a REDUX.OR
+#endif
     // cell + 4: record (its batch has been waited for)
     const uint2 e = hb[STEP * 32];
     const int ex = D.x + 1 == gw ? 0 : D.x + 1;
@@ -785,6 +817,9 @@ __global__ void __launch_bounds__(64, 1)
     if (cell + 9u <= ucells) {  // hot blocks: records up to cell + 8 are requested
       wait_batch((int)cell + 8);  // a block reads records cell + 4 .. cell + 8: this batch, or one already waited for
       bool ran_block = false;
+#if MOSAIC_CHAIN_PAIRS
+      find_pair(S[1], p1, p2, TB);  // (after a cold cell or at the start: the pair of the block's second cell)
+#endif
       for (;;) {
         // probe the batch the NEXT block needs now, look at the answer after this block (near the end of the grid
         // the probe looks at a batch that is certainly there: branches are what this loop cannot afford)
