@@ -716,6 +716,7 @@ __global__ void __launch_bounds__(64, 1)
   uint32_t myr = 0u;
   bool dead = false;
   int done = 0;
+#if MOSAIC_CHAIN_PAIRS
   // first and second valid candidate of a cell (record words: lane << 26 | id; NOKEY if there is none) and the OR of
   // the valid candidates' windows — everything the next-but-one step needs from this cell except who wins the cell
   // in between
@@ -728,6 +729,7 @@ __global__ void __launch_bounds__(64, 1)
     q2 = v2 ? b : NOKEY;
     tt = __reduce_or_sync(0xffffffffu, Cs.km);
   };
+#endif
   auto hot_step = [&](const int STEP, const uint2* hb, CellSet& A, CellSet& B, CellSet& C, CellSet& D, CellSet& E) {
     const uint32_t rc = r;
     const uint32_t chosen = rc & CH_IDMASK;
