@@ -86,6 +86,16 @@ const char* mosaic_exchange_path(const mosaic_ctx* ctx);
 /* number of SMs of the context's device (grid sizing, FP32 roofline of the matching kernel) */
 int mosaic_sm_count(const mosaic_ctx* ctx);
 
+/* ---- page-locked host memory ---------------------------------------------------------------- */
+/* What makes the host-buffer path fast (DESIGN.md (e')): with page-locked buffers the uploads run on their own stream
+ * under the matching, rows are downloaded under the placement chain, and the tiles annealing changed are written straight
+ * into the caller's image.  A host that owns its buffers (a Rust Vec<u8>, an image::RgbImage) registers them once;
+ * a host that lets the library allocate gets page-locked memory directly.  Pageable buffers work everywhere, staged. */
+int mosaic_host_alloc(size_t bytes, void** out);    /* cudaHostAlloc(portable | mapped); release with mosaic_host_release */
+int mosaic_host_release(void* p);
+int mosaic_host_register(void* p, size_t bytes);    /* cudaHostRegister(portable | mapped) of memory the caller owns */
+int mosaic_host_unregister(void* p);
+
 /* ---- inputs -------------------------------------------------------------------------------- */
 /* Host pointers belong to the caller.  Pageable buffers are staged before the call returns.  With PAGE-LOCKED buffers
  * the uploads are asynchronous (single-GPU contexts run them on their own stream — materials first, then the target in

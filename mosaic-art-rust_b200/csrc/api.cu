@@ -1403,6 +1403,28 @@ int mosaic_debug_chain_profile(mosaic_ctx* c, int enable, uint64_t counters[16])
   return MOSAIC_OK;
 }
 
+int mosaic_host_alloc(size_t bytes, void** out) {
+  if (!out) return MOSAIC_ERR_INVALID;
+  *out = nullptr;
+  const cudaError_t e = cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable | cudaHostAllocMapped);
+  return e == cudaSuccess ? MOSAIC_OK : cuda_fail(nullptr, e, "cudaHostAlloc");
+}
+int mosaic_host_release(void* p) {
+  if (!p) return MOSAIC_OK;
+  const cudaError_t e = cudaFreeHost(p);
+  return e == cudaSuccess ? MOSAIC_OK : cuda_fail(nullptr, e, "cudaFreeHost");
+}
+int mosaic_host_register(void* p, size_t bytes) {
+  if (!p || !bytes) return MOSAIC_ERR_INVALID;
+  const cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped);
+  return e == cudaSuccess ? MOSAIC_OK : cuda_fail(nullptr, e, "cudaHostRegister");
+}
+int mosaic_host_unregister(void* p) {
+  if (!p) return MOSAIC_ERR_INVALID;
+  const cudaError_t e = cudaHostUnregister(p);
+  return e == cudaSuccess ? MOSAIC_OK : cuda_fail(nullptr, e, "cudaHostUnregister");
+}
+
 int mosaic_set_progress_callback(mosaic_ctx* c, mosaic_progress_fn fn, void* user) {
   if (!c) return MOSAIC_ERR_INVALID;
   MOSAIC_CUDA(c, cudaSetDevice(c->device));

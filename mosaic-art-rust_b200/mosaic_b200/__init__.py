@@ -119,6 +119,10 @@ def load_library():
         "mosaic_png_decode_rgb8": ([C.c_char_p, C.POINTER(u8p), C.POINTER(C.c_int), C.POINTER(C.c_int)], C.c_int),
         "mosaic_png_encode_rgb8": ([C.c_char_p, vp, C.c_int, C.c_int], C.c_int),
         "mosaic_host_free": ([vp], None),
+        "mosaic_host_alloc": ([C.c_size_t, C.POINTER(vp)], C.c_int),
+        "mosaic_host_release": ([vp], C.c_int),
+        "mosaic_host_register": ([vp, C.c_size_t], C.c_int),
+        "mosaic_host_unregister": ([vp], C.c_int),
     }
     for name, (args, res) in sig.items():
         fn = getattr(L, name)  # AttributeError here = the library does not export what the header declares
@@ -143,6 +147,7 @@ EXPORTED_SYMBOLS = (
     "mosaic_simdb_info", "mosaic_simdb_path", "mosaic_simdb_index_of", "mosaic_simdb_copy",
     "mosaic_simdb_get_similarity",
     "mosaic_set_progress_callback", "mosaic_png_decode_rgb8", "mosaic_png_encode_rgb8", "mosaic_host_free",
+    "mosaic_host_alloc", "mosaic_host_release", "mosaic_host_register", "mosaic_host_unregister",
 )
 
 
@@ -543,3 +548,50 @@ def png_encode(path, img) -> None:
     rc = L.mosaic_png_encode_rgb8(os.fsencode(path), img.ctypes.data_as(C.c_void_p), img.shape[1], img.shape[0])
     if rc != 0:
         raise MosaicError(rc, (L.mosaic_last_error(None) or b"").decode())
+
+
+class PinnedArray:
+    """A numpy array over page-locked host memory of the library (mosaic_host_alloc): uploads and downloads through it are
+    asynchronous.  `register(array)` page-locks memory numpy already owns instead (mosaic_host_register)."""
+
+    def __init__(self, shape, dtype=np.uint8):
+        L = load_library()
+        self._L = L
+        nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = C.c_void_p()
+        rc = L.mosaic_host_alloc(nbytes, C.byref(p))
+        if rc != 0:
+            raise MosaicError(rc, (L.mosaic_last_error(None) or b"").decode())
+        self._p = p
+        buf = (C.c_uint8 * max(nbytes, 1)).from_address(p.value)
+        self.array = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def close(self):
+        if self._p:
+            self.array = None
+            self._L.mosaic_host_release(self._p)
+            self._p = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class register:
+    """Context manager: page-lock an existing C-contiguous numpy array for the duration of the block."""
+
+    def __init__(self, array):
+        assert array.flags["C_CONTIGUOUS"]
+        self.array = array
+
+    def __enter__(self):
+        L = load_library()
+        rc = L.mosaic_host_register(self.array.ctypes.data_as(C.c_void_p), self.array.nbytes)
+        if rc != 0:
+            raise MosaicError(rc, (L.mosaic_last_error(None) or b"").decode())
+        return self.array
+
+    def __exit__(self, *a):
+        load_library().mosaic_host_unregister(self.array.ctypes.data_as(C.c_void_p))

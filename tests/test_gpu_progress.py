@@ -42,3 +42,33 @@ def test_progress_events_follow_the_device(ctx, with_host_image):
     assert ev2 == [] and (placed == placed2).all()
     if with_host_image:
         assert (img == img2).all()
+
+
+def test_page_locked_buffers_of_the_library_and_of_the_caller(ctx):
+    """mosaic_host_alloc / mosaic_host_register: the host-buffer path with page-locked memory (asynchronous uploads, rows
+    downloaded under the chain, patched tiles written straight into the caller's image) gives the pageable path's result."""
+    import mosaic_b200
+    n, gw, gh = 1200, 96, 60
+    mats, tgt = synth.materials(n), synth.target(2304, 1440, seed=11)
+    kw = dict(max_usage=3, adjacency_weight=0.3, color_strength=0.3, enable_optimization=True, optimization_iterations=400, seed=4)
+
+    def run(m, t, img):
+        ctx.set_materials(m)
+        ctx.set_target(t, gw, gh)
+        placed = np.zeros(gw * gh, np.int32)
+        ctx.generate(placed_out=placed, image_out=img, **kw)
+        return placed
+
+    ref_img = np.zeros((gh * (1440 // gh), gw * (2304 // gw), 3), np.uint8)
+    ref_placed = run(mats, tgt, ref_img)                       # pageable everything
+    pm, pt, pi = (mosaic_b200.PinnedArray(a.shape) for a in (mats, tgt, ref_img))
+    pm.array[...] = mats
+    pt.array[...] = tgt
+    assert (run(pm.array, pt.array, pi.array) == ref_placed).all() and (pi.array == ref_img).all()
+    own_img = np.zeros_like(ref_img)
+    with mosaic_b200.register(mats.copy()) as rm, mosaic_b200.register(tgt.copy()) as rt, mosaic_b200.register(own_img) as ri:
+        assert (run(rm, rt, ri) == ref_placed).all()
+        ctx.sync()
+        assert (ri == ref_img).all()
+    for p in (pm, pt, pi):
+        p.close()
