@@ -7,9 +7,8 @@
 // ascending by (d2, material index).  kiddo's order among equal distances is unspecified; the
 // (d2, index) order is the one the oracle defines.
 //
-// Layout: material Lab means as SoA l[], a[], b[] in HBM; a producer warp streams them through shared memory in
-// 512-material stages with 1-D TMA bulk copies (cp.async.bulk; full / empty mbarriers, four stages), so the eight cell
-// warps of a CTA drift apart by up to three stages instead of meeting at a CTA barrier after every stage.
+// Layout: material Lab means as SoA l[], a[], b[] in HBM; a CTA streams them through shared memory in 1024-material
+// stages with 1-D TMA bulk copies (cp.async.bulk + mbarrier, double buffered).
 // Each cell warp owns Q=2 cells whose Lab values live in registers; lanes map to materials, so one stage read (3
 // conflict-free LDS) serves 2x32 pairs.  A pair costs 8 FP32 ops (3 sub, 3 mul, 2 add; FMA contraction would change the
 // bits) + compare + vote.  Selection: a 64-bit key (d2 bits << 32 | index) is appended to a per-cell shared-memory POOL
@@ -27,7 +26,8 @@
 // keeping tau and the counters in registers: passing them by reference to the out-of-line prune had pinned them to the
 // stack), 23 % the appends, 8 % the final sorts, 3 % the prunes.  0.584 -> 0.432 ms.  Measured and dropped: Q=4 cells
 // per warp with 4 warps per CTA (0.58 ms: the kernel wants its warps more than it wants fewer loads per pair); the slack
-// of a prune (2 .. 90 keys: 0.456 .. 0.468 ms, no effect).
+// of a prune (2 .. 90 keys: 0.456 .. 0.468 ms, no effect); a producer warp with four 512-material stages and full / empty
+// mbarriers instead of the CTA barrier per stage (0.435 ms against 0.432: the barrier was not the cost).
 #include "common.cuh"
 
 namespace mosaic {
@@ -36,9 +36,7 @@ namespace {
 
 constexpr int TK_WARPS = 8;
 constexpr int TK_Q = 2;
-constexpr int TK_CHUNK = 512;   // materials per pipeline stage
-constexpr int TK_STAGES = 4;    // a producer warp keeps this many stages in flight: the cell warps drift apart by up to three chunks
-                                // (a warp that prunes or sorts does not hold the others at a CTA barrier)
+constexpr int TK_CHUNK = 1024;  // materials per stage (two stages, double buffered)
 constexpr int TK_SLOTS = 128;
 constexpr int TK_MAX_ROUNDS = 4;  // consecutive cell groups per warp: every group after the first starts from its predecessor's answer
 
@@ -209,46 +207,41 @@ __device__ __forceinline__ void finish_pool(QueryState& st, int cnt, unsigned ta
   __syncwarp();
 }
 
-__global__ void __launch_bounds__((TK_WARPS + 1) * 32, 3) nn_topk_kernel(const float* __restrict__ soa, const float4* __restrict__ lab4,
+__global__ void __launch_bounds__(TK_WARPS * 32, 3) nn_topk_kernel(const float* __restrict__ soa, const float4* __restrict__ lab4,
                                                                 int n, int n_pad, const float* __restrict__ cell_lab,
                                                                 int cell_begin, int cell_end, int k, int rounds, int slack,
                                                                 uint32_t* __restrict__ out_idx, float* __restrict__ out_d2) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  float* mats = reinterpret_cast<float*>(smem_raw);  // [TK_STAGES][3][TK_CHUNK]
-  QueryState* states = reinterpret_cast<QueryState*>(smem_raw + TK_STAGES * 3 * TK_CHUNK * sizeof(float));
-  unsigned long long* full = reinterpret_cast<unsigned long long*>(smem_raw + TK_STAGES * 3 * TK_CHUNK * sizeof(float) +
-                                                                   TK_WARPS * TK_Q * sizeof(QueryState));
-  unsigned long long* empty = full + TK_STAGES;
+  float* mats = reinterpret_cast<float*>(smem_raw);  // [2][3][TK_CHUNK]
+  QueryState* states = reinterpret_cast<QueryState*>(smem_raw + 2 * 3 * TK_CHUNK * sizeof(float));
+  unsigned long long* bars =
+      reinterpret_cast<unsigned long long*>(smem_raw + 2 * 3 * TK_CHUNK * sizeof(float) +
+                                            TK_WARPS * TK_Q * sizeof(QueryState));
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nchunks = (n + TK_CHUNK - 1) / TK_CHUNK;
   const int total_chunks = nchunks * rounds;  // the materials are streamed once per round
 
+  auto issue = [&](int g) {
+    const int s = g & 1, c = g % nchunks;
+    const int cnt = min(TK_CHUNK, n_pad - c * TK_CHUNK);  // n_pad is a multiple of 4 floats -> 16-byte sizes
+    const unsigned bytes = (unsigned)cnt * sizeof(float);
+    mbar_expect_tx(&bars[s], 3 * bytes);
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+      tma_load_1d(mats + (s * 3 + d) * TK_CHUNK, soa + (size_t)d * n_pad + (size_t)c * TK_CHUNK, bytes, &bars[s]);
+  };
+
   if (tid == 0) {
-    for (int i = 0; i < TK_STAGES; ++i) {
-      mbar_init(&full[i], 1);
-      mbar_init(&empty[i], TK_WARPS);
-    }
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   __syncthreads();
-
-  if (warp == TK_WARPS) {
-    // ---- producer warp: chunk g goes to stage g % TK_STAGES once the cell warps have released its previous content
-    if (lane == 0) {
-      for (int g = 0; g < total_chunks; ++g) {
-        const int s = g % TK_STAGES, c = g % nchunks;
-        if (g >= TK_STAGES) mbar_wait(&empty[s], (unsigned)(((g / TK_STAGES) - 1) & 1));
-        const int cnt = min(TK_CHUNK, n_pad - c * TK_CHUNK);  // n_pad is a multiple of 4 floats -> 16-byte sizes
-        const unsigned bytes = (unsigned)cnt * sizeof(float);
-        mbar_expect_tx(&full[s], 3 * bytes);
-#pragma unroll
-        for (int d = 0; d < 3; ++d)
-          tma_load_1d(mats + (s * 3 + d) * TK_CHUNK, soa + (size_t)d * n_pad + (size_t)c * TK_CHUNK, bytes, &full[s]);
-      }
-    }
-    return;
+  if (tid == 0) {
+    issue(0);
+    if (total_chunks > 1) issue(1);
   }
 
   QueryState* st = states + warp * TK_Q;
@@ -295,8 +288,8 @@ __global__ void __launch_bounds__((TK_WARPS + 1) * 32, 3) nn_topk_kernel(const f
     __syncwarp();  // (the previous answer has been read: the pools start empty)
 
     for (int c = 0; c < nchunks; ++c, ++g) {
-      const int s = g % TK_STAGES;
-      mbar_wait(&full[s], (unsigned)((g / TK_STAGES) & 1));
+      const int s = g & 1;
+      mbar_wait(&bars[s], (unsigned)((g >> 1) & 1));
       if (warp_active) {
         const int count = min(TK_CHUNK, n - c * TK_CHUNK);
         const float* pl = mats + (s * 3) * TK_CHUNK + lane;  // l; a and b sit TK_CHUNK and 2 * TK_CHUNK floats behind
@@ -324,8 +317,8 @@ __global__ void __launch_bounds__((TK_WARPS + 1) * 32, 3) nn_topk_kernel(const f
         for (int j0 = 0; j0 < whole; j0 += 32) step(true);
         if (whole < count) step(lane < count - whole);
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&empty[s]);  // this warp is done with stage s
+      __syncthreads();  // every warp is done with stage s
+      if (tid == 0 && g + 2 < total_chunks) issue(g + 2);
     }
 
     if (warp_active) {
@@ -347,7 +340,7 @@ __global__ void __launch_bounds__((TK_WARPS + 1) * 32, 3) nn_topk_kernel(const f
 }
 
 constexpr size_t kTopkSmem =
-    TK_STAGES * 3 * TK_CHUNK * sizeof(float) + TK_WARPS * TK_Q * sizeof(QueryState) + 2 * TK_STAGES * sizeof(unsigned long long);
+    2 * 3 * TK_CHUNK * sizeof(float) + TK_WARPS * TK_Q * sizeof(QueryState) + 2 * sizeof(unsigned long long);
 
 }  // namespace
 
@@ -370,7 +363,7 @@ int launch_topk_range(mosaic_ctx* ctx, int k, int cell_begin, int cell_end) {
   const int blocks = (cells + per_cta - 1) / per_cta;
   {
     StageTimer t(ctx, MOSAIC_STAGE_TOPK);
-    nn_topk_kernel<<<blocks, (TK_WARPS + 1) * 32, kTopkSmem, ctx->stream>>>(ctx->d_mat_soa, ctx->d_mat_lab4, ctx->n, ctx->n_pad,
+    nn_topk_kernel<<<blocks, TK_WARPS * 32, kTopkSmem, ctx->stream>>>(ctx->d_mat_soa, ctx->d_mat_lab4, ctx->n, ctx->n_pad,
                                                                       ctx->d_cell_lab, cell_begin, cell_end, k, rounds, tk_slack,
                                                                       ctx->cand_dst_idx ? ctx->cand_dst_idx : ctx->d_cand_idx,
                                                                       ctx->cand_dst_d2 ? ctx->cand_dst_d2 : ctx->d_cand_d2);
