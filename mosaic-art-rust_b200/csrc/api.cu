@@ -437,7 +437,9 @@ int run_similarity(mosaic_ctx* c, bool gather);
 //                stored into every rank's arena
 //   every rank : renders its rows, reading the placed materials from their owners' memory; one barrier at the end
 //                (nobody overwrites a window a peer may still be reading)
-int run_generate_peer(mosaic_ctx* c, const mosaic_params* p, bool anneal) {
+int run_render(mosaic_ctx* c, float strength, uint8_t* out_rgb);
+
+int run_generate_peer(mosaic_ctx* c, const mosaic_params* p, bool anneal, uint8_t* out_rgb) {
   const int world = c->world, rank = c->rank;
   int mb, me, rb, re;
   shard_mats(c, rank, &mb, &me);
@@ -476,38 +478,107 @@ int run_generate_peer(mosaic_ctx* c, const mosaic_params* p, bool anneal) {
   trace_point(c, "lab_exchanged");
   c->have_mat_lab = true;
   c->have_sim = false;
-  if (p->build_similarity) MOSAIC_TRY(run_similarity(c, /*gather=*/false));
+  bool sim_aside = false;
+  if (p->build_similarity) {
+    // this rank's range of the matrix: nothing on the placement path reads it — built on the render stream
+    MOSAIC_CUDA(c, cudaEventRecord(c->ev_mat_lab, c->stream));
+    MOSAIC_CUDA(c, cudaStreamWaitEvent(c->render_stream, c->ev_mat_lab, 0));
+    cudaStream_t caller = c->stream;
+    c->stream = c->render_stream;
+    const int src = run_similarity(c, /*gather=*/false);
+    c->stream = caller;
+    MOSAIC_TRY(src);
+    MOSAIC_CUDA(c, cudaEventRecord(c->ev_sim_done, c->render_stream));
+    sim_aside = true;
+  }
   trace_point(c, "sim");
-  // --- own rows: cell Lab means + top-K, stored into rank 0's candidate buffers
+  // --- own rows: cell Lab means + top-K, stored into rank 0's candidate buffers.  Rank 0 — whose chain waits for nothing
+  // but its own first rows — matches them in bands of ~3,000 cells and prepares each band's records right away, so the
+  // chain starts behind the first band instead of behind the whole share.
   MOSAIC_TRY(wait_target(c));
-  MOSAIC_TRY(launch_cell_lab_range(c, rb * c->gw, re * c->gw));
+  const bool chain0 = rank == 0 && place_chain_eligible(c, p->max_usage);
+  const int own_rows = re - rb;
+  const int own_bands = chain0 ? std::max(1, std::min(mosaic_ctx::kBands, (int)((size_t)own_rows * c->gw / 3000))) : 1;
+  if (chain0) {
+    MOSAIC_TRY(ensure(c, &c->d_ready_cells, &c->ready_cells_cap, (size_t)1));
+    MOSAIC_CUDA(c, cudaMemsetAsync(c->d_ready_cells, 0, sizeof(unsigned), c->stream));
+  }
   c->have_cell_lab = c->have_cell_rgbsum = true;
   c->cell_lab_gathered = false;
-  c->cand_dst_idx = reinterpret_cast<uint32_t*>(c->pw_peer[mosaic_ctx::PW_CAND_IDX][0]);
-  c->cand_dst_d2 = reinterpret_cast<float*>(c->pw_peer[mosaic_ctx::PW_CAND_D2][0]);
-  int rc = launch_topk_range(c, k, rb * c->gw, re * c->gw);
-  c->cand_dst_idx = nullptr;
-  c->cand_dst_d2 = nullptr;
-  MOSAIC_TRY(rc);
+  for (int b = 0; b < own_bands; ++b) {
+    const int r0 = rb + (int)((long long)own_rows * b / own_bands), r1 = rb + (int)((long long)own_rows * (b + 1) / own_bands);
+    if (r1 <= r0) continue;
+    MOSAIC_TRY(launch_cell_lab_range(c, r0 * c->gw, r1 * c->gw));
+    c->cand_dst_idx = reinterpret_cast<uint32_t*>(c->pw_peer[mosaic_ctx::PW_CAND_IDX][0]);
+    c->cand_dst_d2 = reinterpret_cast<float*>(c->pw_peer[mosaic_ctx::PW_CAND_D2][0]);
+    const int trc = launch_topk_range(c, k, r0 * c->gw, r1 * c->gw);
+    c->cand_dst_idx = nullptr;
+    c->cand_dst_d2 = nullptr;
+    MOSAIC_TRY(trc);
+    if (chain0) {
+      MOSAIC_TRY(launch_place_prep_range(c, p->adjacency_weight, r0 * c->gw, r1 * c->gw));
+      set_u32_kernel<<<1, 1, 0, c->stream>>>(c->d_ready_cells, (unsigned)(r1 * c->gw));
+      c->launches++;
+      if (b == 0) MOSAIC_CUDA(c, cudaEventRecord(c->ev_chain_go, c->stream));
+    }
+  }
   trace_point(c, "topk");
-  const unsigned e_cand = ++c->ep_cand, e_res = ++c->ep_res;
+  const unsigned e_cand = ++c->ep_cand, e_res = ++c->ep_res, e_grd = ++c->ep_grd;
   c->have_cand = true;
   c->cand_gathered = false;
+  // With annealing the GREEDY grid is handed to every rank as soon as the chain ends: the ranks draw (and download) their
+  // rows while rank 0 anneals a copy, and compose again only the cells of their rows that the final grid changes — the
+  // sharded form of the single-GPU schedule.  (Same decision on every rank: `anneal` comes from the parameters.)
+  const bool two_phase = anneal;
+  const size_t arena_bytes = mosaic_ctx::kResultHead + cells_of(c) * sizeof(int32_t);
+  uint8_t* host_dev = nullptr;
+  {
+    cudaPointerAttributes attr;
+    if (out_rgb && cudaPointerGetAttributes(&attr, out_rgb) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer)
+      host_dev = reinterpret_cast<uint8_t*>(attr.devicePointer);
+    (void)cudaGetLastError();
+  }
+  const bool early = two_phase && (out_rgb == nullptr || host_dev != nullptr);  // (a pageable destination is drawn once, at the end)
+  if (two_phase) MOSAIC_TRY(ensure(c, &c->d_placed_greedy, &c->placed_greedy_cap, cells_of(c)));
+  // this rank's rows of the greedy image, from the copy of the greedy grid; every placed material's thumbnail is cached
+  auto draw_greedy_rows = [&](cudaStream_t on) -> int {
+    if (c->mats_sliced) MOSAIC_TRY(dist_peer_wait(c, FLAG_MAT, world, c->ep_mat, on));  // the owners' material slices have landed
+    c->peer_render_ready = true;
+    c->have_placed = true;
+    int32_t* home = c->d_placed;
+    cudaStream_t caller = c->stream;
+    c->d_placed = c->d_placed_greedy;
+    c->stream = on;
+    c->thumb_mark_all = true;
+    const int rc = run_render(c, p->color_strength, out_rgb);
+    c->thumb_mark_all = false;
+    c->stream = caller;
+    c->d_placed = home;
+    return rc;
+  };
   if (rank != 0) {
+    {
+      CollTimer t(c, c->stream);
+      MOSAIC_TRY(dist_peer_signal(c, FLAG_CAND + rank, e_cand, 0, c->stream));
+    }
+    if (two_phase) {
+      {
+        CollTimer t(c, c->stream);
+        MOSAIC_TRY(dist_peer_wait(c, FLAG_GRD, 1, e_grd, c->stream));  // the greedy grid + fallback info have landed in the arena
+      }
+      MOSAIC_CUDA(c, cudaMemcpyAsync(c->d_placed_greedy, c->d_placed, sizeof(int32_t) * cells_of(c), cudaMemcpyDeviceToDevice, c->stream));
+      MOSAIC_TRY(dist_peer_signal(c, FLAG_ACK + rank, e_grd, 0, c->stream));  // rank 0 may overwrite the arena with the final grid
+      if (early) MOSAIC_TRY(draw_greedy_rows(c->stream));
+    }
     CollTimer t(c, c->stream);
-    MOSAIC_TRY(dist_peer_signal(c, FLAG_CAND + rank, e_cand, 0, c->stream));
     MOSAIC_TRY(dist_peer_wait(c, FLAG_RES, 1, e_res, c->stream));  // placements + report from rank 0
   } else {
-    const bool chain = place_chain_eligible(c, p->max_usage);
+    const bool chain = chain0;
     const int place_slot = stage_interval_begin(c, MOSAIC_STAGE_PLACE, c->stream);
-    if (chain) {
-      MOSAIC_TRY(ensure(c, &c->d_ready_cells, &c->ready_cells_cap, (size_t)1));
-      MOSAIC_CUDA(c, cudaMemsetAsync(c->d_ready_cells, 0, sizeof(unsigned), c->stream));
-    }
-    for (int r = 0; r < world; ++r) {
+    for (int r = 1; r < world; ++r) {  // (rank 0's own rows were prepared band by band above)
       int b0, b1;
       shard_rows(c, r, &b0, &b1);
-      if (r > 0) {
+      {
         CollTimer t(c, c->stream);
         MOSAIC_TRY(dist_peer_wait(c, FLAG_CAND + r, 1, e_cand, c->stream));
       }
@@ -516,7 +587,6 @@ int run_generate_peer(mosaic_ctx* c, const mosaic_params* p, bool anneal) {
         set_u32_kernel<<<1, 1, 0, c->stream>>>(c->d_ready_cells, (unsigned)(b1 * c->gw));
         c->launches++;
       }
-      if (chain && r == 0) MOSAIC_CUDA(c, cudaEventRecord(c->ev_chain_go, c->stream));
       trace_point(c, "band_prepared");
     }
     if (chain) {  // (enqueued behind every band's kernels, waits only for the first band: see run_match_place_banded)
@@ -532,11 +602,52 @@ int run_generate_peer(mosaic_ctx* c, const mosaic_params* p, bool anneal) {
     c->have_placed = true;
     trace_point(c, "chain_done");
     emit_progress(c, c->stream, 0.90f, MOSAIC_STAGE_PLACE, "Grid processing completed");  // app_full.rs:2098
-    if (anneal) MOSAIC_TRY(launch_anneal(c, p->optimization_iterations, 100.0f, 0.99995f, p->seed));
-    trace_point(c, "annealed");
-    CollTimer t(c, c->stream);
-    MOSAIC_TRY(dist_peer_push(c, mosaic_ctx::PW_RESULT, 0, mosaic_ctx::kResultHead + cells_of(c) * sizeof(int32_t), -1, c->stream));
-    MOSAIC_TRY(dist_peer_signal(c, FLAG_RES, e_res, -1, c->stream));
+    if (two_phase) {
+      {
+        CollTimer t(c, c->stream);
+        MOSAIC_TRY(dist_peer_push(c, mosaic_ctx::PW_RESULT, 0, arena_bytes, -1, c->stream));  // the greedy grid
+        MOSAIC_TRY(dist_peer_signal(c, FLAG_GRD, e_grd, -1, c->stream));
+      }
+      MOSAIC_TRY(ensure(c, &c->d_placed_work, &c->placed_work_cap, cells_of(c)));
+      MOSAIC_CUDA(c, cudaMemcpyAsync(c->d_placed_greedy, c->d_placed, sizeof(int32_t) * cells_of(c), cudaMemcpyDeviceToDevice, c->stream));
+      MOSAIC_CUDA(c, cudaMemcpyAsync(c->d_placed_work, c->d_placed, sizeof(int32_t) * cells_of(c), cudaMemcpyDeviceToDevice, c->stream));
+      if (early) {  // this rank's own rows on the render stream, beside the annealer
+        MOSAIC_CUDA(c, cudaEventRecord(c->ev_mat_lab, c->stream));
+        MOSAIC_CUDA(c, cudaStreamWaitEvent(c->render_stream, c->ev_mat_lab, 0));
+        MOSAIC_TRY(draw_greedy_rows(c->render_stream));
+        MOSAIC_CUDA(c, cudaEventRecord(c->ev_render_done, c->render_stream));
+      }
+      {
+        int32_t* home = c->d_placed;
+        c->d_placed = c->d_placed_work;  // (the annealer's kernels take the grid from the context)
+        const int rc = launch_anneal(c, p->optimization_iterations, 100.0f, 0.99995f, p->seed);
+        c->d_placed = home;
+        MOSAIC_TRY(rc);
+      }
+      trace_point(c, "annealed");
+      CollTimer t(c, c->stream);
+      if (world > 1) MOSAIC_TRY(dist_peer_wait(c, FLAG_ACK + 1, world - 1, e_grd, c->stream));  // everybody has copied the greedy grid
+      MOSAIC_CUDA(c, cudaMemcpyAsync(c->d_placed, c->d_placed_work, sizeof(int32_t) * cells_of(c), cudaMemcpyDeviceToDevice, c->stream));
+      MOSAIC_TRY(dist_peer_push(c, mosaic_ctx::PW_RESULT, 0, arena_bytes, -1, c->stream));
+      MOSAIC_TRY(dist_peer_signal(c, FLAG_RES, e_res, -1, c->stream));
+      if (early) MOSAIC_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_render_done, 0));
+    } else {
+      if (anneal) MOSAIC_TRY(launch_anneal(c, p->optimization_iterations, 100.0f, 0.99995f, p->seed));
+      trace_point(c, "annealed");
+      CollTimer t(c, c->stream);
+      MOSAIC_TRY(dist_peer_push(c, mosaic_ctx::PW_RESULT, 0, arena_bytes, -1, c->stream));
+      MOSAIC_TRY(dist_peer_signal(c, FLAG_RES, e_res, -1, c->stream));
+    }
+  }
+  c->peer_rendered = false;
+  if (early) {
+    // the final grid is in the arena: this rank's cells that differ from the greedy grid are composed again, into the
+    // device image and — a page-locked destination — straight into the caller's rows
+    if (render_patch_possible(c)) {
+      StageTimer t(c, MOSAIC_STAGE_RENDER);
+      MOSAIC_TRY(launch_render_patch(c, c->d_placed_greedy, host_dev, rb, re));
+      c->peer_rendered = true;
+    }
   }
   c->have_placed = true;
   // the render reads the placed materials from their owners: every owner's slice must have landed
@@ -545,6 +656,7 @@ int run_generate_peer(mosaic_ctx* c, const mosaic_params* p, bool anneal) {
     MOSAIC_TRY(dist_peer_wait(c, FLAG_MAT, world, c->ep_mat, c->stream));
   }
   c->peer_render_ready = true;
+  if (sim_aside) MOSAIC_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_sim_done, 0));
   return MOSAIC_OK;
 }
 
@@ -1231,7 +1343,7 @@ int mosaic_generate(mosaic_ctx* c, const mosaic_params* p, int32_t* placed_out, 
   }
   c->peer_render_ready = false;
   if (peer) {
-    MOSAIC_TRY(run_generate_peer(c, p, anneal));
+    MOSAIC_TRY(run_generate_peer(c, p, anneal, out_rgb));
   } else {
   // main.rs:105-164 (MosaicGenerator::new) ...
   MOSAIC_TRY(run_material_lab(c));
@@ -1339,7 +1451,7 @@ int mosaic_generate(mosaic_ctx* c, const mosaic_params* p, int32_t* placed_out, 
   if (!under_chain) {
   trace_point(c, "placed");
   MOSAIC_TRY(d2h(c, placed_out, c->d_placed, sizeof(int32_t) * cells_of(c)));
-  MOSAIC_TRY(run_render(c, p->color_strength, out_rgb));
+  if (!(peer && c->peer_rendered)) MOSAIC_TRY(run_render(c, p->color_strength, out_rgb));
   trace_point(c, "rendered");
   }
   if (peer) {

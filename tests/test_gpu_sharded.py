@@ -30,15 +30,34 @@ ctx = mosaic_b200.Context(rank, rank, world, ids[0])
 ctx.set_materials(mats); ctx.set_target(tgt, gw, gh)
 placed = np.zeros(gw * gh, np.int32); img = np.zeros(ctx.output_shape(), np.uint8)
 rep = ctx.generate(placed_out=placed, image_out=img, **kw)
+# the same job into a page-locked image: the ranks draw their rows of the GREEDY grid while rank 0 anneals and compose
+# again only the cells the final grid changes (two-phase hand-off); then without annealing (one hand-off)
+pin = mosaic_b200.PinnedArray(img.shape)
+pin.array[...] = 0
+placed2 = np.zeros(gw * gh, np.int32)
+rep2 = ctx.generate(placed_out=placed2, image_out=pin.array, **kw)
+ctx.sync()
+img2 = pin.array.copy()
+kw0 = dict(kw, enable_optimization=False, optimization_iterations=0)
+pin.array[...] = 0
+placed3 = np.zeros(gw * gh, np.int32)
+ctx.generate(placed_out=placed3, image_out=pin.array, **kw0)
+ctx.sync()
+img3 = pin.array.copy()
+placed4 = np.zeros(gw * gh, np.int32)
+rep4 = ctx.generate(placed_out=placed4, **kw)      # image left on the device
 sim = ctx.similarity_tri(); mlab = ctx.material_lab(); clab = ctx.cell_lab(); idx, d2 = ctx.candidates()
 shard = ctx.shard()
 ctx.close()
+pin.close()
 # single-GPU run of the same job on this rank's GPU
 ref = mosaic_b200.Context(rank)
 ref.set_materials(mats); ref.set_target(tgt, gw, gh)
 rplaced = np.zeros(gw * gh, np.int32); rimg = np.zeros(ref.output_shape(), np.uint8)
 rrep = ref.generate(placed_out=rplaced, image_out=rimg, **kw)
 rsim = ref.similarity_tri(); rmlab = ref.material_lab(); rclab = ref.cell_lab(); ridx, rd2 = ref.candidates()
+rplaced0 = np.zeros(gw * gh, np.int32); rimg0 = np.zeros(ref.output_shape(), np.uint8)
+ref.generate(placed_out=rplaced0, image_out=rimg0, **kw0)
 ref.close()
 assert (mlab == rmlab).all() and (clab == rclab).all()
 assert (idx == ridx).all() and (d2.view(np.uint32) == rd2.view(np.uint32)).all()
@@ -46,6 +65,10 @@ assert (sim.view(np.uint32) == rsim.view(np.uint32)).all()
 assert (placed == rplaced).all() and rep.n_fallbacks == rrep.n_fallbacks and rep.opt.accepted_count == rrep.opt.accepted_count
 rb, re_ = shard["rows"]; th = img.shape[0] // gh
 assert (img[rb * th:re_ * th] == rimg[rb * th:re_ * th]).all()      # a sharded context delivers its own row band
+assert (placed2 == rplaced).all() and rep2.opt.accepted_count == rrep.opt.accepted_count
+assert (img2[rb * th:re_ * th] == rimg[rb * th:re_ * th]).all(), "two-phase (page-locked) rows differ"
+assert (placed3 == rplaced0).all() and (img3[rb * th:re_ * th] == rimg0[rb * th:re_ * th]).all()
+assert (placed4 == rplaced).all() and rep4.n_fallbacks == rrep.n_fallbacks
 dist.barrier(); dist.destroy_process_group()
 print("rank", rank, "ok")
 '''
