@@ -438,6 +438,7 @@ int run_similarity(mosaic_ctx* c, bool gather);
 //   every rank : renders its rows, reading the placed materials from their owners' memory; one barrier at the end
 //                (nobody overwrites a window a peer may still be reading)
 int run_render(mosaic_ctx* c, float strength, uint8_t* out_rgb);
+__global__ void wait_progress_kernel(const volatile unsigned* progress, unsigned need);
 
 int run_generate_peer(mosaic_ctx* c, const mosaic_params* p, bool anneal, uint8_t* out_rgb) {
   const int world = c->world, rank = c->rank;
@@ -540,6 +541,71 @@ int run_generate_peer(mosaic_ctx* c, const mosaic_params* p, bool anneal, uint8_
   }
   const bool early = two_phase && (out_rgb == nullptr || host_dev != nullptr);  // (a pageable destination is drawn once, at the end)
   if (two_phase) MOSAIC_TRY(ensure(c, &c->d_placed_greedy, &c->placed_greedy_cap, cells_of(c)));
+  // Rows UNDER the chain: rank 0's chain counts its committed cells in a word of its flag window; every rank polls it
+  // (over NVLink) and draws + downloads a band of its rows as soon as the chain has passed it, reading the placements
+  // from rank 0's arena.  (Same decision on every rank: the chain's eligibility depends on the configuration only.)
+  const bool under_capable = two_phase && place_chain_eligible(c, p->max_usage) && place_chain_has_progress(c);
+  // (each rank decides for itself: with a host destination the download of its rows hides under the chain; an image that
+  // stays on the device gains nothing from it — drawing beside the chain slows the chain — and is drawn beside the annealer)
+  const bool under = under_capable && early && out_rgb != nullptr;
+  unsigned* const progress0 = reinterpret_cast<unsigned*>(c->pw_peer[mosaic_ctx::PW_FLAGS][0]) + FLAG_PROGRESS;
+  const int32_t* const placed0 = reinterpret_cast<const int32_t*>(reinterpret_cast<const unsigned char*>(c->pw_peer[mosaic_ctx::PW_RESULT][0]) +
+                                                                  mosaic_ctx::kResultHead);
+  // this rank's rows as the chain passes them, on stream `on` (copies on the copy stream); ends with the thumbnails of
+  // EVERY placed material cached (the final grid may bring any of them into these rows) once `grid_complete` has fired
+  auto draw_rows_under_chain = [&](cudaStream_t on) -> int {
+    if (c->mats_sliced) MOSAIC_TRY(dist_peer_wait(c, FLAG_MAT, world, c->ep_mat, on));
+    c->peer_render_ready = true;
+    c->have_placed = true;
+    const size_t out_bytes = (size_t)c->gw * c->tile_w * (size_t)c->gh * c->tile_h * 3;
+    MOSAIC_TRY(ensure(c, &c->d_out, &c->out_cap, out_bytes));
+    const size_t row_bytes = (size_t)c->gw * c->tile_w * 3 * (size_t)c->tile_h;
+    const int rows = re - rb;
+    int bands = std::min(mosaic_ctx::kBands, std::max(rows, 1));
+    if ((size_t)rows * row_bytes < ((size_t)8 << 20)) bands = 1;
+    int32_t* home = c->d_placed;
+    cudaStream_t caller = c->stream;
+    c->d_placed = const_cast<int32_t*>(placed0);
+    c->stream = on;
+    int rc = render_reset_cache(c);
+    for (int b = 0; b < bands && rc == MOSAIC_OK; ++b) {
+      const int b0 = rb + (int)((long long)rows * b / bands), b1 = rb + (int)((long long)rows * (b + 1) / bands);
+      if (b1 <= b0) continue;
+      wait_progress_kernel<<<1, 32, 0, on>>>(progress0, (unsigned)(b1 * c->gw));
+      c->launches++;
+      {
+        StageTimer t(c, MOSAIC_STAGE_RENDER);
+        rc = c->ragged ? launch_render_ragged(c, p->color_strength, b0, b1) : launch_render(c, p->color_strength, b0, b1);
+      }
+      if (rc != MOSAIC_OK) break;
+      if (out_rgb) {
+        cudaEventRecord(c->ev_band[b], on);
+        cudaStreamWaitEvent(c->copy_stream, c->ev_band[b], 0);
+        cudaMemcpyAsync(out_rgb + (size_t)b0 * row_bytes, c->d_out + (size_t)b0 * row_bytes, (size_t)(b1 - b0) * row_bytes,
+                        cudaMemcpyDeviceToHost, c->copy_stream);
+      }
+    }
+    c->stream = caller;
+    c->d_placed = home;
+    MOSAIC_TRY(rc);
+    c->have_out = true;
+    return MOSAIC_OK;
+  };
+  // (after the greedy grid is complete and copied) the thumbnails of every placed material: one row drawn again with the
+  // whole grid marked — identical pixels, and the cache then covers whatever the final grid moves into these rows
+  auto cache_all_thumbnails = [&](cudaStream_t on) -> int {
+    if (re <= rb) return MOSAIC_OK;
+    int32_t* home = c->d_placed;
+    cudaStream_t caller = c->stream;
+    c->d_placed = c->d_placed_greedy;
+    c->stream = on;
+    c->thumb_mark_all = true;
+    const int rc = c->ragged ? launch_render_ragged(c, p->color_strength, rb, rb + 1) : launch_render(c, p->color_strength, rb, rb + 1);
+    c->thumb_mark_all = false;
+    c->stream = caller;
+    c->d_placed = home;
+    return rc;
+  };
   // this rank's rows of the greedy image, from the copy of the greedy grid; every placed material's thumbnail is cached
   auto draw_greedy_rows = [&](cudaStream_t on) -> int {
     if (c->mats_sliced) MOSAIC_TRY(dist_peer_wait(c, FLAG_MAT, world, c->ep_mat, on));  // the owners' material slices have landed
@@ -562,13 +628,28 @@ int run_generate_peer(mosaic_ctx* c, const mosaic_params* p, bool anneal, uint8_
       MOSAIC_TRY(dist_peer_signal(c, FLAG_CAND + rank, e_cand, 0, c->stream));
     }
     if (two_phase) {
+      if (under) {
+        {
+          CollTimer t(c, c->stream);
+          MOSAIC_TRY(dist_peer_wait(c, FLAG_CHN, 1, e_grd, c->stream));  // rank 0 has reset its progress counter
+        }
+        MOSAIC_TRY(draw_rows_under_chain(c->stream));
+      }
       {
         CollTimer t(c, c->stream);
         MOSAIC_TRY(dist_peer_wait(c, FLAG_GRD, 1, e_grd, c->stream));  // the greedy grid + fallback info have landed in the arena
       }
       MOSAIC_CUDA(c, cudaMemcpyAsync(c->d_placed_greedy, c->d_placed, sizeof(int32_t) * cells_of(c), cudaMemcpyDeviceToDevice, c->stream));
       MOSAIC_TRY(dist_peer_signal(c, FLAG_ACK + rank, e_grd, 0, c->stream));  // rank 0 may overwrite the arena with the final grid
-      if (early) MOSAIC_TRY(draw_greedy_rows(c->stream));
+      if (under) {
+        MOSAIC_TRY(cache_all_thumbnails(c->stream));
+        if (out_rgb) {
+          MOSAIC_CUDA(c, cudaEventRecord(c->ev_copy_done, c->copy_stream));
+          MOSAIC_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_copy_done, 0));
+        }
+      } else if (early) {
+        MOSAIC_TRY(draw_greedy_rows(c->stream));
+      }
     }
     CollTimer t(c, c->stream);
     MOSAIC_TRY(dist_peer_wait(c, FLAG_RES, 1, e_res, c->stream));  // placements + report from rank 0
@@ -591,8 +672,25 @@ int run_generate_peer(mosaic_ctx* c, const mosaic_params* p, bool anneal, uint8_
     }
     if (chain) {  // (enqueued behind every band's kernels, waits only for the first band: see run_match_place_banded)
       MOSAIC_CUDA(c, cudaStreamWaitEvent(c->chain_stream, c->ev_chain_go, 0));
-      MOSAIC_TRY(launch_place_chain_async(c, p->max_usage, p->adjacency_weight, c->chain_stream, c->d_ready_cells));
+      if (under_capable) {
+        MOSAIC_CUDA(c, cudaMemsetAsync(progress0, 0, sizeof(unsigned), c->chain_stream));
+        MOSAIC_TRY(dist_peer_signal(c, FLAG_CHN, e_grd, -1, c->chain_stream));  // the counter starts at zero: the ranks may poll it
+      }
+      // (row by row only when this rank itself downloads rows — the ranks are expected to agree on the kind of destination;
+      // a rank that polls nevertheless is released when the chain ends)
+      const bool publish_rows = under_capable && out_rgb != nullptr;
+      MOSAIC_TRY(launch_place_chain_async(c, p->max_usage, p->adjacency_weight, c->chain_stream, c->d_ready_cells, publish_rows ? progress0 : nullptr));
+      if (under_capable && !publish_rows) {
+        set_u32_kernel<<<1, 1, 0, c->chain_stream>>>(progress0, (unsigned)cells_of(c));
+        c->launches++;
+      }
       MOSAIC_CUDA(c, cudaEventRecord(c->ev_chain_done, c->chain_stream));
+      if (under) {  // this rank's own rows, on the render stream, as the chain passes them
+        MOSAIC_CUDA(c, cudaEventRecord(c->ev_mat_lab, c->stream));  // (their cell sums are enqueued)
+        MOSAIC_CUDA(c, cudaStreamWaitEvent(c->render_stream, c->ev_mat_lab, 0));
+        MOSAIC_TRY(dist_peer_wait(c, FLAG_CHN, 1, e_grd, c->render_stream));
+        MOSAIC_TRY(draw_rows_under_chain(c->render_stream));
+      }
       MOSAIC_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_chain_done, 0));
       stage_interval_end(c, MOSAIC_STAGE_PLACE, place_slot, c->stream);
     } else {
@@ -611,10 +709,18 @@ int run_generate_peer(mosaic_ctx* c, const mosaic_params* p, bool anneal, uint8_
       MOSAIC_TRY(ensure(c, &c->d_placed_work, &c->placed_work_cap, cells_of(c)));
       MOSAIC_CUDA(c, cudaMemcpyAsync(c->d_placed_greedy, c->d_placed, sizeof(int32_t) * cells_of(c), cudaMemcpyDeviceToDevice, c->stream));
       MOSAIC_CUDA(c, cudaMemcpyAsync(c->d_placed_work, c->d_placed, sizeof(int32_t) * cells_of(c), cudaMemcpyDeviceToDevice, c->stream));
-      if (early) {  // this rank's own rows on the render stream, beside the annealer
-        MOSAIC_CUDA(c, cudaEventRecord(c->ev_mat_lab, c->stream));
+      if (early) {  // on the render stream, beside the annealer: this rank's own rows, or (drawn under the chain) the thumbnails
+        MOSAIC_CUDA(c, cudaEventRecord(c->ev_mat_lab, c->stream));  // (the greedy grid is copied)
         MOSAIC_CUDA(c, cudaStreamWaitEvent(c->render_stream, c->ev_mat_lab, 0));
-        MOSAIC_TRY(draw_greedy_rows(c->render_stream));
+        if (under) {
+          MOSAIC_TRY(cache_all_thumbnails(c->render_stream));
+          if (out_rgb) {
+            MOSAIC_CUDA(c, cudaEventRecord(c->ev_copy_done, c->copy_stream));
+            MOSAIC_CUDA(c, cudaStreamWaitEvent(c->render_stream, c->ev_copy_done, 0));
+          }
+        } else {
+          MOSAIC_TRY(draw_greedy_rows(c->render_stream));
+        }
         MOSAIC_CUDA(c, cudaEventRecord(c->ev_render_done, c->render_stream));
       }
       {
@@ -738,7 +844,7 @@ __global__ void wait_progress_kernel(const volatile unsigned* progress, unsigned
       __nanosleep(200);
       if (clock64() - t0 > 20000000000ll) __trap();  // the chain died: do not hang the GPU
     }
-    __threadfence();
+    __threadfence_system();  // (the counter may live on a peer: the placements it covers were written before it)
   }
 }
 

@@ -328,7 +328,8 @@ __global__ void __launch_bounds__(64, 1)
                         unsigned max_usage, float weight, int32_t* __restrict__ placed, uint32_t* __restrict__ info,
                         uint32_t fallback_cap,
                         const volatile unsigned* ready /* cells whose records exist so far; NULL = all of them */,
-                        volatile unsigned* progress /* GATED: cells committed so far, for whoever renders rows under the chain */) {
+                        volatile unsigned* progress /* GATED: cells committed so far, for whoever renders rows under the chain */,
+                        bool progress_sys /* the counter is read by other GPUs: publish at system scope */) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   HRec* hring = reinterpret_cast<HRec*>(smem_raw);
   XRec* xring = reinterpret_cast<XRec*>(smem_raw + sizeof(HRec) * (CH_DEPTH + CH_SHADOW));
@@ -430,7 +431,10 @@ __global__ void __launch_bounds__(64, 1)
         if (GATED && progress && (base >= next_pub || base >= cells)) {  // the placements of the cells before `base` are in HBM
           // (once per grid row: the fence is a round trip to L2 in the loop that also refills the ring, and whoever
           // renders under the chain waits for whole rows anyway)
-          __threadfence();
+          if (progress_sys)
+            __threadfence_system();  // (a sharded context's peers poll this counter and read the placements over NVLink)
+          else
+            __threadfence();
           *progress = (unsigned)base;
           next_pub = (base / gw + 1) * gw;
         }
@@ -888,7 +892,7 @@ static int launch_chain_impl(mosaic_ctx* ctx, unsigned cap, float weight, size_t
   greedy_chain_kernel<UsageT, PROF, GATED><<<1, 64, smem, stream>>>(
       reinterpret_cast<const HRec*>(ctx->d_place_rec), reinterpret_cast<const XRec*>(ctx->d_place_rec + cells * sizeof(HRec)),
       reinterpret_cast<const float*>(ctx->d_place_rec + cells * (sizeof(HRec) + sizeof(XRec))), ctx->d_cand_idx, ctx->d_cand_d2, ctx->k, ctx->sim_lab4(), ctx->n, ctx->gw, ctx->gh, cap, weight, ctx->d_placed,
-      ctx->d_place_info, mosaic_ctx::kFallbackCap, ready, progress);
+      ctx->d_place_info, mosaic_ctx::kFallbackCap, ready, progress, ctx->world > 1);
   return MOSAIC_OK;
 }
 
