@@ -496,10 +496,12 @@ int run_generate_peer(mosaic_ctx* c, const mosaic_params* p, bool anneal, uint8_
   // --- own rows: cell Lab means + top-K, stored into rank 0's candidate buffers.  Rank 0 — whose chain waits for nothing
   // but its own first rows — matches them in bands of ~3,000 cells and prepares each band's records right away, so the
   // chain starts behind the first band instead of behind the whole share.
-  MOSAIC_TRY(wait_target(c));
   const bool chain0 = rank == 0 && place_chain_eligible(c, p->max_usage);
   const int own_rows = re - rb;
-  const int own_bands = chain0 ? std::max(1, std::min(mosaic_ctx::kBands, (int)((size_t)own_rows * c->gw / 3000))) : 1;
+  // (a target still on its way up arrives in bands of these very rows: mosaic_set_target_rgb8)
+  const bool tgt_banded = chain0 && c->tgt_upload_pending && c->tgt_bands > 0 && c->tgt_band_rows[0] == rb && c->tgt_band_rows[c->tgt_bands] == re;
+  if (!tgt_banded) MOSAIC_TRY(wait_target(c));
+  const int own_bands = tgt_banded ? c->tgt_bands : (chain0 ? std::max(1, std::min(mosaic_ctx::kBands, (int)((size_t)own_rows * c->gw / 3000))) : 1);
   if (chain0) {
     MOSAIC_TRY(ensure(c, &c->d_ready_cells, &c->ready_cells_cap, (size_t)1));
     MOSAIC_CUDA(c, cudaMemsetAsync(c->d_ready_cells, 0, sizeof(unsigned), c->stream));
@@ -507,7 +509,9 @@ int run_generate_peer(mosaic_ctx* c, const mosaic_params* p, bool anneal, uint8_
   c->have_cell_lab = c->have_cell_rgbsum = true;
   c->cell_lab_gathered = false;
   for (int b = 0; b < own_bands; ++b) {
-    const int r0 = rb + (int)((long long)own_rows * b / own_bands), r1 = rb + (int)((long long)own_rows * (b + 1) / own_bands);
+    const int r0 = tgt_banded ? c->tgt_band_rows[b] : rb + (int)((long long)own_rows * b / own_bands);
+    const int r1 = tgt_banded ? c->tgt_band_rows[b + 1] : rb + (int)((long long)own_rows * (b + 1) / own_bands);
+    if (tgt_banded) MOSAIC_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_tgt_band[b], 0));
     if (r1 <= r0) continue;
     MOSAIC_TRY(launch_cell_lab_range(c, r0 * c->gw, r1 * c->gw));
     c->cand_dst_idx = reinterpret_cast<uint32_t*>(c->pw_peer[mosaic_ctx::PW_CAND_IDX][0]);
@@ -523,6 +527,7 @@ int run_generate_peer(mosaic_ctx* c, const mosaic_params* p, bool anneal, uint8_
       if (b == 0) MOSAIC_CUDA(c, cudaEventRecord(c->ev_chain_go, c->stream));
     }
   }
+  c->tgt_upload_pending = false;
   trace_point(c, "topk");
   const unsigned e_cand = ++c->ep_cand, e_res = ++c->ep_res, e_grd = ++c->ep_grd;
   c->have_cand = true;
@@ -1218,10 +1223,23 @@ int mosaic_set_target_rgb8(mosaic_ctx* c, const uint8_t* rgb, int w, int h, int 
   }
   int rb = 0, re = grid_h;
   shard_rows(c, c->rank, &rb, &re);  // only this rank's band of pixel rows is uploaded
-  const size_t y0 = (size_t)rb * c->tile_h, y1 = (c->world > 1) ? (size_t)re * c->tile_h : (size_t)h;
-  if (y1 > y0)
-    MOSAIC_CUDA(c, cudaMemcpyAsync(c->d_target_owned + y0 * row_bytes, rgb + y0 * row_bytes, (y1 - y0) * row_bytes,
-                                   cudaMemcpyHostToDevice, c->stream));
+  // ... on the upload stream, in bands of ~3,000 cells with one event each: the material Lab means and their exchange run
+  // under it, and rank 0 — whose placement chain starts behind its first rows — matches every band as it lands
+  MOSAIC_TRY(begin_upload(c));
+  const int own_rows = re - rb;
+  const int bands = std::max(1, std::min(mosaic_ctx::kBands, (int)((size_t)own_rows * grid_w / 3000)));
+  for (int b = 0; b < bands; ++b) {
+    const int r0 = rb + (int)((long long)own_rows * b / bands), r1 = rb + (int)((long long)own_rows * (b + 1) / bands);
+    const size_t p0 = (size_t)r0 * c->tile_h, p1 = (size_t)r1 * c->tile_h;
+    c->tgt_band_rows[b] = r0;
+    c->tgt_band_rows[b + 1] = r1;
+    if (p1 > p0)
+      MOSAIC_CUDA(c, cudaMemcpyAsync(c->d_target_owned + p0 * row_bytes, rgb + p0 * row_bytes, (p1 - p0) * row_bytes,
+                                     cudaMemcpyHostToDevice, c->upload_stream));
+    MOSAIC_CUDA(c, cudaEventRecord(c->ev_tgt_band[b], c->upload_stream));
+  }
+  c->tgt_bands = bands;
+  c->tgt_upload_pending = true;
   c->have_target = true;
   return MOSAIC_OK;
 }
