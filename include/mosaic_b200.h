@@ -243,6 +243,13 @@ int mosaic_png_decode_rgb8(const char* file, uint8_t** rgb_out, int* width, int*
 /* RgbImage::save(path) for a ".png" path (src/main.rs:668-672): 8-bit RGB, lossless (the file bytes are this
  * writer's own choice of filters and deflate level; the pixels are the contract). */
 int mosaic_png_encode_rgb8(const char* file, const uint8_t* rgb, int width, int height);
+/* The same for a JPEG file (include/mosaic_jpeg.hpp): baseline, extended sequential and progressive Huffman processes, 8-bit,
+ * grey / YCbCr / RGB, any sampling factors, restart intervals — with the arithmetic of the IJG / libjpeg-turbo defaults
+ * (islow inverse DCT, fancy upsampling, 16-bit colour tables: bit-identical to Pillow's decode); the reference's decoder
+ * (image 0.25.6 / zune-jpeg) may differ from any other conforming decoder by +-1 per channel [3P, parity unpinned]. */
+int mosaic_jpeg_decode_rgb8(const char* file, uint8_t** rgb_out, int* width, int* height);
+/* PNG or JPEG, told apart by the file's first bytes (image::open for the two formats this library decodes). */
+int mosaic_image_decode_rgb8(const char* file, uint8_t** rgb_out, int* width, int* height);
 void mosaic_host_free(void* p);
 
 /* ---- self test ------------------------------------------------------------------------------ */

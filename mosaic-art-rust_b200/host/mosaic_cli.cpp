@@ -1,10 +1,11 @@
 // mosaic-b200 — a small C++ host over the C ABI with the reference CLI's flag names (struct Args, main.rs:20-88) and
 // main()'s sequence (main.rs:741-779): target aspect -> MosaicGenerator::new -> generate_mosaic -> save.
 //
-// Images are PNG (include/mosaic_png.hpp: every colour type / bit depth, as `image::open(path)?.to_rgb8()` reads them) or
-// binary PPM (P6, maxval 255), told apart by the extension, case-insensitively like main.rs:175-184; --material-src is a
-// directory of such files of any sizes; the output format follows the extension of --output (main.rs:668-672).  JPEG and
-// WebP — the other two formats the reference accepts — need codecs this image does not have.
+// Images are PNG (include/mosaic_png.hpp: every colour type / bit depth, as `image::open(path)?.to_rgb8()` reads them), JPEG
+// (include/mosaic_jpeg.hpp: baseline + progressive, libjpeg-turbo's default arithmetic) or binary PPM (P6, maxval 255), told
+// apart by the extension, case-insensitively like main.rs:175-184; --material-src is a directory of such files of any sizes;
+// the output is PNG or PPM by the extension of --output (main.rs:668-672).  WebP — the fourth format the reference
+// accepts — needs a codec this image does not have.
 // The material selection follows load_tiles (main.rs:166-261): aspect
 // filter (lib.rs:121-123), no-match fallback to the first min(len, 2*max) files, truncate to --max-materials; files are
 // taken in sorted order (read_dir order is unspecified in the reference).
@@ -21,6 +22,7 @@
 #include <iostream>
 
 #include "mosaic_b200.hpp"
+#include "mosaic_jpeg.hpp"
 #include "mosaic_png.hpp"
 
 using namespace mosaic_b200;
@@ -137,7 +139,20 @@ static std::string lower_ext(const std::string& file) {  // main.rs:177-182: ext
 
 // image::open(path)?.to_rgb8() (main.rs:268, 484) for the formats this host has
 static bool read_image(const std::string& file, RgbImage* img, bool header_only = false) {
-  if (lower_ext(file) != "png") return read_ppm(file, img, header_only);
+  const std::string ext = lower_ext(file);
+  if (ext == "jpg" || ext == "jpeg") {
+    try {
+      if (header_only) return codec::jpeg_dimensions(file, &img->width, &img->height);
+      codec::JpegImage d = codec::decode_jpeg(file);
+      img->width = d.width, img->height = d.height;
+      img->data = std::move(d.rgb);
+      return true;
+    } catch (const std::exception& e) {
+      std::fprintf(stderr, "%s\n", e.what());
+      return false;
+    }
+  }
+  if (ext != "png") return read_ppm(file, img, header_only);
   try {
     if (header_only) return codec::png_dimensions(file, &img->width, &img->height);
     codec::Image d = codec::decode_png(file);
@@ -167,7 +182,7 @@ int main(int argc, char** argv) {
   try {
     const auto t0 = std::chrono::steady_clock::now();
     RgbImage target;
-    if (!read_image(args.target, &target)) throw std::runtime_error("cannot read target (PNG or binary PPM expected): " + args.target);
+    if (!read_image(args.target, &target)) throw std::runtime_error("cannot read target (PNG, JPEG or binary PPM expected): " + args.target);
     const float target_aspect = (float)target.width / (float)target.height;  // main.rs:745-747
     std::printf("Target aspect ratio: %.3f\n", target_aspect);
 
@@ -179,7 +194,7 @@ int main(int argc, char** argv) {
         const std::string name = e->d_name, path = args.material_src + "/" + name;
         struct stat st;
         const std::string ext = lower_ext(name);
-        if ((ext == "png" || ext == "ppm") && stat(path.c_str(), &st) == 0 && S_ISREG(st.st_mode))
+        if ((ext == "png" || ext == "jpg" || ext == "jpeg" || ext == "ppm") && stat(path.c_str(), &st) == 0 && S_ISREG(st.st_mode))
           entries.push_back(path);
       }
       closedir(d);
@@ -191,7 +206,7 @@ int main(int argc, char** argv) {
     std::vector<RgbImage> headers(entries.size());
     for (size_t i = 0; i < entries.size(); ++i) {
       if (!read_image(entries[i], &headers[i], true)) {
-        std::fprintf(stderr, "Error processing \"%s\": not a PNG / binary PPM\n", entries[i].c_str());
+        std::fprintf(stderr, "Error processing \"%s\": not a PNG / JPEG / binary PPM\n", entries[i].c_str());
         continue;
       }
       const float aspect = (float)headers[i].width / (float)headers[i].height;

@@ -118,6 +118,8 @@ def load_library():
         "mosaic_set_progress_callback": ([vp, PROGRESS_FN, vp], C.c_int),
         "mosaic_png_decode_rgb8": ([C.c_char_p, C.POINTER(u8p), C.POINTER(C.c_int), C.POINTER(C.c_int)], C.c_int),
         "mosaic_png_encode_rgb8": ([C.c_char_p, vp, C.c_int, C.c_int], C.c_int),
+        "mosaic_jpeg_decode_rgb8": ([C.c_char_p, C.POINTER(u8p), C.POINTER(C.c_int), C.POINTER(C.c_int)], C.c_int),
+        "mosaic_image_decode_rgb8": ([C.c_char_p, C.POINTER(u8p), C.POINTER(C.c_int), C.POINTER(C.c_int)], C.c_int),
         "mosaic_host_free": ([vp], None),
         "mosaic_host_alloc": ([C.c_size_t, C.POINTER(vp)], C.c_int),
         "mosaic_host_release": ([vp], C.c_int),
@@ -146,7 +148,7 @@ EXPORTED_SYMBOLS = (
     "mosaic_simdb_save_json", "mosaic_simdb_save_json_n", "mosaic_simdb_save_ctx", "mosaic_simdb_load_json", "mosaic_simdb_free",
     "mosaic_simdb_info", "mosaic_simdb_path", "mosaic_simdb_index_of", "mosaic_simdb_copy",
     "mosaic_simdb_get_similarity",
-    "mosaic_set_progress_callback", "mosaic_png_decode_rgb8", "mosaic_png_encode_rgb8", "mosaic_host_free",
+    "mosaic_set_progress_callback", "mosaic_png_decode_rgb8", "mosaic_png_encode_rgb8", "mosaic_jpeg_decode_rgb8", "mosaic_image_decode_rgb8", "mosaic_host_free",
     "mosaic_host_alloc", "mosaic_host_release", "mosaic_host_register", "mosaic_host_unregister",
 )
 
@@ -524,6 +526,29 @@ class Context:
     def output_shape(self):
         d = self.dims()
         return (d["grid_h"] * d["tile_h"], d["grid_w"] * d["tile_w"], 3)
+
+
+def _decode_with(fn_name, path) -> np.ndarray:
+    L = load_library()
+    buf = C.POINTER(C.c_uint8)()
+    w, h = C.c_int(), C.c_int()
+    rc = getattr(L, fn_name)(os.fsencode(path), C.byref(buf), C.byref(w), C.byref(h))
+    if rc != 0:
+        raise MosaicError(rc, (L.mosaic_last_error(None) or b"").decode())
+    try:
+        return np.ctypeslib.as_array(buf, shape=(h.value, w.value, 3)).copy()
+    finally:
+        L.mosaic_host_free(buf)
+
+
+def jpeg_decode(path) -> np.ndarray:
+    """image::open(path)?.to_rgb8() for a JPEG file: (h, w, 3) uint8, libjpeg-turbo's default arithmetic.  Host only."""
+    return _decode_with("mosaic_jpeg_decode_rgb8", path)
+
+
+def image_decode(path) -> np.ndarray:
+    """PNG or JPEG by the file's first bytes.  Host only."""
+    return _decode_with("mosaic_image_decode_rgb8", path)
 
 
 def png_decode(path) -> np.ndarray:

@@ -1,0 +1,122 @@
+"""JPEG in on the host side (include/mosaic_jpeg.hpp through the C ABI): what
+`image::open(path)?.to_rgb8()` (main.rs:263-301) does for the format photo libraries are made of.
+
+CPU only.  The decoder restates the arithmetic of libjpeg-turbo's defaults (islow inverse DCT, fancy upsampling, 16-bit
+colour tables); Pillow decodes through libjpeg-turbo, so every pixel is expected to be EQUAL — baseline and progressive,
+4:4:4 / 4:2:2 / 4:2:0 / 4:1:1, grey, RGB (Adobe transform 0), optimised Huffman tables, restart intervals, sizes that are
+not multiples of the MCU.  (Against the reference's own decoder — image 0.25.6 / zune-jpeg — two conforming decoders
+agree to about +-1 per channel: parity unpinned, see the header.)"""
+import numpy as np
+import pytest
+
+import mosaic_b200
+
+PIL = pytest.importorskip("PIL.Image")
+
+
+def images():
+    rng = np.random.default_rng(20261018)
+    yy, xx = np.mgrid[0:70, 0:101]
+    smooth = np.stack([(xx * 2) % 256, (yy * 3 + xx) % 256, (xx * yy // 7) % 256], -1).astype(np.uint8)
+    noise = rng.integers(0, 256, (53, 67, 3), dtype=np.uint8)
+    return smooth, noise
+
+
+def roundtrip(tmp_path, arr, name, **kw):
+    f = tmp_path / f"{name}.jpg"
+    PIL.fromarray(arr).save(f, **kw)
+    want = np.asarray(PIL.open(f).convert("RGB"))
+    got = mosaic_b200.jpeg_decode(f)
+    assert got.shape == want.shape, name
+    assert (got == want).all(), f"{name}: {np.abs(got.astype(int) - want.astype(int)).max()} max difference to libjpeg-turbo"
+    assert (mosaic_b200.image_decode(f) == want).all()
+
+
+@pytest.mark.parametrize("progressive", [False, True])
+@pytest.mark.parametrize("subsampling", [0, 1, 2, "4:1:1"])
+def test_decode_equals_libjpeg_turbo(tmp_path, progressive, subsampling):
+    smooth, noise = images()
+    roundtrip(tmp_path, smooth, "smooth", quality=85, subsampling=subsampling, progressive=progressive)
+    roundtrip(tmp_path, noise, "noise", quality=60, subsampling=subsampling, progressive=progressive)
+    roundtrip(tmp_path, np.tile(smooth, (3, 3, 1))[:197, :283], "odd", quality=35, subsampling=subsampling, progressive=progressive,
+              optimize=True)
+
+
+@pytest.mark.parametrize("kw", [dict(quality=1), dict(quality=100, subsampling=0), dict(quality=90, optimize=True),
+                                dict(quality=85, subsampling=2, restart_marker_blocks=3),
+                                dict(quality=85, subsampling=1, restart_marker_rows=1, progressive=True),
+                                dict(quality=85, keep_rgb=True), dict(quality=85, keep_rgb=True, progressive=True)])
+def test_decode_variants(tmp_path, kw):
+    smooth, noise = images()
+    try:
+        roundtrip(tmp_path, smooth, "a", **kw)
+        roundtrip(tmp_path, noise, "b", **kw)
+    except TypeError:
+        pytest.skip("this Pillow cannot write that variant")
+
+
+@pytest.mark.parametrize("shape", [(1, 1), (1, 9), (9, 1), (3, 16), (16, 3), (8, 8), (17, 33)])
+@pytest.mark.parametrize("subsampling", [0, 2])
+def test_decode_small_and_grey(tmp_path, shape, subsampling):
+    smooth, _ = images()
+    roundtrip(tmp_path, smooth[:shape[0], :shape[1]], "rgb", quality=80, subsampling=subsampling)
+    roundtrip(tmp_path, np.ascontiguousarray(smooth[:shape[0], :shape[1], 1]), "grey", quality=80)
+    roundtrip(tmp_path, np.ascontiguousarray(smooth[:shape[0], :shape[1], 1]), "greyp", quality=80, progressive=True)
+
+
+def test_decode_errors_and_dispatch(tmp_path):
+    _, noise = images()
+    f = tmp_path / "cmyk.jpg"
+    PIL.fromarray(noise).convert("CMYK").save(f)
+    with pytest.raises(mosaic_b200.MosaicError, match="1- and 3-component"):
+        mosaic_b200.jpeg_decode(f)
+    bad = tmp_path / "bad.jpg"
+    bad.write_bytes(b"\xff\xd8\xff\xe0 not a jpeg")
+    with pytest.raises(mosaic_b200.MosaicError):
+        mosaic_b200.jpeg_decode(bad)
+    good = tmp_path / "good.jpg"
+    PIL.fromarray(noise).save(good, quality=80)
+    trunc = tmp_path / "trunc.jpg"
+    trunc.write_bytes(good.read_bytes()[:200])
+    with pytest.raises(mosaic_b200.MosaicError):
+        mosaic_b200.jpeg_decode(trunc)
+    # image_decode tells the formats apart by content, whatever the extension says
+    png = tmp_path / "really_a_png.jpg"
+    mosaic_b200.png_encode(tmp_path / "x.png", noise)
+    png.write_bytes((tmp_path / "x.png").read_bytes())
+    assert (mosaic_b200.image_decode(png) == noise).all()
+    other = tmp_path / "other.webp"
+    other.write_bytes(b"RIFF\x00\x00\x00\x00WEBPVP8 ")
+    with pytest.raises(mosaic_b200.MosaicError, match="neither PNG nor JPEG"):
+        mosaic_b200.image_decode(other)
+
+
+def test_cli_selects_jpeg_materials(tmp_path):
+    """The host CLI's load_tiles (main.rs:166-261) over a directory of JPEG files: extension matched case-insensitively,
+    dimensions from the frame header for the aspect filter.  (Without a GPU the run then stops with the library's loud
+    error; with one it completes.)"""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "mosaic-art-rust_b200")
+    subprocess.check_call(["make", "-C", pkg, "host/mosaic-b200"], stdout=subprocess.DEVNULL)
+    cli = os.path.join(pkg, "host", "mosaic-b200")
+    rng = np.random.default_rng(3)
+    PIL.fromarray(rng.integers(0, 256, (60, 100, 3), dtype=np.uint8)).save(tmp_path / "target.JPG", quality=90)
+    mdir = tmp_path / "m"
+    mdir.mkdir()
+    sizes = [(50, 30), (64, 64), (25, 15), (30, 70), (100, 60)]  # 3 of 5 match 5:3
+    for i in range(10):
+        w, h = sizes[i % 5]
+        PIL.fromarray(rng.integers(0, 256, (h, w, 3), dtype=np.uint8)).save(
+            mdir / f"f{i:02d}.{'jpeg' if i % 2 else 'jpg'}", quality=85, progressive=bool(i % 3 == 0))
+    (mdir / "broken.jpg").write_bytes(b"\xff\xd8 nothing else")
+    r = subprocess.run([cli, "-t", str(tmp_path / "target.JPG"), "-m", str(mdir), "-o", str(tmp_path / "o.png"), "--grid-w", "5",
+                        "--grid-h", "3", "--similarity-db", str(tmp_path / "db.json")], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 or "no usable CUDA device" in r.stderr, r.stderr[-1500:]
+    assert "Target aspect ratio: 1.667" in r.stdout
+    assert "Loaded 6 tiles" in r.stdout          # 2 rounds x 3 matching sizes
+    assert "broken.jpg" in r.stderr
+    if r.returncode == 0:
+        out = mosaic_b200.png_decode(tmp_path / "o.png")
+        assert out.shape == (60, 100, 3)
