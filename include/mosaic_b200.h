@@ -248,6 +248,9 @@ int mosaic_png_encode_rgb8(const char* file, const uint8_t* rgb, int width, int 
  * (islow inverse DCT, fancy upsampling, 16-bit colour tables: bit-identical to Pillow's decode); the reference's decoder
  * (image 0.25.6 / zune-jpeg) may differ from any other conforming decoder by +-1 per channel [3P, parity unpinned]. */
 int mosaic_jpeg_decode_rgb8(const char* file, uint8_t** rgb_out, int* width, int* height);
+/* RgbImage::save(path) for a ".jpg" / ".jpeg" path (src/main.rs:668-672): baseline, YCbCr 4:4:4, Annex K tables scaled by the
+ * IJG quality formula (quality <= 0: 75, the `image` crate's default) — the file libjpeg writes at that setting. */
+int mosaic_jpeg_encode_rgb8(const char* file, const uint8_t* rgb, int width, int height, int quality);
 /* PNG or JPEG, told apart by the file's first bytes (image::open for the two formats this library decodes). */
 int mosaic_image_decode_rgb8(const char* file, uint8_t** rgb_out, int* width, int* height);
 void mosaic_host_free(void* p);

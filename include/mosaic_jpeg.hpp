@@ -1,4 +1,4 @@
-// mosaic_jpeg.hpp — JPEG in for the host side of the path (C++17, header-only, no library).
+// mosaic_jpeg.hpp — JPEG in and out for the host side of the path (C++17, header-only, no library).
 //
 // the reference reads every material and the target with `image::open(path)` and hands the pixels
 // on as `img.to_rgb8()` (src/main.rs:263-301, 484, 548, 632); JPEG is what photo libraries are made of (main.rs:182 accepts
@@ -617,6 +617,218 @@ inline JpegImage decode_jpeg(const std::string& path) {
   while ((got = std::fread(buf, 1, sizeof buf, f)) > 0) data.insert(data.end(), buf, buf + got);
   std::fclose(f);
   return decode_jpeg_memory(data.data(), data.size());
+}
+
+// ---- encoder: output_img.save("x.jpg") (src/main.rs:668-672 with a .jpg / .jpeg path) ---------------------------------
+// Baseline sequential DCT, 8-bit, YCbCr 4:4:4 (no chroma subsampling), the Annex K quantisation tables scaled by the IJG
+// quality formula, the Annex K Huffman tables, a JFIF APP0 header — the shape of the file the `image` crate's encoder
+// writes at its default quality 75 [3P, restated from memory of image 0.25's JpegEncoder: the exact bytes of a lossy
+// encoder are nobody's contract].  Forward DCT: jfdctint ("islow"), colour conversion: jccolor's 16-bit tables.
+namespace jpeg_detail {
+
+static const uint8_t kStdLumaQ[64] = {16, 11, 10, 16, 24,  40,  51,  61,  12, 12, 14, 19, 26,  58,  60,  55,  14, 13, 16, 24, 40,  57,
+                                      69, 56, 14, 17, 22,  29,  51,  87,  80, 62, 18, 22, 37,  56,  68,  109, 103, 77, 24, 35, 55, 64,
+                                      81, 104, 113, 92, 49, 64,  78,  87,  103, 121, 120, 101, 72, 92,  95,  98,  112, 100, 103, 99};
+static const uint8_t kStdChromaQ[64] = {17, 18, 24, 47, 99, 99, 99, 99, 18, 21, 26, 66, 99, 99, 99, 99, 24, 26, 56, 99, 99, 99,
+                                        99, 99, 47, 66, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99,
+                                        99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99};
+static const uint8_t kDcLumaBits[17] = {0, 0, 1, 5, 1, 1, 1, 1, 1, 1, 0, 0, 0, 0, 0, 0, 0};
+static const uint8_t kDcChromaBits[17] = {0, 0, 3, 1, 1, 1, 1, 1, 1, 1, 1, 1, 0, 0, 0, 0, 0};
+static const uint8_t kDcVals[12] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11};
+static const uint8_t kAcLumaBits[17] = {0, 0, 2, 1, 3, 3, 2, 4, 3, 5, 5, 4, 4, 0, 0, 1, 0x7d};
+static const uint8_t kAcLumaVals[162] = {
+    0x01, 0x02, 0x03, 0x00, 0x04, 0x11, 0x05, 0x12, 0x21, 0x31, 0x41, 0x06, 0x13, 0x51, 0x61, 0x07, 0x22, 0x71, 0x14, 0x32, 0x81,
+    0x91, 0xa1, 0x08, 0x23, 0x42, 0xb1, 0xc1, 0x15, 0x52, 0xd1, 0xf0, 0x24, 0x33, 0x62, 0x72, 0x82, 0x09, 0x0a, 0x16, 0x17, 0x18,
+    0x19, 0x1a, 0x25, 0x26, 0x27, 0x28, 0x29, 0x2a, 0x34, 0x35, 0x36, 0x37, 0x38, 0x39, 0x3a, 0x43, 0x44, 0x45, 0x46, 0x47, 0x48,
+    0x49, 0x4a, 0x53, 0x54, 0x55, 0x56, 0x57, 0x58, 0x59, 0x5a, 0x63, 0x64, 0x65, 0x66, 0x67, 0x68, 0x69, 0x6a, 0x73, 0x74, 0x75,
+    0x76, 0x77, 0x78, 0x79, 0x7a, 0x83, 0x84, 0x85, 0x86, 0x87, 0x88, 0x89, 0x8a, 0x92, 0x93, 0x94, 0x95, 0x96, 0x97, 0x98, 0x99,
+    0x9a, 0xa2, 0xa3, 0xa4, 0xa5, 0xa6, 0xa7, 0xa8, 0xa9, 0xaa, 0xb2, 0xb3, 0xb4, 0xb5, 0xb6, 0xb7, 0xb8, 0xb9, 0xba, 0xc2, 0xc3,
+    0xc4, 0xc5, 0xc6, 0xc7, 0xc8, 0xc9, 0xca, 0xd2, 0xd3, 0xd4, 0xd5, 0xd6, 0xd7, 0xd8, 0xd9, 0xda, 0xe1, 0xe2, 0xe3, 0xe4, 0xe5,
+    0xe6, 0xe7, 0xe8, 0xe9, 0xea, 0xf1, 0xf2, 0xf3, 0xf4, 0xf5, 0xf6, 0xf7, 0xf8, 0xf9, 0xfa};
+static const uint8_t kAcChromaBits[17] = {0, 0, 2, 1, 2, 4, 4, 3, 4, 7, 5, 4, 4, 0, 1, 2, 0x77};
+static const uint8_t kAcChromaVals[162] = {
+    0x00, 0x01, 0x02, 0x03, 0x11, 0x04, 0x05, 0x21, 0x31, 0x06, 0x12, 0x41, 0x51, 0x07, 0x61, 0x71, 0x13, 0x22, 0x32, 0x81, 0x08,
+    0x14, 0x42, 0x91, 0xa1, 0xb1, 0xc1, 0x09, 0x23, 0x33, 0x52, 0xf0, 0x15, 0x62, 0x72, 0xd1, 0x0a, 0x16, 0x24, 0x34, 0xe1, 0x25,
+    0xf1, 0x17, 0x18, 0x19, 0x1a, 0x26, 0x27, 0x28, 0x29, 0x2a, 0x35, 0x36, 0x37, 0x38, 0x39, 0x3a, 0x43, 0x44, 0x45, 0x46, 0x47,
+    0x48, 0x49, 0x4a, 0x53, 0x54, 0x55, 0x56, 0x57, 0x58, 0x59, 0x5a, 0x63, 0x64, 0x65, 0x66, 0x67, 0x68, 0x69, 0x6a, 0x73, 0x74,
+    0x75, 0x76, 0x77, 0x78, 0x79, 0x7a, 0x82, 0x83, 0x84, 0x85, 0x86, 0x87, 0x88, 0x89, 0x8a, 0x92, 0x93, 0x94, 0x95, 0x96, 0x97,
+    0x98, 0x99, 0x9a, 0xa2, 0xa3, 0xa4, 0xa5, 0xa6, 0xa7, 0xa8, 0xa9, 0xaa, 0xb2, 0xb3, 0xb4, 0xb5, 0xb6, 0xb7, 0xb8, 0xb9, 0xba,
+    0xc2, 0xc3, 0xc4, 0xc5, 0xc6, 0xc7, 0xc8, 0xc9, 0xca, 0xd2, 0xd3, 0xd4, 0xd5, 0xd6, 0xd7, 0xd8, 0xd9, 0xda, 0xe2, 0xe3, 0xe4,
+    0xe5, 0xe6, 0xe7, 0xe8, 0xe9, 0xea, 0xf2, 0xf3, 0xf4, 0xf5, 0xf6, 0xf7, 0xf8, 0xf9, 0xfa};
+
+// jfdctint.c ("islow") on a block of level-shifted samples; output scaled by 8 (the quantiser divides it out)
+inline void fdct_islow(int* d) {
+  constexpr int CB = 13, P1 = 2;
+  constexpr long F_0_298631336 = 2446, F_0_390180644 = 3196, F_0_541196100 = 4433, F_0_765366865 = 6270, F_0_899976223 = 7373,
+                 F_1_175875602 = 9633, F_1_501321110 = 12299, F_1_847759065 = 15137, F_1_961570560 = 16069,
+                 F_2_053119869 = 16819, F_2_562915447 = 20995, F_3_072711026 = 25172;
+  auto descale = [](long x, int n) { return (int)((x + (1L << (n - 1))) >> n); };
+  for (int pass = 0; pass < 2; ++pass) {
+    for (int i = 0; i < 8; ++i) {
+      int* p = pass == 0 ? d + 8 * i : d + i;
+      const int st = pass == 0 ? 1 : 8;
+      const long t0 = p[0] + p[7 * st], t7 = p[0] - p[7 * st], t1 = p[st] + p[6 * st], t6 = p[st] - p[6 * st];
+      const long t2 = p[2 * st] + p[5 * st], t5 = p[2 * st] - p[5 * st], t3 = p[3 * st] + p[4 * st], t4 = p[3 * st] - p[4 * st];
+      const long t10 = t0 + t3, t13 = t0 - t3, t11 = t1 + t2, t12 = t1 - t2;
+      if (pass == 0) {
+        p[0] = (int)((t10 + t11) << P1);
+        p[4 * st] = (int)((t10 - t11) << P1);
+      } else {
+        p[0] = descale(t10 + t11, P1);
+        p[4 * st] = descale(t10 - t11, P1);
+      }
+      const int sh = pass == 0 ? CB - P1 : CB + P1;
+      long z1 = (t12 + t13) * F_0_541196100;
+      p[2 * st] = descale(z1 + t13 * F_0_765366865, sh);
+      p[6 * st] = descale(z1 + t12 * (-F_1_847759065), sh);
+      z1 = t4 + t7;
+      long z2 = t5 + t6, z3 = t4 + t6, z4 = t5 + t7;
+      const long z5 = (z3 + z4) * F_1_175875602;
+      long a4 = t4 * F_0_298631336, a5 = t5 * F_2_053119869, a6 = t6 * F_3_072711026, a7 = t7 * F_1_501321110;
+      z1 *= -F_0_899976223, z2 *= -F_2_562915447, z3 *= -F_1_961570560, z4 *= -F_0_390180644;
+      z3 += z5, z4 += z5;
+      p[7 * st] = descale(a4 + z1 + z3, sh);
+      p[5 * st] = descale(a5 + z2 + z4, sh);
+      p[3 * st] = descale(a6 + z2 + z3, sh);
+      p[st] = descale(a7 + z1 + z4, sh);
+    }
+  }
+}
+
+struct BitWriter {
+  std::vector<uint8_t>& out;
+  uint32_t acc = 0;
+  int n = 0;
+  void put(unsigned code, int len) {
+    acc = (acc << len) | (code & ((1u << len) - 1u));
+    n += len;
+    while (n >= 8) {
+      const uint8_t byte = (uint8_t)(acc >> (n - 8));
+      out.push_back(byte);
+      if (byte == 0xFF) out.push_back(0x00);
+      n -= 8;
+    }
+  }
+  void flush() {
+    if (n > 0) put((1u << (8 - n)) - 1u, 8 - n);  // pad with ones
+  }
+};
+
+struct EncTable {
+  uint16_t code[256] = {};
+  uint8_t len[256] = {};
+  void build(const uint8_t* bits, const uint8_t* vals) {
+    int code_ = 0, k = 0;
+    for (int l = 1; l <= 16; ++l) {
+      for (int i = 0; i < bits[l]; ++i, ++k) {
+        code[vals[k]] = (uint16_t)code_++;
+        len[vals[k]] = (uint8_t)l;
+      }
+      code_ <<= 1;
+    }
+  }
+};
+
+}  // namespace jpeg_detail
+
+inline std::vector<uint8_t> encode_jpeg_memory(const uint8_t* rgb, int width, int height, int quality = 75) {
+  using namespace jpeg_detail;
+  if (width <= 0 || height <= 0 || width > 65535 || height > 65535) throw JpegError("jpeg: cannot encode an image of that size");
+  quality = std::min(100, std::max(1, quality));
+  const int scale = quality < 50 ? 5000 / quality : 200 - quality * 2;  // jpeg_quality_scaling
+  uint8_t q[2][64];
+  for (int t = 0; t < 2; ++t)
+    for (int i = 0; i < 64; ++i) {
+      const long v = ((long)(t ? kStdChromaQ[i] : kStdLumaQ[i]) * scale + 50) / 100;
+      q[t][i] = (uint8_t)std::min(255L, std::max(1L, v));  // (baseline: 8-bit entries)
+    }
+  std::vector<uint8_t> out;
+  auto marker = [&](int m, const std::vector<uint8_t>& body) {
+    out.push_back(0xFF), out.push_back((uint8_t)m);
+    const size_t len = body.size() + 2;
+    out.push_back((uint8_t)(len >> 8)), out.push_back((uint8_t)len);
+    out.insert(out.end(), body.begin(), body.end());
+  };
+  out.push_back(0xFF), out.push_back(0xD8);
+  marker(0xE0, {'J', 'F', 'I', 'F', 0, 1, 1, 0, 0, 1, 0, 1, 0, 0});
+  for (int t = 0; t < 2; ++t) {
+    std::vector<uint8_t> b(1, (uint8_t)t);
+    for (int k = 0; k < 64; ++k) b.push_back(q[t][kZigzag[k]]);
+    marker(0xDB, b);
+  }
+  marker(0xC0, {8, (uint8_t)(height >> 8), (uint8_t)height, (uint8_t)(width >> 8), (uint8_t)width, 3, 1, 0x11, 0, 2, 0x11, 1, 3, 0x11, 1});
+  auto dht = [&](int tc_th, const uint8_t* bits, const uint8_t* vals, int nvals) {
+    std::vector<uint8_t> b(1, (uint8_t)tc_th);
+    b.insert(b.end(), bits + 1, bits + 17);
+    b.insert(b.end(), vals, vals + nvals);
+    marker(0xC4, b);
+  };
+  dht(0x00, kDcLumaBits, kDcVals, 12), dht(0x10, kAcLumaBits, kAcLumaVals, 162);
+  dht(0x01, kDcChromaBits, kDcVals, 12), dht(0x11, kAcChromaBits, kAcChromaVals, 162);
+  marker(0xDA, {3, 1, 0x00, 2, 0x11, 3, 0x11, 0, 63, 0});
+  EncTable dc[2], ac[2];
+  dc[0].build(kDcLumaBits, kDcVals), dc[1].build(kDcChromaBits, kDcVals);
+  ac[0].build(kAcLumaBits, kAcLumaVals), ac[1].build(kAcChromaBits, kAcChromaVals);
+  BitWriter bw{out};
+  int pred[3] = {0, 0, 0};
+  const int bx = (width + 7) / 8, by = (height + 7) / 8;
+  for (int yb = 0; yb < by; ++yb)
+    for (int xb = 0; xb < bx; ++xb) {
+      int blk[3][64];
+      for (int y = 0; y < 8; ++y)
+        for (int x = 0; x < 8; ++x) {
+          const int sx = std::min(xb * 8 + x, width - 1), sy = std::min(yb * 8 + y, height - 1);  // edge replication
+          const uint8_t* p = rgb + ((size_t)sy * width + sx) * 3;
+          const long r = p[0], g = p[1], b = p[2];
+          // jccolor.c rgb_ycc_convert: 16-bit fixed point
+          blk[0][8 * y + x] = (int)((19595L * r + 38470L * g + 7471L * b + 32768L) >> 16) - 128;
+          blk[1][8 * y + x] = (int)((-11059L * r - 21709L * g + 32768L * b + (128L << 16) + 32767L) >> 16) - 128;
+          blk[2][8 * y + x] = (int)((32768L * r - 27439L * g - 5329L * b + (128L << 16) + 32767L) >> 16) - 128;
+        }
+      for (int c = 0; c < 3; ++c) {
+        fdct_islow(blk[c]);
+        const int t = c ? 1 : 0;
+        int zz[64];
+        for (int k = 0; k < 64; ++k) {
+          const int v = blk[c][kZigzag[k]], qv = q[t][kZigzag[k]] * 8;  // (the DCT output is scaled by 8)
+          zz[k] = v < 0 ? -((-v + qv / 2) / qv) : (v + qv / 2) / qv;
+        }
+        auto category = [](int v) {
+          int a = v < 0 ? -v : v, s = 0;
+          while (a) ++s, a >>= 1;
+          return s;
+        };
+        const int diff = zz[0] - pred[c];
+        pred[c] = zz[0];
+        int s = category(diff);
+        bw.put(dc[t].code[s], dc[t].len[s]);
+        if (s) bw.put((unsigned)(diff < 0 ? diff - 1 : diff), s);
+        int run = 0;
+        for (int k = 1; k < 64; ++k) {
+          if (zz[k] == 0) {
+            ++run;
+            continue;
+          }
+          while (run > 15) bw.put(ac[t].code[0xF0], ac[t].len[0xF0]), run -= 16;
+          s = category(zz[k]);
+          bw.put(ac[t].code[(run << 4) | s], ac[t].len[(run << 4) | s]);
+          bw.put((unsigned)(zz[k] < 0 ? zz[k] - 1 : zz[k]), s);
+          run = 0;
+        }
+        if (run) bw.put(ac[t].code[0x00], ac[t].len[0x00]);
+      }
+    }
+  bw.flush();
+  out.push_back(0xFF), out.push_back(0xD9);
+  return out;
+}
+
+inline void encode_jpeg(const std::string& path, const uint8_t* rgb, int width, int height, int quality = 75) {
+  const std::vector<uint8_t> file = encode_jpeg_memory(rgb, width, height, quality);
+  FILE* f = std::fopen(path.c_str(), "wb");
+  if (!f) throw JpegError("jpeg: cannot create " + path);
+  const bool ok = std::fwrite(file.data(), 1, file.size(), f) == file.size();
+  if (std::fclose(f) != 0 || !ok) throw JpegError("jpeg: short write to " + path);
 }
 
 // width and height from the frame header alone (the aspect filter, main.rs:269-270)

@@ -1,4 +1,4 @@
-// codec.cu — host-only entry points of the C ABI: PNG files <-> interleaved RGB8 (include/mosaic_png.hpp over zlib), JPEG files ->
+// codec.cu — host-only entry points of the C ABI: PNG files <-> interleaved RGB8 (include/mosaic_png.hpp over zlib), JPEG files <->
 // RGB8 (include/mosaic_jpeg.hpp).
 // what `image::open(path)?.to_rgb8()` (main.rs:263-301, 484, 548, 632) and
 // `output_img.save(path)` (main.rs:668-672) do for the one lossless format the reference accepts.  No device work.
@@ -48,6 +48,16 @@ int mosaic_jpeg_decode_rgb8(const char* file, uint8_t** rgb_out, int* width, int
     *rgb_out = buf;
     *width = img.width;
     *height = img.height;
+    return MOSAIC_OK;
+  } catch (const std::exception& e) {
+    return fail(nullptr, MOSAIC_ERR_INVALID, std::string(e.what()) + " (" + file + ")");
+  }
+}
+
+int mosaic_jpeg_encode_rgb8(const char* file, const uint8_t* rgb, int width, int height, int quality) {
+  if (!file || !rgb) return fail(nullptr, MOSAIC_ERR_INVALID, "jpeg_encode: bad arguments");
+  try {
+    mosaic_b200::codec::encode_jpeg(file, rgb, width, height, quality <= 0 ? 75 : quality);
     return MOSAIC_OK;
   } catch (const std::exception& e) {
     return fail(nullptr, MOSAIC_ERR_INVALID, std::string(e.what()) + " (" + file + ")");

@@ -4,7 +4,7 @@
 // Images are PNG (include/mosaic_png.hpp: every colour type / bit depth, as `image::open(path)?.to_rgb8()` reads them), JPEG
 // (include/mosaic_jpeg.hpp: baseline + progressive, libjpeg-turbo's default arithmetic) or binary PPM (P6, maxval 255), told
 // apart by the extension, case-insensitively like main.rs:175-184; --material-src is a directory of such files of any sizes;
-// the output is PNG or PPM by the extension of --output (main.rs:668-672).  WebP — the fourth format the reference
+// the output is PNG, JPEG or PPM by the extension of --output (main.rs:668-672).  WebP — the fourth format the reference
 // accepts — needs a codec this image does not have.
 // The material selection follows load_tiles (main.rs:166-261): aspect
 // filter (lib.rs:121-123), no-match fallback to the first min(len, 2*max) files, truncate to --max-materials; files are
@@ -166,9 +166,13 @@ static bool read_image(const std::string& file, RgbImage* img, bool header_only 
 }
 
 static bool write_image(const std::string& file, const RgbImage& img) {  // output_img.save(path): by extension
-  if (lower_ext(file) != "png") return write_ppm(file, img);
+  const std::string ext = lower_ext(file);
+  if (ext != "png" && ext != "jpg" && ext != "jpeg") return write_ppm(file, img);
   try {
-    codec::encode_png(file, img.data.data(), img.width, img.height);
+    if (ext == "png")
+      codec::encode_png(file, img.data.data(), img.width, img.height);
+    else
+      codec::encode_jpeg(file, img.data.data(), img.width, img.height, 75);  // (the `image` crate's default quality)
     return true;
   } catch (const std::exception& e) {
     std::fprintf(stderr, "%s\n", e.what());

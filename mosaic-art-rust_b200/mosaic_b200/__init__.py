@@ -118,6 +118,7 @@ def load_library():
         "mosaic_set_progress_callback": ([vp, PROGRESS_FN, vp], C.c_int),
         "mosaic_png_decode_rgb8": ([C.c_char_p, C.POINTER(u8p), C.POINTER(C.c_int), C.POINTER(C.c_int)], C.c_int),
         "mosaic_png_encode_rgb8": ([C.c_char_p, vp, C.c_int, C.c_int], C.c_int),
+        "mosaic_jpeg_encode_rgb8": ([C.c_char_p, vp, C.c_int, C.c_int, C.c_int], C.c_int),
         "mosaic_jpeg_decode_rgb8": ([C.c_char_p, C.POINTER(u8p), C.POINTER(C.c_int), C.POINTER(C.c_int)], C.c_int),
         "mosaic_image_decode_rgb8": ([C.c_char_p, C.POINTER(u8p), C.POINTER(C.c_int), C.POINTER(C.c_int)], C.c_int),
         "mosaic_host_free": ([vp], None),
@@ -148,7 +149,7 @@ EXPORTED_SYMBOLS = (
     "mosaic_simdb_save_json", "mosaic_simdb_save_json_n", "mosaic_simdb_save_ctx", "mosaic_simdb_load_json", "mosaic_simdb_free",
     "mosaic_simdb_info", "mosaic_simdb_path", "mosaic_simdb_index_of", "mosaic_simdb_copy",
     "mosaic_simdb_get_similarity",
-    "mosaic_set_progress_callback", "mosaic_png_decode_rgb8", "mosaic_png_encode_rgb8", "mosaic_jpeg_decode_rgb8", "mosaic_image_decode_rgb8", "mosaic_host_free",
+    "mosaic_set_progress_callback", "mosaic_png_decode_rgb8", "mosaic_png_encode_rgb8", "mosaic_jpeg_decode_rgb8", "mosaic_jpeg_encode_rgb8", "mosaic_image_decode_rgb8", "mosaic_host_free",
     "mosaic_host_alloc", "mosaic_host_release", "mosaic_host_register", "mosaic_host_unregister",
 )
 
@@ -620,3 +621,13 @@ class register:
 
     def __exit__(self, *a):
         load_library().mosaic_host_unregister(self.array.ctypes.data_as(C.c_void_p))
+
+
+def jpeg_encode(path, img, quality=75) -> None:
+    """RgbImage::save(path) for a ".jpg" path (main.rs:668-672): baseline 4:4:4 at the given quality.  Host only."""
+    L = load_library()
+    img = np.ascontiguousarray(img, np.uint8)
+    assert img.ndim == 3 and img.shape[2] == 3
+    rc = L.mosaic_jpeg_encode_rgb8(os.fsencode(path), img.ctypes.data_as(C.c_void_p), img.shape[1], img.shape[0], int(quality))
+    if rc != 0:
+        raise MosaicError(rc, (L.mosaic_last_error(None) or b"").decode())

@@ -120,3 +120,23 @@ def test_cli_selects_jpeg_materials(tmp_path):
     if r.returncode == 0:
         out = mosaic_b200.png_decode(tmp_path / "o.png")
         assert out.shape == (60, 100, 3)
+
+
+@pytest.mark.parametrize("quality", [30, 75, 95])
+@pytest.mark.parametrize("shape", [(1, 1), (5, 3), (70, 101), (120, 200)])
+def test_encode_is_what_libjpeg_writes(tmp_path, quality, shape):
+    """output_img.save("x.jpg") (main.rs:668-672): baseline 4:4:4 with the IJG tables and arithmetic — the file decodes to
+    exactly the pixels of the file libjpeg-turbo (Pillow) writes from the same image at the same quality, and is as large."""
+    rng = np.random.default_rng(7)
+    yy, xx = np.mgrid[0:shape[0], 0:shape[1]]
+    arr = (np.stack([127 + 100 * np.sin(xx / 17.0) * np.cos(yy / 11.0), 127 + 90 * np.sin((xx + yy) / 23.0), 127 + 80 * np.cos(xx / 9.0)], -1)
+           + rng.normal(0, 4, shape + (3,))).clip(0, 255).astype(np.uint8)
+    ours, theirs = tmp_path / "ours.jpg", tmp_path / "theirs.jpg"
+    mosaic_b200.jpeg_encode(ours, arr, quality)
+    PIL.fromarray(arr).save(theirs, quality=quality, subsampling=0)
+    dec = np.asarray(PIL.open(ours).convert("RGB"))
+    assert (dec == np.asarray(PIL.open(theirs).convert("RGB"))).all()
+    assert (mosaic_b200.jpeg_decode(ours) == dec).all()
+    assert abs(ours.stat().st_size - theirs.stat().st_size) <= 64   # (headers may differ by a comment or a density field)
+    with PIL.open(ours) as im:
+        assert im.size == (shape[1], shape[0]) and im.mode == "RGB"
