@@ -251,7 +251,15 @@ int mosaic_jpeg_decode_rgb8(const char* file, uint8_t** rgb_out, int* width, int
 /* RgbImage::save(path) for a ".jpg" / ".jpeg" path (src/main.rs:668-672): baseline, YCbCr 4:4:4, Annex K tables scaled by the
  * IJG quality formula (quality <= 0: 75, the `image` crate's default) — the file libjpeg writes at that setting. */
 int mosaic_jpeg_encode_rgb8(const char* file, const uint8_t* rgb, int width, int height, int quality);
-/* PNG or JPEG, told apart by the file's first bytes (image::open for the two formats this library decodes). */
+/* The same for a WebP file (include/mosaic_webp.hpp; src/main.rs:181 accepts the extension): simple and extended (VP8X)
+ * containers; VP8L lossless — every transform, colour cache, meta prefix codes: the file's own pixels — and VP8 lossy key frames
+ * (RFC 6386) taken to RGB the way libwebp does by default (fancy chroma upsampling, its fixed-point BT.601): bit-identical to
+ * Pillow's decode.  Alpha is dropped like to_rgb8() drops it; animated files are refused.  [3P image-webp: parity unpinned] */
+int mosaic_webp_decode_rgb8(const char* file, uint8_t** rgb_out, int* width, int* height);
+/* RgbImage::save(path) for a ".webp" path (src/main.rs:668-672): lossless VP8L, as the `image` crate writes WebP — the
+ * pixels are the contract, the file bytes this writer's choice (subtract-green, one set of prefix codes, literals). */
+int mosaic_webp_encode_rgb8(const char* file, const uint8_t* rgb, int width, int height);
+/* PNG, JPEG or WebP, told apart by the file's first bytes (image::open for the formats src/main.rs:181 lists). */
 int mosaic_image_decode_rgb8(const char* file, uint8_t** rgb_out, int* width, int* height);
 void mosaic_host_free(void* p);
 

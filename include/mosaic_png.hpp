@@ -3,7 +3,8 @@
 // the reference reads every material and the target with `image::open(path)` and hands the
 // pixels on as `img.to_rgb8()` (src/main.rs:263-301, 484, 548, 632; src/lib.rs:94-96), and writes the mosaic with
 // `output_img.save(output_path)` (src/main.rs:668-672).  PNG is the lossless member of the formats it accepts
-// (main.rs:182: png / jpg / jpeg / webp) and the only one this image has a library for (zlib); JPEG and WebP stay with the host.
+// (main.rs:181: png / jpg / jpeg / webp) and the only one this image has a library for (zlib); JPEG and WebP are decoded by
+// include/mosaic_jpeg.hpp and include/mosaic_webp.hpp.
 //
 //   decode_png(path)  = image::open(path)?.to_rgb8() for a PNG file [3P: image 0.25.6 / png 0.17.16, restated]:
 //                       every colour type (grey, RGB, palette, grey+alpha, RGBA), bit depths 1/2/4/8/16, Adam7 interlace;

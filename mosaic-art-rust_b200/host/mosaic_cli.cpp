@@ -2,10 +2,10 @@
 // main()'s sequence (main.rs:741-779): target aspect -> MosaicGenerator::new -> generate_mosaic -> save.
 //
 // Images are PNG (include/mosaic_png.hpp: every colour type / bit depth, as `image::open(path)?.to_rgb8()` reads them), JPEG
-// (include/mosaic_jpeg.hpp: baseline + progressive, libjpeg-turbo's default arithmetic) or binary PPM (P6, maxval 255), told
-// apart by the extension, case-insensitively like main.rs:175-184; --material-src is a directory of such files of any sizes;
-// the output is PNG, JPEG or PPM by the extension of --output (main.rs:668-672).  WebP — the fourth format the reference
-// accepts — needs a codec this image does not have.
+// (include/mosaic_jpeg.hpp: baseline + progressive, libjpeg-turbo's default arithmetic), WebP (include/mosaic_webp.hpp: VP8 lossy
+// with libwebp's default conversion to RGB, VP8L lossless) or binary PPM (P6, maxval 255), told apart by the extension,
+// case-insensitively like main.rs:175-184 — the four extensions main.rs:181 lists; --material-src is a directory of such files
+// of any sizes; the output is PNG, JPEG, WebP (lossless) or PPM by the extension of --output (main.rs:668-672).
 // The material selection follows load_tiles (main.rs:166-261): aspect
 // filter (lib.rs:121-123), no-match fallback to the first min(len, 2*max) files, truncate to --max-materials; files are
 // taken in sorted order (read_dir order is unspecified in the reference).
@@ -24,6 +24,7 @@
 #include "mosaic_b200.hpp"
 #include "mosaic_jpeg.hpp"
 #include "mosaic_png.hpp"
+#include "mosaic_webp.hpp"
 
 using namespace mosaic_b200;
 
@@ -152,6 +153,18 @@ static bool read_image(const std::string& file, RgbImage* img, bool header_only 
       return false;
     }
   }
+  if (ext == "webp") {
+    try {
+      if (header_only) return codec::webp_dimensions(file, &img->width, &img->height);
+      codec::Image d = codec::decode_webp(file);
+      img->width = d.width, img->height = d.height;
+      img->data = std::move(d.rgb);
+      return true;
+    } catch (const std::exception& e) {
+      std::fprintf(stderr, "%s\n", e.what());
+      return false;
+    }
+  }
   if (ext != "png") return read_ppm(file, img, header_only);
   try {
     if (header_only) return codec::png_dimensions(file, &img->width, &img->height);
@@ -167,10 +180,12 @@ static bool read_image(const std::string& file, RgbImage* img, bool header_only 
 
 static bool write_image(const std::string& file, const RgbImage& img) {  // output_img.save(path): by extension
   const std::string ext = lower_ext(file);
-  if (ext != "png" && ext != "jpg" && ext != "jpeg") return write_ppm(file, img);
+  if (ext != "png" && ext != "jpg" && ext != "jpeg" && ext != "webp") return write_ppm(file, img);
   try {
     if (ext == "png")
       codec::encode_png(file, img.data.data(), img.width, img.height);
+    else if (ext == "webp")
+      codec::encode_webp(file, img.data.data(), img.width, img.height);  // (lossless VP8L, as the `image` crate writes WebP)
     else
       codec::encode_jpeg(file, img.data.data(), img.width, img.height, 75);  // (the `image` crate's default quality)
     return true;
@@ -198,7 +213,7 @@ int main(int argc, char** argv) {
         const std::string name = e->d_name, path = args.material_src + "/" + name;
         struct stat st;
         const std::string ext = lower_ext(name);
-        if ((ext == "png" || ext == "jpg" || ext == "jpeg" || ext == "ppm") && stat(path.c_str(), &st) == 0 && S_ISREG(st.st_mode))
+        if ((ext == "png" || ext == "jpg" || ext == "jpeg" || ext == "webp" || ext == "ppm") && stat(path.c_str(), &st) == 0 && S_ISREG(st.st_mode))
           entries.push_back(path);
       }
       closedir(d);

@@ -121,6 +121,8 @@ def load_library():
         "mosaic_jpeg_encode_rgb8": ([C.c_char_p, vp, C.c_int, C.c_int, C.c_int], C.c_int),
         "mosaic_jpeg_decode_rgb8": ([C.c_char_p, C.POINTER(u8p), C.POINTER(C.c_int), C.POINTER(C.c_int)], C.c_int),
         "mosaic_image_decode_rgb8": ([C.c_char_p, C.POINTER(u8p), C.POINTER(C.c_int), C.POINTER(C.c_int)], C.c_int),
+        "mosaic_webp_decode_rgb8": ([C.c_char_p, C.POINTER(u8p), C.POINTER(C.c_int), C.POINTER(C.c_int)], C.c_int),
+        "mosaic_webp_encode_rgb8": ([C.c_char_p, vp, C.c_int, C.c_int], C.c_int),
         "mosaic_host_free": ([vp], None),
         "mosaic_host_alloc": ([C.c_size_t, C.POINTER(vp)], C.c_int),
         "mosaic_host_release": ([vp], C.c_int),
@@ -149,7 +151,7 @@ EXPORTED_SYMBOLS = (
     "mosaic_simdb_save_json", "mosaic_simdb_save_json_n", "mosaic_simdb_save_ctx", "mosaic_simdb_load_json", "mosaic_simdb_free",
     "mosaic_simdb_info", "mosaic_simdb_path", "mosaic_simdb_index_of", "mosaic_simdb_copy",
     "mosaic_simdb_get_similarity",
-    "mosaic_set_progress_callback", "mosaic_png_decode_rgb8", "mosaic_png_encode_rgb8", "mosaic_jpeg_decode_rgb8", "mosaic_jpeg_encode_rgb8", "mosaic_image_decode_rgb8", "mosaic_host_free",
+    "mosaic_set_progress_callback", "mosaic_png_decode_rgb8", "mosaic_png_encode_rgb8", "mosaic_jpeg_decode_rgb8", "mosaic_jpeg_encode_rgb8", "mosaic_image_decode_rgb8", "mosaic_webp_decode_rgb8", "mosaic_webp_encode_rgb8", "mosaic_host_free",
     "mosaic_host_alloc", "mosaic_host_release", "mosaic_host_register", "mosaic_host_unregister",
 )
 
@@ -547,8 +549,24 @@ def jpeg_decode(path) -> np.ndarray:
     return _decode_with("mosaic_jpeg_decode_rgb8", path)
 
 
+def webp_decode(path) -> np.ndarray:
+    """image::open(path)?.to_rgb8() for a WebP file (VP8 lossy with libwebp's default conversion to RGB, VP8L lossless).  Host only."""
+    return _decode_with("mosaic_webp_decode_rgb8", path)
+
+
+def webp_encode(path, img) -> None:
+    """RgbImage::save(path) for a .webp path: lossless VP8L.  Host only."""
+    L = load_library()
+    img = np.ascontiguousarray(img, np.uint8)
+    if img.ndim != 3 or img.shape[2] != 3:
+        raise ValueError("webp_encode: (h, w, 3) uint8 expected")
+    rc = L.mosaic_webp_encode_rgb8(os.fsencode(path), img.ctypes.data_as(C.c_void_p), img.shape[1], img.shape[0])
+    if rc != 0:
+        raise MosaicError(rc, (L.mosaic_last_error(None) or b"").decode())
+
+
 def image_decode(path) -> np.ndarray:
-    """PNG or JPEG by the file's first bytes.  Host only."""
+    """PNG, JPEG or WebP by the file's first bytes.  Host only."""
     return _decode_with("mosaic_image_decode_rgb8", path)
 
 

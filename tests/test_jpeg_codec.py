@@ -85,10 +85,14 @@ def test_decode_errors_and_dispatch(tmp_path):
     mosaic_b200.png_encode(tmp_path / "x.png", noise)
     png.write_bytes((tmp_path / "x.png").read_bytes())
     assert (mosaic_b200.image_decode(png) == noise).all()
-    other = tmp_path / "other.webp"
-    other.write_bytes(b"RIFF\x00\x00\x00\x00WEBPVP8 ")
-    with pytest.raises(mosaic_b200.MosaicError, match="neither PNG nor JPEG"):
+    other = tmp_path / "other.gif"
+    other.write_bytes(b"GIF89a\x01\x00\x01\x00\x00\x00\x00;")
+    with pytest.raises(mosaic_b200.MosaicError, match="not a PNG, JPEG or WebP"):
         mosaic_b200.image_decode(other)
+    empty_webp = tmp_path / "empty.webp"  # a WebP container without an image chunk: handed to the WebP decoder, which refuses it
+    empty_webp.write_bytes(b"RIFF\x04\x00\x00\x00WEBP")
+    with pytest.raises(mosaic_b200.MosaicError, match="webp"):
+        mosaic_b200.image_decode(empty_webp)
 
 
 def test_cli_selects_jpeg_materials(tmp_path):
