@@ -156,6 +156,155 @@ def test_errors_and_dispatch(tmp_path):
             pass
 
 
+
+def _libwebp_encode(rgb, quality=75.0, **settings):
+    """libwebp's own encoder through its public C API (WebPConfig / WebPPicture / WebPEncode, encode.h), for the bitstream
+    features Pillow's `save` has no switch for: the SIMPLE loop filter, filter sharpness, several token partitions, the
+    segment count.  Uses the libwebp that Pillow bundles; None when it cannot be found."""
+    import ctypes as C
+    import glob
+    import os
+    import PIL as pil_pkg
+    libdir = os.path.join(os.path.dirname(os.path.dirname(pil_pkg.__file__)), "pillow.libs")
+    libs = sorted(glob.glob(os.path.join(libdir, "libwebp-*.so*")))
+    if not libs:
+        return None
+    for dep in glob.glob(os.path.join(libdir, "libsharpyuv-*.so*")):
+        C.CDLL(dep, mode=C.RTLD_GLOBAL)
+    L = C.CDLL(libs[0])
+    ints = ["lossless", None, "method", "image_hint", "target_size", None, "segments", "sns_strength", "filter_strength", "filter_sharpness",
+            "filter_type", "autofilter", "alpha_compression", "alpha_filtering", "alpha_quality", "pass_", "show_compressed", "preprocessing",
+            "partitions", "partition_limit", "emulate_jpeg_size", "thread_level", "low_memory", "near_lossless", "exact", "use_delta_palette",
+            "use_sharp_yuv", "qmin", "qmax"]
+    ints[1], ints[5] = "quality", "target_PSNR"
+
+    class Config(C.Structure):
+        _fields_ = [(n, C.c_float if n in ("quality", "target_PSNR") else C.c_int) for n in ints] + [("pad", C.c_int * 8)]
+
+    writer_t = C.CFUNCTYPE(C.c_int, C.POINTER(C.c_uint8), C.c_size_t, C.c_void_p)
+
+    class Picture(C.Structure):
+        _fields_ = [("use_argb", C.c_int), ("colorspace", C.c_int), ("width", C.c_int), ("height", C.c_int), ("y", C.c_void_p), ("u", C.c_void_p),
+                    ("v", C.c_void_p), ("y_stride", C.c_int), ("uv_stride", C.c_int), ("a", C.c_void_p), ("a_stride", C.c_int), ("pad1", C.c_uint32 * 2),
+                    ("argb", C.c_void_p), ("argb_stride", C.c_int), ("pad2", C.c_uint32 * 3), ("writer", writer_t), ("custom_ptr", C.c_void_p),
+                    ("extra_info_type", C.c_int), ("extra_info", C.c_void_p), ("stats", C.c_void_p), ("error_code", C.c_int), ("progress_hook", C.c_void_p),
+                    ("user_data", C.c_void_p), ("pad3", C.c_uint32 * 3), ("pad4", C.c_void_p), ("pad5", C.c_void_p), ("pad6", C.c_uint32 * 8),
+                    ("memory_", C.c_void_p), ("memory_argb_", C.c_void_p), ("pad7", C.c_void_p * 2), ("slack", C.c_uint8 * 256)]
+
+    abi = 0x020F  # (the library checks the major half only)
+    cfg = Config()
+    if not L.WebPConfigInitInternal(C.byref(cfg), 0, C.c_float(quality), abi):
+        return None
+    if (cfg.segments, cfg.filter_strength, cfg.filter_type, cfg.near_lossless, cfg.qmax) != (4, 60, 1, 100, 100):
+        return None  # not the struct layout this helper was written against
+    for k, v in settings.items():
+        setattr(cfg, k, v)
+    assert L.WebPValidateConfig(C.byref(cfg)), settings
+    pic = Picture()
+    assert L.WebPPictureInitInternal(C.byref(pic), abi)
+    rgb = np.ascontiguousarray(rgb, np.uint8)
+    pic.width, pic.height = rgb.shape[1], rgb.shape[0]
+    assert L.WebPPictureImportRGB(C.byref(pic), rgb.ctypes.data_as(C.c_void_p), rgb.shape[1] * 3)
+    out = bytearray()
+
+    def sink(data, size, _pic):
+        out.extend(C.string_at(data, size))
+        return 1
+
+    cb = writer_t(sink)
+    pic.writer = cb
+    ok = L.WebPEncode(C.byref(cfg), C.byref(pic))
+    L.WebPPictureFree(C.byref(pic))
+    assert ok, settings
+    return bytes(out)
+
+
+def _vp8_header_flags(data):
+    """(simple filter?, sharpness, token partitions) read from the first partition of a simple lossy file — to make sure the
+    files below really carry the features they are meant to."""
+    body = data[data.find(b"VP8 ") + 8:]
+    d = body[10:]
+    st = dict(p=2, v=(d[0] << 8) | d[1], r=255, bc=0)
+
+    def bit(prob):
+        split = 1 + (((st["r"] - 1) * prob) >> 8)
+        big = split << 8
+        if st["v"] >= big:
+            r, st["r"], st["v"] = 1, st["r"] - split, st["v"] - big
+        else:
+            r, st["r"] = 0, split
+        while st["r"] < 128:
+            st["v"] <<= 1
+            st["r"] <<= 1
+            st["bc"] += 1
+            if st["bc"] == 8:
+                st["bc"] = 0
+                st["v"] |= d[st["p"]] if st["p"] < len(d) else 0
+                st["p"] += 1
+        return r
+
+    def lit(n):
+        v = 0
+        for _ in range(n):
+            v = (v << 1) | bit(128)
+        return v
+
+    lit(2)
+    if lit(1):  # segments
+        update_map = lit(1)
+        if lit(1):
+            lit(1)
+            for n in (7, 6):
+                for _ in range(4):
+                    if lit(1):
+                        lit(n + 1)
+        if update_map:
+            for _ in range(3):
+                if lit(1):
+                    lit(8)
+    simple, _level, sharp = lit(1), lit(6), lit(3)
+    if lit(1) and lit(1):
+        for _ in range(8):
+            if lit(1):
+                lit(7)
+    return simple, sharp, 1 << lit(2)
+
+
+SETTINGS = [dict(filter_type=0, filter_strength=60), dict(filter_type=0, filter_strength=20, filter_sharpness=3),
+            dict(filter_type=0, filter_strength=100, filter_sharpness=7, quality=20.0), dict(filter_type=0, filter_strength=100, quality=5.0),
+            dict(method=0, partitions=1), dict(method=1, partitions=2, quality=30.0), dict(method=2, partitions=3, quality=90.0),
+            dict(method=0, partitions=3, filter_type=0, filter_strength=80), dict(filter_sharpness=5, filter_strength=80),
+            dict(filter_sharpness=2, filter_strength=40, quality=10.0), dict(filter_sharpness=7, filter_strength=100, quality=40.0),
+            dict(segments=1), dict(segments=2, sns_strength=100), dict(segments=3, sns_strength=80, quality=35.0), dict(autofilter=1, quality=40.0),
+            dict(filter_strength=0), dict(preprocessing=1), dict(use_sharp_yuv=1), dict(quality=55.0, pass_=6, method=6, partition_limit=50)]
+
+
+def test_lossy_features_pillow_cannot_write(tmp_path):
+    """Simple loop filter, sharpness, 2 / 4 / 8 token partitions, 1-4 segments: files from libwebp's encoder driven through its
+    C API, decoded by libwebp (Pillow) and by this library — equal pixels."""
+    smooth, noise, photo = images()
+    edges = np.zeros((120, 160, 3), np.uint8)
+    edges[::7] = 255
+    edges[:, ::5, 1] = 200
+    edges[30:60, 40:100] = (255, 0, 0)
+    if _libwebp_encode(noise[:16, :16]) is None:
+        pytest.skip("Pillow's bundled libwebp not found (or another struct layout)")
+    seen_simple, seen_sharp, seen_parts = False, set(), set()
+    for img in (photo, edges, noise):
+        for s in SETTINGS:
+            data = _libwebp_encode(img, **s)
+            simple, sharp, parts = _vp8_header_flags(data)
+            seen_simple |= bool(simple)
+            seen_sharp.add(sharp)
+            seen_parts.add(parts)
+            f = tmp_path / "x.webp"
+            f.write_bytes(data)
+            want = np.asarray(PIL.open(f).convert("RGB"))
+            got = mosaic_b200.webp_decode(f)
+            assert got.shape == want.shape and (got == want).all(), s
+    assert seen_simple and {0, 2, 3, 5, 7} <= seen_sharp and {1, 2, 4, 8} <= seen_parts
+
+
 def test_cli_selects_webp_materials(tmp_path):
     """The host CLI's load_tiles (main.rs:166-261) over a directory of WebP files (lossy, lossless, with alpha): extension
     matched case-insensitively, dimensions from the bitstream header for the aspect filter; `-o x.webp` asks for a WebP
