@@ -14,12 +14,14 @@
 #include <dirent.h>
 #include <sys/stat.h>
 
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <fstream>
 #include <iostream>
+#include <thread>
 
 #include "mosaic_b200.hpp"
 #include "mosaic_jpeg.hpp"
@@ -130,6 +132,25 @@ static bool write_ppm(const std::string& file, const RgbImage& img) {
   return (bool)out;
 }
 
+// fn(i) for i in [0, n) on the host's threads (MOSAIC_HOST_THREADS overrides the count); every i writes its own slot
+template <typename F>
+static void parallel_for(size_t n, F fn) {
+  unsigned nt = std::thread::hardware_concurrency();
+  if (const char* e = std::getenv("MOSAIC_HOST_THREADS")) nt = (unsigned)std::max(1, std::atoi(e));
+  nt = (unsigned)std::min<size_t>(std::max(1u, nt), n);
+  if (nt <= 1) {
+    for (size_t i = 0; i < n; ++i) fn(i);
+    return;
+  }
+  std::atomic<size_t> next{0};
+  std::vector<std::thread> pool;
+  for (unsigned t = 0; t < nt; ++t)
+    pool.emplace_back([&] {
+      for (size_t i; (i = next.fetch_add(1)) < n;) fn(i);
+    });
+  for (std::thread& t : pool) t.join();
+}
+
 static std::string lower_ext(const std::string& file) {  // main.rs:177-182: extension, lower-cased
   const size_t dot = file.find_last_of('.'), slash = file.find_last_of('/');
   if (dot == std::string::npos || (slash != std::string::npos && dot < slash)) return "";
@@ -223,9 +244,11 @@ int main(int argc, char** argv) {
     std::sort(entries.begin(), entries.end());
     std::vector<std::string> chosen;
     std::vector<RgbImage> headers(entries.size());
+    std::vector<char> header_ok(entries.size(), 0);
+    parallel_for(entries.size(), [&](size_t i) { header_ok[i] = read_image(entries[i], &headers[i], true) ? 1 : 0; });
     for (size_t i = 0; i < entries.size(); ++i) {
-      if (!read_image(entries[i], &headers[i], true)) {
-        std::fprintf(stderr, "Error processing \"%s\": not a PNG / JPEG / binary PPM\n", entries[i].c_str());
+      if (!header_ok[i]) {
+        std::fprintf(stderr, "Error processing \"%s\": not a PNG / JPEG / WebP / binary PPM\n", entries[i].c_str());
         continue;
       }
       const float aspect = (float)headers[i].width / (float)headers[i].height;
@@ -240,14 +263,18 @@ int main(int argc, char** argv) {
     if (chosen.empty()) throw std::runtime_error("no material images found in " + args.material_src);
     std::vector<RgbImage> images;
     std::vector<std::string> paths;
-    for (const std::string& p : chosen) {
-      RgbImage m;
-      if (!read_image(p, &m)) {
-        std::fprintf(stderr, "Error processing \"%s\": cannot decode\n", p.c_str());
-        continue;
+    {  // main.rs:194: the reference decodes the tiles with rayon's par_iter; here the host threads, results kept in file order
+      std::vector<RgbImage> decoded(chosen.size());
+      std::vector<char> ok(chosen.size(), 0);
+      parallel_for(chosen.size(), [&](size_t i) { ok[i] = read_image(chosen[i], &decoded[i]) ? 1 : 0; });
+      for (size_t i = 0; i < chosen.size(); ++i) {
+        if (!ok[i]) {
+          std::fprintf(stderr, "Error processing \"%s\": cannot decode\n", chosen[i].c_str());
+          continue;
+        }
+        images.push_back(std::move(decoded[i]));
+        paths.push_back(chosen[i]);
       }
-      images.push_back(std::move(m));
-      paths.push_back(p);
     }
     std::printf("Loaded %zu tiles (aspect ratio matched)\n", paths.size());
     const auto t1 = std::chrono::steady_clock::now();

@@ -273,7 +273,7 @@ def test_cli_material_selection_follows_load_tiles(cli, tmp_path):
     r = run(mdir)
     assert "Target aspect ratio: 1.667" in r.stdout
     assert "Loaded 16 tiles" in r.stdout and "No tiles matched" not in r.stdout   # (3 rounds of PPM + 1 of PNG) x 4 matching sizes
-    assert "broken.ppm" in r.stderr and "not a PNG / JPEG / binary PPM" in r.stderr
+    assert "broken.ppm" in r.stderr and "not a PNG / JPEG / WebP / binary PPM" in r.stderr
     assert "broken.png" in r.stderr
     r = run(mdir, "--max-materials", "5")
     assert "Loaded 5 tiles" in r.stdout                                            # truncate (main.rs:255-257)
