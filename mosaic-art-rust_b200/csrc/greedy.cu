@@ -214,9 +214,14 @@ __global__ void __launch_bounds__(32, 1) greedy_generic_kernel(const uint32_t* _
 //   committer (warp 1)    drains the consumer's decisions, up to 32 cells at a time (one per lane): Lab of the
 //                        row above, the placement array in HBM, the `decided` counter; lane 0 re-arms the
 //                        mbarrier of every ring batch that has been fully consumed and issues its next TMA copies.
-constexpr int CH_DEPTH = 64;   // ring slots (records)
+// Ring slots (records): a template parameter of the chain kernel.  A ring position is refilled when its eight cells have
+// been consumed, so the copy of a batch has DEPTH - 8 cells (~100 cycles each) to arrive.  Alone on the GPU 64 slots are
+// plenty (the copy takes ~1.5 us); under the kernels that run beside the chain in a step — matching of later bands, the
+// render of finished rows — the copies take longer and the consumer met missing batches: 3.77 ms -> 3.64 ms per step at the
+// 24,000-tile config with 128 slots (place 2.81 -> 2.68 ms).  The deepest ring that fits beside the usage counters is used.
+constexpr int CH_DEPTH_MAX = 256;
+constexpr int CH_DEPTH_MIN = 64;
 constexpr int CH_BATCH = 8;    // records per TMA copy / mbarrier
-constexpr int CH_NBATCH = CH_DEPTH / CH_BATCH;
 constexpr int CH_SHADOW = 4;   // hot slots 64..67 mirror slots 0..3: a hot block reads five consecutive slots
 constexpr int CH_GUARD = 3;    // slots of the last decided cells stay intact (the exact path re-reads them)
 constexpr int CH_MIN_GW = 33;  // the committer handles up to 32 consecutive cells at once: one per column
@@ -320,7 +325,7 @@ __global__ void __launch_bounds__(256) place_prep_kernel(const uint32_t* __restr
 // [8] cycles waiting for a TMA batch, [9] cycles waiting for the committer (row above), [10] total cycles
 __device__ unsigned long long g_chain_prof[16];
 
-template <typename UsageT, bool PROF, bool GATED>
+template <typename UsageT, bool PROF, bool GATED, int DEPTH>
 __global__ void __launch_bounds__(64, 1)
     greedy_chain_kernel(const HRec* __restrict__ hrec, const XRec* __restrict__ xrec, const float* __restrict__ glab,
                         const uint32_t* __restrict__ cand_idx, const float* __restrict__ cand_d2, int k,
@@ -330,6 +335,8 @@ __global__ void __launch_bounds__(64, 1)
                         const volatile unsigned* ready /* cells whose records exist so far; NULL = all of them */,
                         volatile unsigned* progress /* GATED: cells committed so far, for whoever renders rows under the chain */,
                         bool progress_sys /* the counter is read by other GPUs: publish at system scope */) {
+  constexpr int CH_DEPTH = DEPTH;
+  constexpr int CH_NBATCH = DEPTH / CH_BATCH;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   HRec* hring = reinterpret_cast<HRec*>(smem_raw);
   XRec* xring = reinterpret_cast<XRec*>(smem_raw + sizeof(HRec) * (CH_DEPTH + CH_SHADOW));
@@ -880,20 +887,33 @@ __global__ void __launch_bounds__(64, 1)
 
 }  // namespace
 
-template <typename UsageT, bool PROF, bool GATED = false>
-static int launch_chain_impl(mosaic_ctx* ctx, unsigned cap, float weight, size_t smem, cudaStream_t stream, const unsigned* ready,
-                             unsigned* progress = nullptr) {
+static size_t chain_smem_at(const mosaic_ctx* ctx, unsigned cap, int depth);
+static int chain_depth(const mosaic_ctx* ctx, unsigned cap);
+
+template <typename UsageT, bool PROF, bool GATED, int DEPTH>
+static int launch_chain_depth(mosaic_ctx* ctx, unsigned cap, float weight, cudaStream_t stream, const unsigned* ready, unsigned* progress) {
+  size_t smem = chain_smem_at(ctx, cap, DEPTH);
   const size_t cells = (size_t)ctx->gw * ctx->gh;
   // under the chain other kernels run (matching of later bands, the render of finished rows): claiming all of the SM's
   // shared memory keeps their CTAs off the SM of the one warp everything waits for
   if (GATED) smem = std::max(smem, (size_t)226 * 1024);
-  MOSAIC_CUDA(ctx, cudaFuncSetAttribute(greedy_chain_kernel<UsageT, PROF, GATED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  MOSAIC_CUDA(ctx, cudaFuncSetAttribute(greedy_chain_kernel<UsageT, PROF, GATED, DEPTH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)smem));
-  greedy_chain_kernel<UsageT, PROF, GATED><<<1, 64, smem, stream>>>(
+  greedy_chain_kernel<UsageT, PROF, GATED, DEPTH><<<1, 64, smem, stream>>>(
       reinterpret_cast<const HRec*>(ctx->d_place_rec), reinterpret_cast<const XRec*>(ctx->d_place_rec + cells * sizeof(HRec)),
       reinterpret_cast<const float*>(ctx->d_place_rec + cells * (sizeof(HRec) + sizeof(XRec))), ctx->d_cand_idx, ctx->d_cand_d2, ctx->k, ctx->sim_lab4(), ctx->n, ctx->gw, ctx->gh, cap, weight, ctx->d_placed,
       ctx->d_place_info, mosaic_ctx::kFallbackCap, ready, progress, ctx->world > 1);
   return MOSAIC_OK;
+}
+
+template <typename UsageT, bool PROF, bool GATED = false>
+static int launch_chain_impl(mosaic_ctx* ctx, unsigned cap, float weight, size_t /*smem: follows from the depth*/, cudaStream_t stream,
+                             const unsigned* ready, unsigned* progress = nullptr) {
+  switch (chain_depth(ctx, cap)) {
+    case 256: return launch_chain_depth<UsageT, PROF, GATED, 256>(ctx, cap, weight, stream, ready, progress);
+    case 128: return launch_chain_depth<UsageT, PROF, GATED, 128>(ctx, cap, weight, stream, ready, progress);
+    default: return launch_chain_depth<UsageT, PROF, GATED, 64>(ctx, cap, weight, stream, ready, progress);
+  }
 }
 
 static int ensure_place_records(mosaic_ctx* ctx) {
@@ -947,15 +967,26 @@ int launch_place_prep_range(mosaic_ctx* ctx, float weight, int cell_begin, int c
 }
 
 // shared-memory footprint of the chain kernel, or 0 when the grid / cap / material count need the generic kernel
-static size_t chain_smem(const mosaic_ctx* ctx, unsigned cap) {
+static size_t chain_smem_at(const mosaic_ctx* ctx, unsigned cap, int depth) {
   const size_t smem_limit = 220 * 1024;
   const int n = ctx->n, gw = ctx->gw;
-  const size_t ring_fixed = sizeof(HRec) * (CH_DEPTH + CH_SHADOW) + sizeof(XRec) * CH_DEPTH + 8 * CH_NBATCH + 8 * CH_DEPTH + 16 +
-                            sizeof(float4) * (size_t)gw + sizeof(int32_t) * (size_t)((gw + 3) & ~3);
+  const size_t ring_fixed = sizeof(HRec) * (size_t)(depth + CH_SHADOW) + sizeof(XRec) * (size_t)depth + 8 * (size_t)(depth / CH_BATCH) +
+                            8 * (size_t)depth + 16 + sizeof(float4) * (size_t)gw + sizeof(int32_t) * (size_t)((gw + 3) & ~3);
   const size_t usage_bytes = cap <= 255u ? (size_t)n + 1 : (cap <= 65535u ? ((size_t)n + 1) * 2 : (size_t)-1);
   if (gw >= CH_MIN_GW && n < (1 << 26) && usage_bytes != (size_t)-1 && ring_fixed + usage_bytes + 16 <= smem_limit)
     return ring_fixed + usage_bytes + 16;
   return 0;
+}
+// the deepest ring that fits (MOSAIC_CHAIN_DEPTH caps it: a measurement knob); 0 when not even the shallowest does
+static int chain_depth(const mosaic_ctx* ctx, unsigned cap) {
+  static const int limit = getenv("MOSAIC_CHAIN_DEPTH") ? atoi(getenv("MOSAIC_CHAIN_DEPTH")) : CH_DEPTH_MAX;
+  for (int d = CH_DEPTH_MAX; d >= CH_DEPTH_MIN; d >>= 1)
+    if (d <= std::max(limit, CH_DEPTH_MIN) && chain_smem_at(ctx, cap, d)) return d;
+  return 0;
+}
+static size_t chain_smem(const mosaic_ctx* ctx, unsigned cap) {
+  const int d = chain_depth(ctx, cap);
+  return d ? chain_smem_at(ctx, cap, d) : 0;
 }
 bool place_chain_has_progress(const mosaic_ctx* ctx) { return use_v1_chain(ctx); }
 
