@@ -57,6 +57,7 @@ struct Huffman {  // T.81 Annex C / F.2.2.3: canonical codes by length
       mincode[l] = code;
       code += bits[l];
       k += bits[l];
+      if (code > (1 << l)) throw JpegError("jpeg: over-subscribed Huffman table");  // (more codes of this length than bit patterns)
       maxcode[l] = bits[l] ? code - 1 : -1;
       code <<= 1;
     }
@@ -170,7 +171,7 @@ inline void idct_islow(const int16_t* coef, const uint16_t* q, uint8_t* out, int
     long z1 = (z2 + z3) * F_0_541196100;
     long tmp2 = z1 + z3 * (-F_1_847759065), tmp3 = z1 + z2 * F_0_765366865;
     z2 = i0, z3 = i4;
-    long tmp0 = (z2 + z3) << CB, tmp1 = (z2 - z3) << CB;
+    long tmp0 = (z2 + z3) * (1L << CB), tmp1 = (z2 - z3) * (1L << CB);  // (a multiplication: the operands may be negative)
     const long tmp10 = tmp0 + tmp3, tmp13 = tmp0 - tmp3, tmp11 = tmp1 + tmp2, tmp12 = tmp1 - tmp2;
     tmp0 = i7, tmp1 = i5, tmp2 = i3, tmp3 = i1;
     z1 = tmp0 + tmp3, z2 = tmp1 + tmp2, z3 = tmp0 + tmp2;
@@ -190,7 +191,7 @@ inline void idct_islow(const int16_t* coef, const uint16_t* q, uint8_t* out, int
     long z2 = w[2], z3 = w[6];
     long z1 = (z2 + z3) * F_0_541196100;
     long tmp2 = z1 + z3 * (-F_1_847759065), tmp3 = z1 + z2 * F_0_765366865;
-    long tmp0 = ((long)w[0] + w[4]) << CB, tmp1 = ((long)w[0] - w[4]) << CB;
+    long tmp0 = ((long)w[0] + w[4]) * (1L << CB), tmp1 = ((long)w[0] - w[4]) * (1L << CB);
     const long tmp10 = tmp0 + tmp3, tmp13 = tmp0 - tmp3, tmp11 = tmp1 + tmp2, tmp12 = tmp1 - tmp2;
     tmp0 = w[7], tmp1 = w[5], tmp2 = w[3], tmp3 = w[1];
     z1 = tmp0 + tmp3, z2 = tmp1 + tmp2, z3 = tmp0 + tmp2;
@@ -437,6 +438,11 @@ inline JpegImage decode_jpeg_memory(const uint8_t* data, size_t size) {
         width = (s[3] << 8) | s[4];
         const int nf = s[5];
         if (width <= 0 || height <= 0) throw JpegError("jpeg: bad dimensions");
+        // A header can claim 65535 x 65535 pixels in front of a few bytes of data.  Every 8x8 block costs at least one bit of
+        // entropy-coded data per scan that covers its DC term, so a real file holds fewer than ~350 pixels per byte (4:2:0,
+        // progressive); refuse what is far beyond that, and what would not fit the 4 GiB of RGB this library hands out.
+        if ((uint64_t)width * (uint64_t)height > (uint64_t)size * 2048u + 65536u) throw JpegError("jpeg: the file is too short for the dimensions in its header");
+        if ((uint64_t)width * (uint64_t)height * 3u > ((uint64_t)1 << 32)) throw JpegError("jpeg: more than 4 GiB of pixels");
         if (nf != 1 && nf != 3) throw JpegError("jpeg: only 1- and 3-component files are supported");
         if (n < 6 + 3 * nf) throw JpegError("jpeg: bad SOF");
         progressive = m == 0xC2;
@@ -671,8 +677,8 @@ inline void fdct_islow(int* d) {
       const long t2 = p[2 * st] + p[5 * st], t5 = p[2 * st] - p[5 * st], t3 = p[3 * st] + p[4 * st], t4 = p[3 * st] - p[4 * st];
       const long t10 = t0 + t3, t13 = t0 - t3, t11 = t1 + t2, t12 = t1 - t2;
       if (pass == 0) {
-        p[0] = (int)((t10 + t11) << P1);
-        p[4 * st] = (int)((t10 - t11) << P1);
+        p[0] = (int)((t10 + t11) * (1L << P1));
+        p[4 * st] = (int)((t10 - t11) * (1L << P1));
       } else {
         p[0] = descale(t10 + t11, P1);
         p[4 * st] = descale(t10 - t11, P1);

@@ -153,6 +153,10 @@ inline Image decode_png_memory(const uint8_t* data, size_t size) {
     const uint32_t pw = (width + P.dx - 1 - P.x0) / P.dx, ph = (height + P.dy - 1 - P.y0) / P.dy;
     if (pw && ph) raw_size += (size_t)ph * (1 + line_bytes(pw));
   }
+  // A header can claim 2^31 x 2^31 pixels in front of a few bytes of data: deflate expands by at most ~1032 : 1, so the IDAT
+  // stream bounds the image it can hold — checked before anything of the claimed size is allocated
+  if (raw_size > idat.size() * 1032 + 65536) throw PngError("png: the IDAT stream is too short for the dimensions in the header");
+  if ((uint64_t)width * (uint64_t)height * 3u > ((uint64_t)1 << 32)) throw PngError("png: more than 4 GiB of pixels");
   std::vector<uint8_t> raw(raw_size);
   {
     z_stream zs;

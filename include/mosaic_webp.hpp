@@ -503,12 +503,19 @@ struct BoolDecoder {
   const uint8_t* end = nullptr;
   uint32_t value = 0, range = 255;
   int bit_count = 0;
+  int over = 0;  // bytes taken from behind the end: up to two are the decoder's own look-ahead, more means a truncated stream
+  inline uint32_t next_byte() {
+    if (p < end) return *p++;
+    ++over;
+    return 0u;
+  }
   void init(const uint8_t* data, size_t size) {
     p = data, end = data + size;
-    value = 0;
-    for (int i = 0; i < 2; ++i) value = (value << 8) | (p < end ? *p++ : 0u);
+    value = 0, over = 0;
+    for (int i = 0; i < 2; ++i) value = (value << 8) | next_byte();
     range = 255, bit_count = 0;
   }
+  bool truncated() const { return over > 2; }
   inline int bit(int prob) {
     const uint32_t split = 1 + (((range - 1) * (uint32_t)prob) >> 8);
     const uint32_t big = split << 8;
@@ -522,7 +529,7 @@ struct BoolDecoder {
       value <<= 1, range <<= 1;
       if (++bit_count == 8) {
         bit_count = 0;
-        value |= p < end ? *p++ : 0u;
+        value |= next_byte();
       }
     }
     return r;
@@ -1079,6 +1086,9 @@ inline Image decode_vp8(const uint8_t* d, size_t n) {
             inverse_dct_add(coeffs + (16 + ch * 4 + by * 2 + bx) * 16, cd + (size_t)(by * 4) * P.stride + bx * 4, P.stride);
       }
     }
+    // (a stream that ends early would decode on as zeros, at the size its header claims: an error, like libwebp's
+    // "premature end of partition")
+    if (br.truncated() || tb.truncated()) throw WebpError("webp: truncated lossy stream");
   }
 
   // §15: loop filter, macroblocks in raster order, each: left edge, inner vertical edges, top edge, inner horizontal edges

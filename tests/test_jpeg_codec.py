@@ -80,6 +80,21 @@ def test_decode_errors_and_dispatch(tmp_path):
     trunc.write_bytes(good.read_bytes()[:200])
     with pytest.raises(mosaic_b200.MosaicError):
         mosaic_b200.jpeg_decode(trunc)
+    # hostile headers: an over-subscribed Huffman table (more codes of a length than bit patterns) and dimensions no file of
+    # this size can hold are refused before anything is built or allocated from them
+    raw = bytearray(good.read_bytes())
+    dht = raw.find(b"\xff\xc4")
+    bad_dht = bytearray(raw)
+    bad_dht[dht + 5] = 7  # seven codes of length 1
+    (tmp_path / "dht.jpg").write_bytes(bytes(bad_dht))
+    with pytest.raises(mosaic_b200.MosaicError, match="Huffman"):
+        mosaic_b200.jpeg_decode(tmp_path / "dht.jpg")
+    sof = raw.find(b"\xff\xc0")
+    huge = bytearray(raw)
+    huge[sof + 5:sof + 9] = b"\xff\xff\xff\xff"  # 65535 x 65535
+    (tmp_path / "huge.jpg").write_bytes(bytes(huge))
+    with pytest.raises(mosaic_b200.MosaicError, match="too short for the dimensions"):
+        mosaic_b200.jpeg_decode(tmp_path / "huge.jpg")
     # image_decode tells the formats apart by content, whatever the extension says
     png = tmp_path / "really_a_png.jpg"
     mosaic_b200.png_encode(tmp_path / "x.png", noise)

@@ -154,3 +154,20 @@ def test_decode_errors_are_reported_not_thrown(tmp_path):
     trunc.write_bytes(good.read_bytes()[:-30])
     with pytest.raises(mosaic_b200.MosaicError):
         mosaic_b200.png_decode(trunc)
+
+
+def test_header_larger_than_the_data_can_hold(tmp_path):
+    """A header that claims 16M x 16M pixels in front of a 4x4 image's IDAT: refused before anything of the claimed size is
+    allocated (deflate expands by at most ~1032 : 1, so the compressed stream bounds the image)."""
+    import time
+    rows = [bytes(12)] * 4
+    data = bytearray(hand_png(4, 4, 8, 2, rows))
+    ihdr = data.find(b"IHDR")
+    data[ihdr + 4:ihdr + 12] = struct.pack(">II", 1 << 24, 1 << 24)
+    data[ihdr + 17:ihdr + 21] = struct.pack(">I", zlib.crc32(bytes(data[ihdr:ihdr + 17])) & 0xFFFFFFFF)
+    f = tmp_path / "huge.png"
+    f.write_bytes(bytes(data))
+    t0 = time.time()
+    with pytest.raises(mosaic_b200.MosaicError, match="too short for the dimensions"):
+        mosaic_b200.png_decode(f)
+    assert time.time() - t0 < 2.0

@@ -137,6 +137,10 @@ def test_errors_and_dispatch(tmp_path):
     frames[0].save(anim, save_all=True, append_images=frames[1:], duration=50)
     with pytest.raises(mosaic_b200.MosaicError, match="animated"):
         mosaic_b200.webp_decode(anim)
+    for cut in (len(data) // 3, len(data) // 2, len(data) - 40):  # a lossy stream that ends early: an error, not a picture of zeros
+        (tmp_path / "t.webp").write_bytes(data[:cut])
+        with pytest.raises(mosaic_b200.MosaicError, match="truncated"):
+            mosaic_b200.webp_decode(tmp_path / "t.webp")
     lossless = tmp_path / "l.webp"
     PIL.fromarray(smooth).save(lossless, lossless=True)
     raw = bytearray(lossless.read_bytes())
