@@ -206,7 +206,8 @@ int mosaic_generate(mosaic_ctx* ctx, const mosaic_params* params, int32_t* place
  *  "similarities": [packed upper triangle]} in serde_json's pretty layout, f32 in shortest round-trip form.
  * Host-only: no CUDA device is needed for these calls (except mosaic_simdb_save_ctx). */
 typedef struct mosaic_simdb mosaic_simdb;
-/* paths[i] = path of material i (UTF-8), lab = n*3, sim = n(n-1)/2 (NULL allowed when n < 2). */
+/* paths[i] = path of material i (UTF-8; anything else is refused like serde refuses a non-UTF-8 PathBuf), lab = n*3,
+ * sim = n(n-1)/2 (NULL allowed when n < 2). */
 int mosaic_simdb_save_json(const char* file, const char* const* paths, int n, const float* lab, const float* sim);
 /* Same with an explicit number of similarity entries: the reference serialises whatever `similarities` holds, also a
  * list that is out of date because tiles were added after the last build_similarities (similarity.rs:112-116). */
@@ -214,11 +215,16 @@ int mosaic_simdb_save_json_n(const char* file, const char* const* paths, int n, 
                              uint64_t n_similarities);
 /* Lab means + freshly computed packed matrix of a context -> file (main.rs:122-131). */
 int mosaic_simdb_save_ctx(mosaic_ctx* ctx, const char* file, const char* const* paths);
-int mosaic_simdb_load_json(const char* file, mosaic_simdb** out); /* SimilarityDatabase::load_from_file */
+/* SimilarityDatabase::load_from_file (similarity.rs:119-123).  Accepts what `serde_json::from_str` accepts for the struct —
+ * UTF-8 only, strict JSON numbers and strings, unknown fields skipped, duplicate or missing fields refused, `usize` keys and
+ * values as plain integer literals — because `load_or_new` (similarity.rs:126-139) rebuilds from scratch on ANY error:
+ * what loads and what does not is behaviour.  On error *out is NULL and mosaic_last_error(NULL) says where. */
+int mosaic_simdb_load_json(const char* file, mosaic_simdb** out);
 void mosaic_simdb_free(mosaic_simdb* db);
 /* rows of lab_colors, entries of similarities, entries of path_to_index (they differ in GUI-touched files) */
 int mosaic_simdb_info(const mosaic_simdb* db, int* n_rows, uint64_t* n_similarities, int* n_paths);
-const char* mosaic_simdb_path(const mosaic_simdb* db, int index);       /* index_to_path; "" if absent */
+const char* mosaic_simdb_path(const mosaic_simdb* db, int index);       /* index_to_path; "" if the file has no entry for
+                                                                          * that row, NULL outside lab_colors' rows */
 int64_t mosaic_simdb_index_of(const mosaic_simdb* db, const char* path); /* path_to_index; -1 if absent */
 int mosaic_simdb_copy(const mosaic_simdb* db, float* lab_out, float* sim_out); /* either may be NULL */
 /* SimilarityDatabase::get_similarity (similarity.rs:85-103); MOSAIC_ERR_STATE where the reference returns None */
