@@ -44,6 +44,7 @@ struct Args {  // main.rs:23-88, same defaults
   float color_adjustment_strength = 0.3f;
   bool show_time = true, show_grid = true;
   unsigned long long seed = 0;  // extension: the reference's annealer is OS-seeded (optimizer.rs:48)
+  bool list_tiles = false;      // extension: print what load_tiles selects and stop (no device needed)
 };
 
 static bool parse_bool(const std::string& v) { return v == "true" || v == "1"; }
@@ -52,7 +53,7 @@ static bool parse(int argc, char** argv, Args* a) {
   for (int i = 1; i < argc; ++i) {
     std::string k = argv[i], v;
     const size_t eq = k.find('=');
-    const bool flag_only = k == "--rebuild-similarity-db";
+    const bool flag_only = k == "--rebuild-similarity-db" || k == "--list-tiles";
     if (eq != std::string::npos) {
       v = k.substr(eq + 1);
       k = k.substr(0, eq);
@@ -80,11 +81,13 @@ static bool parse(int argc, char** argv, Args* a) {
     else if (k == "--show-time") a->show_time = parse_bool(v);
     else if (k == "--show-grid") a->show_grid = parse_bool(v);
     else if (k == "--seed") a->seed = std::stoull(v);
+    else if (k == "--list-tiles") a->list_tiles = true;
     else {
       std::fprintf(stderr, "error: unexpected argument '%s'\n", k.c_str());
       return false;
     }
   }
+  if (a->list_tiles && a->output.empty()) a->output = "-";
   if (a->target.empty() || a->material_src.empty() || a->output.empty()) {
     std::fprintf(stderr, "error: the following required arguments were not provided: --target --material-src --output\n");
     return false;
@@ -216,6 +219,73 @@ static bool write_image(const std::string& file, const RgbImage& img) {  // outp
   }
 }
 
+// load_tiles (main.rs:166-261).  The reference decodes EVERY file of the directory in its first pass (`process_tile` opens
+// the image, main.rs:268), drops the ones that fail with a message and the ones off the target's aspect (lib.rs:121-123), falls
+// back to the first min(len, 2 * max) files without the aspect filter when NOTHING is left (main.rs:211-253), and keeps the
+// first `max_materials` of what it has (main.rs:255-257).  The same tiles come out of this function with fewer decodes: the
+// aspect test needs only the header, and the survivors are decoded in order, a batch at a time on the host's threads (the
+// reference's par_iter, main.rs:194), until `max_materials` of them have succeeded — a file whose body is damaged does not
+// take a slot, exactly as in the reference, where truncation comes after the failures are gone.  Files are taken in sorted
+// order (read_dir's order is unspecified).
+static void decode_in_order(const std::vector<std::string>& files, size_t want, std::vector<std::string>* paths, std::vector<RgbImage>* images) {
+  size_t next = 0;
+  while (paths->size() < want && next < files.size()) {
+    const size_t batch = std::min(files.size() - next, want - paths->size());
+    std::vector<RgbImage> decoded(batch);
+    std::vector<char> ok(batch, 0);
+    parallel_for(batch, [&](size_t i) { ok[i] = read_image(files[next + i], &decoded[i]) ? 1 : 0; });
+    for (size_t i = 0; i < batch; ++i) {
+      if (!ok[i]) {
+        std::fprintf(stderr, "Error processing \"%s\": cannot decode\n", files[next + i].c_str());
+        continue;
+      }
+      images->push_back(std::move(decoded[i]));
+      paths->push_back(files[next + i]);
+    }
+    next += batch;
+  }
+}
+
+static void load_tiles(const std::string& material_dir, float target_aspect, float aspect_tolerance, size_t max_materials,
+                       std::vector<std::string>* paths, std::vector<RgbImage>* images) {
+  std::printf("Collecting material images...\n");
+  std::vector<std::string> entries;
+  if (DIR* d = opendir(material_dir.c_str())) {
+    while (dirent* e = readdir(d)) {
+      const std::string name = e->d_name, path = material_dir + "/" + name;
+      struct stat st;
+      const std::string ext = lower_ext(name);  // main.rs:175-184: is_file() && the extension, lower-cased, is one of the four
+      if ((ext == "png" || ext == "jpg" || ext == "jpeg" || ext == "webp" || ext == "ppm") && stat(path.c_str(), &st) == 0 && S_ISREG(st.st_mode))
+        entries.push_back(path);
+    }
+    closedir(d);
+  } else {
+    throw std::runtime_error("cannot read directory " + material_dir);
+  }
+  std::sort(entries.begin(), entries.end());
+  std::vector<RgbImage> headers(entries.size());
+  std::vector<char> header_ok(entries.size(), 0);
+  parallel_for(entries.size(), [&](size_t i) { header_ok[i] = read_image(entries[i], &headers[i], true) ? 1 : 0; });
+  std::vector<std::string> matching;
+  for (size_t i = 0; i < entries.size(); ++i) {
+    if (!header_ok[i]) {
+      std::fprintf(stderr, "Error processing \"%s\": not a PNG / JPEG / WebP / binary PPM\n", entries[i].c_str());
+      continue;
+    }
+    const float aspect = (float)headers[i].width / (float)headers[i].height;  // main.rs:270
+    if (MosaicGeneratorImpl::is_aspect_ratio_match(aspect, target_aspect, aspect_tolerance)) matching.push_back(entries[i]);
+  }
+  decode_in_order(matching, max_materials, paths, images);
+  if (paths->empty()) {  // main.rs:211-253
+    std::printf("No tiles matched target aspect ratio %.3f, loading tiles without aspect filtering...\n", target_aspect);
+    const size_t take = std::min(entries.size(), max_materials * 2);
+    std::printf("Processing %zu material images (sampled from %zu total)...\n", take, entries.size());
+    const std::vector<std::string> sampled(entries.begin(), entries.begin() + (std::ptrdiff_t)take);
+    decode_in_order(sampled, max_materials, paths, images);  // main.rs:255-257: the first max_materials that decoded
+  }
+  std::printf("Loaded %zu tiles (aspect ratio matched)\n", paths->size());
+}
+
 int main(int argc, char** argv) {
   Args args;
   if (!parse(argc, argv, &args)) return 2;
@@ -226,57 +296,14 @@ int main(int argc, char** argv) {
     const float target_aspect = (float)target.width / (float)target.height;  // main.rs:745-747
     std::printf("Target aspect ratio: %.3f\n", target_aspect);
 
-    // ---- load_tiles (main.rs:166-261)
-    std::printf("Collecting material images...\n");
-    std::vector<std::string> entries;
-    if (DIR* d = opendir(args.material_src.c_str())) {
-      while (dirent* e = readdir(d)) {
-        const std::string name = e->d_name, path = args.material_src + "/" + name;
-        struct stat st;
-        const std::string ext = lower_ext(name);
-        if ((ext == "png" || ext == "jpg" || ext == "jpeg" || ext == "webp" || ext == "ppm") && stat(path.c_str(), &st) == 0 && S_ISREG(st.st_mode))
-          entries.push_back(path);
-      }
-      closedir(d);
-    } else {
-      throw std::runtime_error("cannot read directory " + args.material_src);
-    }
-    std::sort(entries.begin(), entries.end());
-    std::vector<std::string> chosen;
-    std::vector<RgbImage> headers(entries.size());
-    std::vector<char> header_ok(entries.size(), 0);
-    parallel_for(entries.size(), [&](size_t i) { header_ok[i] = read_image(entries[i], &headers[i], true) ? 1 : 0; });
-    for (size_t i = 0; i < entries.size(); ++i) {
-      if (!header_ok[i]) {
-        std::fprintf(stderr, "Error processing \"%s\": not a PNG / JPEG / WebP / binary PPM\n", entries[i].c_str());
-        continue;
-      }
-      const float aspect = (float)headers[i].width / (float)headers[i].height;
-      if (std::fabs(aspect - target_aspect) <= args.aspect_tolerance) chosen.push_back(entries[i]);  // lib.rs:121-123
-    }
-    if (chosen.empty()) {  // main.rs:211-253
-      std::printf("No tiles matched target aspect ratio %.3f, loading tiles without aspect filtering...\n", target_aspect);
-      const size_t take = std::min(entries.size(), args.max_materials * 2);
-      chosen.assign(entries.begin(), entries.begin() + (std::ptrdiff_t)take);
-    }
-    if (chosen.size() > args.max_materials) chosen.resize(args.max_materials);  // main.rs:255-257
-    if (chosen.empty()) throw std::runtime_error("no material images found in " + args.material_src);
     std::vector<RgbImage> images;
     std::vector<std::string> paths;
-    {  // main.rs:194: the reference decodes the tiles with rayon's par_iter; here the host threads, results kept in file order
-      std::vector<RgbImage> decoded(chosen.size());
-      std::vector<char> ok(chosen.size(), 0);
-      parallel_for(chosen.size(), [&](size_t i) { ok[i] = read_image(chosen[i], &decoded[i]) ? 1 : 0; });
-      for (size_t i = 0; i < chosen.size(); ++i) {
-        if (!ok[i]) {
-          std::fprintf(stderr, "Error processing \"%s\": cannot decode\n", chosen[i].c_str());
-          continue;
-        }
-        images.push_back(std::move(decoded[i]));
-        paths.push_back(chosen[i]);
-      }
+    load_tiles(args.material_src, target_aspect, args.aspect_tolerance, args.max_materials, &paths, &images);
+    if (args.list_tiles) {  // the selection alone (no device needed): what load_tiles would hand to MosaicGenerator::new
+      for (size_t i = 0; i < paths.size(); ++i) std::printf("tile: %s %dx%d\n", paths[i].c_str(), images[i].width, images[i].height);
+      return 0;
     }
-    std::printf("Loaded %zu tiles (aspect ratio matched)\n", paths.size());
+    if (paths.empty()) throw std::runtime_error("no material images found in " + args.material_src);
     const auto t1 = std::chrono::steady_clock::now();
 
     MosaicGenerator generator(paths, images, args.max_usage_per_image, args.similarity_db, args.rebuild_similarity_db,

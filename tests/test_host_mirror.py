@@ -170,6 +170,104 @@ def test_cli_flags_and_errors(cli, tmp_path):
     assert r.returncode == 1 and "cannot read target" in r.stderr
 
 
+def _reference_load_tiles(files, target_aspect, tolerance, max_materials):
+    """load_tiles of the reference (main.rs:166-261) over `files` = [(name, aspect or None if the decode fails)] in the
+    order the CLI takes them (sorted)."""
+    f32 = np.float32
+    entries = [(n, a) for n, a in files
+               if n.rsplit(".", 1)[-1].lower() in ("png", "jpg", "jpeg", "webp", "ppm") and "." in n]
+    tiles = [n for n, a in entries if a is not None and abs(f32(a) - f32(target_aspect)) <= f32(tolerance)]
+    if not tiles:
+        tiles = [n for n, a in entries[:min(len(entries), 2 * max_materials)] if a is not None]
+    return tiles[:max_materials]
+
+
+def test_cli_selects_the_tiles_load_tiles_selects(cli, tmp_path):
+    """The material selection alone (--list-tiles stops before anything needs a device): extension filter, aspect filter
+    with the f32 comparison of lib.rs:121-123, failures dropped BEFORE the truncation, the no-match fallback."""
+    from PIL import Image
+    rng = np.random.default_rng(5)
+    tgt = rng.integers(0, 256, (90, 160, 3), dtype=np.uint8)         # 16:9
+    Image.fromarray(tgt).save(tmp_path / "target.png")
+
+    def listed(mdir, *flags):
+        r = subprocess.run([cli, "--target", str(tmp_path / "target.png"), "--material-src", str(mdir), "--list-tiles", *flags],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        return [os.path.basename(line.split()[1]) for line in r.stdout.splitlines() if line.startswith("tile: ")], r
+
+    # ---- a directory with matching, non-matching, damaged and foreign files
+    mdir = tmp_path / "mixed"
+    mdir.mkdir()
+    files = []
+
+    def add(name, w, h, damage=None, fmt=None):
+        img = Image.fromarray(rng.integers(0, 256, (h, w, 3), dtype=np.uint8))
+        path = mdir / name
+        img.save(path, format=fmt) if fmt else img.save(path)
+        if damage == "body":                                          # header intact, data cut off
+            data = path.read_bytes()
+            path.write_bytes(data[:len(data) // 2])
+        elif damage == "all":
+            path.write_bytes(b"not an image")
+        files.append((name, None if damage else w / h))
+
+    add("a_wide.png", 64, 36)
+    add("b_square.png", 48, 48)
+    add("c_wide_cut.png", 64, 36, damage="body")                      # matches the aspect, cannot be decoded: takes no slot
+    add("d_wide.JPG", 128, 72, fmt="JPEG")                            # extension matched case-insensitively
+    add("e_garbage.jpeg", 10, 10, damage="all")
+    add("f_almost.webp", 66, 36, fmt="WEBP")                          # 1.833: inside the default tolerance 0.1 of 1.778
+    add("g_outside.png", 68, 36)                                      # 1.889: outside
+    add("h_edge.png", 169, 90)                                        # 1.8778: |d| = 0.1 to within f32 rounding
+    add("i_wide.png", 32, 18)
+    add("j_wide.png", 16, 9)
+    (mdir / "notes.txt").write_text("text")
+    (mdir / "noext").write_bytes((mdir / "a_wide.png").read_bytes())
+    (mdir / "k_dir.png").mkdir()                                      # is_file() fails
+    files.sort()
+    for max_materials in (500, 4, 3, 1):
+        got, _ = listed(mdir, "--max-materials", str(max_materials))
+        assert got == _reference_load_tiles(files, 160 / 90, 0.1, max_materials), max_materials
+    got, r = listed(mdir, "--max-materials", "3")
+    assert got == ["a_wide.png", "d_wide.JPG", "f_almost.webp"]      # c_wide_cut did not use up one of the three
+    assert "c_wide_cut.png" in r.stderr and "Loaded 3 tiles" in r.stdout
+    got, _ = listed(mdir, "--aspect-tolerance", "0.0")
+    assert got == _reference_load_tiles(files, 160 / 90, 0.0, 500) == ["a_wide.png", "d_wide.JPG", "i_wide.png", "j_wide.png"]
+
+    # ---- nothing matches: the fallback takes the first min(len, 2 * max) files, drops failures, keeps max
+    sq = tmp_path / "square"
+    sq.mkdir()
+    files = []
+    for i in range(9):
+        name = f"s{i}.png"
+        Image.fromarray(rng.integers(0, 256, (20, 20, 3), dtype=np.uint8)).save(sq / name)
+        files.append((name, 1.0))
+    (sq / "s1.png").write_bytes((sq / "s1.png").read_bytes()[:40])   # damaged inside the sampled range
+    files[1] = ("s1.png", None)
+    for max_materials in (2, 3, 4, 100):
+        got, r = listed(sq, "--max-materials", str(max_materials))
+        assert got == _reference_load_tiles(files, 160 / 90, 0.1, max_materials), max_materials
+        assert "No tiles matched target aspect ratio 1.778" in r.stdout
+    got, _ = listed(sq, "--max-materials", "2")
+    assert got == ["s0.png", "s2.png"]
+
+    # ---- every matching file is damaged: the reference's `tiles.is_empty()` is true AFTER decoding -> fallback
+    bad = tmp_path / "allbad"
+    bad.mkdir()
+    Image.fromarray(rng.integers(0, 256, (36, 64, 3), dtype=np.uint8)).save(bad / "wide.png")
+    (bad / "wide.png").write_bytes((bad / "wide.png").read_bytes()[:60])
+    Image.fromarray(rng.integers(0, 256, (30, 30, 3), dtype=np.uint8)).save(bad / "square.png")
+    got, r = listed(bad)
+    assert got == ["square.png"] and "No tiles matched" in r.stdout
+
+    # ---- an empty directory lists nothing
+    empty = tmp_path / "empty"
+    empty.mkdir()
+    got, _ = listed(empty)
+    assert got == []
+
+
 @pytest.mark.gpu
 def test_cli_end_to_end(cli, ctx, tmp_path):
     from mosaic_b200 import synth
