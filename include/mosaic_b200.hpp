@@ -6,7 +6,9 @@
 //
 //   SimilarityDatabase           src/similarity.rs:31-138   add_tile, build_similarities, get_similarity,
 //                                                           get_lab_color, save_to_file, load_from_file, load_or_new
-//   AdjacencyPenaltyCalculator   src/adjacency.rs:49-130    new(db, weight), calculate_total_cost(grid)
+//                                src/similarity.rs:141-178  calculate_lab_distance, calculate_delta_e_2000 (free functions)
+//   AdjacencyPenaltyCalculator   src/adjacency.rs:49-214    new(db, weight), calculate_penalty, calculate_total_cost(grid),
+//                                                           calculate_swap_delta(grid, pos1, pos2)
 //   OptimizationConfig/Result,
 //   MosaicOptimizer              src/optimizer.rs:7-220           new(calculator, config), optimize(grid), optimize_greedy(grid, n)
 //   MosaicGeneratorImpl          src/lib.rs:91-119          calculate_average_lab(image)
@@ -217,6 +219,36 @@ inline void unknown_lab(size_t i, float out[3]) {
 }
 }  // namespace detail
 
+// similarity.rs:141-146: Euclidean distance of two Lab colours, `(dl*dl + da*da + db*db).sqrt()` in f32.  One pair; the
+// n(n-1)/2 pairs of build_similarities are K3's (similarity.cu), with this operation order.
+inline float calculate_lab_distance(const Lab& lab1, const Lab& lab2) {
+  const float dl = lab1.l - lab2.l, da = lab1.a - lab2.a, db = lab1.b - lab2.b;
+  const float s = dl * dl + da * da;
+  return std::sqrt(s + db * db);
+}
+
+// similarity.rs:150-178: the reference's simplified CIE2000 difference (`#[allow(dead_code)]` there: nothing on the path
+// calls it; public surface, kept with its operation order)
+inline float calculate_delta_e_2000(const Lab& lab1, const Lab& lab2) {
+  const float kl = 1.0f, kc = 1.0f, kh = 1.0f;
+  const float dl = std::fabs(lab2.l - lab1.l);
+  const float da = lab2.a - lab1.a;
+  const float db = lab2.b - lab1.b;
+  const float c1 = std::sqrt(lab1.a * lab1.a + lab1.b * lab1.b);
+  const float c2 = std::sqrt(lab2.a * lab2.a + lab2.b * lab2.b);
+  const float dc = std::fabs(c2 - c1);
+  const float dh2 = da * da + db * db - dc * dc;
+  const float dh = dh2 > 0.0f ? std::sqrt(dh2) : 0.0f;
+  const float sl = 1.0f;
+  const float c_avg = (c1 + c2) / 2.0f;
+  const float sc = 1.0f + 0.045f * c_avg;
+  const float sh = 1.0f + 0.015f * c_avg;
+  const float dl_kl_sl = dl / (kl * sl);
+  const float dc_kc_sc = dc / (kc * sc);
+  const float dh_kh_sh = dh / (kh * sh);
+  return std::sqrt(dl_kl_sl * dl_kl_sl + dc_kc_sc * dc_kc_sc + dh_kh_sh * dh_kh_sh);
+}
+
 // ---- src/adjacency.rs -------------------------------------------------------------------------------------
 struct GridPosition {  // adjacency.rs:4-47
   size_t x = 0, y = 0;
@@ -267,6 +299,44 @@ class AdjacencyPenaltyCalculator {
     mosaic_opt_result res{};
     ctx.check(mosaic_anneal(ctx.get(), 0, 100.0f, 0.99995f, 0, nullptr, &res));  // 0 iterations: the cost only
     return res.initial_cost;
+  }
+
+  // adjacency.rs:133-214: the change of the (unweighted) energy if the tiles at pos1 and pos2 trade places — pos1's
+  // neighbours without pos2, then pos2's without pos1, each up / down / left / right, old and new term side by side, then
+  // the mutual term on both sides if the two are adjacent; 0 for an empty cell or equal paths.  A two-cell query (≤ 14
+  // lookups) over the GPU-built matrix, like calculate_penalty; the annealing kernel evaluates the same expression with the
+  // same operation order on the device (anneal.cu), where the 1000-iteration loop that calls it lives.
+  float calculate_swap_delta(const PathGrid& grid, GridPosition pos1, GridPosition pos2) const {
+    const size_t grid_height = grid.size();
+    if (grid_height == 0) return 0.0f;
+    const size_t grid_width = grid[0].size();
+    const auto& path1 = grid[pos1.y][pos1.x];
+    const auto& path2 = grid[pos2.y][pos2.x];
+    if (!path1 || !path2 || *path1 == *path2) return 0.0f;
+    float old_cost = 0.0f, new_cost = 0.0f;
+    const std::vector<GridPosition> adj1 = pos1.get_adjacent_positions(grid_width, grid_height);
+    for (const GridPosition& adj : adj1) {
+      if (adj == pos2) continue;
+      const auto& adj_path = grid[adj.y][adj.x];
+      if (!adj_path) continue;
+      if (const auto old_sim = db_.get_similarity(*path1, *adj_path)) old_cost += 1.0f / (*old_sim + 1.0f);
+      if (const auto new_sim = db_.get_similarity(*path2, *adj_path)) new_cost += 1.0f / (*new_sim + 1.0f);
+    }
+    for (const GridPosition& adj : pos2.get_adjacent_positions(grid_width, grid_height)) {
+      if (adj == pos1) continue;
+      const auto& adj_path = grid[adj.y][adj.x];
+      if (!adj_path) continue;
+      if (const auto old_sim = db_.get_similarity(*path2, *adj_path)) old_cost += 1.0f / (*old_sim + 1.0f);
+      if (const auto new_sim = db_.get_similarity(*path1, *adj_path)) new_cost += 1.0f / (*new_sim + 1.0f);
+    }
+    if (std::find(adj1.begin(), adj1.end(), pos2) != adj1.end()) {
+      if (const auto sim = db_.get_similarity(*path1, *path2)) {
+        const float cost = 1.0f / (*sim + 1.0f);
+        old_cost += cost;
+        new_cost += cost;
+      }
+    }
+    return new_cost - old_cost;
   }
 
   const SimilarityDatabase& database() const { return db_; }

@@ -16,6 +16,8 @@
 //! | `AdjacencyPenaltyCalculator::calculate_total_cost` (adjacency.rs:91-133) | `total_cost` below (K5's cost pass) |
 //! | `MosaicOptimizer::optimize` (optimizer.rs:41-129)                   | `optimize` below (K5)                    |
 //! | `MosaicOptimizer::optimize_greedy` (optimizer.rs:132-198)           | `optimize_greedy` below (K5, greedy mode)|
+//! | `AdjacencyPenaltyCalculator::calculate_penalty` / `calculate_swap_delta` (adjacency.rs:63-88, 133-214) | unchanged: one- and two-cell queries over `get_similarity`; the loops that call them thousands of times are `mosaic_place` and `optimize` |
+//! | `calculate_lab_distance`, `calculate_delta_e_2000` (similarity.rs:141-178) | unchanged (one pair; the n(n-1)/2 pairs are `build_similarities`) |
 //! | `UsageTracker`, `Tile`, `GridPosition`, config / result structs     | unchanged                                |
 use std::collections::HashMap;
 use std::os::raw::{c_float, c_int};

@@ -189,6 +189,109 @@ static void test_save_to_file_writes_a_stale_matrix() {  // similarity.rs:112-11
   std::remove(f.c_str());
 }
 
+static void test_lab_distance_and_delta_e_2000() {  // similarity.rs:363-402 (+ the fixtures of :185-232 for the distance)
+  const Lab lab1{50.0f, 0.0f, 0.0f}, lab2{50.0f, 0.0f, 0.0f}, lab3{60.0f, 10.0f, 10.0f};
+  CHECK(calculate_delta_e_2000(lab1, lab2) == 0.0f);
+  CHECK(calculate_delta_e_2000(lab1, lab3) > 0.0f);
+  CHECK(calculate_delta_e_2000(lab1, lab3) == calculate_delta_e_2000(lab3, lab1));
+  const Lab a{50.0f, 20.0f, -30.0f}, b{70.0f, -10.0f, 40.0f};
+  CHECK(calculate_lab_distance(a, b) > 0.0f && calculate_delta_e_2000(a, b) > 0.0f);
+  CHECK(calculate_lab_distance(a, b) == calculate_lab_distance(b, a));
+  CHECK(calculate_delta_e_2000(a, b) == calculate_delta_e_2000(b, a));
+  CHECK(calculate_lab_distance(a, a) == 0.0f && calculate_delta_e_2000(a, a) == 0.0f);
+  CHECK(calculate_lab_distance(lab1, lab3) == std::sqrt(300.0f));                      // the value build_similarities stores
+  CHECK(calculate_lab_distance(lab3, Lab{40.0f, -10.0f, -10.0f}) == std::sqrt(1200.0f));
+  // by hand: dl 10, c1 0, c2 sqrt(200), dc = c2, dh2 = 200 - 200 -> dh 0, sc = 1 + 0.045 * c2 / 2
+  const float c2 = std::sqrt(200.0f), sc = 1.0f + 0.045f * (c2 / 2.0f);
+  CHECK(std::fabs(calculate_delta_e_2000(lab1, lab3) - std::sqrt(100.0f + (c2 / sc) * (c2 / sc))) < 1e-5f);
+}
+
+// a database as the reference would have saved it, built WITHOUT a device: colours + host-side distances through the file
+static SimilarityDatabase database_from_file(const std::vector<std::string>& names, const std::vector<Lab>& labs) {
+  const int n = (int)names.size();
+  std::vector<const char*> paths;
+  std::vector<float> lab, sim;
+  for (int i = 0; i < n; ++i) {
+    paths.push_back(names[i].c_str());
+    lab.insert(lab.end(), {labs[i].l, labs[i].a, labs[i].b});
+  }
+  for (int i = 0; i < n; ++i)
+    for (int j = i + 1; j < n; ++j) sim.push_back(calculate_lab_distance(labs[i], labs[j]));  // packed order, similarity.rs:100
+  const std::string f = tmp_path("swap_delta_db.json");
+  if (mosaic_simdb_save_json(f.c_str(), paths.data(), n, lab.data(), sim.data()) != MOSAIC_OK) throw std::runtime_error("save failed");
+  SimilarityDatabase db = SimilarityDatabase::load_from_file(f);
+  std::remove(f.c_str());
+  return db;
+}
+
+static float host_total_cost(const SimilarityDatabase& db, const PathGrid& grid) {  // adjacency.rs:91-130, for this test only
+  float total = 0.0f;
+  for (size_t y = 0; y < grid.size(); ++y)
+    for (size_t x = 0; x < grid[y].size(); ++x) {
+      if (!grid[y][x]) continue;
+      if (x + 1 < grid[y].size() && grid[y][x + 1])
+        if (const auto s = db.get_similarity(*grid[y][x], *grid[y][x + 1])) total += 1.0f / (*s + 1.0f);
+      if (y + 1 < grid.size() && grid[y + 1][x])
+        if (const auto s = db.get_similarity(*grid[y][x], *grid[y + 1][x])) total += 1.0f / (*s + 1.0f);
+    }
+  return total;
+}
+
+static void test_swap_delta() {  // adjacency.rs:133-214 (the optimizer's inner call, optimizer.rs:76, 164)
+  std::vector<std::string> names;
+  std::vector<Lab> labs;
+  uint64_t state = 12345;
+  auto next = [&]() {
+    state = state * 6364136223846793005ull + 1442695040888963407ull;
+    return (uint32_t)(state >> 33);
+  };
+  for (int i = 0; i < 9; ++i) {
+    names.push_back("tile" + std::to_string(i) + ".png");
+    labs.push_back(Lab{(float)(next() % 1000) / 10.0f, (float)(next() % 2000) / 10.0f - 100.0f, (float)(next() % 2000) / 10.0f - 100.0f});
+  }
+  const SimilarityDatabase db = database_from_file(names, labs);
+  CHECK(db.len() == 9);
+  const AdjacencyPenaltyCalculator calc(db, 0.3f);
+  // the 2x2 fixture of adjacency.rs:243-290 style: neighbours, mutual term
+  {
+    PathGrid grid = {{names[0], names[1]}, {names[2], names[3]}};
+    const float before = host_total_cost(db, grid);
+    const float delta = calc.calculate_swap_delta(grid, GridPosition(0, 0), GridPosition(1, 0));  // adjacent cells
+    std::swap(grid[0][0], grid[0][1]);
+    CHECK(std::fabs((host_total_cost(db, grid) - before) - delta) < 1e-5f);
+  }
+  const size_t gw = 5, gh = 4;
+  for (int trial = 0; trial < 400; ++trial) {
+    PathGrid grid(gh, std::vector<std::optional<std::string>>(gw));
+    for (auto& row : grid)
+      for (auto& cell : row) {
+        const uint32_t r = next() % 12;
+        if (r < 9) cell = names[r];                 // duplicates on purpose
+        else if (r == 9) cell = "unknown.png";      // a path the database does not know: its terms are skipped
+      }                                             // else: an empty cell
+    const GridPosition p1(next() % gw, next() % gh), p2(next() % gw, next() % gh);
+    const float delta = calc.calculate_swap_delta(grid, p1, p2);
+    const auto& a = grid[p1.y][p1.x];
+    const auto& b = grid[p2.y][p2.x];
+    if (!a || !b || *a == *b) {
+      CHECK(delta == 0.0f);                         // adjacency.rs:146-158
+      continue;
+    }
+    const float before = host_total_cost(db, grid);
+    PathGrid swapped = grid;
+    std::swap(swapped[p1.y][p1.x], swapped[p2.y][p2.x]);
+    CHECK(std::fabs((host_total_cost(db, swapped) - before) - delta) < 2e-5f);
+    CHECK(calc.calculate_swap_delta(swapped, p1, p2) == -delta || std::fabs(calc.calculate_swap_delta(swapped, p1, p2) + delta) < 1e-6f);
+  }
+  CHECK(calc.calculate_swap_delta(PathGrid{}, GridPosition(0, 0), GridPosition(0, 0)) == 0.0f);  // adjacency.rs:139-142
+  // calculate_penalty over the same database (adjacency.rs:63-88): weight * sum of 1 / (sim + 1) over placed neighbours
+  PathGrid grid(3, std::vector<std::optional<std::string>>(3));
+  grid[0][1] = names[1];
+  grid[1][0] = names[2];
+  const float want = (1.0f / (calculate_lab_distance(labs[0], labs[1]) + 1.0f) + 1.0f / (calculate_lab_distance(labs[0], labs[2]) + 1.0f)) * 0.3f;
+  CHECK(calc.calculate_penalty(names[0], GridPosition(1, 1), grid, 3, 3) == want);
+}
+
 static void test_no_gpu_is_loud() {  // there is no CPU fallback behind the mirror: without a device the call throws
   SimilarityDatabase db;
   db.add_tile("a.png", Lab{50.0f, 0.0f, 0.0f});
@@ -601,6 +704,8 @@ int main(int argc, char** argv) {
   RUN(test_tile_creation);
   RUN(test_usage_tracker);
   RUN(test_save_to_file_writes_a_stale_matrix);
+  RUN(test_lab_distance_and_delta_e_2000);
+  RUN(test_swap_delta);
   if (cpu_only) {
     RUN(test_no_gpu_is_loud);
   } else {
