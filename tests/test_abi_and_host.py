@@ -207,3 +207,80 @@ def test_header_is_plain_c(tmp_path):
                            "-fsyntax-only", str(src)])
     text = open(os.path.join(root, "include", "mosaic_b200.h")).read()
     assert "torch::" not in text and "std::" not in text and "at::" not in text and "#include <torch" not in text
+
+
+# ---------------------------------------------------------------- the Rust side (unverified source) against the header
+_RUST_TO_C = {
+    "c_int": "int", "i32": "int32_t", "u32": "uint32_t", "u64": "uint64_t", "i64": "int64_t", "c_float": "float", "f32": "float",
+    "u8": "uint8_t", "c_char": "char", "mosaic_ctx": "mosaic_ctx", "mosaic_simdb": "mosaic_simdb",
+    "mosaic_opt_result": "mosaic_opt_result", "mosaic_params": "mosaic_params", "mosaic_report": "mosaic_report",
+}
+
+
+def _rust_type_to_c(t):
+    t = t.strip()
+    stars = []
+    while t.startswith("*"):
+        m = re.match(r"\*(const|mut)\s+", t)
+        stars.append(m.group(1))
+        t = t[m.end():]
+    base = _RUST_TO_C[t]
+    # `*const T` -> `const T*`; `*mut *mut T` -> `T**`; `*const *const c_char` -> `const char* const*`
+    out = base
+    for kind in reversed(stars):
+        out = ("const " + out if kind == "const" and "*" not in out else out + (" const" if kind == "const" else "")) + "*"
+    return re.sub(r"\s+", " ", out).strip()
+
+
+def _norm_c(t):
+    t = re.sub(r"\s+", " ", t.strip())
+    t = re.sub(r"\s*\*\s*", "*", t)
+    t = re.sub(r"\bint32_t\b", "int32_t", t)
+    return t
+
+
+def _c_params(decl):
+    out = []
+    for p in decl.split(","):
+        p = p.strip()
+        if p in ("", "void"):
+            continue
+        p = re.sub(r"\[[^\]]*\]", "", p)
+        m = re.match(r"(.*?[\s\*])([A-Za-z_][A-Za-z0-9_]*)$", p)         # strip the parameter name
+        out.append(_norm_c(m.group(1)))
+    return out
+
+
+def test_rust_ffi_declarations_match_the_header():
+    """integration/rust/ cannot be compiled here (no rustc): at least its `extern "C"` blocks are held against the header —
+    every function exists, with the same number of parameters, the same C types in the same order and the same return type;
+    the #[repr(C)] structs list the header's fields in the header's order."""
+    hdr = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    c_decls = {}
+    for m in re.finditer(r"^([A-Za-z_][A-Za-z0-9_ \*]*?)\b(mosaic_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", hdr, flags=re.M | re.S):
+        c_decls[m.group(2)] = (_norm_c(m.group(1)), _c_params(m.group(3)))
+    checked = 0
+    for name in ("b200.rs", "lib_compat.rs"):
+        src = open(os.path.join(ROOT, "integration", "rust", "src", name)).read()
+        src = re.sub(r"//[^\n]*", "", src)
+        for block in re.findall(r'extern\s+"C"\s*\{(.*?)\n\}', src, flags=re.S):
+            for m in re.finditer(r"fn\s+(mosaic_[a-z0-9_]+)\s*\((.*?)\)\s*(?:->\s*([^;]+))?;", block, flags=re.S):
+                fn, params, ret = m.group(1), m.group(2), (m.group(3) or "").strip()
+                assert fn in c_decls, f"{name}: {fn} is not declared in include/mosaic_b200.h"
+                c_ret, c_params = c_decls[fn]
+                r_params = [_norm_c(_rust_type_to_c(p.split(":", 1)[1])) for p in re.split(r",\s*(?=[a-z_0-9]+\s*:)", params.strip()) if p.strip()]
+                assert r_params == c_params, f"{name}: {fn}: {r_params} != {c_params}"
+                r_ret = _norm_c(_rust_type_to_c(ret)) if ret else "void"
+                assert r_ret == c_ret, f"{name}: {fn}: returns {r_ret}, the header says {c_ret}"
+                checked += 1
+    assert checked >= 30
+    # struct layouts: field names and order
+    b200 = open(os.path.join(ROOT, "integration", "rust", "src", "b200.rs")).read()
+    for struct in ("mosaic_opt_result", "mosaic_params", "mosaic_report"):
+        c_body = re.search(r"typedef struct \{([^}]*)\}\s*" + struct + r"\s*;", hdr, flags=re.S).group(1)
+        c_fields = [(re.sub(r"\s+", " ", t.strip()), n) for t, n in re.findall(r"([A-Za-z_][A-Za-z0-9_ ]*?)\s+([a-z_0-9]+(?:\s*,\s*[a-z_0-9]+)*)\s*;", c_body)]
+        c_flat = [(t, n.strip()) for t, names in c_fields for n in names.split(",")]
+        r_body = re.search(r"pub struct " + struct + r"\s*\{(.*?)\n\}", b200, flags=re.S).group(1)
+        r_body = re.sub(r"//[^\n]*", "", r_body)
+        r_flat = [(_RUST_TO_C[t.strip()], n) for n, t in re.findall(r"pub\s+([a-z_0-9]+)\s*:\s*([A-Za-z_0-9]+)\s*,", r_body)]
+        assert [(t.replace("int", "int") if t != "int" else "int", n) for t, n in r_flat] == c_flat, (struct, r_flat, c_flat)
