@@ -69,7 +69,10 @@ int mosaic_ctx_create_sharded(mosaic_ctx** out, int device, int rank, int world,
                               const void* nccl_unique_id, size_t id_bytes);
 int mosaic_nccl_unique_id(void* id_out, size_t id_bytes);
 void mosaic_ctx_destroy(mosaic_ctx* ctx);
-const char* mosaic_last_error(const mosaic_ctx* ctx); /* ctx may be NULL: creation errors */
+/* ctx may be NULL: the last failure of a call WITHOUT a context (creation, mosaic_simdb_*, the image codecs) on the CALLING
+ * THREAD — such calls may run concurrently on several threads (the reference decodes tiles on rayon workers,
+ * main.rs:193-208) and each thread reads its own message.  The pointer is valid until the thread's next such call. */
+const char* mosaic_last_error(const mosaic_ctx* ctx);
 /* Launch on a caller-owned CUDA stream (cudaStream_t as void*); NULL restores the context's own. */
 int mosaic_ctx_set_stream(mosaic_ctx* ctx, void* cuda_stream);
 int mosaic_ctx_sync(mosaic_ctx* ctx);

@@ -11,13 +11,12 @@
 
 namespace mosaic {
 
-static std::mutex g_err_mu;
-static std::string g_err;  // errors that happen before a context exists
+// errors of calls that have no context (creation, the similarity-database file, the image codecs): one message PER THREAD —
+// the reference decodes its tiles on rayon's workers (main.rs:193-208), and a worker that asks for the message of its own
+// failed call must not read the message of its neighbour's
+static thread_local std::string g_err;
 
-void set_global_error(const std::string& msg) {
-  std::lock_guard<std::mutex> lk(g_err_mu);
-  g_err = msg;
-}
+void set_global_error(const std::string& msg) { g_err = msg; }
 
 int fail(mosaic_ctx* ctx, int code, const std::string& msg) {
   if (ctx)
@@ -910,10 +909,7 @@ extern "C" {
 
 const char* mosaic_last_error(const mosaic_ctx* ctx) {
   if (ctx) return ctx->err.c_str();
-  std::lock_guard<std::mutex> lk(g_err_mu);
-  static thread_local std::string copy;
-  copy = g_err;
-  return copy.c_str();
+  return g_err.c_str();  // the calling thread's own last context-less failure; valid until its next such call
 }
 
 static int ctx_create_common(mosaic_ctx** out, int device) {

@@ -284,3 +284,36 @@ def test_rust_ffi_declarations_match_the_header():
         r_body = re.sub(r"//[^\n]*", "", r_body)
         r_flat = [(_RUST_TO_C[t.strip()], n) for n, t in re.findall(r"pub\s+([a-z_0-9]+)\s*:\s*([A-Za-z_0-9]+)\s*,", r_body)]
         assert [(t.replace("int", "int") if t != "int" else "int", n) for t, n in r_flat] == c_flat, (struct, r_flat, c_flat)
+
+
+def test_context_less_errors_are_per_thread(lib_built, tmp_path):
+    """The codecs and the database reader have no context and may run on many threads at once (the reference decodes its
+    tiles on rayon workers, main.rs:193-208): every thread reads the message of ITS failed call from mosaic_last_error(NULL)."""
+    import threading
+    import mosaic_b200
+    L = ctypes.CDLL(mosaic_b200.LIB_PATH)
+    L.mosaic_last_error.restype = ctypes.c_char_p
+    L.mosaic_last_error.argtypes = [ctypes.c_void_p]
+    L.mosaic_simdb_load_json.argtypes = [ctypes.c_char_p, ctypes.POINTER(ctypes.c_void_p)]
+    n_threads, rounds = 8, 300
+    bad = []
+    barrier = threading.Barrier(n_threads)
+
+    def worker(t):
+        name = f"no_such_database_{t}.json"
+        path = os.fsencode(str(tmp_path / name))
+        barrier.wait()
+        for _ in range(rounds):
+            h = ctypes.c_void_p()
+            rc = L.mosaic_simdb_load_json(path, ctypes.byref(h))
+            msg = (L.mosaic_last_error(None) or b"").decode()
+            if rc == 0 or name not in msg:
+                bad.append((t, rc, msg))
+                return
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(n_threads)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not bad, bad[:3]
