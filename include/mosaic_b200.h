@@ -16,8 +16,11 @@
  *    after truncate (main.rs:255-257) = similarity-DB index of a freshly built DB (main.rs:123-125).
  *  - there is NO CPU fallback: every compute entry point runs hand-written sm_100a CUDA kernels
  *    and fails with MOSAIC_ERR_CUDA when no usable device is present.
- *  - results: placements / annealed grids bit-exact, similarity entries bit-equal, Lab means
- *    <= 1e-4 relative, output pixels <= 1 LSB vs the CPU oracle.
+ *  - results, stage by stage against the CPU oracle: Lab means <= 1e-4 relative (the cube root runs on the
+ *    MUFU pipe, the sums in tree order); FROM THE SAME Lab means the candidate lists (index and distance bits), the
+ *    placements, the fallback cells, the annealed grid with its counters and cost bits and the similarity entries are
+ *    identical; output pixels <= 1 LSB.  From PIXELS, a run and the oracle's can part ways where two candidates are tied to
+ *    within the Lab tolerance (tests/test_gpu_c3.py reports the rate on the 24,000-tile configuration).
  */
 #ifndef MOSAIC_B200_H
 #define MOSAIC_B200_H
