@@ -15,6 +15,11 @@
 //   MosaicGenerator              src/main.rs:92-685         new(...), generate_mosaic(...)  (the CLI's private struct,
 //                                                           minus directory scan and codecs: images come in memory)
 //
+// Not mirrored: `color_adjustment::{ColorAdjustment, calculate_optimal_adjustment}` (color_adjustment.rs:6-154) as
+// free-standing items — their one caller on the path is the per-cell adjust of generate_mosaic (main.rs:551-567, 636-652),
+// which is inside mosaic_render / mosaic_generate (K4's compose pass) with the strength as its only parameter; in the Rust
+// crate they stay as they are (integration/rust/src/lib_compat.rs).
+//
 // `Option<PathBuf>` grids are std::vector<std::vector<std::optional<std::string>>>; `anyhow::Result` errors are
 // exceptions (mosaic_b200::Error carries the status code and mosaic_last_error's text).  Every computation of the
 // hot path is forwarded to the GPU library; what stays here is bookkeeping (path <-> index maps) and the single-cell
