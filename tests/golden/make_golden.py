@@ -5,7 +5,7 @@ crates not vendored, no network), so these vectors are NOT outputs of the refere
 restatement (oracle/mosaic_oracle.cpp, strict build), which tests/test_oracle_golden.py pins to every known answer the
 reference's own tests hold (those literal vectors are in reference_known_answers.json next to this file).  What the
 committed file adds: (1) the restatement cannot drift unnoticed — a compiler upgrade, a flag change or an edit that moves
-one bit of one stage fails tests/test_golden_fixtures.py on the CPU; (2) the CUDA path is compared with vectors that exist
+one bit of one stage fails tests/test_zz_golden_fixtures.py on the CPU; (2) the CUDA path is compared with vectors that exist
 independently of the checker's build on the GPU box.
 
     python tests/golden/make_golden.py            # rewrites the file; commit it together with the change that moved it
