@@ -273,6 +273,10 @@ int mosaic_webp_decode_rgb8(const char* file, uint8_t** rgb_out, int* width, int
 int mosaic_webp_encode_rgb8(const char* file, const uint8_t* rgb, int width, int height);
 /* PNG, JPEG or WebP, told apart by the file's first bytes (image::open for the formats src/main.rs:181 lists). */
 int mosaic_image_decode_rgb8(const char* file, uint8_t** rgb_out, int* width, int* height);
+/* image::open(path)?.to_rgb8() with image::open's own rule — "the image's format is determined from the path's file
+ * extension" (lower-cased; png / jpg / jpeg / webp): the content is NOT sniffed, a JPEG file named x.png fails in the PNG
+ * decoder like it does in the reference, where load_tiles then drops the tile with a message (src/main.rs:198-206). */
+int mosaic_image_open_rgb8(const char* file, uint8_t** rgb_out, int* width, int* height);
 void mosaic_host_free(void* p);
 
 /* ---- self test ------------------------------------------------------------------------------ */

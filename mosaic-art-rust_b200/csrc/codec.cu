@@ -106,6 +106,24 @@ int mosaic_image_decode_rgb8(const char* file, uint8_t** rgb_out, int* width, in
   return fail(nullptr, MOSAIC_ERR_INVALID, std::string("image_decode: not a PNG, JPEG or WebP file (the formats src/main.rs:181 accepts): ") + file);
 }
 
+// image::open(path)?.to_rgb8() with image::open's own rule: "the image's format is determined from the path's file
+// extension" (ImageFormat::from_path, lower-cased) — the content is not sniffed, so a JPEG file called x.png is an error
+// of the PNG decoder and the tile is dropped with a message, as in the reference (main.rs:198-206)
+int mosaic_image_open_rgb8(const char* file, uint8_t** rgb_out, int* width, int* height) {
+  if (!file || !rgb_out || !width || !height) return fail(nullptr, MOSAIC_ERR_INVALID, "image_open: bad arguments");
+  *rgb_out = nullptr;
+  const char* slash = std::strrchr(file, '/');
+  const char* dot = std::strrchr(slash ? slash + 1 : file, '.');
+  std::string ext = dot && dot != (slash ? slash + 1 : file) ? dot + 1 : "";  // ".png" alone is a file name, not an extension
+  for (char& ch : ext)
+    if (ch >= 'A' && ch <= 'Z') ch = (char)(ch - 'A' + 'a');
+  if (ext == "png") return mosaic_png_decode_rgb8(file, rgb_out, width, height);
+  if (ext == "jpg" || ext == "jpeg") return mosaic_jpeg_decode_rgb8(file, rgb_out, width, height);
+  if (ext == "webp") return mosaic_webp_decode_rgb8(file, rgb_out, width, height);
+  return fail(nullptr, MOSAIC_ERR_INVALID, std::string("image_open: the extension of ") + file +
+                                               " is not one of png / jpg / jpeg / webp (the formats src/main.rs:181 accepts)");
+}
+
 void mosaic_host_free(void* p) { std::free(p); }
 
 }  // extern "C"

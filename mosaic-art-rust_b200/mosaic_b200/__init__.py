@@ -121,6 +121,7 @@ def load_library():
         "mosaic_jpeg_encode_rgb8": ([C.c_char_p, vp, C.c_int, C.c_int, C.c_int], C.c_int),
         "mosaic_jpeg_decode_rgb8": ([C.c_char_p, C.POINTER(u8p), C.POINTER(C.c_int), C.POINTER(C.c_int)], C.c_int),
         "mosaic_image_decode_rgb8": ([C.c_char_p, C.POINTER(u8p), C.POINTER(C.c_int), C.POINTER(C.c_int)], C.c_int),
+        "mosaic_image_open_rgb8": ([C.c_char_p, C.POINTER(u8p), C.POINTER(C.c_int), C.POINTER(C.c_int)], C.c_int),
         "mosaic_webp_decode_rgb8": ([C.c_char_p, C.POINTER(u8p), C.POINTER(C.c_int), C.POINTER(C.c_int)], C.c_int),
         "mosaic_webp_encode_rgb8": ([C.c_char_p, vp, C.c_int, C.c_int], C.c_int),
         "mosaic_host_free": ([vp], None),
@@ -151,7 +152,7 @@ EXPORTED_SYMBOLS = (
     "mosaic_simdb_save_json", "mosaic_simdb_save_json_n", "mosaic_simdb_save_ctx", "mosaic_simdb_load_json", "mosaic_simdb_free",
     "mosaic_simdb_info", "mosaic_simdb_path", "mosaic_simdb_index_of", "mosaic_simdb_copy",
     "mosaic_simdb_get_similarity",
-    "mosaic_set_progress_callback", "mosaic_png_decode_rgb8", "mosaic_png_encode_rgb8", "mosaic_jpeg_decode_rgb8", "mosaic_jpeg_encode_rgb8", "mosaic_image_decode_rgb8", "mosaic_webp_decode_rgb8", "mosaic_webp_encode_rgb8", "mosaic_host_free",
+    "mosaic_set_progress_callback", "mosaic_png_decode_rgb8", "mosaic_png_encode_rgb8", "mosaic_jpeg_decode_rgb8", "mosaic_jpeg_encode_rgb8", "mosaic_image_decode_rgb8", "mosaic_image_open_rgb8", "mosaic_webp_decode_rgb8", "mosaic_webp_encode_rgb8", "mosaic_host_free",
     "mosaic_host_alloc", "mosaic_host_release", "mosaic_host_register", "mosaic_host_unregister",
 )
 
@@ -568,6 +569,12 @@ def webp_encode(path, img) -> None:
 def image_decode(path) -> np.ndarray:
     """PNG, JPEG or WebP by the file's first bytes.  Host only."""
     return _decode_with("mosaic_image_decode_rgb8", path)
+
+
+def image_open(path) -> np.ndarray:
+    """image::open(path)?.to_rgb8(): the format follows the path's EXTENSION (lower-cased), as in the `image` crate; the
+    content is not sniffed.  Host only."""
+    return _decode_with("mosaic_image_open_rgb8", path)
 
 
 def png_decode(path) -> np.ndarray:

@@ -159,3 +159,30 @@ def test_encode_is_what_libjpeg_writes(tmp_path, quality, shape):
     assert abs(ours.stat().st_size - theirs.stat().st_size) <= 64   # (headers may differ by a comment or a density field)
     with PIL.open(ours) as im:
         assert im.size == (shape[1], shape[0]) and im.mode == "RGB"
+
+
+def test_image_open_goes_by_the_extension_like_image_open(tmp_path):
+    """`image::open`: "the image's format is determined from the path's file extension" — no content sniffing.  A JPEG file
+    named .png fails in the PNG decoder (the reference then drops the tile with a message, main.rs:198-206)."""
+    rng = np.random.default_rng(4)
+    img = rng.integers(0, 256, (21, 34, 3), dtype=np.uint8)
+    mosaic_b200.png_encode(tmp_path / "a.png", img)
+    mosaic_b200.jpeg_encode(tmp_path / "a.jpg", img)
+    mosaic_b200.webp_encode(tmp_path / "a.webp", img)
+    assert (mosaic_b200.image_open(tmp_path / "a.png") == img).all()
+    assert (mosaic_b200.image_open(tmp_path / "a.jpg") == mosaic_b200.jpeg_decode(tmp_path / "a.jpg")).all()
+    assert (mosaic_b200.image_open(tmp_path / "a.webp") == img).all()
+    for name, src in (("B.PNG", "a.png"), ("c.JpEg", "a.jpg"), ("d.tar.WEBP", "a.webp")):     # lower-cased, last extension
+        (tmp_path / name).write_bytes((tmp_path / src).read_bytes())
+        assert mosaic_b200.image_open(tmp_path / name).shape == img.shape
+    for name, src in (("jpeg_inside.png", "a.jpg"), ("png_inside.jpg", "a.png"), ("png_inside.webp", "a.png"),
+                      ("no_extension", "a.png"), (".png", "a.png"), ("a.gif", "a.png"), ("a.png.bak", "a.png")):
+        (tmp_path / name).write_bytes((tmp_path / src).read_bytes())
+        with pytest.raises(mosaic_b200.MosaicError):
+            mosaic_b200.image_open(tmp_path / name)
+    d = tmp_path / "dir.png"
+    d.mkdir()
+    (d / "plain").write_bytes((tmp_path / "a.png").read_bytes())     # the dot belongs to the directory, not to the file
+    with pytest.raises(mosaic_b200.MosaicError, match="extension"):
+        mosaic_b200.image_open(d / "plain")
+    assert (mosaic_b200.image_decode(tmp_path / "jpeg_inside.png") == mosaic_b200.jpeg_decode(tmp_path / "a.jpg")).all()  # the sniffing call
