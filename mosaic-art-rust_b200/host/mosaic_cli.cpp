@@ -311,6 +311,9 @@ int main(int argc, char** argv) {
     if (!generator.save_warning().empty()) std::fprintf(stderr, "%s\n", generator.save_warning().c_str());
     const auto t2 = std::chrono::steady_clock::now();
 
+    if (args.grid_w == 0 || args.grid_h == 0 || args.grid_w > (unsigned)target.width || args.grid_h > (unsigned)target.height)
+      throw std::runtime_error("the grid (" + std::to_string(args.grid_w) + "x" + std::to_string(args.grid_h) +
+                               ") needs at least one pixel of the target per tile (the reference divides by zero here, main.rs:495-496)");
     std::printf("Target image: %dx%d\n", target.width, target.height);
     std::printf("Grid: %ux%u, Tile size: %ux%u\n", args.grid_w, args.grid_h, target.width / args.grid_w, target.height / args.grid_h);
     mosaic_report rep{};
