@@ -233,3 +233,76 @@ def test_cuda_meets_the_reference_known_answers(ctx):
 @pytest.mark.gpu
 def test_cuda_reproduces_the_committed_pipeline(ctx):
     check_pipeline(CudaImpl(ctx), exact_lab=False)
+
+
+# ------------------------------------------------------------------------------------------------ the adapter, checked on the CPU
+class _StandInContext:
+    """The methods of mosaic_b200.Context that CudaImpl calls, over the oracle, with the binding's shapes and return types —
+    so that the adapter and the checks above are exercised on the CPU too (a mistake in the TEST must not show up for the
+    first time on the GPU box).  Test infrastructure only."""
+
+    def __init__(self):
+        self.mats = self.tgt = self.mlab = self.clab = self.placed = self.cand = None
+        self.gw = self.gh = 0
+
+    def set_materials(self, mats):
+        self.mats, self.mlab = np.ascontiguousarray(mats, np.uint8), None
+
+    def material_lab(self, fetch=True):
+        if self.mlab is None:
+            self.mlab = orc.material_lab(self.mats)
+        return self.mlab.copy() if fetch else None
+
+    def set_target(self, tgt, gw, gh):
+        self.tgt, self.gw, self.gh, self.clab = tgt, gw, gh, None
+
+    def cell_lab(self, fetch=True):
+        if self.clab is None:
+            self.clab = orc.cell_lab(self.tgt, self.gw, self.gh)
+        return self.clab.copy() if fetch else None
+
+    def set_material_lab(self, lab):
+        self.mlab, self.mats = np.ascontiguousarray(lab, np.float32), None
+
+    def set_cell_lab(self, lab, gw, gh):
+        lab = np.ascontiguousarray(lab, np.float32)
+        assert lab.shape == (gw * gh, 3)
+        self.clab, self.gw, self.gh = lab, gw, gh
+
+    def candidates(self, k=100, fetch=True):
+        self.cand = orc.topk(self.mlab, self.clab, min(k if 0 < k <= 100 else 100, len(self.mlab)))
+        return self.cand
+
+    def place(self, max_usage=3, adjacency_weight=0.3, fetch=True):
+        placed, nfb, self.fb, _ = orc.place(self.cand[0], self.cand[1], self.mlab, self.gw, self.gh, max_usage, adjacency_weight)
+        self.placed = placed
+        return placed, nfb
+
+    def fallback_cells(self, cap=4096):
+        return self.fb
+
+    def similarity_tri(self, fetch=True):
+        return orc.similarity_tri(self.mlab)
+
+    def set_placement(self, placed):
+        placed = np.ascontiguousarray(placed, np.int32).ravel()
+        assert placed.shape == (self.gw * self.gh,)
+        self.placed = placed
+
+    def anneal(self, iterations=1000, seed=0, t0=100.0, decay=0.99995, fetch=True):
+        g, r = orc.anneal(self.mlab, self.placed.reshape(self.gh, self.gw), iterations, seed, t0, decay)
+        self.placed = g.reshape(-1).astype(np.int32)
+        return self.placed, r
+
+    def optimize_greedy(self, max_iterations=1000, seed=0, fetch=True):
+        g, r = orc.anneal_greedy(self.mlab, self.placed.reshape(self.gh, self.gw), max_iterations, seed)
+        self.placed = g.reshape(-1).astype(np.int32)
+        return self.placed, r
+
+    def render(self, color_strength=0.3, out=None, fetch=True):
+        return orc.render(self.tgt, self.gw, self.gh, self.mats, self.placed, color_strength)
+
+
+def test_cuda_adapter_over_a_stand_in_context():
+    check_reference_known_answers(CudaImpl(_StandInContext()))
+    check_pipeline(CudaImpl(_StandInContext()), exact_lab=False)
