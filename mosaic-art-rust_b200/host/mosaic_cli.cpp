@@ -275,13 +275,19 @@ static void load_tiles(const std::string& material_dir, float target_aspect, flo
     const float aspect = (float)headers[i].width / (float)headers[i].height;  // main.rs:270
     if (MosaicGeneratorImpl::is_aspect_ratio_match(aspect, target_aspect, aspect_tolerance)) matching.push_back(entries[i]);
   }
-  decode_in_order(matching, max_materials, paths, images);
+  // (at least one, whatever the limit: whether the fallback fires depends on `tiles.is_empty()` BEFORE the truncation,
+  // main.rs:211 vs 255 — `--max-materials 0` keeps nothing but does not fall back when a matching tile exists)
+  decode_in_order(matching, std::max<size_t>(max_materials, 1), paths, images);
   if (paths->empty()) {  // main.rs:211-253
     std::printf("No tiles matched target aspect ratio %.3f, loading tiles without aspect filtering...\n", target_aspect);
     const size_t take = std::min(entries.size(), max_materials * 2);
     std::printf("Processing %zu material images (sampled from %zu total)...\n", take, entries.size());
     const std::vector<std::string> sampled(entries.begin(), entries.begin() + (std::ptrdiff_t)take);
     decode_in_order(sampled, max_materials, paths, images);  // main.rs:255-257: the first max_materials that decoded
+  }
+  if (paths->size() > max_materials) {  // main.rs:255-257
+    paths->resize(max_materials);
+    images->resize(max_materials);
   }
   std::printf("Loaded %zu tiles (aspect ratio matched)\n", paths->size());
 }

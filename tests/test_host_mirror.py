@@ -226,6 +226,7 @@ def test_cli_selects_the_tiles_load_tiles_selects(cli, tmp_path):
     (mdir / "noext").write_bytes((mdir / "a_wide.png").read_bytes())
     (mdir / "k_dir.png").mkdir()                                      # is_file() fails
     files.sort()
+    mixed_files = list(files)
     for max_materials in (500, 4, 3, 1):
         got, _ = listed(mdir, "--max-materials", str(max_materials))
         assert got == _reference_load_tiles(files, 160 / 90, 0.1, max_materials), max_materials
@@ -260,6 +261,16 @@ def test_cli_selects_the_tiles_load_tiles_selects(cli, tmp_path):
     Image.fromarray(rng.integers(0, 256, (30, 30, 3), dtype=np.uint8)).save(bad / "square.png")
     got, r = listed(bad)
     assert got == ["square.png"] and "No tiles matched" in r.stdout
+
+    # ---- the reference's own edge cases: main.rs:1987-2022
+    got, r = listed(mdir, "--max-materials", "0")                     # test_zero_max_materials: nothing, and no fallback
+    assert got == [] and "No tiles matched" not in r.stdout and "Loaded 0 tiles" in r.stdout
+    got, r = listed(mdir, "--aspect-tolerance=-0.1")                  # test_negative_aspect_tolerance: nothing matches ...
+    assert "No tiles matched" in r.stdout                             # ... so load_tiles falls back to the unfiltered files
+    assert got == _reference_load_tiles(mixed_files, 160 / 90, -0.1, 500) and len(got) == 8
+    got, r = listed(mdir, "--aspect-tolerance", "1000")               # test_extreme_aspect_tolerance: everything matches
+    assert "No tiles matched" not in r.stdout
+    assert got == _reference_load_tiles(mixed_files, 160 / 90, 1000.0, 500) and len(got) == 8
 
     # ---- an empty directory lists nothing
     empty = tmp_path / "empty"
