@@ -379,3 +379,72 @@ def test_kdtree_topk_equals_brute_force():
     assert (a[0] == b[0]).all() and (a[1].view(np.uint32) == b[1].view(np.uint32)).all()
     m, q = np.zeros((500, 3), np.float32), np.ones((5, 3), np.float32)  # every material the same colour: one big leaf
     assert (orc.topk(m, q, 100)[0] == orc.topk_kdtree(m, q, 100)[0]).all()
+
+
+# ---------------------------------------------------------------- independent implementations found in this image
+def test_chacha_block_against_an_independent_chacha20():
+    """The block function with ARBITRARY keys and 64-bit counters against the ChaCha20 of the `cryptography` package
+    (OpenSSL): its 16-byte nonce is state words 12..15, so `counter (u64 LE) || 8 zero bytes` is the djb layout rand_chacha
+    uses (64-bit block counter, stream 0).  The 12-round variant the annealer draws from shares everything but the loop count
+    (pinned by the zero-key vectors above)."""
+    ciphers = pytest.importorskip("cryptography.hazmat.primitives.ciphers")
+    rng = np.random.default_rng(12)
+    for trial in range(40):
+        key = rng.integers(0, 2 ** 32, 8, dtype=np.uint64).astype(np.uint32)
+        counter = int(rng.integers(0, 2 ** 62)) if trial % 3 else int(rng.integers(0, 1000)) + (trial % 2) * (2 ** 32 - 500)
+        nonce = counter.to_bytes(8, "little") + bytes(8)
+        enc = ciphers.Cipher(ciphers.algorithms.ChaCha20(key.tobytes(), nonce), mode=None).encryptor()
+        want = enc.update(bytes(64 * 3))                                    # three consecutive blocks of key stream
+        got = b"".join(orc.chacha_block(key, counter + i, 20).tobytes() for i in range(3))
+        if (counter & 0xFFFFFFFF) + 2 >= 2 ** 32:
+            want = want[:64 * ((2 ** 32 - (counter & 0xFFFFFFFF)))]         # (OpenSSL's counter is 32-bit: compare up to its wrap)
+            got = got[:len(want)]
+        assert got == want, (trial, counter)
+
+
+def test_hsv_against_colorsys():
+    """The hexcone conversions against Python's colorsys (same model, hue in turns instead of degrees, different operation
+    order): agreement to float rounding guards the restatement against a wrong sector or sign, not against the last ulp."""
+    import colorsys
+    rng = np.random.default_rng(8)
+    samples = [tuple(rng.random(3).astype(np.float32)) for _ in range(2000)]
+    samples += [(0.0, 0.0, 0.0), (1.0, 1.0, 1.0), (0.5, 0.5, 0.5), (1.0, 0.0, 0.0), (0.0, 1.0, 0.0), (0.0, 0.0, 1.0), (1.0, 1.0, 0.0),
+                (0.0, 1.0, 1.0), (1.0, 0.0, 1.0), (0.2, 0.2, 0.7), (0.7, 0.2, 0.2000001)]
+    for r, g, b in samples:
+        h, s, v = orc.rgb_to_hsv(r, g, b)
+        ch, cs, cv = colorsys.rgb_to_hsv(float(r), float(g), float(b))
+        assert abs(float(s) - cs) < 1e-5 and abs(float(v) - cv) < 1e-6
+        if cs > 1e-4:
+            dh = (float(h) % 360.0 - ch * 360.0 + 180.0) % 360.0 - 180.0
+            assert abs(dh) < 1e-2 * max(1.0, 1e-2 / cs), (r, g, b, h, ch * 360.0)
+        back = orc.hsv_to_rgb(float(h), float(s), float(v))
+        want = colorsys.hsv_to_rgb((float(h) % 360.0) / 360.0, float(s), float(v))
+        assert np.allclose(back, want, atol=2e-6), (r, g, b)
+        for shift in (-400.0, -123.0, 77.0, 360.0, 725.0):                  # hues outside [0, 360): into_positive_degrees
+            assert np.allclose(orc.hsv_to_rgb(float(h) + shift, float(s), float(v)),
+                               colorsys.hsv_to_rgb(((float(h) + shift) % 360.0) / 360.0, float(s), float(v)), atol=3e-5)
+
+
+def test_lab_against_float64_formula_and_opencv():
+    """sRGB -> CIE L*a*b* (D65) over the whole cube INCLUDING the dark colours, where the sRGB decode takes its linear segment
+    (c <= 0.04045) and f(t) its linear branch (t <= (6/29)^3) — the reference's own vectors (red, grey, black) never enter
+    those branches.  (1) the published formula evaluated in float64 with numpy: the f32 restatement agrees to 2e-4;
+    (2) OpenCV's float path, an independent implementation (other matrix digits, table-interpolated gamma and cube root, good
+    to ~0.5): agreement to 0.6 rules out a wrong white point, matrix or branch, which move Lab by whole units."""
+    rng = np.random.default_rng(6)
+    cols = np.concatenate([rng.integers(0, 256, (3000, 3)), rng.integers(0, 12, (500, 3)), rng.integers(0, 40, (500, 3)),
+                           [[0, 0, 0], [1, 1, 1], [10, 10, 10], [11, 11, 11], [2, 0, 0], [0, 3, 0], [0, 0, 9], [255, 255, 255]]]).astype(np.uint8)
+    got = np.array([orc.rgb8_to_lab(*c) for c in cols], np.float32)
+    c = cols.astype(np.float64) / 255.0
+    lin = np.where(c <= 0.04045, c / 12.92, ((c + 0.055) / 1.055) ** 2.4)
+    m = np.array([[0.4124564, 0.3575761, 0.1804375], [0.2126729, 0.7151522, 0.0721750], [0.0193339, 0.1191920, 0.9503041]])
+    xyz = lin @ m.T / np.array([0.95047, 1.0, 1.08883])
+    f = np.where(xyz > (6 / 29) ** 3, np.cbrt(xyz), (841 / 108) * xyz + 4 / 29)
+    want = np.stack([116 * f[:, 1] - 16, 500 * (f[:, 0] - f[:, 1]), 200 * (f[:, 1] - f[:, 2])], 1)
+    assert np.abs(got - want).max() < 2e-4, np.abs(got - want).max()
+    dark = cols.max(1) < 11                                              # every channel on the linear segment of the decode
+    assert dark.sum() > 300 and (got[dark, 0] < 3.5).all() and (got[dark, 0] >= 0).all()
+    assert ((xyz <= (6 / 29) ** 3).any(1)).sum() > 300                   # f(t)'s linear branch is really taken
+    cv2 = pytest.importorskip("cv2")
+    cv = cv2.cvtColor((cols.astype(np.float32) / np.float32(255.0)).reshape(-1, 1, 3), cv2.COLOR_RGB2Lab).reshape(-1, 3)
+    assert np.abs(got - cv).max() < 0.6, np.abs(got - cv).max()
