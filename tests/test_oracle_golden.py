@@ -448,3 +448,21 @@ def test_lab_against_float64_formula_and_opencv():
     cv2 = pytest.importorskip("cv2")
     cv = cv2.cvtColor((cols.astype(np.float32) / np.float32(255.0)).reshape(-1, 1, 3), cv2.COLOR_RGB2Lab).reshape(-1, 3)
     assert np.abs(got - cv).max() < 0.6, np.abs(got - cv).max()
+
+
+def test_topk_against_scipy_kdtree():
+    """`nearest_n::<SquaredEuclidean>(query, k)` = the k smallest squared Euclidean distances, ascending (main.rs:348-352):
+    the brute force and the bucketed k-d tree of the oracle against scipy's cKDTree (float64) — same neighbours in the same
+    order wherever consecutive distances are further apart than float rounding, same distances to 1e-5."""
+    spatial = pytest.importorskip("scipy.spatial")
+    rng = np.random.default_rng(21)
+    pts = np.stack([rng.uniform(0, 100, 3000), rng.uniform(-100, 100, 3000), rng.uniform(-100, 100, 3000)], 1).astype(np.float32)
+    qs = np.stack([rng.uniform(0, 100, 200), rng.uniform(-100, 100, 200), rng.uniform(-100, 100, 200)], 1).astype(np.float32)
+    k = 100
+    dist, ref = spatial.cKDTree(pts.astype(np.float64)).query(qs.astype(np.float64), k=k)
+    for idx, d2 in (orc.topk(pts, qs, k), orc.topk_kdtree(pts, qs, k)):
+        assert np.allclose(d2, dist ** 2, rtol=1e-5)
+        assert (np.diff(d2.astype(np.float64), axis=1) >= 0).all()
+        gaps = np.diff(dist ** 2, axis=1)
+        clear = np.concatenate([np.ones((len(qs), 1), bool), gaps > 1e-3], 1) & np.concatenate([gaps > 1e-3, np.ones((len(qs), 1), bool)], 1)
+        assert clear.mean() > 0.9 and (idx[clear] == ref[clear]).all()
