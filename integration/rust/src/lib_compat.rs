@@ -68,9 +68,11 @@ pub fn build_similarities(ctx: &mut Ctx, lab_colors: &[[f32; 3]]) -> Result<Vec<
     Ok(sim)
 }
 
-/// A grid of paths as the kernels want it: indices into the database (`-1` = empty cell).  Paths the database does not
-/// know are occupied cells without similarity terms (similarity.rs:85-103 returns None): they get pseudo indices behind
-/// the database's, with colours that are never read (the C++ mirror does the same, `detail::grid_ids`).
+/// A grid of paths as the kernels want it: indices into the database (`-1` = empty cell).  A path the database does not
+/// know is an OCCUPIED cell for the reference (the optimiser swaps it, draws for it and cools down, optimizer.rs:71-102);
+/// only its similarity terms are skipped, because `get_similarity` returns None — also against itself (similarity.rs:85-90).
+/// Every such CELL gets its own pseudo index behind the database's (two cells with the same unknown path must not look
+/// like the same material: `sim(i, i)` would be 0.0 and the term 1.0), exactly as the C++ mirror does (`detail::grid_ids`).
 fn grid_ids(path_to_index: &HashMap<PathBuf, usize>, n: usize, grid: &[Vec<Option<PathBuf>>]) -> (Vec<i32>, Vec<PathBuf>) {
     let mut unknown: Vec<PathBuf> = Vec::new();
     let mut ids = Vec::new();
@@ -81,11 +83,8 @@ fn grid_ids(path_to_index: &HashMap<PathBuf, usize>, n: usize, grid: &[Vec<Optio
                 Some(p) => match path_to_index.get(p) {
                     Some(&i) => i as i32,
                     None => {
-                        let k = unknown.iter().position(|u| u == p).unwrap_or_else(|| {
-                            unknown.push(p.clone());
-                            unknown.len() - 1
-                        });
-                        (n + k) as i32
+                        unknown.push(p.clone());
+                        (n + unknown.len() - 1) as i32
                     }
                 },
             });
@@ -95,11 +94,14 @@ fn grid_ids(path_to_index: &HashMap<PathBuf, usize>, n: usize, grid: &[Vec<Optio
 }
 
 fn load_grid(ctx: &mut Ctx, lab_colors: &[[f32; 3]], ids: &[i32], gw: usize, gh: usize, n_unknown: usize) -> Result<()> {
-    // unknown paths: colours far outside Lab so that no similarity term is ever small — the kernels treat an index
-    // >= n_known as "no similarity" through mosaic_set_similarity_lab's override in the C++ mirror; here the simple
-    // form: the database's colours followed by NaN rows (a NaN distance contributes no term, adjacency.rs:76-84)
+    // pseudo materials of the unknown cells: colours so far apart (steps of 3e19 in L) that every squared distance to
+    // anything overflows to +inf: 1 / (sqrt(inf) + 1) = 0, the term the reference skips contributes +0.0 and x + 0.0 == x
+    // (`detail::unknown_lab` in include/mosaic_b200.hpp; NaN would NOT do: it poisons the sums)
     let mut lab: Vec<[f32; 3]> = lab_colors.to_vec();
-    lab.extend(std::iter::repeat([f32::NAN; 3]).take(n_unknown));
+    lab.extend((0..n_unknown).map(|k| [3.0e19f32 * (k as f32 + 1.0), 0.0, 0.0]));
+    if lab.is_empty() {
+        lab.push([0.0; 3]); // a grid of empty cells over an empty database: nothing is ever read
+    }
     let zeros = vec![[0f32; 3]; gw * gh];
     unsafe {
         ok(mosaic_set_material_lab(ctx.raw(), lab.as_ptr() as *const c_float, lab.len() as c_int), "set_material_lab")?;
