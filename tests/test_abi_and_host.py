@@ -212,7 +212,7 @@ def test_header_is_plain_c(tmp_path):
 # ---------------------------------------------------------------- the Rust side (unverified source) against the header
 _RUST_TO_C = {
     "c_int": "int", "i32": "int32_t", "u32": "uint32_t", "u64": "uint64_t", "i64": "int64_t", "c_float": "float", "f32": "float",
-    "u8": "uint8_t", "c_char": "char", "mosaic_ctx": "mosaic_ctx", "mosaic_simdb": "mosaic_simdb",
+    "u8": "uint8_t", "c_char": "char", "c_void": "void", "usize": "size_t", "mosaic_ctx": "mosaic_ctx", "mosaic_simdb": "mosaic_simdb",
     "mosaic_opt_result": "mosaic_opt_result", "mosaic_params": "mosaic_params", "mosaic_report": "mosaic_report",
 }
 
@@ -260,8 +260,10 @@ def test_rust_ffi_declarations_match_the_header():
     for m in re.finditer(r"^([A-Za-z_][A-Za-z0-9_ \*]*?)\b(mosaic_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", hdr, flags=re.M | re.S):
         c_decls[m.group(2)] = (_norm_c(m.group(1)), _c_params(m.group(3)))
     checked = 0
-    for name in ("b200.rs", "lib_compat.rs"):
-        src = open(os.path.join(ROOT, "integration", "rust", "src", name)).read()
+    sources = [(name, open(os.path.join(ROOT, "integration", "rust", "src", name)).read()) for name in ("b200.rs", "lib_compat.rs")]
+    # the same declarations as INTEGRATION.md prints them
+    sources.append(("INTEGRATION.md", "\n".join(re.findall(r"```rust\n(.*?)```", open(os.path.join(ROOT, "INTEGRATION.md")).read(), flags=re.S))))
+    for name, src in sources:
         src = re.sub(r"//[^\n]*", "", src)
         for block in re.findall(r'extern\s+"C"\s*\{(.*?)\n\}', src, flags=re.S):
             for m in re.finditer(r"fn\s+(mosaic_[a-z0-9_]+)\s*\((.*?)\)\s*(?:->\s*([^;]+))?;", block, flags=re.S):
