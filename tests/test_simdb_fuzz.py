@@ -394,3 +394,31 @@ def test_number_text_does_not_follow_the_locale(tmp_path):
         assert (got.view(np.uint32) == lab.view(np.uint32)).all()
     finally:
         locale.setlocale(locale.LC_NUMERIC, "C")
+
+
+def test_float_text_over_random_bit_patterns(tmp_path):
+    """ryu prints the shortest digits that read back as the same f32; so does numpy's `unique` mode.  30,000 random f32 BIT
+    PATTERNS (denormals, the extremes): the writer's digits are numpy's, and the reader returns the bits."""
+    rng = np.random.default_rng(5)
+    vals = rng.integers(0, 2 ** 32, 40000, dtype=np.uint64).astype(np.uint32).view(np.float32)
+    vals = vals[np.isfinite(vals)][:30000]
+    n = len(vals) // 3
+    lab = vals[:3 * n].reshape(n, 3)
+    f = tmp_path / "bits.json"
+    import ctypes as C
+    L = mosaic_b200.load_library()                                          # (no matrix: the stale-list form of the writer)
+    paths = (C.c_char_p * n)(*[b"p%d" % i for i in range(n)])
+    L.mosaic_simdb_save_json_n.argtypes = [C.c_char_p, C.POINTER(C.c_char_p), C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float),
+                                           C.c_uint64]
+    assert L.mosaic_simdb_save_json_n(os.fsencode(str(f)), paths, n, lab.ctypes.data_as(C.POINTER(C.c_float)), None, 0) == 0
+    nums = re.findall(r'"[lab]": (-?[0-9.e+-]+)', f.read_text())
+    assert len(nums) == 3 * n
+    for s, v in zip(nums, lab.ravel()):
+        if v == 0:
+            assert s in ("0.0", "-0.0")
+            continue
+        mine = re.sub(r"e.*$", "", s).replace("-", "").replace(".", "").lstrip("0").rstrip("0")
+        ref = np.format_float_scientific(v, unique=True, trim="-").split("e")[0].replace("-", "").replace(".", "").rstrip("0")
+        assert mine == ref and np.float32(float(s)) == v, (s, v)
+    got, _ = mosaic_b200.SimilarityDb.load(str(f)).arrays()
+    assert (got.view(np.uint32) == lab.view(np.uint32)).all()
