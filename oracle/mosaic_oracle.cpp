@@ -9,7 +9,11 @@
  * Citations are file:line under /root/reference/src/.  [3P] marks arithmetic that lives
  * in a third-party crate whose source is not in /root/reference (pinned in Cargo.lock):
  * the algorithm is restated from the published crate and is "parity unpinned" beyond the
- * reference's own test vectors.
+ * reference's own test vectors.  What this image allows beyond those vectors is in
+ * tests/test_oracle_golden.py: the ChaCha block function against OpenSSL's ChaCha20 for arbitrary
+ * keys and counters, HSV against Python's colorsys, sRGB->Lab against the formula in float64 and
+ * OpenCV, the resize against Pillow's LANCZOS, top-K against scipy's k-d tree — and
+ * tests/golden/pipeline_small.npz pins every stage's output bits against drift.
  */
 #include "mosaic_oracle.h"
 
