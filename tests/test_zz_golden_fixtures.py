@@ -306,3 +306,15 @@ class _StandInContext:
 def test_cuda_adapter_over_a_stand_in_context():
     check_reference_known_answers(CudaImpl(_StandInContext()))
     check_pipeline(CudaImpl(_StandInContext()), exact_lab=False)
+
+
+def test_timed_cpu_arm_computes_the_same_bits():
+    """`bench.py --impl reference` / `cpu_baseline` time the -O3 -march=native build of the restatement; with
+    -ffp-contract=off and no fast-math it has to produce the strict build's results bit for bit — the timed CPU arm is the
+    same computation as the parity oracle, only compiled for speed."""
+    try:
+        orc.select("fast")
+        check_pipeline(OracleImpl(), exact_lab=True)
+        check_reference_known_answers(OracleImpl())
+    finally:
+        orc.select("strict")
