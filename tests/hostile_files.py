@@ -7,7 +7,6 @@ filter bytes, short / long / missing / garbage IDAT streams, chunk order and len
 VP8X flags and canvas, VP8 frame tags / start codes / dimensions / first-partition bytes, VP8L header and bitstream bytes,
 ALPH headers).  Each generator yields (tag, bytes)."""
 import itertools
-import os
 import struct
 import zlib
 

@@ -8,7 +8,6 @@ import os
 import numpy as np
 import pytest
 
-import mosaic_b200
 from mosaic_b200 import synth
 from oracle import oracle as orc
 
