@@ -204,7 +204,11 @@ static bool read_image(const std::string& file, RgbImage* img, bool header_only 
 
 static bool write_image(const std::string& file, const RgbImage& img) {  // output_img.save(path): by extension
   const std::string ext = lower_ext(file);
-  if (ext != "png" && ext != "jpg" && ext != "jpeg" && ext != "webp") return write_ppm(file, img);
+  if (ext == "ppm") return write_ppm(file, img);
+  if (ext != "png" && ext != "jpg" && ext != "jpeg" && ext != "webp") {  // `save` fails on an extension it has no encoder for
+    std::fprintf(stderr, "unsupported output extension \"%s\" (png, jpg, jpeg, webp or ppm)\n", ext.c_str());
+    return false;
+  }
   try {
     if (ext == "png")
       codec::encode_png(file, img.data.data(), img.width, img.height);
