@@ -422,3 +422,52 @@ def test_float_text_over_random_bit_patterns(tmp_path):
         assert mine == ref and np.float32(float(s)) == v, (s, v)
     got, _ = mosaic_b200.SimilarityDb.load(str(f)).arrays()
     assert (got.view(np.uint32) == lab.view(np.uint32)).all()
+
+
+def test_reader_loads_any_layout_of_a_valid_document(tmp_path):
+    """The same database written in layouts the library's writer never produces — any key order, any whitespace, compact or
+    indented, ASCII-escaped or raw UTF-8 strings, integers / exponents for floats, unknown fields at both levels, structs as
+    sequences: serde_json reads them all (similarity.rs:121), so the reader must, with the same values."""
+    rng = np.random.default_rng(77)
+    f = tmp_path / "layout.json"
+    for trial in range(300):
+        n = int(rng.integers(0, 7))
+        paths = [f"m/{i}-é🖼\"\\\t.png" if i % 3 == 0 else f"dir {i}/tile.JPG" for i in range(n)]
+        lab = np.round(rng.uniform(-100, 100, (n, 3)), int(rng.integers(0, 5))).astype(np.float32)
+        sim = np.round(rng.uniform(0, 250, n * (n - 1) // 2), int(rng.integers(0, 5))).astype(np.float32)
+
+        def num(v):
+            v = float(v)
+            if v != 0 and v == int(v) and abs(v) < 1e15 and rng.integers(0, 2):   # (not -0.0: "0" is +0.0)
+                return int(v)                                            # an integer literal where an f32 is expected
+            return v
+
+        def lab_struct(c):
+            if rng.integers(0, 4) == 0:
+                return [num(c[0]), num(c[1]), num(c[2])]                 # the struct as a sequence
+            items = [("l", num(c[0])), ("a", num(c[1])), ("b", num(c[2]))]
+            if rng.integers(0, 3) == 0:
+                items.append(("alpha", [1, {"x": None}, "y"]))           # unknown field: skipped
+            order = rng.permutation(len(items))
+            return {items[i][0]: items[i][1] for i in order}
+
+        fields = [("path_to_index", {p: i for i, p in enumerate(paths)}), ("index_to_path", {str(i): p for i, p in enumerate(paths)}),
+                  ("lab_colors", [lab_struct(c) for c in lab]), ("similarities", [num(v) for v in sim])]
+        if trial % 5 == 4:
+            doc = [v for _, v in fields]                                  # the struct as a sequence of its fields
+        else:
+            if rng.integers(0, 2):
+                fields.append(("version", {"major": 2, "notes": ["a", 1.5e300, True]}))
+            order = rng.permutation(len(fields))
+            doc = {fields[i][0]: fields[i][1] for i in order}
+        indent = [None, 0, 1, 4, "\t"][int(rng.integers(0, 5))]
+        seps = [(",", ":"), (", ", ": "), (" ,\n", " :\t")][int(rng.integers(0, 3))] if indent is None else None
+        text = json.dumps(doc, indent=indent, separators=seps, ensure_ascii=bool(rng.integers(0, 2)))
+        text = " \n\t" * int(rng.integers(0, 2)) + text + "\r\n " * int(rng.integers(0, 2))
+        f.write_bytes(text.encode("utf-8"))
+        db = mosaic_b200.SimilarityDb.load(str(f))
+        assert db.info() == dict(rows=n, similarities=len(sim), paths=n), text[:300]
+        glab, gsim = db.arrays()
+        assert (glab.reshape(-1, 3).view(np.uint32) == lab.view(np.uint32)).all() and (gsim.view(np.uint32) == sim.view(np.uint32)).all(), text[:300]
+        assert [db.path(i) for i in range(n)] == paths and [db.index_of(p) for p in paths] == list(range(n))
+        db.close()
