@@ -51,3 +51,77 @@ def test_decoders_survive_mutated_files(tmp_path):
     r = subprocess.run([str(exe), "400"] + files, capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0, (r.stdout + r.stderr)[-3000:]
     assert "fuzz_codecs:" in r.stdout
+
+
+def test_random_valid_files_decode_like_pillow(tmp_path):
+    """The other side of robustness: 700 random VALID files — sizes 1..200, noise / smooth / blocky / flat content, JPEG at every
+    quality with random progressive / optimise / subsampling / restart settings, WebP lossy and lossless at random quality and
+    effort with and without alpha, PNG in seven modes at every compression level — decode to exactly Pillow's pixels."""
+    import mosaic_b200
+    rng = np.random.default_rng(123)
+
+    def img(h, w, kind):
+        if kind == 0:
+            a = rng.integers(0, 256, (h, w, 3))
+        elif kind == 1:
+            yy, xx = np.mgrid[0:h, 0:w]
+            a = np.stack([127 + 120 * np.sin(xx / 7.0 + yy / 11.0), 127 + 120 * np.cos(xx / 5.0), (xx * 3 + yy * 5) % 256], -1)
+        elif kind == 2:
+            a = np.kron(rng.integers(0, 256, ((h + 7) // 8, (w + 7) // 8, 3)), np.ones((8, 8, 1)))[:h, :w]
+        else:
+            a = np.full((h, w, 3), rng.integers(0, 256))
+        return np.clip(a, 0, 255).astype(np.uint8)
+
+    def save(im, f, **kw):
+        try:
+            im.save(f, **kw)
+            return True
+        except (OSError, KeyError, ValueError):      # a Pillow without that format
+            return False
+
+    done = 0
+    for trial in range(300):
+        a = img(int(rng.integers(1, 200)), int(rng.integers(1, 200)), int(rng.integers(0, 4)))
+        im = PIL.fromarray(a)
+        if rng.integers(0, 5) == 0:
+            im = im.convert("L")
+        kw = dict(quality=int(rng.integers(1, 101)), progressive=bool(rng.integers(0, 2)), optimize=bool(rng.integers(0, 2)))
+        if im.mode == "RGB":
+            kw["subsampling"] = int(rng.integers(0, 3))
+        if rng.integers(0, 3) == 0:
+            kw["restart_marker_blocks"] = int(rng.integers(1, 9))
+        f = tmp_path / "t.jpg"
+        if save(im, f, **kw):
+            assert (mosaic_b200.jpeg_decode(f) == np.asarray(PIL.open(f).convert("RGB"))).all(), (a.shape, im.mode, kw)
+            done += 1
+    for trial in range(200):
+        h, w = int(rng.integers(1, 160)), int(rng.integers(1, 160))
+        a = img(h, w, int(rng.integers(0, 4)))
+        if rng.integers(0, 4) == 0:
+            a = np.dstack([a, rng.integers(0, 256, (h, w, 1)).astype(np.uint8)])
+        kw = dict(quality=int(rng.integers(0, 101)), method=int(rng.integers(0, 7)), lossless=bool(rng.integers(0, 2)))
+        f = tmp_path / "t.webp"
+        if save(PIL.fromarray(a), f, **kw):
+            assert (mosaic_b200.webp_decode(f) == np.asarray(PIL.open(f).convert("RGB"))).all(), (a.shape, kw)
+            done += 1
+    for trial in range(200):
+        h, w = int(rng.integers(1, 120)), int(rng.integers(1, 120))
+        a = img(h, w, int(rng.integers(0, 4)))
+        mode = ["RGB", "L", "P", "RGBA", "LA", "1", "I;16"][int(rng.integers(0, 7))]
+        if mode == "I;16":
+            im = PIL.fromarray(a[:, :, 0].astype(np.uint16) * int(rng.integers(1, 258)))
+        elif mode == "RGBA":
+            im = PIL.fromarray(np.dstack([a, a[:, :, :1]]))
+        else:
+            im = PIL.fromarray(a).convert(mode)
+        f = tmp_path / "t.png"
+        assert save(im, f, optimize=bool(rng.integers(0, 2)), compress_level=int(rng.integers(0, 10)))
+        ref = PIL.open(f)
+        if mode == "I;16":                            # image's to_rgb8(): (v + 128) / 257 (Pillow's own 16 -> 8 conversion differs)
+            g = ((np.asarray(ref).astype(np.uint32) + 128) // 257).astype(np.uint8)
+            want = np.dstack([g, g, g])
+        else:
+            want = np.asarray(ref.convert("RGB"))
+        assert (mosaic_b200.png_decode(f) == want).all(), (h, w, mode)
+        done += 1
+    assert done >= 500
