@@ -125,3 +125,38 @@ def test_random_valid_files_decode_like_pillow(tmp_path):
         assert (mosaic_b200.png_decode(f) == want).all(), (h, w, mode)
         done += 1
     assert done >= 500
+
+
+def test_random_images_through_the_encoders(tmp_path):
+    """output_img.save(path) (main.rs:668-672) over 200 random images (1..180 pixels a side; noise, smooth, blocky, flat, four-level
+    content): Pillow reads back exactly what the PNG and WebP writers were given, and the JPEG writer's file decodes to the pixels
+    of the file libjpeg-turbo writes from the same image at the same quality (4:4:4)."""
+    import mosaic_b200
+    rng = np.random.default_rng(321)
+    for trial in range(200):
+        h, w, kind = int(rng.integers(1, 180)), int(rng.integers(1, 180)), int(rng.integers(0, 5))
+        if kind == 0:
+            a = rng.integers(0, 256, (h, w, 3))
+        elif kind == 1:
+            yy, xx = np.mgrid[0:h, 0:w]
+            a = np.stack([127 + 120 * np.sin(xx / 7.0 + yy / 11.0), 127 + 120 * np.cos(xx / 5.0), (xx * 3 + yy * 5) % 256], -1)
+        elif kind == 2:
+            a = np.kron(rng.integers(0, 256, ((h + 7) // 8, (w + 7) // 8, 3)), np.ones((8, 8, 1)))[:h, :w]
+        elif kind == 3:
+            a = np.full((h, w, 3), rng.integers(0, 256))
+        else:
+            a = rng.integers(0, 4, (h, w, 3)) * 80
+        a = np.clip(a, 0, 255).astype(np.uint8)
+        mosaic_b200.png_encode(tmp_path / "e.png", a)
+        assert (np.asarray(PIL.open(tmp_path / "e.png").convert("RGB")) == a).all(), (h, w, kind)
+        try:
+            mosaic_b200.webp_encode(tmp_path / "e.webp", a)
+            im = PIL.open(tmp_path / "e.webp")
+            assert im.format == "WEBP" and (np.asarray(im.convert("RGB")) == a).all(), (h, w, kind)
+        except OSError:                               # a Pillow without WebP
+            pass
+        q = int(rng.integers(1, 101))
+        mosaic_b200.jpeg_encode(tmp_path / "e.jpg", a, q)
+        PIL.fromarray(a).save(tmp_path / "r.jpg", quality=q, subsampling=0)
+        got, ref = (np.asarray(PIL.open(tmp_path / n).convert("RGB")) for n in ("e.jpg", "r.jpg"))
+        assert got.shape == ref.shape and (got == ref).all(), (h, w, kind, q)
