@@ -113,17 +113,33 @@ static bool read_ppm(const std::string& file, RgbImage* img, bool header_only = 
     }
     while ((c = in.peek()) != EOF && !std::isspace(c)) t->push_back((char)in.get());
   };
+  auto number = [](const std::string& t) -> int {  // decimal digits only, at most 2^24 (no atoi: overflow is undefined)
+    if (t.empty() || t.size() > 8) return -1;
+    int v = 0;
+    for (char c : t) {
+      if (c < '0' || c > '9') return -1;
+      v = v * 10 + (c - '0');
+    }
+    return v <= (1 << 24) ? v : -1;
+  };
   std::string t;
   token(&magic);
-  token(&t), w = std::atoi(t.c_str());
-  token(&t), h = std::atoi(t.c_str());
-  token(&t), maxv = std::atoi(t.c_str());
+  token(&t), w = number(t);
+  token(&t), h = number(t);
+  token(&t), maxv = number(t);
   if (magic != "P6" || w <= 0 || h <= 0 || maxv != 255) return false;
   in.get();  // the single whitespace after maxval
+  // a header may claim any size: the pixels have to BE in the file before anything of that size is allocated
+  const std::streamoff at = in.tellg();
+  in.seekg(0, std::ios::end);
+  const std::streamoff end = in.tellg();
+  const uint64_t need = (uint64_t)w * (uint64_t)h * 3u;
+  if (at < 0 || end < at || (uint64_t)(end - at) < need) return false;
+  in.seekg(at);
   img->width = w;
   img->height = h;
   if (header_only) return true;
-  img->data.resize((size_t)w * h * 3);
+  img->data.resize((size_t)need);
   in.read((char*)img->data.data(), (std::streamsize)img->data.size());
   return (size_t)in.gcount() == img->data.size();
 }

@@ -272,6 +272,22 @@ def test_cli_selects_the_tiles_load_tiles_selects(cli, tmp_path):
     assert "No tiles matched" not in r.stdout
     assert got == _reference_load_tiles(mixed_files, 160 / 90, 1000.0, 500) and len(got) == 8
 
+    # ---- PPM headers that lie (found with the CLI under AddressSanitizer: 99999999999 x 99999999999 went to atoi and resize)
+    pp = tmp_path / "ppm"
+    pp.mkdir()
+    px = bytes(range(48))
+    for name, data in {"ok.ppm": b"P6\n4 4\n255\n" + px, "comment.ppm": b"P6\n# c\n4 # x\n4\n255\n" + px, "nows.ppm": b"P6 4 4 255 " + px,
+                       "crlf.ppm": b"P6\r\n4 4\r\n255\r\n" + px, "short.ppm": b"P6\n4 4\n255\n" + px[:10],
+                       "huge.ppm": b"P6\n99999999999 99999999999\n255\n" + px, "big.ppm": b"P6\n65536 65536\n255\n" + px,
+                       "neg.ppm": b"P6\n-4 4\n255\n" + px, "zero.ppm": b"P6\n0 4\n255\n", "maxval.ppm": b"P6\n4 4\n65535\n" + px + px,
+                       "p3.ppm": b"P3\n1 1\n255\n1 2 3\n", "empty.ppm": b"", "p6only.ppm": b"P6", "nonum.ppm": b"P6\nabc def\n255\n" + px,
+                       "eofincomment.ppm": b"P6\n# never ends"}.items():
+        (pp / name).write_bytes(data)
+    got, r = listed(pp, "--aspect-tolerance", "100")
+    assert got == ["comment.ppm", "crlf.ppm", "nows.ppm", "ok.ppm"]
+    for name in ("huge.ppm", "big.ppm", "short.ppm", "neg.ppm", "zero.ppm", "maxval.ppm", "p3.ppm", "empty.ppm"):
+        assert name in r.stderr
+
     # ---- an empty directory lists nothing
     empty = tmp_path / "empty"
     empty.mkdir()
