@@ -17,7 +17,9 @@
 #include <atomic>
 #include <chrono>
 #include <cmath>
+#include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <iostream>
@@ -49,6 +51,31 @@ struct Args {  // main.rs:23-88, same defaults
 
 static bool parse_bool(const std::string& v) { return v == "true" || v == "1"; }
 
+// clap's value parsers (main.rs:23-88): `usize` / `u32` take decimal digits only, `f32` what str::parse::<f32> takes; anything
+// else is a usage error (exit code 2), not an exception
+struct BadValue : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+static unsigned long long parse_unsigned(const std::string& flag, const std::string& v, unsigned long long max) {
+  unsigned long long x = 0;
+  bool ok = !v.empty() && v.size() <= 20;
+  for (size_t i = 0; ok && i < v.size(); ++i) {
+    const char c = v[i];
+    if (c == '+' && i == 0 && v.size() > 1) continue;  // (Rust's integer parser accepts a leading '+')
+    if (c < '0' || c > '9' || x > (max - (unsigned)(c - '0')) / 10) ok = false;
+    else x = x * 10 + (unsigned)(c - '0');
+  }
+  if (!ok) throw BadValue("error: invalid value '" + v + "' for '" + flag + "': not an unsigned integer in range");
+  return x;
+}
+static float parse_float(const std::string& flag, const std::string& v) {
+  char* end = nullptr;
+  const float x = v.empty() || std::isspace((unsigned char)v[0]) ? 0.0f : std::strtof(v.c_str(), &end);
+  if (!end || end == v.c_str() || *end != 0 || (v.size() > 1 && (v[1] == 'x' || v[1] == 'X')))  // (no hex floats in Rust)
+    throw BadValue("error: invalid value '" + v + "' for '" + flag + "': invalid float literal");
+  return x;
+}
+
 static bool parse(int argc, char** argv, Args* a) {
   for (int i = 1; i < argc; ++i) {
     std::string k = argv[i], v;
@@ -67,20 +94,20 @@ static bool parse(int argc, char** argv, Args* a) {
     if (k == "-t" || k == "--target") a->target = v;
     else if (k == "-m" || k == "--material-src") a->material_src = v;
     else if (k == "-o" || k == "--output") a->output = v;
-    else if (k == "--grid-w") a->grid_w = (unsigned)std::stoul(v);
-    else if (k == "--grid-h") a->grid_h = (unsigned)std::stoul(v);
-    else if (k == "--max-materials") a->max_materials = std::stoul(v);
-    else if (k == "--aspect-tolerance") a->aspect_tolerance = std::stof(v);
-    else if (k == "--max-usage-per-image") a->max_usage_per_image = std::stoul(v);
-    else if (k == "--adjacency-penalty-weight") a->adjacency_penalty_weight = std::stof(v);
+    else if (k == "--grid-w") a->grid_w = (unsigned)parse_unsigned(k, v, 0xFFFFFFFFull);
+    else if (k == "--grid-h") a->grid_h = (unsigned)parse_unsigned(k, v, 0xFFFFFFFFull);
+    else if (k == "--max-materials") a->max_materials = (size_t)parse_unsigned(k, v, SIZE_MAX);
+    else if (k == "--aspect-tolerance") a->aspect_tolerance = parse_float(k, v);
+    else if (k == "--max-usage-per-image") a->max_usage_per_image = (size_t)parse_unsigned(k, v, SIZE_MAX);
+    else if (k == "--adjacency-penalty-weight") a->adjacency_penalty_weight = parse_float(k, v);
     else if (k == "--enable-optimization") a->enable_optimization = parse_bool(v);
-    else if (k == "--optimization-iterations") a->optimization_iterations = std::stoul(v);
+    else if (k == "--optimization-iterations") a->optimization_iterations = (size_t)parse_unsigned(k, v, SIZE_MAX);
     else if (k == "--similarity-db") a->similarity_db = v;
     else if (k == "--rebuild-similarity-db") a->rebuild_similarity_db = true;
-    else if (k == "--color-adjustment-strength") a->color_adjustment_strength = std::stof(v);
+    else if (k == "--color-adjustment-strength") a->color_adjustment_strength = parse_float(k, v);
     else if (k == "--show-time") a->show_time = parse_bool(v);
     else if (k == "--show-grid") a->show_grid = parse_bool(v);
-    else if (k == "--seed") a->seed = std::stoull(v);
+    else if (k == "--seed") a->seed = parse_unsigned(k, v, ~0ull);
     else if (k == "--list-tiles") a->list_tiles = true;
     else {
       std::fprintf(stderr, "error: unexpected argument '%s'\n", k.c_str());
@@ -314,7 +341,12 @@ static void load_tiles(const std::string& material_dir, float target_aspect, flo
 
 int main(int argc, char** argv) {
   Args args;
-  if (!parse(argc, argv, &args)) return 2;
+  try {
+    if (!parse(argc, argv, &args)) return 2;
+  } catch (const BadValue& e) {
+    std::fprintf(stderr, "%s\n", e.what());
+    return 2;
+  }
   try {
     const auto t0 = std::chrono::steady_clock::now();
     RgbImage target;

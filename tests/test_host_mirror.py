@@ -168,6 +168,15 @@ def test_cli_flags_and_errors(cli, tmp_path):
     r = subprocess.run([cli, "-t", str(tmp_path / "none.ppm"), "-m", str(tmp_path), "-o", str(tmp_path / "o.ppm")],
                        capture_output=True, text=True)
     assert r.returncode == 1 and "cannot read target" in r.stderr
+    # clap's value parsers: a malformed number is a usage error (exit code 2), never an exception out of main
+    for flag, value in (("--grid-w", "abc"), ("--max-materials", "-5"), ("--aspect-tolerance", "xyz"), ("--grid-h", "99999999999"),
+                        ("--seed", "1e3"), ("--aspect-tolerance", "0x1p3"), ("--optimization-iterations", "12x"),
+                        ("--adjacency-penalty-weight", ""), ("--max-usage-per-image", " 3")):
+        r = subprocess.run([cli, "-t", "a", "-m", "b", "-o", "c.png", flag, value], capture_output=True, text=True)
+        assert r.returncode == 2 and "invalid value" in r.stderr and flag in r.stderr, (flag, value, r.returncode, r.stderr)
+    r = subprocess.run([cli, "-t", str(tmp_path / "none.ppm"), "-m", str(tmp_path), "-o", "c.png", "--aspect-tolerance", "-0.1",
+                        "--grid-w", "+5", "--color-adjustment-strength", "1e-1"], capture_output=True, text=True)
+    assert r.returncode == 1 and "cannot read target" in r.stderr       # well-formed values get past the parser
 
 
 def _reference_load_tiles(files, target_aspect, tolerance, max_materials):
