@@ -455,6 +455,15 @@ struct RgbImage {  // image::RgbImage: interleaved RGB8, row-major
   RgbImage(int w, int h) : width(w), height(h), data((size_t)w * h * 3, 0) {}
 };
 
+namespace detail {
+// the C ABI takes a pointer and trusts width * height * 3 bytes behind it: an RgbImage whose buffer disagrees with its
+// dimensions (image::RgbImage cannot be in that state; this struct can) is refused here instead of being read out of bounds
+inline void check_image(const RgbImage& img, const char* what) {
+  if (img.width <= 0 || img.height <= 0 || img.data.size() != (size_t)img.width * (size_t)img.height * 3)
+    throw Error(MOSAIC_ERR_INVALID, std::string(what) + ": the pixel buffer does not hold width * height * 3 bytes");
+}
+}  // namespace detail
+
 // UsageTracker (lib.rs:57-89): per-path use counts with a cap.  The placement kernel keeps its own counters in shared
 // memory (u8 / u16 per material, greedy_window.cu) with exactly these semantics; this class is the public type of
 // lib.rs for host code that tracks usage itself.
@@ -483,6 +492,7 @@ struct MosaicGeneratorImpl {  // impl MosaicGenerator for MosaicGeneratorImpl (t
   static Lab calculate_average_lab(const RgbImage& img) { return calculate_average_lab(detail::scratch_context(), img); }
   static Lab calculate_average_lab(Context& ctx, const RgbImage& img) {
     float lab[3];
+    detail::check_image(img, "calculate_average_lab");
     ctx.check(mosaic_set_materials_rgb8(ctx.get(), img.data.data(), 1, img.width, img.height));
     ctx.check(mosaic_material_lab(ctx.get(), lab));
     return Lab{lab[0], lab[1], lab[2]};
@@ -531,6 +541,7 @@ class MosaicGenerator {
     std::vector<uint64_t> offsets;
     std::vector<int32_t> widths, heights;
     for (const RgbImage& im : images) {
+      detail::check_image(im, "MosaicGenerator: material");
       offsets.push_back(blob.size());
       widths.push_back(im.width);
       heights.push_back(im.height);
@@ -591,6 +602,7 @@ class MosaicGenerator {
   RgbImage generate_mosaic(const RgbImage& target, int grid_w, int grid_h, bool enable_optimization,
                            size_t optimization_iterations, uint64_t seed = 0, PathGrid* placed = nullptr,
                            mosaic_report* report = nullptr) {
+    detail::check_image(target, "generate_mosaic: target");
     ctx_.check(mosaic_set_target_rgb8(ctx_.get(), target.data.data(), target.width, target.height, grid_w, grid_h));
     mosaic_params p{};
     p.max_usage = (int)std::min<size_t>(max_usage_, (size_t)0x7fffffff);  // usize -> int: a huge cap stays "no cap"

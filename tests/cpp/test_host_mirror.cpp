@@ -292,6 +292,31 @@ static void test_swap_delta() {  // adjacency.rs:133-214 (the optimizer's inner 
   CHECK(calc.calculate_penalty(names[0], GridPosition(1, 1), grid, 3, 3) == want);
 }
 
+static void test_image_buffers_are_checked() {  // an RgbImage whose buffer disagrees with its size never reaches the C ABI
+  RgbImage ok(4, 3);
+  bool threw = false;
+  try {
+    detail::check_image(ok, "test");
+  } catch (const Error&) {
+    threw = true;
+  }
+  CHECK(!threw);
+  RgbImage shorter(4, 3);
+  shorter.data.resize(10);
+  RgbImage empty;
+  RgbImage negative(4, 3);
+  negative.width = -4;
+  for (const RgbImage* bad : {&shorter, &empty, &negative}) {
+    threw = false;
+    try {
+      detail::check_image(*bad, "test");
+    } catch (const Error& e) {
+      threw = e.code == MOSAIC_ERR_INVALID;
+    }
+    CHECK(threw);
+  }
+}
+
 static void test_no_gpu_is_loud() {  // there is no CPU fallback behind the mirror: without a device the call throws
   SimilarityDatabase db;
   db.add_tile("a.png", Lab{50.0f, 0.0f, 0.0f});
@@ -706,6 +731,7 @@ int main(int argc, char** argv) {
   RUN(test_save_to_file_writes_a_stale_matrix);
   RUN(test_lab_distance_and_delta_e_2000);
   RUN(test_swap_delta);
+  RUN(test_image_buffers_are_checked);
   if (cpu_only) {
     RUN(test_no_gpu_is_loud);
   } else {
