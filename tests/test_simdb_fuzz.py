@@ -471,3 +471,30 @@ def test_reader_loads_any_layout_of_a_valid_document(tmp_path):
         assert (glab.reshape(-1, 3).view(np.uint32) == lab.view(np.uint32)).all() and (gsim.view(np.uint32) == sim.view(np.uint32)).all(), text[:300]
         assert [db.path(i) for i in range(n)] == paths and [db.index_of(p) for p in paths] == list(range(n))
         db.close()
+
+
+def test_utf8_boundaries(tmp_path):
+    """`read_to_string` (similarity.rs:120) takes exactly the well-formed UTF-8 sequences: the first and last code point of every
+    length load, overlong forms, surrogates, code points past U+10FFFF, stray continuation bytes and truncated sequences do not
+    (Python's strict decoder is the model)."""
+    f = tmp_path / "u.json"
+    seqs = [b"\x7f", b"\xc2\x80", b"\xdf\xbf", b"\xe0\xa0\x80", b"\xed\x9f\xbf", b"\xee\x80\x80", b"\xef\xbf\xbf", b"\xf0\x90\x80\x80",
+            b"\xf4\x8f\xbf\xbf", b"\xc0\x80", b"\xc1\xbf", b"\xe0\x9f\xbf", b"\xed\xa0\x80", b"\xed\xbf\xbf", b"\xf0\x8f\xbf\xbf",
+            b"\xf4\x90\x80\x80", b"\xf5\x80\x80\x80", b"\xf8\x88\x80\x80\x80", b"\x80", b"\xbf", b"\xe2\x82", b"\xf0\x9f\x96", b"\xc2",
+            b"\xc2\x41", b"\xe2\x41\x80", b"\xfe", b"\xff"]
+    for seq in seqs:
+        data = b'{"path_to_index": {"a' + seq + b'z": 0}, "index_to_path": {"0": "a' + seq + b'z"}, "lab_colors": [[1, 2, 3]], "similarities": []}'
+        f.write_bytes(data)
+        try:
+            want = data.decode("utf-8")
+        except UnicodeDecodeError:
+            want = None
+        try:
+            db = mosaic_b200.SimilarityDb.load(str(f))
+            got = db.path(0)
+            db.close()
+        except mosaic_b200.MosaicError:
+            got = None
+        assert (got is None) == (want is None), seq
+        if want is not None:
+            assert got == "a" + seq.decode("utf-8") + "z"
